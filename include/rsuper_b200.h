@@ -1,0 +1,222 @@
+/* rsuper_b200.h — C-ABI of librsuper_b200.so (hand-written sm_100a kernels for the R-Super
+ * 3D segmentation train step).
+ *
+ * The reference (MrGiovanni/R-Super @ 7f811ce1) is pure Python and has NO native interface of its
+ * own: every entry point below replaces an ATen / cuDNN *library call* that
+ * the reference makes, and each declaration cites that call site (file:line under
+ * /root/reference/rsuper_train).  The reference-side binding a maintainer would add is a ctypes
+ * stub; it is shown in INTEGRATION.md and implemented in r-super_b200/rsuper_b200/_lib.py.
+ *
+ * Conventions (all entry points)
+ *   - plain pointers + sizes; no torch types; every pointer is a DEVICE pointer unless noted.
+ *   - the caller (PyTorch caching allocator) owns all memory; kernels never allocate, free, or
+ *     keep pointers after return.
+ *   - `stream` is a cudaStream_t passed as void*; launches are asynchronous on it, there is no
+ *     internal synchronisation and no default-stream use (=> CUDA-graph capturable).
+ *   - return 0 on success, negative on error; rsb_last_error() gives the message (thread-local).
+ *   - activations are channels-last NDHWC with an explicit channel pitch (elements between
+ *     consecutive voxels), so a kernel can read/write a channel slice of a wider (concatenated)
+ *     buffer: torch.cat at unet_utils.py:71 costs nothing.
+ *   - `dtype`: RSB_BF16 (0) = bf16 storage, RSB_F32 (1) = fp32 storage.  Tensor-core operands are
+ *     always bf16 with fp32 accumulation in TMEM.
+ *   - InstanceNorm statistics travel as raw per-(n,c) pairs (sum, sumsq) in fp32:
+ *     stats[(n*C + c)*2 + {0,1}].  Producers accumulate them in their epilogue, consumers derive
+ *     mean / rstd with eps = 1e-4 (conv_layers.py:39-42).
+ */
+#ifndef RSUPER_B200_H_
+#define RSUPER_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSB_BF16 0
+#define RSB_F32 1
+
+/* ---------------------------------------------------------------------------------------------
+ * library
+ * ------------------------------------------------------------------------------------------ */
+const char* rsb_version(void);
+const char* rsb_last_error(void);
+/* number of SMs of the current device (grid sizing for the persistent kernels) */
+int rsb_num_sms(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * 3x3x3 convolution, stride 1, pad 1, no bias — nn.Conv3d inside ConvNormAct
+ * (model/dim3/conv_layers.py:29-38), with the pre-activation InstanceNorm + (Leaky)ReLU of
+ * conv_layers.py:47-49 fused into the operand staging, the residual add of BasicBlock
+ * (conv_layers.py:92) and the next layer's InstanceNorm statistics fused into the epilogue.
+ * Implicit GEMM on tcgen05 (M = 128 voxels, N = Cout tile, K = 27*Cin), accumulators in TMEM.
+ * The same kernel is the data gradient (dgrad) when given flipped/transposed weights.
+ * ------------------------------------------------------------------------------------------ */
+
+/* bytes of the packed bf16 weight image for a (Cout, Cin) 3x3x3 conv */
+size_t rsb_conv3_packed_weight_bytes(int Cout, int Cin);
+
+/* fp32 OIDHW [Cout][Cin][3][3][3] (the nn.Parameter layout) -> packed bf16 UMMA tiles.
+ * transpose_flip = 0: forward operand.  1: dgrad operand (taps flipped, Cin/Cout swapped: the
+ * packed image then describes a conv with Cin' = Cout, Cout' = Cin). */
+int rsb_conv3_pack_weights(const float* w_oidhw, void* packed, int Cout, int Cin,
+                           int transpose_flip, void* stream);
+
+typedef struct RsbConv3Args {
+  /* geometry */
+  int N, D, H, W;
+  int Cin, Cout;
+  int dtype; /* storage dtype of x, y, res, mask_x */
+  /* input (raw, pre-norm) NDHWC */
+  const void* x;
+  int x_pitch;
+  /* prologue: a = act((x - mean) * rstd); in_stats == NULL => identity (no norm, no act) */
+  const float* in_stats; /* [N][Cin][2] (sum, sumsq) over D*H*W */
+  float eps;             /* 1e-4 */
+  float slope;           /* 0 => ReLU (reference default), 0.01 => LeakyReLU */
+  /* packed weights from rsb_conv3_pack_weights */
+  const void* w_packed;
+  /* output */
+  void* y;
+  int y_pitch;
+  /* epilogue (all optional) */
+  const void* res; /* y = conv + res  (BasicBlock residual) */
+  int res_pitch;
+  float* out_stats; /* [N][Cout][2] += (sum, sumsq) of y  (fp32, pre-rounding) */
+  /* dgrad epilogue: y = conv * act'(xhat), xhat from (mask_x, mask_stats);
+   * bwd_sums[(n*Cout+c)*2+{0,1}] += (sum y, sum y*xhat)  — InstanceNorm backward reductions */
+  const void* mask_x;
+  int mask_x_pitch;
+  const float* mask_stats;
+  float* bwd_sums;
+  /* tuning (0 = auto) */
+  int planes_per_item; /* PZ in {1,2,4} */
+  int n_tile;          /* multiple of 16, <= 256 */
+  int max_ctas;        /* 0 => number of SMs */
+} RsbConv3Args;
+
+int rsb_conv3_forward(const RsbConv3Args* args, void* stream);
+
+/* weight gradient of the same conv: dW[co][ci][tap] = sum_v dy[v][co] * a[v+tap-1][ci],
+ * a = act(norm(x)) recomputed in the staging.  tcgen05 with MN-major operands (K = voxels).
+ * Writes fp32 OIDHW (overwrites or accumulates). */
+typedef struct RsbConv3WgradArgs {
+  int N, D, H, W;
+  int Cin, Cout;
+  int dtype;
+  const void* x;
+  int x_pitch;
+  const float* in_stats;
+  float eps, slope;
+  const void* dy;
+  int dy_pitch;
+  float* dw_oidhw;    /* [Cout][Cin][27] fp32 */
+  int accumulate;     /* 0: overwrite, 1: += */
+  void* workspace;    /* rsb_conv3_wgrad_workspace_bytes() */
+  size_t workspace_bytes;
+  int max_ctas;
+} RsbConv3WgradArgs;
+
+size_t rsb_conv3_wgrad_workspace_bytes(int Cout, int Cin, int max_ctas);
+int rsb_conv3_wgrad(const RsbConv3WgradArgs* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * stem conv 3x3x3 with Cin = 1 (inconv.conv1, model/dim3/unet_utils.py:15,18) — direct
+ * CUDA-core kernel (K = 27 is too small for the tensor pipe); fp32 NCDHW(C=1) in, NDHWC out,
+ * InstanceNorm statistics of the output accumulated in the epilogue.
+ * ------------------------------------------------------------------------------------------ */
+int rsb_stem_conv_forward(const float* x, const float* w_oidhw, void* y, int y_pitch, int dtype,
+                          float* out_stats, int N, int D, int H, int W, int Cout, void* stream);
+/* dW[co][tap] = sum_v dy[v][co] * x[v+tap-1] */
+int rsb_stem_conv_wgrad(const float* x, const void* dy, int dy_pitch, int dtype, float* dw_oidhw,
+                        int N, int D, int H, int W, int Cout, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * 1x1x1 head with bias (UNet.outc, model/dim3/unet.py:47,62): NDHWC raw features -> fp32 NCDHW
+ * logits, and its backward (d features, dW, db).
+ * ------------------------------------------------------------------------------------------ */
+int rsb_head_forward(const void* x, int x_pitch, int dtype, const float* w /*[C][Cin]*/,
+                     const float* bias, float* logits_ncdhw, int N, int D, int H, int W, int Cin,
+                     int C, void* stream);
+int rsb_head_backward(const void* x, int x_pitch, int dtype, const float* w,
+                      const float* dlogits_ncdhw, void* dx, int dx_pitch, float* dw, float* db,
+                      int N, int D, int H, int W, int Cin, int C, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * nn.MaxPool3d(2) (unet_utils.py:36) on NDHWC, output statistics fused; backward routes the
+ * gradient to the first maximum in ATen scan order (d, h, w) and adds an optional second
+ * gradient stream (the decoder skip) in the same pass.
+ * ------------------------------------------------------------------------------------------ */
+int rsb_maxpool2_forward(const void* x, int x_pitch, void* y, int y_pitch, int dtype,
+                         float* out_stats, int N, int D, int H, int W, int C, void* stream);
+int rsb_maxpool2_backward(const void* x, int x_pitch, const void* dy, int dy_pitch,
+                          const void* dskip, int dskip_pitch, void* dx, int dx_pitch, int dtype,
+                          int N, int D, int H, int W, int C, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * F.interpolate(mode='trilinear', align_corners=True) (unet_utils.py:69), NDHWC, output
+ * statistics fused, and its adjoint (deterministic gather).
+ * ------------------------------------------------------------------------------------------ */
+int rsb_upsample_trilinear_forward(const void* x, int x_pitch, void* y, int y_pitch, int dtype,
+                                   float* out_stats, int N, int Di, int Hi, int Wi, int Do, int Ho,
+                                   int Wo, int C, void* stream);
+int rsb_upsample_trilinear_backward(const void* dy, int dy_pitch, void* dx, int dx_pitch,
+                                    int dtype, int N, int Di, int Hi, int Wi, int Do, int Ho,
+                                    int Wo, int C, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * InstanceNorm backward (affine=False), applied after the dgrad epilogue produced
+ * g = dL/da * act'(xhat) and the reductions S1 = sum g, S2 = sum g*xhat:
+ *   dx = rstd * (g - S1/V - xhat * S2/V)  [+ add]
+ * (autograd of F.instance_norm as called by conv_layers.py:39-49).
+ * ------------------------------------------------------------------------------------------ */
+int rsb_instnorm_backward_apply(const void* g, int g_pitch, const void* x, int x_pitch,
+                                const float* x_stats, const float* bwd_sums, const void* add,
+                                int add_pitch, void* dx, int dx_pitch, int dtype, float eps,
+                                int N, int D, int H, int W, int C, void* stream);
+
+/* layout helpers: fp32 NCDHW <-> NDHWC(dtype, pitch) */
+int rsb_ncdhw_to_ndhwc(const float* src, void* dst, int dst_pitch, int dtype, int N, int C,
+                       int D, int H, int W, void* stream);
+int rsb_ndhwc_to_ncdhw(const void* src, int src_pitch, int dtype, float* dst, int N, int C,
+                       int D, int H, int W, void* stream);
+/* per-(n,c) (sum, sumsq) of an NDHWC tensor (used by tests and as a fallback producer) */
+int rsb_channel_stats(const void* x, int x_pitch, int dtype, float* stats, int N, int D, int H,
+                      int W, int C, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Segmentation loss: mean(BCEWithLogits(r, l) * known) + DiceLossMultiClass(r, l, known)
+ * (training/losses_foundation.py:945-956, 541-607), fp32 NCDHW logits.
+ *   pass 1: one read of (logits, label, known) -> per-(b,c) partial sums {bce, TP, FP, FN}
+ *   finalize: alpha_c (batch-coupled, clamped [0.2,0.8], carries gradient), loss scalars
+ *   pass 2: dlogits = dloss * d(loss)/d(logits)   (includes d/d alpha terms)
+ * label / known are uint8 (0/1).  class_weights may be NULL ([B][C] otherwise).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct RsbSegLossArgs {
+  int B, C;
+  long long V; /* D*H*W */
+  const float* logits;
+  const uint8_t* label;
+  const uint8_t* known; /* NULL => all ones */
+  const float* class_weights;
+  float* partials;  /* [B*C*4] workspace, zeroed by forward */
+  float* coef;      /* [B*C*4] workspace (per-(b,c) backward coefficients) */
+  float* loss_out;  /* [3]: total, bce, dice */
+} RsbSegLossArgs;
+int rsb_seg_loss_forward(const RsbSegLossArgs* args, void* stream);
+/* dlogits (+)= grad_scale[0] * dL/dlogits ; grad_scale is a device scalar */
+int rsb_seg_loss_backward(const RsbSegLossArgs* args, const float* grad_scale, float* dlogits,
+                          int accumulate, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Binary ball dilation — dilate_volume / dilate_volume_conv / create_ball_kernel
+ * (losses_foundation.py:22-99, 1161-1232): iterated passes with the exact ball structuring
+ * elements the reference builds; uint8 0/1 volumes [n_vol][D][H][W].
+ * ------------------------------------------------------------------------------------------ */
+int rsb_dilate_ball(const uint8_t* src, uint8_t* dst, uint8_t* tmp, int n_vol, int D, int H, int W,
+                    int kernel_size, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSUPER_B200_H_ */
