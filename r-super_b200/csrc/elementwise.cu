@@ -1,0 +1,488 @@
+// elementwise.cu — HBM-bound satellites of the UNet train step on NDHWC tensors with a channel
+// pitch: layout conversion, per-(n,c) statistics, MaxPool3d(2) fwd/bwd, trilinear(align_corners)
+// upsample fwd/bwd, and the InstanceNorm backward apply.  All kernels move 8 channels per thread
+// with 128-bit (bf16) / 2x128-bit (fp32) accesses; consecutive threads walk consecutive channel
+// groups of a voxel, then the next voxel, so every warp access is a contiguous span.
+//
+// Reference call sites replaced (rsuper_train/model/dim3):
+//   nn.MaxPool3d(down_scale)                                   unet_utils.py:36
+//   F.interpolate(mode='trilinear', align_corners=True)        unet_utils.py:69
+//   nn.InstanceNorm3d(eps=1e-4) backward (autograd)            conv_layers.py:39-49
+#include "rsb_common.cuh"
+
+#include "../../include/rsuper_b200.h"
+
+namespace rsb {
+
+// Thread mapping shared by all kernels here: blockIdx.y = sample n; inside a sample the linear
+// element id e = voxel * CG + cg (CG = C/8 channel groups); blockDim.x is a multiple of CG so a
+// thread keeps the same channel group over its grid-stride loop.
+struct ClMap {
+  int cg;        // channel group of this thread
+  long long e0;  // first element id
+  long long stride;
+};
+RSB_DEVICE ClMap cl_map(int CG) {
+  ClMap m;
+  m.e0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  m.stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  m.cg = static_cast<int>(m.e0 % CG);
+  return m;
+}
+
+static inline int cl_block(int CG) {
+  if (CG >= 256) return CG <= 1024 ? CG : 0;
+  return (256 / CG) * CG;
+}
+static inline int cl_grid(long long elems, int block, int sms, int waves = 8) {
+  long long want = (elems + block - 1) / block;
+  long long cap = static_cast<long long>(sms) * waves;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  return static_cast<int>(want);
+}
+
+// Block-level accumulation of per-channel (a, b) pairs into global stats[(n*C + c)*2 + {0,1}].
+// sm_acc must hold 2*C floats, zeroed before use (done here) — one shared atomic per value per
+// thread, one global atomic per value per block.
+RSB_DEVICE void block_stats_flush(float* sm_acc, const float (&s1)[8], const float (&s2)[8], int cg,
+                                  int C, float* stats_n) {
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm_acc[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&sm_acc[(cg * 8 + j) * 2 + 0], s1[j]);
+    atomicAdd(&sm_acc[(cg * 8 + j) * 2 + 1], s2[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&stats_n[i], sm_acc[i]);
+}
+
+// ------------------------------------------------------------------------------------------
+// layout conversion
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void ncdhw_to_ndhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, long long pitch,
+                                      int C, long long V) {
+  const int CG = C / 8;
+  const int n = blockIdx.y;
+  ClMap m = cl_map(CG);
+  for (long long e = m.e0; e < V * CG; e += m.stride) {
+    const long long v = e / CG;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = src[(static_cast<long long>(n) * C + m.cg * 8 + j) * V + v];
+    Vec8<T>::store(dst + (static_cast<long long>(n) * V + v) * pitch + m.cg * 8, f);
+  }
+}
+
+template <typename T>
+__global__ void ndhwc_to_ncdhw_kernel(const T* __restrict__ src, long long pitch, float* __restrict__ dst,
+                                      int C, long long V) {
+  const int CG = C / 8;
+  const int n = blockIdx.y;
+  ClMap m = cl_map(CG);
+  for (long long e = m.e0; e < V * CG; e += m.stride) {
+    const long long v = e / CG;
+    float f[8];
+    Vec8<T>::load(src + (static_cast<long long>(n) * V + v) * pitch + m.cg * 8, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dst[(static_cast<long long>(n) * C + m.cg * 8 + j) * V + v] = f[j];
+  }
+}
+
+template <typename T>
+__global__ void channel_stats_kernel(const T* __restrict__ x, long long pitch, float* __restrict__ stats,
+                                     int C, long long V) {
+  extern __shared__ float sm_acc[];
+  const int CG = C / 8;
+  const int n = blockIdx.y;
+  ClMap m = cl_map(CG);
+  float s1[8] = {0}, s2[8] = {0};
+  for (long long e = m.e0; e < V * CG; e += m.stride) {
+    const long long v = e / CG;
+    float f[8];
+    Vec8<T>::load(x + (static_cast<long long>(n) * V + v) * pitch + m.cg * 8, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1[j] += f[j]; s2[j] = fmaf(f[j], f[j], s2[j]); }
+  }
+  block_stats_flush(sm_acc, s1, s2, m.cg, C, stats + static_cast<long long>(n) * C * 2);
+}
+
+// ------------------------------------------------------------------------------------------
+// MaxPool3d(2)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void maxpool2_fwd_kernel(const T* __restrict__ x, long long xp, T* __restrict__ y, long long yp,
+                                    float* __restrict__ stats, int D, int H, int W, int C) {
+  extern __shared__ float sm_acc[];
+  const int CG = C / 8;
+  const int n = blockIdx.y;
+  const int Do = D / 2, Ho = H / 2, Wo = W / 2;
+  const long long Vo = static_cast<long long>(Do) * Ho * Wo;
+  ClMap m = cl_map(CG);
+  float s1[8] = {0}, s2[8] = {0};
+  for (long long e = m.e0; e < Vo * CG; e += m.stride) {
+    const long long v = e / CG;
+    const int xo = static_cast<int>(v % Wo);
+    const int yo = static_cast<int>((v / Wo) % Ho);
+    const int zo = static_cast<int>(v / (static_cast<long long>(Wo) * Ho));
+    float best[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) best[j] = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int z = 2 * zo + (k >> 2), yy = 2 * yo + ((k >> 1) & 1), xx = 2 * xo + (k & 1);
+      const long long vin = ((static_cast<long long>(n) * D + z) * H + yy) * W + xx;
+      float f[8];
+      Vec8<T>::load(x + vin * xp + m.cg * 8, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) best[j] = fmaxf(best[j], f[j]);
+    }
+    Vec8<T>::store(y + (static_cast<long long>(n) * Vo + v) * yp + m.cg * 8, best);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1[j] += best[j]; s2[j] = fmaf(best[j], best[j], s2[j]); }
+  }
+  if (stats != nullptr) block_stats_flush(sm_acc, s1, s2, m.cg, C, stats + static_cast<long long>(n) * C * 2);
+}
+
+// dx[window voxel k] = (k is the first maximum in (d,h,w) scan order ? dy : 0) + dskip
+// (ATen max_pool3d_with_indices keeps the first maximum: it updates only on `val > max`).
+template <typename T>
+__global__ void maxpool2_bwd_kernel(const T* __restrict__ x, long long xp, const T* __restrict__ dy,
+                                    long long dyp, const T* __restrict__ dskip, long long dsp,
+                                    T* __restrict__ dx, long long dxp, int D, int H, int W, int C) {
+  const int CG = C / 8;
+  const int n = blockIdx.y;
+  const int Do = D / 2, Ho = H / 2, Wo = W / 2;
+  const long long Vo = static_cast<long long>(Do) * Ho * Wo;
+  ClMap m = cl_map(CG);
+  for (long long e = m.e0; e < Vo * CG; e += m.stride) {
+    const long long v = e / CG;
+    const int xo = static_cast<int>(v % Wo);
+    const int yo = static_cast<int>((v / Wo) % Ho);
+    const int zo = static_cast<int>(v / (static_cast<long long>(Wo) * Ho));
+    float best[8];
+    int arg[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; arg[j] = 0; }
+    long long vin[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int z = 2 * zo + (k >> 2), yy = 2 * yo + ((k >> 1) & 1), xx = 2 * xo + (k & 1);
+      vin[k] = ((static_cast<long long>(n) * D + z) * H + yy) * W + xx;
+      float f[8];
+      Vec8<T>::load(x + vin[k] * xp + m.cg * 8, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (f[j] > best[j]) { best[j] = f[j]; arg[j] = k; }
+    }
+    float g[8];
+    Vec8<T>::load(dy + (static_cast<long long>(n) * Vo + v) * dyp + m.cg * 8, g);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float o[8];
+      if (dskip != nullptr) {
+        Vec8<T>::load(dskip + vin[k] * dsp + m.cg * 8, o);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += (arg[j] == k) ? g[j] : 0.f;
+      Vec8<T>::store(dx + vin[k] * dxp + m.cg * 8, o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// trilinear upsample, align_corners=True (ATen upsample_trilinear3d semantics:
+// src = dst * (in-1)/(out-1) in fp32, i0 = (int)src, i1 = i0 + (i0 < in-1), lambda = src - i0)
+// ------------------------------------------------------------------------------------------
+struct Lerp {
+  int i0, i1;
+  float w0, w1;
+};
+RSB_DEVICE Lerp lerp_src(int o, float scale, int in_size) {
+  Lerp l;
+  const float src = scale * static_cast<float>(o);
+  l.i0 = static_cast<int>(src);
+  if (l.i0 > in_size - 1) l.i0 = in_size - 1;
+  l.i1 = l.i0 + (l.i0 < in_size - 1 ? 1 : 0);
+  l.w1 = src - static_cast<float>(l.i0);
+  l.w0 = 1.f - l.w1;
+  return l;
+}
+static inline float ac_scale(int in_size, int out_size) {
+  return out_size > 1 ? static_cast<float>(in_size - 1) / static_cast<float>(out_size - 1) : 0.f;
+}
+
+template <typename T>
+__global__ void upsample_fwd_kernel(const T* __restrict__ x, long long xp, T* __restrict__ y, long long yp,
+                                    float* __restrict__ stats, int Di, int Hi, int Wi, int Do, int Ho,
+                                    int Wo, int C, float sd, float sh, float sw) {
+  extern __shared__ float sm_acc[];
+  const int CG = C / 8;
+  const int n = blockIdx.y;
+  const long long Vo = static_cast<long long>(Do) * Ho * Wo;
+  ClMap m = cl_map(CG);
+  float s1[8] = {0}, s2[8] = {0};
+  for (long long e = m.e0; e < Vo * CG; e += m.stride) {
+    const long long v = e / CG;
+    const int xo = static_cast<int>(v % Wo);
+    const int yo = static_cast<int>((v / Wo) % Ho);
+    const int zo = static_cast<int>(v / (static_cast<long long>(Wo) * Ho));
+    const Lerp lz = lerp_src(zo, sd, Di), ly = lerp_src(yo, sh, Hi), lx = lerp_src(xo, sw, Wi);
+    float acc[8] = {0};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int z = (k & 4) ? lz.i1 : lz.i0;
+      const int yy = (k & 2) ? ly.i1 : ly.i0;
+      const int xx = (k & 1) ? lx.i1 : lx.i0;
+      const float wgt = ((k & 4) ? lz.w1 : lz.w0) * ((k & 2) ? ly.w1 : ly.w0) * ((k & 1) ? lx.w1 : lx.w0);
+      const long long vin = ((static_cast<long long>(n) * Di + z) * Hi + yy) * Wi + xx;
+      float f[8];
+      Vec8<T>::load(x + vin * xp + m.cg * 8, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(wgt, f[j], acc[j]);
+    }
+    Vec8<T>::store(y + (static_cast<long long>(n) * Vo + v) * yp + m.cg * 8, acc);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1[j] += acc[j]; s2[j] = fmaf(acc[j], acc[j], s2[j]); }
+  }
+  if (stats != nullptr) block_stats_flush(sm_acc, s1, s2, m.cg, C, stats + static_cast<long long>(n) * C * 2);
+}
+
+// Adjoint as a deterministic gather: for input index i, candidate outputs o with src(o) in (i-1, i+1).
+struct Taps {
+  int o[6];
+  float w[6];
+  int cnt;
+};
+RSB_DEVICE Taps adjoint_taps(int i, float scale, int in_size, int out_size) {
+  Taps t;
+  t.cnt = 0;
+  int lo, hi;
+  if (scale > 0.f) {
+    lo = static_cast<int>(floorf((static_cast<float>(i) - 1.f) / scale)) - 1;
+    hi = static_cast<int>(ceilf((static_cast<float>(i) + 1.f) / scale)) + 1;
+  } else {
+    lo = 0;
+    hi = out_size - 1;
+  }
+  if (lo < 0) lo = 0;
+  if (hi > out_size - 1) hi = out_size - 1;
+  for (int o = lo; o <= hi; ++o) {
+    const Lerp l = lerp_src(o, scale, in_size);
+    float w = 0.f;
+    if (l.i0 == i) w += l.w0;
+    if (l.i1 == i) w += l.w1;
+    if (w != 0.f && t.cnt < 6) {
+      t.o[t.cnt] = o;
+      t.w[t.cnt] = w;
+      ++t.cnt;
+    }
+  }
+  return t;
+}
+
+template <typename T>
+__global__ void upsample_bwd_kernel(const T* __restrict__ dy, long long dyp, T* __restrict__ dx, long long dxp,
+                                    int Di, int Hi, int Wi, int Do, int Ho, int Wo, int C, float sd,
+                                    float sh, float sw) {
+  const int CG = C / 8;
+  const int n = blockIdx.y;
+  const long long Vi = static_cast<long long>(Di) * Hi * Wi;
+  ClMap m = cl_map(CG);
+  for (long long e = m.e0; e < Vi * CG; e += m.stride) {
+    const long long v = e / CG;
+    const int xi = static_cast<int>(v % Wi);
+    const int yi = static_cast<int>((v / Wi) % Hi);
+    const int zi = static_cast<int>(v / (static_cast<long long>(Wi) * Hi));
+    const Taps tz = adjoint_taps(zi, sd, Di, Do), ty = adjoint_taps(yi, sh, Hi, Ho), tx = adjoint_taps(xi, sw, Wi, Wo);
+    float acc[8] = {0};
+    for (int a = 0; a < tz.cnt; ++a)
+      for (int b = 0; b < ty.cnt; ++b) {
+        const float wzy = tz.w[a] * ty.w[b];
+        const long long rowb = ((static_cast<long long>(n) * Do + tz.o[a]) * Ho + ty.o[b]) * Wo;
+        for (int c = 0; c < tx.cnt; ++c) {
+          const float wgt = wzy * tx.w[c];
+          float f[8];
+          Vec8<T>::load(dy + (rowb + tx.o[c]) * dyp + m.cg * 8, f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(wgt, f[j], acc[j]);
+        }
+      }
+    Vec8<T>::store(dx + (static_cast<long long>(n) * Vi + v) * dxp + m.cg * 8, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// InstanceNorm backward apply: dx = rstd * (g - S1/V - xhat * S2/V) + add
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void instnorm_bwd_apply_kernel(const T* __restrict__ g, long long gp, const T* __restrict__ x,
+                                          long long xp, const float* __restrict__ x_stats,
+                                          const float* __restrict__ bwd_sums, const T* __restrict__ add,
+                                          long long ap, T* __restrict__ dx, long long dxp, float eps, int C,
+                                          long long V) {
+  const int CG = C / 8;
+  const int n = blockIdx.y;
+  ClMap m = cl_map(CG);
+  const float inv = 1.f / static_cast<float>(V);
+  float mean[8], rstd[8], m1[8], m2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const long long sidx = (static_cast<long long>(n) * C + m.cg * 8 + j) * 2;
+    stats_to_mean_rstd(x_stats[sidx], x_stats[sidx + 1], inv, eps, mean[j], rstd[j]);
+    m1[j] = bwd_sums[sidx] * inv;
+    m2[j] = bwd_sums[sidx + 1] * inv;
+  }
+  for (long long e = m.e0; e < V * CG; e += m.stride) {
+    const long long v = static_cast<long long>(n) * V + e / CG;
+    float gv[8], xv[8], o[8];
+    Vec8<T>::load(g + v * gp + m.cg * 8, gv);
+    Vec8<T>::load(x + v * xp + m.cg * 8, xv);
+    if (add != nullptr) {
+      Vec8<T>::load(add + v * ap + m.cg * 8, o);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (xv[j] - mean[j]) * rstd[j];
+      o[j] += rstd[j] * (gv[j] - m1[j] - xh * m2[j]);
+    }
+    Vec8<T>::store(dx + v * dxp + m.cg * 8, o);
+  }
+}
+
+}  // namespace rsb
+
+using namespace rsb;
+
+#define RSB_CL_COMMON(C_, N_)                                                            \
+  RSB_REQUIRE((C_) > 0 && (C_) % 8 == 0, "channel count must be a positive multiple of 8 (got %d)", (C_)); \
+  const int CG = (C_) / 8;                                                               \
+  const int block = cl_block(CG);                                                        \
+  RSB_REQUIRE(block > 0, "too many channels (%d)", (C_));                                \
+  const int sms = rsb_num_sms();                                                         \
+  RSB_REQUIRE(sms > 0, "no CUDA device");                                                \
+  RSB_REQUIRE((N_) > 0 && (N_) <= 65535, "bad batch size %d", (N_));                     \
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+#define RSB_BY_DTYPE(dtype, CALL_BF16, CALL_F32)           \
+  if ((dtype) == RSB_BF16) { CALL_BF16; }                  \
+  else if ((dtype) == RSB_F32) { CALL_F32; }               \
+  else { set_last_error("bad dtype %d", (dtype)); return -1; }
+
+extern "C" int rsb_ncdhw_to_ndhwc(const float* src, void* dst, int dst_pitch, int dtype, int N, int C,
+                                  int D, int H, int W, void* stream) {
+  RSB_REQUIRE(src && dst, "ncdhw_to_ndhwc: null pointer");
+  RSB_CL_COMMON(C, N)
+  const long long V = static_cast<long long>(D) * H * W;
+  dim3 grid(cl_grid(V * CG, block, sms), N);
+  RSB_BY_DTYPE(dtype,
+               (ncdhw_to_ndhwc_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(src, (__nv_bfloat16*)dst, dst_pitch, C, V)),
+               (ncdhw_to_ndhwc_kernel<float><<<grid, block, 0, st>>>(src, (float*)dst, dst_pitch, C, V)))
+  return check_launch("ncdhw_to_ndhwc");
+}
+
+extern "C" int rsb_ndhwc_to_ncdhw(const void* src, int src_pitch, int dtype, float* dst, int N, int C,
+                                  int D, int H, int W, void* stream) {
+  RSB_REQUIRE(src && dst, "ndhwc_to_ncdhw: null pointer");
+  RSB_CL_COMMON(C, N)
+  const long long V = static_cast<long long>(D) * H * W;
+  dim3 grid(cl_grid(V * CG, block, sms), N);
+  RSB_BY_DTYPE(dtype,
+               (ndhwc_to_ncdhw_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)src, src_pitch, dst, C, V)),
+               (ndhwc_to_ncdhw_kernel<float><<<grid, block, 0, st>>>((const float*)src, src_pitch, dst, C, V)))
+  return check_launch("ndhwc_to_ncdhw");
+}
+
+extern "C" int rsb_channel_stats(const void* x, int x_pitch, int dtype, float* stats, int N, int D, int H,
+                                 int W, int C, void* stream) {
+  RSB_REQUIRE(x && stats, "channel_stats: null pointer");
+  RSB_CL_COMMON(C, N)
+  const long long V = static_cast<long long>(D) * H * W;
+  dim3 grid(cl_grid(V * CG, block, sms, 4), N);
+  const size_t sm = sizeof(float) * 2 * C;
+  RSB_BY_DTYPE(dtype,
+               (channel_stats_kernel<__nv_bfloat16><<<grid, block, sm, st>>>((const __nv_bfloat16*)x, x_pitch, stats, C, V)),
+               (channel_stats_kernel<float><<<grid, block, sm, st>>>((const float*)x, x_pitch, stats, C, V)))
+  return check_launch("channel_stats");
+}
+
+extern "C" int rsb_maxpool2_forward(const void* x, int x_pitch, void* y, int y_pitch, int dtype,
+                                    float* out_stats, int N, int D, int H, int W, int C, void* stream) {
+  RSB_REQUIRE(x && y, "maxpool2_forward: null pointer");
+  RSB_REQUIRE(D % 2 == 0 && H % 2 == 0 && W % 2 == 0 && D > 0, "maxpool2: spatial dims must be even (%d,%d,%d)", D, H, W);
+  RSB_CL_COMMON(C, N)
+  const long long Vo = static_cast<long long>(D / 2) * (H / 2) * (W / 2);
+  dim3 grid(cl_grid(Vo * CG, block, sms, 4), N);
+  const size_t sm = sizeof(float) * 2 * C;
+  RSB_BY_DTYPE(dtype,
+               (maxpool2_fwd_kernel<__nv_bfloat16><<<grid, block, sm, st>>>((const __nv_bfloat16*)x, x_pitch, (__nv_bfloat16*)y, y_pitch, out_stats, D, H, W, C)),
+               (maxpool2_fwd_kernel<float><<<grid, block, sm, st>>>((const float*)x, x_pitch, (float*)y, y_pitch, out_stats, D, H, W, C)))
+  return check_launch("maxpool2_forward");
+}
+
+extern "C" int rsb_maxpool2_backward(const void* x, int x_pitch, const void* dy, int dy_pitch,
+                                     const void* dskip, int dskip_pitch, void* dx, int dx_pitch, int dtype,
+                                     int N, int D, int H, int W, int C, void* stream) {
+  RSB_REQUIRE(x && dy && dx, "maxpool2_backward: null pointer");
+  RSB_REQUIRE(D % 2 == 0 && H % 2 == 0 && W % 2 == 0 && D > 0, "maxpool2: spatial dims must be even (%d,%d,%d)", D, H, W);
+  RSB_CL_COMMON(C, N)
+  const long long Vo = static_cast<long long>(D / 2) * (H / 2) * (W / 2);
+  dim3 grid(cl_grid(Vo * CG, block, sms), N);
+  RSB_BY_DTYPE(dtype,
+               (maxpool2_bwd_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)x, x_pitch, (const __nv_bfloat16*)dy, dy_pitch, (const __nv_bfloat16*)dskip, dskip_pitch, (__nv_bfloat16*)dx, dx_pitch, D, H, W, C)),
+               (maxpool2_bwd_kernel<float><<<grid, block, 0, st>>>((const float*)x, x_pitch, (const float*)dy, dy_pitch, (const float*)dskip, dskip_pitch, (float*)dx, dx_pitch, D, H, W, C)))
+  return check_launch("maxpool2_backward");
+}
+
+extern "C" int rsb_upsample_trilinear_forward(const void* x, int x_pitch, void* y, int y_pitch, int dtype,
+                                              float* out_stats, int N, int Di, int Hi, int Wi, int Do, int Ho,
+                                              int Wo, int C, void* stream) {
+  RSB_REQUIRE(x && y, "upsample_forward: null pointer");
+  RSB_REQUIRE(Di > 0 && Hi > 0 && Wi > 0 && Do > 0 && Ho > 0 && Wo > 0, "upsample: bad geometry");
+  RSB_CL_COMMON(C, N)
+  const long long Vo = static_cast<long long>(Do) * Ho * Wo;
+  dim3 grid(cl_grid(Vo * CG, block, sms, 4), N);
+  const size_t sm = sizeof(float) * 2 * C;
+  const float sd = ac_scale(Di, Do), sh = ac_scale(Hi, Ho), sw = ac_scale(Wi, Wo);
+  RSB_BY_DTYPE(dtype,
+               (upsample_fwd_kernel<__nv_bfloat16><<<grid, block, sm, st>>>((const __nv_bfloat16*)x, x_pitch, (__nv_bfloat16*)y, y_pitch, out_stats, Di, Hi, Wi, Do, Ho, Wo, C, sd, sh, sw)),
+               (upsample_fwd_kernel<float><<<grid, block, sm, st>>>((const float*)x, x_pitch, (float*)y, y_pitch, out_stats, Di, Hi, Wi, Do, Ho, Wo, C, sd, sh, sw)))
+  return check_launch("upsample_trilinear_forward");
+}
+
+extern "C" int rsb_upsample_trilinear_backward(const void* dy, int dy_pitch, void* dx, int dx_pitch, int dtype,
+                                               int N, int Di, int Hi, int Wi, int Do, int Ho, int Wo, int C,
+                                               void* stream) {
+  RSB_REQUIRE(dy && dx, "upsample_backward: null pointer");
+  RSB_REQUIRE(Di > 0 && Hi > 0 && Wi > 0 && Do > 0 && Ho > 0 && Wo > 0, "upsample: bad geometry");
+  RSB_CL_COMMON(C, N)
+  const long long Vi = static_cast<long long>(Di) * Hi * Wi;
+  dim3 grid(cl_grid(Vi * CG, block, sms), N);
+  const float sd = ac_scale(Di, Do), sh = ac_scale(Hi, Ho), sw = ac_scale(Wi, Wo);
+  RSB_BY_DTYPE(dtype,
+               (upsample_bwd_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)dy, dy_pitch, (__nv_bfloat16*)dx, dx_pitch, Di, Hi, Wi, Do, Ho, Wo, C, sd, sh, sw)),
+               (upsample_bwd_kernel<float><<<grid, block, 0, st>>>((const float*)dy, dy_pitch, (float*)dx, dx_pitch, Di, Hi, Wi, Do, Ho, Wo, C, sd, sh, sw)))
+  return check_launch("upsample_trilinear_backward");
+}
+
+extern "C" int rsb_instnorm_backward_apply(const void* g, int g_pitch, const void* x, int x_pitch,
+                                           const float* x_stats, const float* bwd_sums, const void* add,
+                                           int add_pitch, void* dx, int dx_pitch, int dtype, float eps, int N,
+                                           int D, int H, int W, int C, void* stream) {
+  RSB_REQUIRE(g && x && x_stats && bwd_sums && dx, "instnorm_backward_apply: null pointer");
+  RSB_CL_COMMON(C, N)
+  const long long V = static_cast<long long>(D) * H * W;
+  dim3 grid(cl_grid(V * CG, block, sms), N);
+  RSB_BY_DTYPE(dtype,
+               (instnorm_bwd_apply_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)g, g_pitch, (const __nv_bfloat16*)x, x_pitch, x_stats, bwd_sums, (const __nv_bfloat16*)add, add_pitch, (__nv_bfloat16*)dx, dx_pitch, eps, C, V)),
+               (instnorm_bwd_apply_kernel<float><<<grid, block, 0, st>>>((const float*)g, g_pitch, (const float*)x, x_pitch, x_stats, bwd_sums, (const float*)add, add_pitch, (float*)dx, dx_pitch, eps, C, V)))
+  return check_launch("instnorm_backward_apply");
+}

@@ -1,0 +1,396 @@
+// stem_head.cu — the two convolutions of the UNet that do not belong on the tensor pipe:
+//   * stem  inconv.conv1 = nn.Conv3d(1, base, 3, padding=1, bias=False)   unet_utils.py:15,18
+//     K = 27: bandwidth-bound; direct CUDA-core conv, one voxel per thread, all Cout in registers.
+//   * head  UNet.outc   = nn.Conv3d(base, num_classes, kernel_size=1)     unet.py:47,62
+//     N = num_classes (2..42): a per-voxel mat-vec, reads NDHWC features once, writes NCDHW fp32
+//     logits (the layout calculate_loss consumes, losses_foundation.py:859).
+#include "rsb_common.cuh"
+
+#include "../../include/rsuper_b200.h"
+
+namespace rsb {
+
+// butterfly over 32 lanes for 16 values (same scheme as conv3_igemm.cu's epilogue)
+RSB_DEVICE float bfly16(float (&v)[16], int lane) {
+  float b8[8], b4[4], b2[2];
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float send = up ? v[j] : v[j + 8], keep = up ? v[j + 8] : v[j];
+      b8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool up = lane & 8;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float send = up ? b8[j] : b8[j + 4], keep = up ? b8[j + 4] : b8[j];
+      b4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool up = lane & 4;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      float send = up ? b4[j] : b4[j + 2], keep = up ? b4[j + 2] : b4[j];
+      b2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  const bool up = lane & 2;
+  float send = up ? b2[0] : b2[1], keep = up ? b2[1] : b2[0];
+  float b1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  b1 += __shfl_xor_sync(0xffffffffu, b1, 1);
+  return b1;
+}
+RSB_DEVICE int bfly_col(int lane) {
+  return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+}
+
+constexpr int kStemThreads = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(kStemThreads) stem_fwd_kernel(const float* __restrict__ x,
+                                                                const float* __restrict__ w, T* __restrict__ y,
+                                                                long long yp, float* __restrict__ stats,
+                                                                int D, int H, int W, int Cout) {
+  extern __shared__ float sm[];
+  float* sw = sm;                    // [27][CoutPad16]
+  const int cpad = (Cout + 15) / 16 * 16;
+  float* sacc = sm + 27 * cpad;      // [Cout][2]
+  for (int i = threadIdx.x; i < 27 * cpad; i += blockDim.x) {
+    const int tap = i / cpad, co = i % cpad;
+    sw[i] = co < Cout ? w[co * 27 + tap] : 0.f;
+  }
+  for (int i = threadIdx.x; i < 2 * Cout; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int n = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const long long V = static_cast<long long>(D) * H * W;
+  const long long vbase = static_cast<long long>(blockIdx.x) * blockDim.x;
+  const long long v = vbase + threadIdx.x;
+  const bool ok = v < V;
+  float xin[27];
+  {
+    const int xq = static_cast<int>(v % W), yq = static_cast<int>((v / W) % H), zq = static_cast<int>(v / (static_cast<long long>(W) * H));
+#pragma unroll
+    for (int tap = 0; tap < 27; ++tap) {
+      const int z = zq + tap / 9 - 1, yy = yq + (tap / 3) % 3 - 1, xx = xq + tap % 3 - 1;
+      const bool inb = ok && z >= 0 && z < D && yy >= 0 && yy < H && xx >= 0 && xx < W;
+      xin[tap] = inb ? x[((static_cast<long long>(n) * D + z) * H + yy) * W + xx] : 0.f;
+    }
+  }
+  for (int c0 = 0; c0 < Cout; c0 += 16) {
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 27; ++tap) {
+      const float* wr = sw + tap * cpad + c0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = fmaf(xin[tap], wr[j], acc[j]);
+    }
+    const int nvalid = Cout - c0;
+    if (ok) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = acc[j];
+      Vec8<T>::store(y + (static_cast<long long>(n) * V + v) * yp + c0, o);
+      if (nvalid > 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = acc[8 + j];
+        Vec8<T>::store(y + (static_cast<long long>(n) * V + v) * yp + c0 + 8, o);
+      }
+    }
+    if (stats != nullptr) {
+      float s1[16], s2[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        s1[j] = ok ? acc[j] : 0.f;
+        s2[j] = s1[j] * s1[j];
+      }
+      const float t1 = bfly16(s1, lane), t2 = bfly16(s2, lane);
+      const int col = c0 + bfly_col(lane);
+      if ((lane & 1) == 0 && col < Cout) {
+        atomicAdd(&sacc[col * 2], t1);
+        atomicAdd(&sacc[col * 2 + 1], t2);
+      }
+    }
+  }
+  if (stats != nullptr) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * Cout; i += blockDim.x)
+      atomicAdd(&stats[static_cast<long long>(n) * Cout * 2 + i], sacc[i]);
+  }
+}
+
+// dW[co][tap] = sum_{n,v} dy[v][co] * x[v + tap - 1]; thread = (tap, 8-channel group), block = voxel span
+template <typename T>
+__global__ void stem_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, long long dyp,
+                                  float* __restrict__ dw, int N, int D, int H, int W, int Cout,
+                                  int vox_per_block) {
+  const int CG = Cout / 8;
+  const int tap = threadIdx.x / CG, cg = threadIdx.x % CG;
+  if (tap >= 27) return;
+  const int dz = tap / 9 - 1, dyy = (tap / 3) % 3 - 1, dxx = tap % 3 - 1;
+  const long long V = static_cast<long long>(D) * H * W;
+  const long long total = V * N;
+  const long long v0 = static_cast<long long>(blockIdx.x) * vox_per_block;
+  long long v1 = v0 + vox_per_block;
+  if (v1 > total) v1 = total;
+  float acc[8] = {0};
+  for (long long gv = v0; gv < v1; ++gv) {
+    const long long v = gv % V;
+    const int n = static_cast<int>(gv / V);
+    const int xq = static_cast<int>(v % W), yq = static_cast<int>((v / W) % H), zq = static_cast<int>(v / (static_cast<long long>(W) * H));
+    const int z = zq + dz, yy = yq + dyy, xx = xq + dxx;
+    if (z < 0 || z >= D || yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+    const float xv = x[((static_cast<long long>(n) * D + z) * H + yy) * W + xx];
+    float g[8];
+    Vec8<T>::load(dy + gv * dyp + cg * 8, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, g[j], acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) atomicAdd(&dw[(cg * 8 + j) * 27 + tap], acc[j]);
+}
+
+// ------------------------------------------------------------------------------------------
+// head 1x1x1 + bias
+// ------------------------------------------------------------------------------------------
+constexpr int kHeadMaxCin = 64;
+
+template <typename T>
+__global__ void head_fwd_kernel(const T* __restrict__ x, long long xp, const float* __restrict__ w,
+                                const float* __restrict__ bias, float* __restrict__ logits, long long V,
+                                int Cin, int C) {
+  extern __shared__ float sm[];  // [C][Cin] + [C]
+  for (int i = threadIdx.x; i < C * Cin; i += blockDim.x) sm[i] = w[i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sm[C * Cin + i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const int n = blockIdx.y;
+  for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < V;
+       v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float f[kHeadMaxCin];
+    const T* px = x + (static_cast<long long>(n) * V + v) * xp;
+#pragma unroll
+    for (int k = 0; k < kHeadMaxCin; k += 8) {
+      if (k < Cin) {
+        float t[8];
+        Vec8<T>::load(px + k, t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[k + j] = t[j];
+      }
+    }
+    for (int c = 0; c < C; ++c) {
+      float acc = sm[C * Cin + c];
+      const float* wr = sm + c * Cin;
+#pragma unroll
+      for (int k = 0; k < kHeadMaxCin; ++k)
+        if (k < Cin) acc = fmaf(f[k], wr[k], acc);
+      logits[(static_cast<long long>(n) * C + c) * V + v] = acc;
+    }
+  }
+}
+
+// dx[v][ci] = sum_c dl[c][v] w[c][ci]
+template <typename T>
+__global__ void head_bwd_data_kernel(const float* __restrict__ dl, const float* __restrict__ w,
+                                     T* __restrict__ dx, long long dxp, long long V, int Cin, int C) {
+  extern __shared__ float sm[];
+  for (int i = threadIdx.x; i < C * Cin; i += blockDim.x) sm[i] = w[i];
+  __syncthreads();
+  const int n = blockIdx.y;
+  for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < V;
+       v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float acc[kHeadMaxCin];
+#pragma unroll
+    for (int k = 0; k < kHeadMaxCin; ++k) acc[k] = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float g = dl[(static_cast<long long>(n) * C + c) * V + v];
+      const float* wr = sm + c * Cin;
+#pragma unroll
+      for (int k = 0; k < kHeadMaxCin; ++k)
+        if (k < Cin) acc[k] = fmaf(g, wr[k], acc[k]);
+    }
+    T* pd = dx + (static_cast<long long>(n) * V + v) * dxp;
+#pragma unroll
+    for (int k = 0; k < kHeadMaxCin; k += 8) {
+      if (k < Cin) {
+        float t[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = acc[k + j];
+        Vec8<T>::store(pd + k, t);
+      }
+    }
+  }
+}
+
+// dW[c][ci] = sum_v dl[c][v] x[v][ci];  db[c] = sum_v dl[c][v].
+// Block stages 128 voxels of x (fp32) and dl in smem; thread (c, ci) reduces over them.
+constexpr int kHeadWgTile = 128;
+template <typename T>
+__global__ void head_bwd_weight_kernel(const T* __restrict__ x, long long xp, const float* __restrict__ dl,
+                                       float* __restrict__ dw, float* __restrict__ db, long long V, int Cin,
+                                       int C, int tiles_per_block) {
+  extern __shared__ float sm[];
+  float* sx = sm;                          // [tile][Cin+1]
+  float* sd = sm + kHeadWgTile * (Cin + 1);  // [C][tile]
+  const int n = blockIdx.y;
+  const int CG = Cin / 8;
+  const int nout = C * Cin + C;
+  // every thread may own several outputs
+  float acc[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+  for (int t = 0; t < tiles_per_block; ++t) {
+    const long long vt = (static_cast<long long>(blockIdx.x) * tiles_per_block + t) * kHeadWgTile;
+    if (vt >= V) break;
+    __syncthreads();
+    for (int i = threadIdx.x; i < kHeadWgTile * CG; i += blockDim.x) {
+      const int vi = i / CG, cg = i % CG;
+      float f[8];
+      if (vt + vi < V) {
+        Vec8<T>::load(x + (static_cast<long long>(n) * V + vt + vi) * xp + cg * 8, f);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sx[vi * (Cin + 1) + cg * 8 + j] = f[j];
+    }
+    for (int i = threadIdx.x; i < C * kHeadWgTile; i += blockDim.x) {
+      const int c = i / kHeadWgTile, vi = i % kHeadWgTile;
+      sd[i] = (vt + vi < V) ? dl[(static_cast<long long>(n) * C + c) * V + vt + vi] : 0.f;
+    }
+    __syncthreads();
+    int q = 0;
+    for (int o = threadIdx.x; o < nout && q < 8; o += blockDim.x, ++q) {
+      float a = 0.f;
+      if (o < C * Cin) {
+        const int c = o / Cin, ci = o % Cin;
+        for (int vi = 0; vi < kHeadWgTile; ++vi) a = fmaf(sd[c * kHeadWgTile + vi], sx[vi * (Cin + 1) + ci], a);
+      } else {
+        const int c = o - C * Cin;
+        for (int vi = 0; vi < kHeadWgTile; ++vi) a += sd[c * kHeadWgTile + vi];
+      }
+      acc[q] += a;
+    }
+  }
+  int q = 0;
+  for (int o = threadIdx.x; o < nout && q < 8; o += blockDim.x, ++q) {
+    if (o < C * Cin) atomicAdd(&dw[o], acc[q]);
+    else atomicAdd(&db[o - C * Cin], acc[q]);
+  }
+}
+
+}  // namespace rsb
+
+using namespace rsb;
+
+extern "C" int rsb_stem_conv_forward(const float* x, const float* w_oidhw, void* y, int y_pitch, int dtype,
+                                     float* out_stats, int N, int D, int H, int W, int Cout, void* stream) {
+  RSB_REQUIRE(x && w_oidhw && y, "stem_conv_forward: null pointer");
+  RSB_REQUIRE(Cout > 0 && Cout % 8 == 0 && Cout <= 256, "stem_conv: Cout must be a multiple of 8 <= 256 (got %d)", Cout);
+  RSB_REQUIRE(N > 0 && N <= 65535 && D > 0 && H > 0 && W > 0, "stem_conv: bad geometry");
+  const long long V = static_cast<long long>(D) * H * W;
+  dim3 grid(static_cast<unsigned>((V + kStemThreads - 1) / kStemThreads), N);
+  const int cpad = (Cout + 15) / 16 * 16;
+  const size_t sm = sizeof(float) * (27 * cpad + 2 * Cout);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == RSB_BF16)
+    stem_fwd_kernel<__nv_bfloat16><<<grid, kStemThreads, sm, st>>>(x, w_oidhw, (__nv_bfloat16*)y, y_pitch, out_stats, D, H, W, Cout);
+  else if (dtype == RSB_F32)
+    stem_fwd_kernel<float><<<grid, kStemThreads, sm, st>>>(x, w_oidhw, (float*)y, y_pitch, out_stats, D, H, W, Cout);
+  else { set_last_error("bad dtype %d", dtype); return -1; }
+  return check_launch("stem_conv_forward");
+}
+
+extern "C" int rsb_stem_conv_wgrad(const float* x, const void* dy, int dy_pitch, int dtype, float* dw_oidhw,
+                                   int N, int D, int H, int W, int Cout, void* stream) {
+  RSB_REQUIRE(x && dy && dw_oidhw, "stem_conv_wgrad: null pointer");
+  RSB_REQUIRE(Cout > 0 && Cout % 8 == 0 && 27 * (Cout / 8) <= 1024, "stem_conv_wgrad: unsupported Cout %d", Cout);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(dw_oidhw, 0, sizeof(float) * Cout * 27, st);
+  RSB_REQUIRE(e == cudaSuccess, "stem_conv_wgrad: memset failed: %s", cudaGetErrorString(e));
+  const long long total = static_cast<long long>(N) * D * H * W;
+  const int sms = rsb_num_sms();
+  RSB_REQUIRE(sms > 0, "no CUDA device");
+  long long blocks = static_cast<long long>(sms) * 8;
+  long long vpb = (total + blocks - 1) / blocks;
+  if (vpb < 64) vpb = 64;
+  blocks = (total + vpb - 1) / vpb;
+  const int threads = ((27 * (Cout / 8)) + 31) / 32 * 32;
+  if (dtype == RSB_BF16)
+    stem_wgrad_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), threads, 0, st>>>(x, (const __nv_bfloat16*)dy, dy_pitch, dw_oidhw, N, D, H, W, Cout, static_cast<int>(vpb));
+  else if (dtype == RSB_F32)
+    stem_wgrad_kernel<float><<<static_cast<unsigned>(blocks), threads, 0, st>>>(x, (const float*)dy, dy_pitch, dw_oidhw, N, D, H, W, Cout, static_cast<int>(vpb));
+  else { set_last_error("bad dtype %d", dtype); return -1; }
+  return check_launch("stem_conv_wgrad");
+}
+
+extern "C" int rsb_head_forward(const void* x, int x_pitch, int dtype, const float* w, const float* bias,
+                                float* logits_ncdhw, int N, int D, int H, int W, int Cin, int C, void* stream) {
+  RSB_REQUIRE(x && w && logits_ncdhw, "head_forward: null pointer");
+  RSB_REQUIRE(Cin > 0 && Cin % 8 == 0 && Cin <= kHeadMaxCin, "head: Cin must be a multiple of 8 <= %d (got %d)", kHeadMaxCin, Cin);
+  RSB_REQUIRE(C > 0 && C <= 128 && N > 0 && N <= 65535, "head: bad class count / batch");
+  const long long V = static_cast<long long>(D) * H * W;
+  const int sms = rsb_num_sms();
+  RSB_REQUIRE(sms > 0, "no CUDA device");
+  long long bx = (V + 255) / 256;
+  if (bx > sms * 16LL) bx = sms * 16LL;
+  dim3 grid(static_cast<unsigned>(bx), N);
+  const size_t sm = sizeof(float) * (C * Cin + C);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == RSB_BF16)
+    head_fwd_kernel<__nv_bfloat16><<<grid, 256, sm, st>>>((const __nv_bfloat16*)x, x_pitch, w, bias, logits_ncdhw, V, Cin, C);
+  else if (dtype == RSB_F32)
+    head_fwd_kernel<float><<<grid, 256, sm, st>>>((const float*)x, x_pitch, w, bias, logits_ncdhw, V, Cin, C);
+  else { set_last_error("bad dtype %d", dtype); return -1; }
+  return check_launch("head_forward");
+}
+
+extern "C" int rsb_head_backward(const void* x, int x_pitch, int dtype, const float* w,
+                                 const float* dlogits_ncdhw, void* dx, int dx_pitch, float* dw, float* db,
+                                 int N, int D, int H, int W, int Cin, int C, void* stream) {
+  RSB_REQUIRE(x && w && dlogits_ncdhw && dx && dw && db, "head_backward: null pointer");
+  RSB_REQUIRE(Cin > 0 && Cin % 8 == 0 && Cin <= kHeadMaxCin, "head: Cin must be a multiple of 8 <= %d (got %d)", kHeadMaxCin, Cin);
+  RSB_REQUIRE(C > 0 && C <= 128 && N > 0 && N <= 65535, "head: bad class count / batch");
+  RSB_REQUIRE(C * Cin + C <= 256 * 8, "head_backward: too many weights");
+  const long long V = static_cast<long long>(D) * H * W;
+  const int sms = rsb_num_sms();
+  RSB_REQUIRE(sms > 0, "no CUDA device");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * C * Cin, st);
+  RSB_REQUIRE(e == cudaSuccess, "head_backward: memset failed: %s", cudaGetErrorString(e));
+  e = cudaMemsetAsync(db, 0, sizeof(float) * C, st);
+  RSB_REQUIRE(e == cudaSuccess, "head_backward: memset failed: %s", cudaGetErrorString(e));
+  {
+    long long bx = (V + 255) / 256;
+    if (bx > sms * 16LL) bx = sms * 16LL;
+    dim3 grid(static_cast<unsigned>(bx), N);
+    const size_t sm = sizeof(float) * (C * Cin);
+    if (dtype == RSB_BF16)
+      head_bwd_data_kernel<__nv_bfloat16><<<grid, 256, sm, st>>>(dlogits_ncdhw, w, (__nv_bfloat16*)dx, dx_pitch, V, Cin, C);
+    else if (dtype == RSB_F32)
+      head_bwd_data_kernel<float><<<grid, 256, sm, st>>>(dlogits_ncdhw, w, (float*)dx, dx_pitch, V, Cin, C);
+    else { set_last_error("bad dtype %d", dtype); return -1; }
+    int rc = check_launch("head_bwd_data_kernel");
+    if (rc) return rc;
+  }
+  {
+    const long long tiles = (V + kHeadWgTile - 1) / kHeadWgTile;
+    long long bx = sms * 4LL;
+    if (bx > tiles) bx = tiles;
+    const int tpb = static_cast<int>((tiles + bx - 1) / bx);
+    bx = (tiles + tpb - 1) / tpb;
+    dim3 grid(static_cast<unsigned>(bx), N);
+    const size_t sm = sizeof(float) * (kHeadWgTile * (Cin + 1) + C * kHeadWgTile);
+    RSB_REQUIRE(sm <= 48 * 1024, "head_backward: shared memory budget exceeded");
+    if (dtype == RSB_BF16)
+      head_bwd_weight_kernel<__nv_bfloat16><<<grid, 256, sm, st>>>((const __nv_bfloat16*)x, x_pitch, dlogits_ncdhw, dw, db, V, Cin, C, tpb);
+    else
+      head_bwd_weight_kernel<float><<<grid, 256, sm, st>>>((const float*)x, x_pitch, dlogits_ncdhw, dw, db, V, Cin, C, tpb);
+  }
+  return check_launch("head_bwd_weight_kernel");
+}
