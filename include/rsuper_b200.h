@@ -19,9 +19,11 @@
  *     buffer: torch.cat at unet_utils.py:71 costs nothing.
  *   - `dtype`: RSB_BF16 (0) = bf16 storage, RSB_F32 (1) = fp32 storage.  Tensor-core operands are
  *     always bf16 with fp32 accumulation in TMEM.
- *   - InstanceNorm statistics travel as raw per-(n,c) pairs (sum, sumsq) in fp32:
- *     stats[(n*C + c)*2 + {0,1}].  Producers accumulate them in their epilogue, consumers derive
- *     mean / rstd with eps = 1e-4 (conv_layers.py:39-42).
+ *   - InstanceNorm statistics travel as raw per-(n,c) pairs (sum, sumsq) in fp32.  A statistics
+ *     array ALWAYS shares the channel pitch of the activation buffer it describes:
+ *     stats[(n*pitch + c)*2 + {0,1}], so the statistics of a channel slice are the same slice of
+ *     the statistics array (pointer offset by 2*c0 floats).  Producers accumulate them in their
+ *     epilogue, consumers derive mean / rstd with eps = 1e-4 (conv_layers.py:39-42).
  */
 #ifndef RSUPER_B200_H_
 #define RSUPER_B200_H_
@@ -71,7 +73,7 @@ typedef struct RsbConv3Args {
   const void* x;
   int x_pitch;
   /* prologue: a = act((x - mean) * rstd); in_stats == NULL => identity (no norm, no act) */
-  const float* in_stats; /* [N][Cin][2] (sum, sumsq) over D*H*W */
+  const float* in_stats; /* [N][x_pitch][2] (sum, sumsq) over D*H*W */
   float eps;             /* 1e-4 */
   float slope;           /* 0 => ReLU (reference default), 0.01 => LeakyReLU */
   /* packed weights from rsb_conv3_pack_weights */
@@ -82,9 +84,10 @@ typedef struct RsbConv3Args {
   /* epilogue (all optional) */
   const void* res; /* y = conv + res  (BasicBlock residual) */
   int res_pitch;
-  float* out_stats; /* [N][Cout][2] += (sum, sumsq) of y  (fp32, pre-rounding) */
+  float* out_stats; /* [N][y_pitch][2] += (sum, sumsq) of y  (fp32, pre-rounding) */
   /* dgrad epilogue: y = conv * act'(xhat), xhat from (mask_x, mask_stats);
-   * bwd_sums[(n*Cout+c)*2+{0,1}] += (sum y, sum y*xhat)  — InstanceNorm backward reductions */
+   * bwd_sums[(n*mask_x_pitch+c)*2+{0,1}] += (sum y, sum y*xhat) — InstanceNorm backward
+   * reductions; mask_stats uses the same indexing */
   const void* mask_x;
   int mask_x_pitch;
   const float* mask_stats;

@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3_igemm_kernel(const Conv3Dev
         for (int j = 0; j < 8; ++j) { sc[j] = 1.f; sh[j] = 0.f; }
         const bool has_norm = a.in_stats != nullptr;
         if (has_norm && ch_ok) {
-          const float* st = a.in_stats + (static_cast<size_t>(ic.n) * a.Cin + ch0) * 2;
+          const float* st = a.in_stats + (static_cast<size_t>(ic.n) * a.x_pitch + ch0) * 2;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float mean, rstd;
@@ -354,6 +354,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3_igemm_kernel(const Conv3Dev
     const bool want_stats = (a.out_stats != nullptr) || (a.bwd_sums != nullptr);
     const bool mask_mode = a.mask_x != nullptr;
     float* stat_dst = mask_mode ? a.bwd_sums : a.out_stats;
+    const long long stat_pitch = mask_mode ? a.mask_x_pitch : a.y_pitch;
     uint32_t acc_it = 0;
     for (int item = blockIdx.x; item < a.num_items; item += gridDim.x) {
       const ItemCoord ic = decode_item(a, item, PZ);
@@ -362,7 +363,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3_igemm_kernel(const Conv3Dev
         for (int cidx = et; cidx < a.NT; cidx += 128) {
           float mean = 0.f, rstd = 1.f;
           if (ic.n0 + cidx < a.Cout) {
-            const float* st = a.mask_stats + (static_cast<size_t>(ic.n) * a.Cout + ic.n0 + cidx) * 2;
+            const float* st = a.mask_stats + (static_cast<size_t>(ic.n) * a.mask_x_pitch + ic.n0 + cidx) * 2;
             stats_to_mean_rstd(st[0], st[1], a.inv_count, a.eps, mean, rstd);
           }
           sm.mstat[cidx][0] = mean;
@@ -462,7 +463,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3_igemm_kernel(const Conv3Dev
         __syncwarp();
         for (int col = lane; col < a.NT; col += 32) {
           if (ic.n0 + col < a.Cout) {
-            float* dst = stat_dst + (static_cast<size_t>(ic.n) * a.Cout + ic.n0 + col) * 2;
+            float* dst = stat_dst + (static_cast<size_t>(ic.n) * stat_pitch + ic.n0 + col) * 2;
             atomicAdd(dst, sm.stat[warp - kEpiWarp0][col][0]);
             atomicAdd(dst + 1, sm.stat[warp - kEpiWarp0][col][1]);
           }

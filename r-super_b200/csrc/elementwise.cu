@@ -106,7 +106,7 @@ __global__ void channel_stats_kernel(const T* __restrict__ x, long long pitch, f
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s1[j] += f[j]; s2[j] = fmaf(f[j], f[j], s2[j]); }
   }
-  block_stats_flush(sm_acc, s1, s2, m.cg, C, stats + static_cast<long long>(n) * C * 2);
+  block_stats_flush(sm_acc, s1, s2, m.cg, C, stats + static_cast<long long>(n) * pitch * 2);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -143,7 +143,7 @@ __global__ void maxpool2_fwd_kernel(const T* __restrict__ x, long long xp, T* __
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s1[j] += best[j]; s2[j] = fmaf(best[j], best[j], s2[j]); }
   }
-  if (stats != nullptr) block_stats_flush(sm_acc, s1, s2, m.cg, C, stats + static_cast<long long>(n) * C * 2);
+  if (stats != nullptr) block_stats_flush(sm_acc, s1, s2, m.cg, C, stats + static_cast<long long>(n) * yp * 2);
 }
 
 // dx[window voxel k] = (k is the first maximum in (d,h,w) scan order ? dy : 0) + dskip
@@ -250,7 +250,7 @@ __global__ void upsample_fwd_kernel(const T* __restrict__ x, long long xp, T* __
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s1[j] += acc[j]; s2[j] = fmaf(acc[j], acc[j], s2[j]); }
   }
-  if (stats != nullptr) block_stats_flush(sm_acc, s1, s2, m.cg, C, stats + static_cast<long long>(n) * C * 2);
+  if (stats != nullptr) block_stats_flush(sm_acc, s1, s2, m.cg, C, stats + static_cast<long long>(n) * yp * 2);
 }
 
 // Adjoint as a deterministic gather: for input index i, candidate outputs o with src(o) in (i-1, i+1).
@@ -333,7 +333,7 @@ __global__ void instnorm_bwd_apply_kernel(const T* __restrict__ g, long long gp,
   float mean[8], rstd[8], m1[8], m2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const long long sidx = (static_cast<long long>(n) * C + m.cg * 8 + j) * 2;
+    const long long sidx = (static_cast<long long>(n) * xp + m.cg * 8 + j) * 2;
     stats_to_mean_rstd(x_stats[sidx], x_stats[sidx + 1], inv, eps, mean[j], rstd[j]);
     m1[j] = bwd_sums[sidx] * inv;
     m2[j] = bwd_sums[sidx + 1] * inv;

@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kStemThreads) stem_fwd_kernel(const float* __r
   if (stats != nullptr) {
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * Cout; i += blockDim.x)
-      atomicAdd(&stats[static_cast<long long>(n) * Cout * 2 + i], sacc[i]);
+      atomicAdd(&stats[static_cast<long long>(n) * yp * 2 + i], sacc[i]);
   }
 }
 

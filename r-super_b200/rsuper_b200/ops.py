@@ -38,12 +38,25 @@ def _check_cl(t: torch.Tensor, name: str) -> int:
     if t.dim() != 5 or not t.is_cuda:
         raise ValueError(f"{name}: expected a 5-D CUDA tensor [N,D,H,W,C], got {tuple(t.shape)}")
     n, d, h, w, c = t.shape
-    pitch = t.stride(3)
-    if t.stride(4) != 1 or t.stride(2) != w * pitch or t.stride(1) != h * w * pitch or t.stride(0) != d * h * w * pitch:
-        raise ValueError(f"{name}: not a dense NDHWC view with a channel pitch (strides {t.stride()})")
-    if pitch % 8 or (t.storage_offset() % 8):
-        raise ValueError(f"{name}: channel pitch/offset must be multiples of 8")
+    pitch = t.stride(3) if w > 1 else (t.stride(2) // max(w, 1) if h > 1 else t.stride(3))
+    want = (d * h * w * pitch, h * w * pitch, w * pitch, pitch, 1)
+    for i, (sz, st, wt) in enumerate(zip(t.shape, t.stride(), want)):
+        if sz > 1 and st != wt:
+            raise ValueError(f"{name}: not a dense NDHWC view with a channel pitch (strides {t.stride()})")
+    if pitch % 8 or (t.storage_offset() % 8) or c % 8:
+        raise ValueError(f"{name}: channel count/pitch/offset must be multiples of 8")
     return pitch
+
+
+def _st(stats: Optional[torch.Tensor], act: torch.Tensor, name: str) -> Optional[C.c_void_p]:
+    """Statistics pointer; the array must share the activation's channel pitch (see rsuper_b200.h)."""
+    if stats is None:
+        return None
+    pitch = _check_cl(act, name)
+    if stats.dtype != torch.float32 or stats.dim() != 3 or stats.shape[1] != act.shape[4] or stats.shape[2] != 2 \
+            or stats.stride(2) != 1 or stats.stride(1) != 2 or (stats.shape[0] > 1 and stats.stride(0) != 2 * pitch):
+        raise ValueError(f"{name}: statistics {tuple(stats.shape)}/{stats.stride()} do not match activation pitch {pitch}")
+    return C.c_void_p(stats.data_ptr())
 
 
 def new_act(n, d, h, w, c, dtype, device) -> torch.Tensor:
@@ -80,18 +93,223 @@ def conv3_forward(x, w_packed, y, *, in_stats=None, slope=0.0, res=None, out_sta
     a.N, a.D, a.H, a.W, a.Cin, a.Cout = n, d, h, w_, cin, cout
     a.dtype = dtype_code(x)
     a.x, a.x_pitch = _p(x), _check_cl(x, "x")
-    a.in_stats = _p(in_stats)
+    a.in_stats = _st(in_stats, x, "in_stats")
     a.eps, a.slope = eps, slope
     a.w_packed = _p(w_packed)
     a.y, a.y_pitch = _p(y), _check_cl(y, "y")
     if res is not None:
         assert res.shape == y.shape and res.dtype == y.dtype
         a.res, a.res_pitch = _p(res), _check_cl(res, "res")
-    a.out_stats = _p(out_stats)
+    a.out_stats = _st(out_stats, y, "out_stats")
     if mask_x is not None:
         assert mask_x.shape == y.shape and mask_x.dtype == y.dtype
         a.mask_x, a.mask_x_pitch = _p(mask_x), _check_cl(mask_x, "mask_x")
-        a.mask_stats, a.bwd_sums = _p(mask_stats), _p(bwd_sums)
+        a.mask_stats, a.bwd_sums = _st(mask_stats, mask_x, "mask_stats"), _st(bwd_sums, mask_x, "bwd_sums")
     a.planes_per_item, a.n_tile, a.max_ctas = planes_per_item, n_tile, max_ctas
     check(lib().rsb_conv3_forward(C.byref(a), _stream()), "conv3_forward")
     return y
+
+
+_WG_WS = {}
+
+
+def _wgrad_workspace(cout: int, cin: int, device) -> torch.Tensor:
+    key = (cout, cin, str(device))
+    ws = _WG_WS.get(key)
+    if ws is None:
+        nbytes = lib().rsb_conv3_wgrad_workspace_bytes(cout, cin, 0)
+        if nbytes == 0:
+            raise RuntimeError(f"rsuper_b200: no wgrad tiling for Cout={cout} Cin={cin}")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _WG_WS[key] = ws
+    return ws
+
+
+def conv3_wgrad(x, dy, dw, *, in_stats=None, slope=0.0, accumulate=False, eps=EPS_IN, max_ctas=0):
+    """dw[Cout,Cin,3,3,3] (fp32) = wgrad(dy, act(instnorm(x)))."""
+    a = _lib.RsbConv3WgradArgs()
+    n, d, h, w_, cin = x.shape
+    cout = dy.shape[4]
+    assert dy.shape[:4] == x.shape[:4] and dy.dtype == x.dtype
+    assert dw.dtype == torch.float32 and dw.is_contiguous() and tuple(dw.shape) == (cout, cin, 3, 3, 3)
+    a.N, a.D, a.H, a.W, a.Cin, a.Cout = n, d, h, w_, cin, cout
+    a.dtype = dtype_code(x)
+    a.x, a.x_pitch = _p(x), _check_cl(x, "x")
+    a.in_stats = _st(in_stats, x, "in_stats")
+    a.eps, a.slope = eps, slope
+    a.dy, a.dy_pitch = _p(dy), _check_cl(dy, "dy")
+    a.dw_oidhw, a.accumulate = _p(dw), int(accumulate)
+    ws = _wgrad_workspace(cout, cin, x.device)
+    a.workspace, a.workspace_bytes = _p(ws), ws.numel()
+    a.max_ctas = max_ctas
+    check(lib().rsb_conv3_wgrad(C.byref(a), _stream()), "conv3_wgrad")
+    return dw
+
+
+# --------------------------------------------------------------------------------------------
+# stem / head
+# --------------------------------------------------------------------------------------------
+def stem_conv_forward(x, w, y, out_stats=None):
+    """x fp32 [N,1,D,H,W] (== NDHWC with C=1), w fp32 [Cout,1,3,3,3] -> y NDHWC."""
+    n, _, d, h, w_ = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] == 1
+    assert w.dtype == torch.float32 and w.is_contiguous()
+    cout = y.shape[4]
+    check(lib().rsb_stem_conv_forward(_p(x), _p(w), _p(y), _check_cl(y, "y"), dtype_code(y), _st(out_stats, y, "out_stats"),
+                                      n, d, h, w_, cout, _stream()), "stem_conv_forward")
+    return y
+
+
+def stem_conv_wgrad(x, dy, dw):
+    n, _, d, h, w_ = x.shape
+    cout = dy.shape[4]
+    assert dw.dtype == torch.float32 and dw.is_contiguous() and dw.numel() == cout * 27
+    check(lib().rsb_stem_conv_wgrad(_p(x), _p(dy), _check_cl(dy, "dy"), dtype_code(dy), _p(dw),
+                                    n, d, h, w_, cout, _stream()), "stem_conv_wgrad")
+    return dw
+
+
+def head_forward(x, w, bias, logits):
+    """x NDHWC [N,D,H,W,Cin]; w fp32 [C,Cin(,1,1,1)]; logits fp32 NCDHW [N,C,D,H,W]."""
+    n, d, h, w_, cin = x.shape
+    c = logits.shape[1]
+    assert logits.dtype == torch.float32 and logits.is_contiguous() and w.is_contiguous()
+    check(lib().rsb_head_forward(_p(x), _check_cl(x, "x"), dtype_code(x), _p(w), _p(bias), _p(logits),
+                                 n, d, h, w_, cin, c, _stream()), "head_forward")
+    return logits
+
+
+def head_backward(x, w, dlogits, dx, dw, db):
+    n, d, h, w_, cin = x.shape
+    c = dlogits.shape[1]
+    assert dlogits.dtype == torch.float32 and dlogits.is_contiguous()
+    assert dw.is_contiguous() and db.is_contiguous() and dw.dtype == torch.float32
+    check(lib().rsb_head_backward(_p(x), _check_cl(x, "x"), dtype_code(x), _p(w), _p(dlogits), _p(dx),
+                                  _check_cl(dx, "dx"), _p(dw), _p(db), n, d, h, w_, cin, c, _stream()),
+          "head_backward")
+
+
+# --------------------------------------------------------------------------------------------
+# pool / upsample / instnorm backward / layout
+# --------------------------------------------------------------------------------------------
+def maxpool2_forward(x, y, out_stats=None):
+    n, d, h, w_, c = x.shape
+    check(lib().rsb_maxpool2_forward(_p(x), _check_cl(x, "x"), _p(y), _check_cl(y, "y"), dtype_code(x),
+                                     _st(out_stats, y, "out_stats"), n, d, h, w_, c, _stream()), "maxpool2_forward")
+    return y
+
+
+def maxpool2_backward(x, dy, dx, dskip=None):
+    n, d, h, w_, c = x.shape
+    check(lib().rsb_maxpool2_backward(_p(x), _check_cl(x, "x"), _p(dy), _check_cl(dy, "dy"), _p(dskip),
+                                      _check_cl(dskip, "dskip") if dskip is not None else 0, _p(dx),
+                                      _check_cl(dx, "dx"), dtype_code(x), n, d, h, w_, c, _stream()),
+          "maxpool2_backward")
+    return dx
+
+
+def upsample_forward(x, y, out_stats=None):
+    n, di, hi, wi, c = x.shape
+    _, do, ho, wo, _ = y.shape
+    check(lib().rsb_upsample_trilinear_forward(_p(x), _check_cl(x, "x"), _p(y), _check_cl(y, "y"),
+                                               dtype_code(x), _st(out_stats, y, "out_stats"), n, di, hi, wi, do, ho, wo, c,
+                                               _stream()), "upsample_forward")
+    return y
+
+
+def upsample_backward(dy, dx):
+    n, do, ho, wo, c = dy.shape
+    _, di, hi, wi, _ = dx.shape
+    check(lib().rsb_upsample_trilinear_backward(_p(dy), _check_cl(dy, "dy"), _p(dx), _check_cl(dx, "dx"),
+                                                dtype_code(dy), n, di, hi, wi, do, ho, wo, c, _stream()),
+          "upsample_backward")
+    return dx
+
+
+def instnorm_backward_apply(g, x, x_stats, bwd_sums, dx, add=None, eps=EPS_IN):
+    n, d, h, w_, c = x.shape
+    check(lib().rsb_instnorm_backward_apply(_p(g), _check_cl(g, "g"), _p(x), _check_cl(x, "x"), _st(x_stats, x, "x_stats"),
+                                            _st(bwd_sums, x, "bwd_sums"), _p(add), _check_cl(add, "add") if add is not None else 0,
+                                            _p(dx), _check_cl(dx, "dx"), dtype_code(x), eps, n, d, h, w_, c,
+                                            _stream()), "instnorm_backward_apply")
+    return dx
+
+
+def ncdhw_to_ndhwc(src, dst):
+    n, c, d, h, w_ = src.shape
+    assert src.dtype == torch.float32 and src.is_contiguous()
+    check(lib().rsb_ncdhw_to_ndhwc(_p(src), _p(dst), _check_cl(dst, "dst"), dtype_code(dst), n, c, d, h, w_,
+                                   _stream()), "ncdhw_to_ndhwc")
+    return dst
+
+
+def ndhwc_to_ncdhw(src, dst):
+    n, d, h, w_, c = src.shape
+    assert dst.dtype == torch.float32 and dst.is_contiguous()
+    check(lib().rsb_ndhwc_to_ncdhw(_p(src), _check_cl(src, "src"), dtype_code(src), _p(dst), n, c, d, h, w_,
+                                   _stream()), "ndhwc_to_ncdhw")
+    return dst
+
+
+def channel_stats(x, stats=None):
+    n, d, h, w_, c = x.shape
+    if stats is None:
+        pitch = _check_cl(x, "x")
+        c0 = x.storage_offset() % pitch
+        stats = torch.zeros((n, pitch, 2), dtype=torch.float32, device=x.device)[:, c0:c0 + c]
+    check(lib().rsb_channel_stats(_p(x), _check_cl(x, "x"), dtype_code(x), _st(stats, x, "stats"), n, d, h, w_, c,
+                                  _stream()), "channel_stats")
+    return stats
+
+
+# --------------------------------------------------------------------------------------------
+# segmentation loss
+# --------------------------------------------------------------------------------------------
+class SegLossState:
+    """Device workspaces of one fused BCE+Dice evaluation (kept for the backward pass)."""
+
+    def __init__(self, logits, label_u8, known_u8, class_weights):
+        b, c = logits.shape[:2]
+        v = logits[0, 0].numel()
+        dev = logits.device
+        self.args = _lib.RsbSegLossArgs()
+        self.keep = (logits, label_u8, known_u8, class_weights)
+        self.partials = torch.empty(b * c * 4, dtype=torch.float32, device=dev)
+        self.coef = torch.empty(b * c * 4, dtype=torch.float32, device=dev)
+        self.loss_out = torch.empty(3, dtype=torch.float32, device=dev)
+        a = self.args
+        a.B, a.C, a.V = b, c, v
+        a.logits, a.label, a.known = _p(logits), _p(label_u8), _p(known_u8)
+        a.class_weights = _p(class_weights)
+        a.partials, a.coef, a.loss_out = _p(self.partials), _p(self.coef), _p(self.loss_out)
+
+
+def seg_loss_forward(logits, label_u8, known_u8=None, class_weights=None) -> SegLossState:
+    assert logits.dtype == torch.float32 and logits.is_contiguous() and logits.dim() == 5
+    assert label_u8.dtype == torch.uint8 and label_u8.is_contiguous() and label_u8.shape == logits.shape
+    if known_u8 is not None:
+        assert known_u8.dtype == torch.uint8 and known_u8.is_contiguous() and known_u8.shape == logits.shape
+    if class_weights is not None:
+        assert class_weights.dtype == torch.float32 and class_weights.is_contiguous()
+    st = SegLossState(logits, label_u8, known_u8, class_weights)
+    check(lib().rsb_seg_loss_forward(C.byref(st.args), _stream()), "seg_loss_forward")
+    return st
+
+
+def seg_loss_backward(st: SegLossState, grad_scale, dlogits, accumulate=False):
+    assert dlogits.dtype == torch.float32 and dlogits.is_contiguous()
+    check(lib().rsb_seg_loss_backward(C.byref(st.args), _p(grad_scale), _p(dlogits), int(accumulate),
+                                      _stream()), "seg_loss_backward")
+    return dlogits
+
+
+def dilate_ball(src_u8, kernel_size: int):
+    """dilate_volume(volume, kernel_size) on uint8 0/1 volumes [..., D, H, W]."""
+    assert src_u8.dtype == torch.uint8 and src_u8.is_contiguous() and src_u8.dim() >= 3
+    d, h, w_ = src_u8.shape[-3:]
+    nvol = src_u8.numel() // (d * h * w_)
+    dst = torch.empty_like(src_u8)
+    tmp = torch.empty_like(src_u8)
+    check(lib().rsb_dilate_ball(_p(src_u8), _p(dst), _p(tmp), nvol, d, h, w_, int(kernel_size), _stream()),
+          "dilate_ball")
+    return dst

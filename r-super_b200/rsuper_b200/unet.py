@@ -1,0 +1,381 @@
+"""B200UNet — drop-in for the reference 3D UNet (rsuper_train/model/dim3/unet.py:12-64).
+
+Same constructor arguments, same parameter names / shapes / init (the state dict is
+interchangeable with the reference's `UNet(..., block='BasicBlock', norm='in')`), but forward and
+backward run entirely on the hand-written sm_100a kernels of librsuper_b200.so:
+
+  reference op (file:line)                                   kernel
+  ---------------------------------------------------------  ---------------------------------
+  inconv.conv1  Conv3d(1,b,3)          unet_utils.py:15,18    rsb_stem_conv_forward / _wgrad
+  ConvNormAct preact IN->ReLU->Conv3d  conv_layers.py:47-49   rsb_conv3_forward (fused prologue)
+  BasicBlock `out += shortcut(x)`      conv_layers.py:92      rsb_conv3_forward epilogue (res)
+  BasicBlock conv1 || shortcut conv    conv_layers.py:85-92   ONE GEMM with N = 2*Cout (same
+                                                              IN(x): affine-free norms coincide)
+  nn.MaxPool3d                         unet_utils.py:36       rsb_maxpool2_forward / _backward
+  F.interpolate trilinear              unet_utils.py:69       rsb_upsample_trilinear_*
+  torch.cat([skip, up], 1)             unet_utils.py:71       free: producers write channel slices
+  outc Conv3d(b,C,1)                   unet.py:47,62          rsb_head_forward / _backward
+  autograd of all of the above                                dgrad (same tcgen05 kernel, flipped
+                                                              weights), rsb_conv3_wgrad,
+                                                              rsb_instnorm_backward_apply
+
+`negative_slope` (0 => the reference's ReLU, 0.01 => LeakyReLU) is the north-star variant knob.
+There is no fallback path: without the CUDA library every call raises.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter containers with the reference's module tree (names only; forward is never called)
+# ------------------------------------------------------------------------------------------------
+class _CNA(nn.Module):
+    """ConvNormAct(preact=True, norm=InstanceNorm3d) — only the conv carries parameters."""
+
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.conv = nn.Conv3d(cin, cout, kernel_size=3, padding=1, bias=False)
+
+
+class _BasicBlock(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.conv1 = _CNA(cin, cout)
+        self.conv2 = _CNA(cout, cout)
+        self.shortcut = nn.Sequential()
+        if cin != cout:
+            self.shortcut = _CNA(cin, cout)
+
+    def weights(self):
+        sc = self.shortcut.conv.weight if isinstance(self.shortcut, _CNA) else None
+        return self.conv1.conv.weight, self.conv2.conv.weight, sc
+
+
+class _InConv(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.conv1 = nn.Conv3d(cin, cout, kernel_size=3, padding=1, bias=False)
+        self.conv2 = _BasicBlock(cout, cout)
+
+
+class _Stage(nn.Module):
+    """down_block (index 0 is the parameter-free MaxPool3d) / up_block."""
+
+    def __init__(self, cin, cout, down: bool):
+        super().__init__()
+        blocks: List[nn.Module] = []
+        if down:
+            blocks.append(nn.Identity())  # placeholder for nn.MaxPool3d: keeps the index -> name map
+        blocks.append(_BasicBlock(cin, cout))
+        blocks.append(_BasicBlock(cout, cout))
+        self.conv = nn.Sequential(*blocks)
+
+    def blocks(self):
+        return [m for m in self.conv if isinstance(m, _BasicBlock)]
+
+
+# ------------------------------------------------------------------------------------------------
+# activation buffers: NDHWC data + statistics sharing the channel pitch
+# ------------------------------------------------------------------------------------------------
+class Act:
+    __slots__ = ("t", "st")
+
+    def __init__(self, t: torch.Tensor, st: Optional[torch.Tensor]):
+        self.t = t
+        self.st = st
+
+    @staticmethod
+    def new(n, d, h, w, c, dtype, device, stats=True) -> "Act":
+        t = torch.empty((n, d, h, w, c), dtype=dtype, device=device)
+        st = torch.zeros((n, c, 2), dtype=torch.float32, device=device) if stats else None
+        return Act(t, st)
+
+    def view(self, c0, c1) -> "Act":
+        return Act(self.t[..., c0:c1], None if self.st is None else self.st[:, c0:c1])
+
+    @property
+    def C(self):
+        return self.t.shape[4]
+
+
+def _sums_like(a: Act) -> torch.Tensor:
+    """Zeroed (S1,S2) buffer indexed like a's statistics (same pitch, same channel offset)."""
+    pitch = a.t.stride(3)
+    n = a.t.shape[0]
+    full = torch.zeros((n, pitch, 2), dtype=torch.float32, device=a.t.device)
+    c0 = (a.t.storage_offset() % pitch) if pitch > 0 else 0
+    return full[:, c0:c0 + a.C]
+
+
+class _Engine:
+    """Kernel schedule of one forward / backward pass (pure host logic; all compute is in the .so)."""
+
+    def __init__(self, base_ch: int, slope: float, dtype: torch.dtype):
+        self.b = base_ch
+        self.slope = float(slope)
+        self.dtype = dtype
+
+    # ---- forward -------------------------------------------------------------------------------
+    def _block_fwd(self, x: Act, w1, w2, wsc, out: Act, saved: list):
+        n, d, h, w_, _ = x.t.shape
+        cout = w2.shape[0]
+        dev = x.t.device
+        if wsc is not None:
+            wcat = torch.cat([w1, wsc], dim=0).contiguous()
+            hs = Act.new(n, d, h, w_, 2 * cout, self.dtype, dev)
+            ops.conv3_forward(x.t, ops.conv3_pack_weights(wcat), hs.t, in_stats=x.st, slope=self.slope,
+                              out_stats=hs.st)
+            hh, ss = hs.view(0, cout), hs.view(cout, 2 * cout)
+            ops.conv3_forward(hh.t, ops.conv3_pack_weights(w2), out.t, in_stats=hh.st, slope=self.slope,
+                              res=ss.t, out_stats=out.st)
+            saved.append((x, hh))
+        else:
+            hh = Act.new(n, d, h, w_, cout, self.dtype, dev)
+            ops.conv3_forward(x.t, ops.conv3_pack_weights(w1), hh.t, in_stats=x.st, slope=self.slope,
+                              out_stats=hh.st)
+            ops.conv3_forward(hh.t, ops.conv3_pack_weights(w2), out.t, in_stats=hh.st, slope=self.slope,
+                              res=x.t, out_stats=out.st)
+            saved.append((x, hh))
+
+    def forward(self, x: torch.Tensor, P: dict, num_classes: int, save: bool):
+        """x fp32 [N,1,D,H,W]; P maps parameter names to fp32 tensors. Returns (logits, saved)."""
+        b, dt, dev = self.b, self.dtype, x.device
+        n, cin0, D, H, W = x.shape
+        if cin0 != 1:
+            raise ValueError("B200UNet supports in_ch == 1 (CT), like every R-Super config")
+        if D % 16 or H % 16 or W % 16:
+            raise ValueError(f"spatial dims must be multiples of 16 (4 MaxPool3d(2) levels), got {(D, H, W)}")
+        ch = [b, 2 * b, 4 * b, 8 * b, 10 * b]
+        dims = [(D >> l, H >> l, W >> l) for l in range(5)]
+        saved: list = []
+
+        # skip/concat buffers of decoder levels 0..3: [skip ch[l] | upsampled ch_up[l]]
+        up_in = [ch[1], ch[2], ch[3], ch[4]]  # channels arriving from below at level l
+        cat = [Act.new(n, *dims[l], ch[l] + up_in[l], dt, dev) for l in range(4)]
+
+        # inc: stem conv + BasicBlock(b, b)
+        t0 = Act.new(n, *dims[0], b, dt, dev)
+        ops.stem_conv_forward(x, P["inc.conv1.weight"], t0.t, t0.st)
+        self._block_fwd(t0, P["inc.conv2.conv1.conv.weight"], P["inc.conv2.conv2.conv.weight"], None,
+                        cat[0].view(0, ch[0]), saved)
+        enc_out = [cat[0].view(0, ch[0])]
+        pooled = []
+        for l in range(1, 5):
+            p = Act.new(n, *dims[l], ch[l - 1], dt, dev)
+            ops.maxpool2_forward(enc_out[l - 1].t, p.t, p.st)
+            pooled.append(p)
+            y = Act.new(n, *dims[l], ch[l], dt, dev)
+            pre = f"down{l}.conv."
+            self._block_fwd(p, P[pre + "1.conv1.conv.weight"], P[pre + "1.conv2.conv.weight"],
+                            P[pre + "1.shortcut.conv.weight"], y, saved)
+            out = cat[l].view(0, ch[l]) if l < 4 else Act.new(n, *dims[4], ch[4], dt, dev)
+            self._block_fwd(y, P[pre + "2.conv1.conv.weight"], P[pre + "2.conv2.conv.weight"], None, out, saved)
+            enc_out.append(out)
+        cur = enc_out[4]
+        for j, l in enumerate((3, 2, 1, 0), start=1):
+            upv = cat[l].view(ch[l], ch[l] + up_in[l])
+            ops.upsample_forward(cur.t, upv.t, upv.st)
+            y = Act.new(n, *dims[l], ch[l], dt, dev)
+            pre = f"up{j}.conv."
+            self._block_fwd(cat[l], P[pre + "0.conv1.conv.weight"], P[pre + "0.conv2.conv.weight"],
+                            P[pre + "0.shortcut.conv.weight"], y, saved)
+            out = Act.new(n, *dims[l], ch[l], dt, dev, stats=(l != 0))
+            self._block_fwd(y, P[pre + "1.conv1.conv.weight"], P[pre + "1.conv2.conv.weight"], None, out, saved)
+            cur = out
+        logits = torch.empty((n, num_classes, D, H, W), dtype=torch.float32, device=dev)
+        w_out = P["outc.weight"].reshape(num_classes, b).contiguous()
+        ops.head_forward(cur.t, w_out, P["outc.bias"], logits)
+        if not save:
+            return logits, None
+        return logits, dict(saved=saved, cat=cat, enc_out=enc_out, final=cur, x=x, dims=dims, ch=ch, up_in=up_in)
+
+    # ---- backward ------------------------------------------------------------------------------
+    def _new(self, like: torch.Tensor, c: int) -> torch.Tensor:
+        n, d, h, w_, _ = like.shape
+        return torch.empty((n, d, h, w_, c), dtype=self.dtype, device=like.device)
+
+    def _block_bwd_identity(self, x: Act, hh: Act, w1, w2, d_out: torch.Tensor, dx_dest: torch.Tensor):
+        s = self.slope
+        c = w2.shape[0]
+        g_h = self._new(d_out, c)
+        sums_h = _sums_like(hh)
+        ops.conv3_forward(d_out, ops.conv3_pack_weights(w2, True), g_h, mask_x=hh.t, mask_stats=hh.st,
+                          bwd_sums=sums_h, slope=s)
+        dw2 = torch.empty_like(w2)
+        ops.conv3_wgrad(hh.t, d_out, dw2, in_stats=hh.st, slope=s)
+        ops.instnorm_backward_apply(g_h, hh.t, hh.st, sums_h, g_h)  # in place: g_h becomes d(h)
+        g_x = self._new(d_out, x.C)
+        sums_x = _sums_like(x)
+        ops.conv3_forward(g_h, ops.conv3_pack_weights(w1, True), g_x, mask_x=x.t, mask_stats=x.st,
+                          bwd_sums=sums_x, slope=s)
+        dw1 = torch.empty_like(w1)
+        ops.conv3_wgrad(x.t, g_h, dw1, in_stats=x.st, slope=s)
+        ops.instnorm_backward_apply(g_x, x.t, x.st, sums_x, dx_dest, add=d_out)
+        return dw1, dw2
+
+    def _block_bwd_shortcut(self, x: Act, hh: Act, w1, w2, wsc, dcat2: torch.Tensor, dx_dest: torch.Tensor):
+        """dcat2 [.., 2C]: channels [C:2C] hold d(out) on entry; [0:C] receives d(h)."""
+        s = self.slope
+        c = w2.shape[0]
+        d_out = dcat2[..., c:]
+        dh = dcat2[..., :c]
+        sums_h = _sums_like(hh)
+        ops.conv3_forward(d_out, ops.conv3_pack_weights(w2, True), dh, mask_x=hh.t, mask_stats=hh.st,
+                          bwd_sums=sums_h, slope=s)
+        dw2 = torch.empty_like(w2)
+        ops.conv3_wgrad(hh.t, d_out, dw2, in_stats=hh.st, slope=s)
+        ops.instnorm_backward_apply(dh, hh.t, hh.st, sums_h, dh)
+        wcat = torch.cat([w1, wsc], dim=0).contiguous()
+        g_x = self._new(dcat2, x.C)
+        sums_x = _sums_like(x)
+        ops.conv3_forward(dcat2, ops.conv3_pack_weights(wcat, True), g_x, mask_x=x.t, mask_stats=x.st,
+                          bwd_sums=sums_x, slope=s)
+        dwcat = torch.empty_like(wcat)
+        ops.conv3_wgrad(x.t, dcat2, dwcat, in_stats=x.st, slope=s)
+        ops.instnorm_backward_apply(g_x, x.t, x.st, sums_x, dx_dest)
+        return dwcat[:c], dw2, dwcat[c:]
+
+    def backward(self, S: dict, P: dict, dlogits: torch.Tensor) -> dict:
+        ch, up_in, cat = S["ch"], S["up_in"], S["cat"]
+        saved = S["saved"]
+        b = self.b
+        G = {}
+        num_classes = dlogits.shape[1]
+        final = S["final"]
+        # block index map (forward order): 0 inc | 1,2 down1 | 3,4 down2 | 5,6 down3 | 7,8 down4 |
+        #                                  9,10 up1 | 11,12 up2 | 13,14 up3 | 15,16 up4
+        w_out = P["outc.weight"].reshape(num_classes, b).contiguous()
+        d_cur = self._new(final.t, b)
+        dw_out = torch.empty_like(w_out)
+        db_out = torch.empty_like(P["outc.bias"])
+        ops.head_backward(final.t, w_out, dlogits, d_cur, dw_out, db_out)
+        G["outc.weight"] = dw_out.reshape(P["outc.weight"].shape)
+        G["outc.bias"] = db_out
+
+        dskip = [None] * 4
+        for j, l in zip((4, 3, 2, 1), (0, 1, 2, 3)):  # up4 .. up1
+            pre = f"up{j}.conv."
+            ia, ib = 7 + 2 * j, 8 + 2 * j
+            # block B (identity shortcut): d_out = d_cur, dx goes into the d(out) slot of block A
+            xb, hb = saved[ib]
+            dcat2 = self._new(xb.t, 2 * ch[l])
+            dw1, dw2 = self._block_bwd_identity(xb, hb, P[pre + "1.conv1.conv.weight"], P[pre + "1.conv2.conv.weight"],
+                                                d_cur, dcat2[..., ch[l]:])
+            G[pre + "1.conv1.conv.weight"], G[pre + "1.conv2.conv.weight"] = dw1, dw2
+            # block A (conv shortcut) on the concat buffer
+            xa, ha = saved[ia]
+            d_cat = self._new(xa.t, xa.C)
+            dw1, dw2, dwsc = self._block_bwd_shortcut(xa, ha, P[pre + "0.conv1.conv.weight"],
+                                                      P[pre + "0.conv2.conv.weight"],
+                                                      P[pre + "0.shortcut.conv.weight"], dcat2, d_cat)
+            G[pre + "0.conv1.conv.weight"], G[pre + "0.conv2.conv.weight"] = dw1, dw2
+            G[pre + "0.shortcut.conv.weight"] = dwsc
+            dskip[l] = d_cat[..., :ch[l]]
+            n, d, h, w_, _ = d_cat.shape
+            d_cur = torch.empty((n, d // 2, h // 2, w_ // 2, up_in[l]), dtype=self.dtype, device=d_cat.device)
+            ops.upsample_backward(d_cat[..., ch[l]:], d_cur)
+        # encoder
+        for l in (4, 3, 2, 1):
+            pre = f"down{l}.conv."
+            ia, ib = 2 * l - 1, 2 * l
+            xb, hb = saved[ib]
+            dcat2 = self._new(xb.t, 2 * ch[l])
+            dw1, dw2 = self._block_bwd_identity(xb, hb, P[pre + "2.conv1.conv.weight"], P[pre + "2.conv2.conv.weight"],
+                                                d_cur, dcat2[..., ch[l]:])
+            G[pre + "2.conv1.conv.weight"], G[pre + "2.conv2.conv.weight"] = dw1, dw2
+            xa, ha = saved[ia]  # xa = pooled input
+            d_p = self._new(xa.t, xa.C)
+            dw1, dw2, dwsc = self._block_bwd_shortcut(xa, ha, P[pre + "1.conv1.conv.weight"],
+                                                      P[pre + "1.conv2.conv.weight"],
+                                                      P[pre + "1.shortcut.conv.weight"], dcat2, d_p)
+            G[pre + "1.conv1.conv.weight"], G[pre + "1.conv2.conv.weight"] = dw1, dw2
+            G[pre + "1.shortcut.conv.weight"] = dwsc
+            x_prev = S["enc_out"][l - 1]
+            d_cur = self._new(x_prev.t, ch[l - 1])
+            ops.maxpool2_backward(x_prev.t, d_p, d_cur, dskip=dskip[l - 1])
+        # inc block + stem
+        x0, h0 = saved[0]
+        d_t0 = self._new(x0.t, b)
+        dw1, dw2 = self._block_bwd_identity(x0, h0, P["inc.conv2.conv1.conv.weight"], P["inc.conv2.conv2.conv.weight"],
+                                            d_cur, d_t0)
+        G["inc.conv2.conv1.conv.weight"], G["inc.conv2.conv2.conv.weight"] = dw1, dw2
+        dws = torch.empty_like(P["inc.conv1.weight"])
+        ops.stem_conv_wgrad(S["x"], d_t0, dws)
+        G["inc.conv1.weight"] = dws
+        return G
+
+
+class _UNetFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, engine, names, num_classes, *params):
+        P = dict(zip(names, [p.detach() for p in params]))
+        need_grad = any(p.requires_grad for p in params)
+        with torch.no_grad():
+            logits, saved = engine.forward(x.detach().contiguous(), P, num_classes, save=need_grad)
+        ctx.engine, ctx.names, ctx.saved_acts = engine, names, saved
+        ctx.save_for_backward(*params)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        if ctx.saved_acts is None:
+            raise RuntimeError("B200UNet: backward called but no parameter required grad in forward")
+        params = ctx.saved_tensors
+        P = dict(zip(ctx.names, [p.detach() for p in params]))
+        with torch.no_grad():
+            G = ctx.engine.backward(ctx.saved_acts, P, dlogits.contiguous().float())
+        ctx.saved_acts = None
+        grads = tuple(G[nm] if p.requires_grad else None for nm, p in zip(ctx.names, params))
+        return (None, None, None, None) + grads
+
+
+class B200UNet(nn.Module):
+    """Constructor mirrors `UNet(in_ch, base_ch, scale, kernel_size, num_classes, block, pool, norm)`
+    (rsuper_train/model/dim3/unet.py:13); unsupported variants raise instead of silently differing."""
+
+    def __init__(self, in_ch, base_ch, scale=((2, 2, 2),) * 4, kernel_size=((3, 3, 3),) * 5, num_classes=1,
+                 block="BasicBlock", pool=True, norm="in", negative_slope: float = 0.0,
+                 precision: str = "bf16", return_dict: bool = True):
+        super().__init__()
+        if in_ch != 1:
+            raise NotImplementedError("B200UNet: in_ch must be 1")
+        if block != "BasicBlock" or norm != "in" or not pool:
+            raise NotImplementedError("B200UNet implements block='BasicBlock', norm='in', pool=True "
+                                      "(config/abdomenatlas/resunet_3d.yaml:9-14)")
+        if base_ch % 8:
+            raise ValueError("base_ch must be a multiple of 8 (16-byte channel groups)")
+        sc = [list(s) if isinstance(s, (list, tuple)) else [s] * 3 for s in scale]
+        ks = [list(k) if isinstance(k, (list, tuple)) else [k] * 3 for k in kernel_size]
+        if any(s != [2, 2, 2] for s in sc) or len(sc) != 4 or any(k != [3, 3, 3] for k in ks):
+            raise NotImplementedError("B200UNet implements scale=[[2,2,2]]*4 and kernel_size=[[3,3,3]]*5")
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' (bf16 storage) or 'fp32' (fp32 storage)")
+        b = base_ch
+        self.base_ch, self.num_classes = b, num_classes
+        self.negative_slope, self.precision, self.return_dict = negative_slope, precision, return_dict
+        self.inc = _InConv(in_ch, b)
+        self.down1 = _Stage(b, 2 * b, True)
+        self.down2 = _Stage(2 * b, 4 * b, True)
+        self.down3 = _Stage(4 * b, 8 * b, True)
+        self.down4 = _Stage(8 * b, 10 * b, True)
+        self.up1 = _Stage(10 * b + 8 * b, 8 * b, False)
+        self.up2 = _Stage(8 * b + 4 * b, 4 * b, False)
+        self.up3 = _Stage(4 * b + 2 * b, 2 * b, False)
+        self.up4 = _Stage(2 * b + b, b, False)
+        self.outc = nn.Conv3d(b, num_classes, kernel_size=1)
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("B200UNet has no CPU path: inputs must live on a CUDA (sm_100a) device")
+        names, params = zip(*self.named_parameters())
+        dtype = torch.bfloat16 if self.precision == "bf16" else torch.float32
+        engine = _Engine(self.base_ch, self.negative_slope, dtype)
+        out = _UNetFunction.apply(x.float(), engine, names, self.num_classes, *params)
+        # calculate_loss indexes model_output['segmentation'] (losses_foundation.py:859)
+        return {"segmentation": out} if self.return_dict else out
