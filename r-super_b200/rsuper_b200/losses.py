@@ -1,0 +1,92 @@
+"""calculate_loss — host-side mirror of rsuper_train/training/losses_foundation.py:685-1076 for the
+hot path, computing on the librsuper_b200.so kernels (no torch math on [B,C,V] tensors, no host
+syncs in the segmentation path).
+
+Same call signature, same returned dict keys ('segmentation', 'report' | 'ball_loss_bce' /
+'ball_loss_dice' / 'dice_volume_loss', 'overall'), same error behaviour (ValueError / AssertionError
+on inconsistent report batches).  Baseline-only branches (classification head, CLIP, Model Genesis,
+Hungarian matching) are out of scope and raise NotImplementedError.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from . import ops
+
+
+def _as_u8(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """Masks arrive as uint8 / int64 / float 0-1 tensors (train_ddp.py:246-262); kernels take uint8."""
+    if t is None:
+        return None
+    if t.dtype != torch.uint8:
+        t = t.to(torch.uint8)
+    return t.contiguous()
+
+
+class _SegLoss(torch.autograd.Function):
+    """mean(BCEWithLogits * known) + DiceLossMultiClass — losses_foundation.py:945-956, 541-607."""
+
+    @staticmethod
+    def forward(ctx, logits, label_u8, known_u8, class_weights):
+        lg = logits.detach().contiguous().float()
+        st = ops.seg_loss_forward(lg, label_u8, known_u8, class_weights)
+        ctx.state = st
+        return st.loss_out[0].clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        st = ctx.state
+        dl = torch.empty_like(st.keep[0])
+        ops.seg_loss_backward(st, grad_out.detach().reshape(1).float().contiguous(), dl)
+        ctx.state = None
+        return dl, None, None, None
+
+
+def seg_loss(logits, label, known=None, class_weights=None) -> torch.Tensor:
+    cw = None
+    if class_weights is not None:
+        cw = class_weights.reshape(logits.shape[0], logits.shape[1]).float().contiguous()
+    return _SegLoss.apply(logits, _as_u8(label), _as_u8(known), cw)
+
+
+def get_known_voxels(unk_voxels: torch.Tensor, dilation: int = 5) -> torch.Tensor:
+    """1 - dilate(unk, 5) as a uint8 mask (losses_foundation.py:150-199)."""
+    unk = _as_u8(unk_voxels)
+    if dilation > 0:
+        unk = ops.dilate_ball(unk, dilation)
+    return unk.logical_not().to(torch.uint8)
+
+
+def calculate_loss(model_output, label, unk_voxels, args, matcher, chosen_segment_mask, tumor_volumes_report,
+                   tumor_diameters, classes, input_tensor=None, class_weights=None, model_genesis=False,
+                   clip_only=False, report_embeddings=None, dist=None) -> Dict[str, torch.Tensor]:
+    if model_genesis or clip_only or getattr(args, "classification_branch", False) or getattr(args, "multi_ch_tumor", False):
+        raise NotImplementedError("rsuper_b200.calculate_loss implements the R-Super segmentation/report path only")
+    result = model_output["segmentation"]
+    heads = list(result) if isinstance(result, (tuple, list)) else [result]
+    deep = isinstance(result, (tuple, list))
+    assert len(classes) == label.shape[1], \
+        f"Number of classes in classes: {len(classes)} does not match the number of channels in label: {label.shape[1]}"
+    assert len(classes) == heads[0].shape[1]
+    report_w = float(args.report_volume_loss_basic)
+    if report_w > 0 and chosen_segment_mask is not None:
+        from . import report_losses  # Volume / Ball loss kernels
+        return report_losses.calculate_loss_with_reports(heads, deep, label, unk_voxels, args, chosen_segment_mask,
+                                                         tumor_volumes_report, tumor_diameters, classes, class_weights)
+    if class_weights is not None and torch.equal(class_weights, torch.ones_like(class_weights)):
+        class_weights = None
+    label_u8 = _as_u8(label)
+    known = get_known_voxels(unk_voxels) if unk_voxels is not None else None
+    loss_seg = 0
+    for j, r in enumerate(heads):
+        aw = args.aux_weight[j] if deep else 1.0
+        loss_seg = loss_seg + aw * args.seg_loss * seg_loss(r, label_u8, known, class_weights)
+    zero = torch.zeros((), dtype=torch.float32, device=heads[0].device)
+    loss = {"segmentation": loss_seg, "report": zero}
+    loss["overall"] = loss["segmentation"] + loss["report"]
+    if getattr(args, "nan_check", True) and torch.isnan(loss["overall"]).any():  # losses_foundation.py:1070-1071
+        raise ValueError("loss is nan, propagating this can destroy the network weights, STOP!")
+    assert loss["overall"].requires_grad, "Loss overall should require grad"
+    return loss
