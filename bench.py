@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py — Mvoxels/s of the R-Super 3D segmentation TRAIN STEP on synthetic 128^3 CT patches.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's B200 path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on host cores
+
+One step = train_epoch's body (rsuper_train/train_ddp.py:310-357): zero_grad -> UNet forward ->
+calculate_loss (masked BCE + adaptive-Tversky Dice) -> backward (DDP gradient all-reduce on NCCL for
+N > 1) -> clip_grad_norm_(1.0) -> AdamW(eps 1e-5, wd 0.05) -> EMA update.  Workload = BASELINE.json
+configs[1]: reference UNet (base 32, 5 levels, BasicBlock/IN/ReLU), batch 2 per GPU, 128^3, 2 classes,
+mask-only batches, bf16 tensor-core operands + bf16 activation storage, fp32 accumulate/params/optimizer.
+
+Prints ONE JSON line (rank 0).  `value` = whole-job Mvoxels/s with inputs resident in HBM (CUDA events,
+max over ranks); `e2e` = the same through the public module API with pinned HOST buffers (H2D of image +
+label and D2H of the loss inside the timed region); `roofline` = live CUDA-event time of the dominant
+kernel (tcgen05 implicit-GEMM conv: fprop + dgrad launches) vs its algorithmic FLOPs and the measured
+bf16 peak; `cpu_baseline` = the oracle port of the reference step timed on this box's host cores on a
+bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "r-super_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch
+
+METRIC = "Mvoxels/sec (train step) on 128^3 CT patches"
+UNIT = "Mvoxels/s"
+MFLOP_PER_VOXEL_STEP = 3.705  # 3 x 1.235 MFLOP/voxel (fprop + dgrad + wgrad), base-32 UNet
+CLASSES = ["organ", "pancreatic_lesion"]
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], source="measured")
+    return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+# --------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi, during the timed region)
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (oracle port) on host cores
+# --------------------------------------------------------------------------------------------
+def cpu_step_factory(base: int, side: int, batch: int):
+    """One reference train step on CPU fp32 (order of train_ddp.py:310-357), via the oracle port."""
+    from oracle import losses_ref as LR
+    from oracle import synth
+    from oracle.unet_ref import synthetic_image, synthetic_state_dict, unet_forward
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = {k: torch.nn.Parameter(v) for k, v in synthetic_state_dict(base, len(CLASSES)).items()}
+    params = list(sd.values())
+    ema = [p.detach().clone() for p in params]
+    opt = torch.optim.AdamW(params, lr=6e-4, betas=(0.9, 0.999), weight_decay=0.05, eps=1e-5)
+    x = synthetic_image(batch, side, side, side, seed=11)
+    lab = synth.make_batch(["mask"] * batch, CLASSES, (side,) * 3, seed=12)["label"].long()
+    args = LR.default_args(report_volume_loss_basic=0.0)
+    state = {"step": 0}
+
+    def step():
+        opt.zero_grad()
+        logits = unet_forward(x, sd)
+        loss = LR.calculate_loss({"segmentation": logits}, lab, None, args, None, None, None, None, CLASSES)
+        loss["overall"].backward()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        alpha = min(1 - 1 / (state["step"] + 1), 0.99)
+        with torch.no_grad():
+            for e, p in zip(ema, params):
+                e.mul_(alpha).add_(p.detach(), alpha=1 - alpha)
+        state["step"] += 1
+        return loss["overall"].item()
+
+    return step
+
+
+def pick_cpu_sample(base: int, budget_s: float, nsteps: int):
+    """Largest cubic crop of the workload whose nsteps fit the budget (calibrated on a 32^3 step)."""
+    step = cpu_step_factory(base, 32, 1)
+    step()
+    t0 = time.perf_counter(); step(); t32 = time.perf_counter() - t0
+    per_vox = t32 / 32 ** 3
+    for side in (128, 96, 64, 48, 32):
+        if per_vox * side ** 3 * nsteps <= budget_s:
+            return side
+    return 32
+
+
+def run_cpu_arm(args, as_reference_impl: bool):
+    base = 32
+    nsteps = (args.steps + args.warmup) if as_reference_impl else 3
+    side = pick_cpu_sample(base, 150.0 if as_reference_impl else 25.0, nsteps)
+    step = cpu_step_factory(base, side, 1)
+    warm = args.warmup if as_reference_impl else 1
+    timed = args.steps if as_reference_impl else 2
+    for _ in range(warm):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(timed):
+        step()
+    dt = (time.perf_counter() - t0) / timed
+    val = side ** 3 / dt / 1e6
+    return dict(value=val, unit=UNIT, cores=torch.get_num_threads(), kind="port",
+                sample=f"oracle port of the reference step (UNet base 32 fwd+loss+bwd+clip+AdamW+EMA, fp32, torch CPU), "
+                       f"batch 1 x {side}^3 crop of the 2 x 128^3 workload, {timed} timed steps"), dt * 1e3
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=128)
+    ap.add_argument("--batch", type=int, default=2, help="per-GPU batch")
+    ap.add_argument("--base", type=int, default=32)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb, ms = run_cpu_arm(args, as_reference_impl=True)
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "reference UNet base32 5-level train step, batch 2 x 128^3 per GPU, 2-class masked BCE+Dice "
+                                       "(BASELINE.json configs[1]); CPU arm runs a bounded crop (see cpu_baseline.sample)"},
+                "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    if args.warmup < 3:
+        args.warmup = 3
+    from oracle import losses_ref as LR  # only for default_args (plain namespace of hyper-parameters)
+    from oracle import synth
+    from oracle.unet_ref import synthetic_image
+    from rsuper_b200 import losses, ops
+    from rsuper_b200.unet import B200UNet
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(1234 + rank)
+    S, B = args.size, args.batch
+    net = B200UNet(1, args.base, num_classes=len(CLASSES), precision=args.precision).to(dev)
+    model = net
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local_rank], find_unused_parameters=False,
+                                                          gradient_as_bucket_view=True, bucket_cap_mb=64)
+    ema = [p.detach().clone() for p in net.parameters()]
+    params = list(net.parameters())
+    opt = torch.optim.AdamW(params, lr=6e-4, betas=(0.9, 0.999), weight_decay=0.05, eps=1e-5, fused=True)
+    largs = LR.default_args(report_volume_loss_basic=0.0)
+    # synthetic batch (seeded per rank); host copies pinned for the e2e leg
+    img_h = synthetic_image(B, S, S, S, seed=1234 + rank).pin_memory()
+    lab_h = synth.make_batch(["mask"] * B, CLASSES, (S, S, S), seed=4321 + rank)["label"].pin_memory()
+    img_d, lab_d = img_h.to(dev), lab_h.to(dev)
+    state = {"step": 0}
+
+    def train_step(img, lab):
+        opt.zero_grad(set_to_none=True)
+        out = model(img)
+        loss = losses.calculate_loss(out, lab, None, largs, None, None, None, None, CLASSES)
+        loss["overall"].backward()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        alpha = min(1 - 1 / (state["step"] + 1), 0.99)
+        with torch.no_grad():
+            torch._foreach_mul_(ema, alpha)
+            torch._foreach_add_(ema, [p.detach() for p in params], alpha=1 - alpha)
+        state["step"] += 1
+        return loss["overall"]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    largs.nan_check = True
+    for _ in range(args.warmup):
+        train_step(img_d, lab_d)
+    barrier()
+
+    # ---- timed region 1: device-resident inputs, CUDA events, per-kernel-family events ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ops.PROFILE = []
+    ops.LAUNCHES = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        train_step(img_d, lab_d)
+    e1.record()
+    barrier()
+    launches = ops.LAUNCHES
+    prof, ops.PROFILE = ops.PROFILE, None
+    ms_dev = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- timed region 2: end to end through the module API with host buffers ----
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        img = img_h.to(dev, non_blocking=True)
+        lab = lab_h.to(dev, non_blocking=True)
+        lv = train_step(img, lab).item()
+    torch.cuda.synchronize()
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
+    if lv != lv:
+        raise RuntimeError("NaN loss in the benchmark")
+
+    t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = t.tolist()
+    vox = world * B * S ** 3
+    value = vox / (ms_dev * 1e-3) / 1e6
+    e2e = vox / (ms_e2e * 1e-3) / 1e6
+
+    if rank == 0:
+        peaks = load_peaks()
+        fam = {}
+        for name, flops, a, b in prof:
+            d = fam.setdefault(name, [0.0, 0.0, 0])
+            d[0] += a.elapsed_time(b); d[1] += flops; d[2] += 1
+        kern = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[2] / args.steps,
+                    "tflops": (v[1] / (v[0] * 1e-3) / 1e12) if v[0] > 0 and v[1] > 0 else None} for k, v in fam.items()}
+        dom = fam.get("conv3_igemm", [0.0, 0.0, 0])
+        achieved = dom[1] / (dom[0] * 1e-3) / 1e12 if dom[0] > 0 else None
+        roof = {"bound": "tensor", "kernel": "conv3_igemm_kernel (tcgen05 implicit GEMM, fprop+dgrad launches)",
+                "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                "frac": (achieved / peaks["tf_sustained"]) if achieved else None, "traffic": None,
+                "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)",
+                "avg_launch_ms": dom[0] / dom[2] if dom[2] else None, "launches_per_step": dom[2] / args.steps,
+                "share_of_step": (dom[0] / args.steps) / ms_dev if ms_dev else None}
+        cb = None
+        if not args.no_cpu_baseline and world == 1:
+            cb, _ = run_cpu_arm(args, as_reference_impl=False)
+        flop_roof_mvox = peaks["tf_sustained"] * 1e12 / (MFLOP_PER_VOXEL_STEP * 1e6) / 1e6 * world
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if args.precision == "bf16" else "bf16 operands / f32 storage", "data": "synthetic",
+                "config": {"workload": f"reference UNet base{args.base} 5-level (BasicBlock/IN/ReLU) train step, batch {B} x {S}^3 per GPU, "
+                                       "2-class masked BCE+Dice on synthetic masks (BASELINE.json configs[1])",
+                           "global_batch": B * world, "parallelism": f"dp{world}" if world > 1 else "single",
+                           "l2": "per-step working set (~3 GB of activations) >> 126 MB L2; no flush needed"},
+                "conv3d_flop_roofline_frac": value / flop_roof_mvox,
+                "roofline": roof, "kernels": kern, "cpu_baseline": cb,
+                "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e,
+                        "h2d_bytes_per_step": int(img_h.numel() * 4 + lab_h.numel()) * 1, "d2h_bytes_per_step": 4},
+                "gpu_launches": launches, "clocks": clocks}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

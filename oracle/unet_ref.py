@@ -76,18 +76,21 @@ def _basic_block(xs, xf, sd, prefix, cfg):
 
 
 def unet_forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], slope: float = 0.0, emulate: bool = False,
-                 storage: str = "fp32") -> torch.Tensor:
-    """x [N,1,D,H,W] fp32 -> logits [N,C,D,H,W] (unet.py:50-64)."""
+                 storage: str = "fp32", trace: Optional[dict] = None) -> torch.Tensor:
+    """x [N,1,D,H,W] fp32 -> logits [N,C,D,H,W] (unet.py:50-64).  `trace` collects stage outputs."""
     cfg = _Cfg(slope, emulate, storage)
+    tr = trace if trace is not None else {}
     # inconv: raw conv then BasicBlock (unet_utils.py:17-21)
     t_full = F.conv3d(x, sd["inc.conv1.weight"], padding=1)
     t_st = cfg.store(t_full)
     xs, xf = _basic_block(t_st, t_full, sd, "inc.conv2.", cfg)
+    tr["t0"], tr["inc"] = t_st, xs
     skips = [(xs, xf)]
     for l in range(1, 5):  # down_block: MaxPool3d then two blocks (unet_utils.py:33-41)
         ps = F.max_pool3d(xs, 2)
         ys, yf = _basic_block(ps, ps, sd, f"down{l}.conv.1.", cfg)
         xs, xf = _basic_block(ys, yf, sd, f"down{l}.conv.2.", cfg)
+        tr[f"pool{l}"], tr[f"down{l}.1"], tr[f"down{l}.2"] = ps, ys, xs
         skips.append((xs, xf))
     cur = skips[4][0]
     for j, l in enumerate((3, 2, 1, 0), start=1):  # up_block (unet_utils.py:68-75)
@@ -98,6 +101,7 @@ def unet_forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], slope: float = 0.
         cat_f = torch.cat([sk_f, up_full], dim=1)
         ys, yf = _basic_block(cat_s, cat_f, sd, f"up{j}.conv.0.", cfg)
         cur, _ = _basic_block(ys, yf, sd, f"up{j}.conv.1.", cfg)
+        tr[f"up{j}.cat"], tr[f"up{j}.0"], tr[f"up{j}.1"] = cat_s, ys, cur
     w = sd["outc.weight"]
     return F.conv3d(cur, w, sd["outc.bias"])  # unet.py:62
 
