@@ -16,6 +16,26 @@ from ._lib import RSB_BF16, RSB_F32, check, lib
 
 EPS_IN = 1e-4  # nn.InstanceNorm3d(ch, eps=1e-4) — reference conv_layers.py:39-42
 
+# Instrumentation used by bench.py: LAUNCHES counts kernels launched through this module; when
+# PROFILE is a list every call is bracketed by CUDA events on the launching stream and recorded as
+# (kernel family, algorithmic FLOPs, start_event, end_event).
+LAUNCHES = 0
+PROFILE = None
+
+
+def _call(family: str, nkern: int, flops: float, fn, *args, what: str):
+    global LAUNCHES
+    LAUNCHES += nkern
+    if PROFILE is None:
+        check(fn(*args), what)
+        return
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    rc = fn(*args)
+    b.record()
+    PROFILE.append((family, flops, a, b))
+    check(rc, what)
+
 
 def _stream() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -77,8 +97,7 @@ def conv3_pack_weights(w: torch.Tensor, transpose_flip: bool = False) -> torch.T
     co_eff, ci_eff = (cin, cout) if transpose_flip else (cout, cin)
     nbytes = lib().rsb_conv3_packed_weight_bytes(co_eff, ci_eff)
     out = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
-    check(lib().rsb_conv3_pack_weights(_p(w), _p(out), cout, cin, int(transpose_flip), _stream()),
-          "conv3_pack_weights")
+    _call("pack_weights", 1, 0.0, lib().rsb_conv3_pack_weights, _p(w), _p(out), cout, cin, int(transpose_flip), _stream(), what="conv3_pack_weights")
     return out
 
 
@@ -106,7 +125,7 @@ def conv3_forward(x, w_packed, y, *, in_stats=None, slope=0.0, res=None, out_sta
         a.mask_x, a.mask_x_pitch = _p(mask_x), _check_cl(mask_x, "mask_x")
         a.mask_stats, a.bwd_sums = _st(mask_stats, mask_x, "mask_stats"), _st(bwd_sums, mask_x, "bwd_sums")
     a.planes_per_item, a.n_tile, a.max_ctas = planes_per_item, n_tile, max_ctas
-    check(lib().rsb_conv3_forward(C.byref(a), _stream()), "conv3_forward")
+    _call("conv3_igemm", 1, 2.0 * 27 * cin * cout * n * d * h * w_, lib().rsb_conv3_forward, C.byref(a), _stream(), what="conv3_forward")
     return y
 
 
@@ -142,7 +161,7 @@ def conv3_wgrad(x, dy, dw, *, in_stats=None, slope=0.0, accumulate=False, eps=EP
     ws = _wgrad_workspace(cout, cin, x.device)
     a.workspace, a.workspace_bytes = _p(ws), ws.numel()
     a.max_ctas = max_ctas
-    check(lib().rsb_conv3_wgrad(C.byref(a), _stream()), "conv3_wgrad")
+    _call("conv3_wgrad", 2, 2.0 * 27 * cin * cout * n * d * h * w_, lib().rsb_conv3_wgrad, C.byref(a), _stream(), what="conv3_wgrad")
     return dw
 
 
@@ -155,8 +174,8 @@ def stem_conv_forward(x, w, y, out_stats=None):
     assert x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] == 1
     assert w.dtype == torch.float32 and w.is_contiguous()
     cout = y.shape[4]
-    check(lib().rsb_stem_conv_forward(_p(x), _p(w), _p(y), _check_cl(y, "y"), dtype_code(y), _st(out_stats, y, "out_stats"),
-                                      n, d, h, w_, cout, _stream()), "stem_conv_forward")
+    _call("stem", 1, 2.0 * 27 * cout * n * d * h * w_, lib().rsb_stem_conv_forward, _p(x), _p(w), _p(y), _check_cl(y, "y"), dtype_code(y), _st(out_stats, y, "out_stats"),
+                                      n, d, h, w_, cout, _stream(), what="stem_conv_forward")
     return y
 
 
@@ -164,8 +183,8 @@ def stem_conv_wgrad(x, dy, dw):
     n, _, d, h, w_ = x.shape
     cout = dy.shape[4]
     assert dw.dtype == torch.float32 and dw.is_contiguous() and dw.numel() == cout * 27
-    check(lib().rsb_stem_conv_wgrad(_p(x), _p(dy), _check_cl(dy, "dy"), dtype_code(dy), _p(dw),
-                                    n, d, h, w_, cout, _stream()), "stem_conv_wgrad")
+    _call("stem", 1, 2.0 * 27 * cout * n * d * h * w_, lib().rsb_stem_conv_wgrad, _p(x), _p(dy), _check_cl(dy, "dy"), dtype_code(dy), _p(dw),
+                                    n, d, h, w_, cout, _stream(), what="stem_conv_wgrad")
     return dw
 
 
@@ -174,8 +193,8 @@ def head_forward(x, w, bias, logits):
     n, d, h, w_, cin = x.shape
     c = logits.shape[1]
     assert logits.dtype == torch.float32 and logits.is_contiguous() and w.is_contiguous()
-    check(lib().rsb_head_forward(_p(x), _check_cl(x, "x"), dtype_code(x), _p(w), _p(bias), _p(logits),
-                                 n, d, h, w_, cin, c, _stream()), "head_forward")
+    _call("head", 1, 0.0, lib().rsb_head_forward, _p(x), _check_cl(x, "x"), dtype_code(x), _p(w), _p(bias), _p(logits),
+                                 n, d, h, w_, cin, c, _stream(), what="head_forward")
     return logits
 
 
@@ -184,9 +203,8 @@ def head_backward(x, w, dlogits, dx, dw, db):
     c = dlogits.shape[1]
     assert dlogits.dtype == torch.float32 and dlogits.is_contiguous()
     assert dw.is_contiguous() and db.is_contiguous() and dw.dtype == torch.float32
-    check(lib().rsb_head_backward(_p(x), _check_cl(x, "x"), dtype_code(x), _p(w), _p(dlogits), _p(dx),
-                                  _check_cl(dx, "dx"), _p(dw), _p(db), n, d, h, w_, cin, c, _stream()),
-          "head_backward")
+    _call("head", 2, 0.0, lib().rsb_head_backward, _p(x), _check_cl(x, "x"), dtype_code(x), _p(w), _p(dlogits), _p(dx),
+                                  _check_cl(dx, "dx"), _p(dw), _p(db), n, d, h, w_, cin, c, _stream(), what="head_backward")
 
 
 # --------------------------------------------------------------------------------------------
@@ -194,60 +212,58 @@ def head_backward(x, w, dlogits, dx, dw, db):
 # --------------------------------------------------------------------------------------------
 def maxpool2_forward(x, y, out_stats=None):
     n, d, h, w_, c = x.shape
-    check(lib().rsb_maxpool2_forward(_p(x), _check_cl(x, "x"), _p(y), _check_cl(y, "y"), dtype_code(x),
-                                     _st(out_stats, y, "out_stats"), n, d, h, w_, c, _stream()), "maxpool2_forward")
+    _call("pool", 1, 0.0, lib().rsb_maxpool2_forward, _p(x), _check_cl(x, "x"), _p(y), _check_cl(y, "y"), dtype_code(x),
+                                     _st(out_stats, y, "out_stats"), n, d, h, w_, c, _stream(), what="maxpool2_forward")
     return y
 
 
 def maxpool2_backward(x, dy, dx, dskip=None):
     n, d, h, w_, c = x.shape
-    check(lib().rsb_maxpool2_backward(_p(x), _check_cl(x, "x"), _p(dy), _check_cl(dy, "dy"), _p(dskip),
+    _call("pool", 1, 0.0, lib().rsb_maxpool2_backward, _p(x), _check_cl(x, "x"), _p(dy), _check_cl(dy, "dy"), _p(dskip),
                                       _check_cl(dskip, "dskip") if dskip is not None else 0, _p(dx),
-                                      _check_cl(dx, "dx"), dtype_code(x), n, d, h, w_, c, _stream()),
-          "maxpool2_backward")
+                                      _check_cl(dx, "dx"), dtype_code(x), n, d, h, w_, c, _stream(), what="maxpool2_backward")
     return dx
 
 
 def upsample_forward(x, y, out_stats=None):
     n, di, hi, wi, c = x.shape
     _, do, ho, wo, _ = y.shape
-    check(lib().rsb_upsample_trilinear_forward(_p(x), _check_cl(x, "x"), _p(y), _check_cl(y, "y"),
+    _call("upsample", 1, 0.0, lib().rsb_upsample_trilinear_forward, _p(x), _check_cl(x, "x"), _p(y), _check_cl(y, "y"),
                                                dtype_code(x), _st(out_stats, y, "out_stats"), n, di, hi, wi, do, ho, wo, c,
-                                               _stream()), "upsample_forward")
+                                               _stream(), what="upsample_forward")
     return y
 
 
 def upsample_backward(dy, dx):
     n, do, ho, wo, c = dy.shape
     _, di, hi, wi, _ = dx.shape
-    check(lib().rsb_upsample_trilinear_backward(_p(dy), _check_cl(dy, "dy"), _p(dx), _check_cl(dx, "dx"),
-                                                dtype_code(dy), n, di, hi, wi, do, ho, wo, c, _stream()),
-          "upsample_backward")
+    _call("upsample", 1, 0.0, lib().rsb_upsample_trilinear_backward, _p(dy), _check_cl(dy, "dy"), _p(dx), _check_cl(dx, "dx"),
+                                                dtype_code(dy), n, di, hi, wi, do, ho, wo, c, _stream(), what="upsample_backward")
     return dx
 
 
 def instnorm_backward_apply(g, x, x_stats, bwd_sums, dx, add=None, eps=EPS_IN):
     n, d, h, w_, c = x.shape
-    check(lib().rsb_instnorm_backward_apply(_p(g), _check_cl(g, "g"), _p(x), _check_cl(x, "x"), _st(x_stats, x, "x_stats"),
+    _call("instnorm_bwd", 1, 0.0, lib().rsb_instnorm_backward_apply, _p(g), _check_cl(g, "g"), _p(x), _check_cl(x, "x"), _st(x_stats, x, "x_stats"),
                                             _st(bwd_sums, x, "bwd_sums"), _p(add), _check_cl(add, "add") if add is not None else 0,
                                             _p(dx), _check_cl(dx, "dx"), dtype_code(x), eps, n, d, h, w_, c,
-                                            _stream()), "instnorm_backward_apply")
+                                            _stream(), what="instnorm_backward_apply")
     return dx
 
 
 def ncdhw_to_ndhwc(src, dst):
     n, c, d, h, w_ = src.shape
     assert src.dtype == torch.float32 and src.is_contiguous()
-    check(lib().rsb_ncdhw_to_ndhwc(_p(src), _p(dst), _check_cl(dst, "dst"), dtype_code(dst), n, c, d, h, w_,
-                                   _stream()), "ncdhw_to_ndhwc")
+    _call("layout", 1, 0.0, lib().rsb_ncdhw_to_ndhwc, _p(src), _p(dst), _check_cl(dst, "dst"), dtype_code(dst), n, c, d, h, w_,
+                                   _stream(), what="ncdhw_to_ndhwc")
     return dst
 
 
 def ndhwc_to_ncdhw(src, dst):
     n, d, h, w_, c = src.shape
     assert dst.dtype == torch.float32 and dst.is_contiguous()
-    check(lib().rsb_ndhwc_to_ncdhw(_p(src), _check_cl(src, "src"), dtype_code(src), _p(dst), n, c, d, h, w_,
-                                   _stream()), "ndhwc_to_ncdhw")
+    _call("layout", 1, 0.0, lib().rsb_ndhwc_to_ncdhw, _p(src), _check_cl(src, "src"), dtype_code(src), _p(dst), n, c, d, h, w_,
+                                   _stream(), what="ndhwc_to_ncdhw")
     return dst
 
 
@@ -257,8 +273,8 @@ def channel_stats(x, stats=None):
         pitch = _check_cl(x, "x")
         c0 = x.storage_offset() % pitch
         stats = torch.zeros((n, pitch, 2), dtype=torch.float32, device=x.device)[:, c0:c0 + c]
-    check(lib().rsb_channel_stats(_p(x), _check_cl(x, "x"), dtype_code(x), _st(stats, x, "stats"), n, d, h, w_, c,
-                                  _stream()), "channel_stats")
+    _call("stats", 1, 0.0, lib().rsb_channel_stats, _p(x), _check_cl(x, "x"), dtype_code(x), _st(stats, x, "stats"), n, d, h, w_, c,
+                                  _stream(), what="channel_stats")
     return stats
 
 
@@ -292,14 +308,14 @@ def seg_loss_forward(logits, label_u8, known_u8=None, class_weights=None) -> Seg
     if class_weights is not None:
         assert class_weights.dtype == torch.float32 and class_weights.is_contiguous()
     st = SegLossState(logits, label_u8, known_u8, class_weights)
-    check(lib().rsb_seg_loss_forward(C.byref(st.args), _stream()), "seg_loss_forward")
+    _call("seg_loss", 2, 0.0, lib().rsb_seg_loss_forward, C.byref(st.args), _stream(), what="seg_loss_forward")
     return st
 
 
 def seg_loss_backward(st: SegLossState, grad_scale, dlogits, accumulate=False):
     assert dlogits.dtype == torch.float32 and dlogits.is_contiguous()
-    check(lib().rsb_seg_loss_backward(C.byref(st.args), _p(grad_scale), _p(dlogits), int(accumulate),
-                                      _stream()), "seg_loss_backward")
+    _call("seg_loss", 1, 0.0, lib().rsb_seg_loss_backward, C.byref(st.args), _p(grad_scale), _p(dlogits), int(accumulate),
+                                      _stream(), what="seg_loss_backward")
     return dlogits
 
 
@@ -310,6 +326,5 @@ def dilate_ball(src_u8, kernel_size: int):
     nvol = src_u8.numel() // (d * h * w_)
     dst = torch.empty_like(src_u8)
     tmp = torch.empty_like(src_u8)
-    check(lib().rsb_dilate_ball(_p(src_u8), _p(dst), _p(tmp), nvol, d, h, w_, int(kernel_size), _stream()),
-          "dilate_ball")
+    _call("dilate", 1, 0.0, lib().rsb_dilate_ball, _p(src_u8), _p(dst), _p(tmp), nvol, d, h, w_, int(kernel_size), _stream(), what="dilate_ball")
     return dst

@@ -131,9 +131,12 @@ def test_conv3_wgrad(cuda_dev, shape):
     (F.conv3d(a, wz, padding=1) * bf16r(nc(dy))).sum().backward()
     dw = torch.full((Cout, Cin, 3, 3, 3), 7.0, device=cuda_dev)
     ops.conv3_wgrad(x, dy, dw, in_stats=stats_of(x))
-    assert rel(dw, wz.grad) <= 3e-4  # operands identical (bf16-rounded) up to rare rounding flips, fp32 accumulate
+    # operands are identical bf16 values except for rare rounding FLIPS (the kernel's normalised value and
+    # ATen's differ by ~1e-7, which can cross a bf16 rounding boundary): one flip is a 2^-8 change of one
+    # operand, i.e. up to ~2e-3 of max|dW| when K is only 128 voxels (probe: error confined to one channel)
+    assert rel(dw, wz.grad) <= 3e-3
     ops.conv3_wgrad(x, dy, dw, in_stats=stats_of(x), accumulate=True)
-    assert rel(dw, 2 * wz.grad) <= 3e-4
+    assert rel(dw, 2 * wz.grad) <= 3e-3
 
 
 def test_stem_and_head(cuda_dev):
