@@ -6,11 +6,11 @@
 // NEXT InstanceNorm needs.  With flipped/transposed weights the same kernel is the data gradient,
 // whose epilogue applies act'(xhat) and accumulates the two InstanceNorm-backward reductions.
 //
-// Design (B200 / sm_100a, one persistent CTA per SM, 320 threads):
+// Design (B200 / sm_100a, one persistent CTA per SM, 448 threads = MMA + loader + 4 epilogue + 8 producer warps):
 //   GEMM view   M = 128 output voxels (16 y x 8 x of one z-plane), N = Cout tile, K = 27 * Cin.
 //   work item   (n, z-block of PZ planes, y-tile, x-tile, N-tile): PZ accumulators of 128 x NT fp32
 //               live in TMEM (double-buffered when 2*PZ*NT <= 512 columns).
-//   A operand   "im2col in registers": 4 producer warps read the raw NDHWC halo box
+//   A operand   "im2col in registers": 8 producer warps read the raw NDHWC halo box
 //               (PZ+2) x 18 x 10 voxels x 32 channels, apply (x-mean)*rstd and (Leaky)ReLU in
 //               registers, force the zero padding, and write bf16 into shared memory in the
 //               SWIZZLE_NONE K-major core-matrix layout [plane][k/8][voxel][8 ch].  In that layout
@@ -20,7 +20,7 @@
 //               pipe; nothing is re-fetched per tap.
 //   B operand   weights pre-packed (rsb_conv3_pack_weights) into the matching core-matrix image so
 //               that one (chunk, tap, N-tile) slice is a single contiguous bulk copy
-//               (cp.async.bulk -> UBLKCP) completing on an mbarrier; 6-stage ring.
+//               (cp.async.bulk -> UBLKCP) completing on an mbarrier; 8-stage ring.
 //   MMA         one thread issues tcgen05.mma.cta_group::1.kind::f16 (bf16 x bf16 -> fp32),
 //               tcgen05.commit releases smem stages / publishes accumulators.
 //   epilogue    4 warps: tcgen05.ld 32x32b.x16, + residual, InstanceNorm (sum, sumsq) via a
@@ -39,10 +39,10 @@ constexpr int kPlaneVox = kHaloY * kHaloX;        // 180
 constexpr int kChunk = 32;                        // channels per K chunk
 constexpr int kChunkPlaneBytes = kPlaneVox * 16;  // one 8-channel plane of the halo box: 2880
 constexpr int kZPlaneBytes = 4 * kChunkPlaneBytes;  // 11520
-constexpr int kNumBStages = 6;
-constexpr int kThreads = 320;
+constexpr int kNumBStages = 8;
+constexpr int kThreads = 448;
 constexpr int kProducerWarp0 = 6;
-constexpr int kNumProducerWarps = 4;
+constexpr int kNumProducerWarps = 8;
 constexpr int kEpiWarp0 = 2;
 constexpr int kMaxNT = 256;
 
@@ -262,15 +262,35 @@ __global__ void __launch_bounds__(kThreads, 1) conv3_igemm_kernel(const Conv3Dev
     }
   } else if (warp >= kProducerWarp0) {
     // =========================== A producers ===========================
+    // 8 warps.  A thread owns a fixed 8-channel group (cj) and up to 3 in-plane voxel slots; index
+    // math is done once per item, then every chunk issues (planes x slots) independent 16/32-byte
+    // loads before converting, so one global-memory latency is paid per batch instead of per voxel.
     const int pw = warp - kProducerWarp0;
     const int cj = lane >> 3;  // 8-channel group inside the 32-channel chunk
     const int vi = lane & 7;
-    constexpr int kTotalVox = (PZ + 2) * kPlaneVox;
-    constexpr int kGroups = (kTotalVox + 7) / 8;
+    constexpr int kSlots = 3;  // ceil(23 groups of 8 voxels / 8 warps)
+    constexpr int NP = PZ + 2;
+    constexpr int PB = (sizeof(T) == 2) ? 3 : 2;  // planes per load batch
     const T* __restrict__ xg = reinterpret_cast<const T*>(a.x);
+    const long long plane_stride = static_cast<long long>(a.H) * a.W * a.x_pitch;
+    const bool has_norm = a.in_stats != nullptr;
     uint32_t a_it = 0;
     for (int item = blockIdx.x; item < a.num_items; item += gridDim.x) {
       const ItemCoord ic = decode_item(a, item, PZ);
+      int soff[kSlots];
+      long long goff[kSlots];
+      bool ok[kSlots];
+#pragma unroll
+      for (int s = 0; s < kSlots; ++s) {
+        const int vox = (pw + kNumProducerWarps * s) * 8 + vi;
+        const int yy = vox / kHaloX, xx = vox - yy * kHaloX;
+        const int y = ic.y0 - 1 + yy, xq = ic.x0 - 1 + xx;
+        const bool in_tile = vox < kPlaneVox;
+        ok[s] = in_tile && y >= 0 && y < a.H && xq >= 0 && xq < a.W;
+        goff[s] = (static_cast<long long>(y) * a.W + xq) * a.x_pitch;
+        soff[s] = in_tile ? (cj * kPlaneVox + vox) * 16 : -1;
+      }
+      const long long nbase = static_cast<long long>(ic.n) * a.D * plane_stride;
       for (int c = 0; c < a.nchunks; ++c) {
         const uint32_t ab = a_it & 1u;
         mbar_wait(smem_u32(&sm.a_empty[ab]), ((a_it >> 1) & 1u) ^ 1u);
@@ -280,7 +300,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv3_igemm_kernel(const Conv3Dev
         float sc[8], sh[8];  // a = act(x * sc + sh)
 #pragma unroll
         for (int j = 0; j < 8; ++j) { sc[j] = 1.f; sh[j] = 0.f; }
-        const bool has_norm = a.in_stats != nullptr;
         if (has_norm && ch_ok) {
           const float* st = a.in_stats + (static_cast<size_t>(ic.n) * a.x_pitch + ch0) * 2;
 #pragma unroll
@@ -291,49 +310,46 @@ __global__ void __launch_bounds__(kThreads, 1) conv3_igemm_kernel(const Conv3Dev
             sh[j] = -mean * rstd;
           }
         }
-        constexpr int U = 4;
-        for (int g0 = pw; g0 < kGroups; g0 += kNumProducerWarps * U) {
-          float f[U][8];
-          int soff[U];
-          bool inb[U];
 #pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int g = g0 + u * kNumProducerWarps;
-            const int L = g * 8 + vi;
-            soff[u] = -1;
-            inb[u] = false;
-            if (g < kGroups && L < kTotalVox) {
-              const int p = L / kPlaneVox;
-              const int rem = L - p * kPlaneVox;
-              const int yy = rem / kHaloX;
-              const int xx = rem - yy * kHaloX;
-              const int z = ic.z0 - 1 + p, y = ic.y0 - 1 + yy, xq = ic.x0 - 1 + xx;
-              soff[u] = ((p * 4 + cj) * kPlaneVox + rem) * 16;
-              inb[u] = ch_ok && z >= 0 && z < a.D && y >= 0 && y < a.H && xq >= 0 && xq < a.W;
-              if (inb[u]) {
-                const size_t vox = ((static_cast<size_t>(ic.n) * a.D + z) * a.H + y) * a.W + xq;
-                Vec8<T>::load(xg + vox * a.x_pitch + ch0, f[u]);
-              }
+        for (int p0 = 0; p0 < NP; p0 += PB) {
+          Raw8<T> raw[PB][kSlots];
+          bool inb[PB][kSlots];
+#pragma unroll
+          for (int pb = 0; pb < PB; ++pb) {
+            const int p = p0 + pb;
+            const int z = ic.z0 - 1 + p;
+            const bool zok = (p < NP) && ch_ok && z >= 0 && z < a.D;
+#pragma unroll
+            for (int s = 0; s < kSlots; ++s) {
+              inb[pb][s] = zok && ok[s];
+              if (inb[pb][s]) raw[pb][s].load(xg + nbase + z * plane_stride + goff[s] + ch0);
             }
           }
 #pragma unroll
-          for (int u = 0; u < U; ++u) {
-            if (soff[u] >= 0) {
-              uint4 o = make_uint4(0u, 0u, 0u, 0u);
-              if (inb[u]) {
-                float r[8];
+          for (int pb = 0; pb < PB; ++pb) {
+            const int p = p0 + pb;
+            if (p < NP) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  float t = fmaf(f[u][j], sc[j], sh[j]);
-                  if (has_norm) t = t > 0.f ? t : t * a.slope;
-                  r[j] = t;
+              for (int s = 0; s < kSlots; ++s) {
+                if (soff[s] >= 0) {
+                  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                  if (inb[pb][s]) {
+                    float f[8];
+                    raw[pb][s].to_float(f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                      float t = fmaf(f[j], sc[j], sh[j]);
+                      if (has_norm) t = t > 0.f ? t : t * a.slope;
+                      f[j] = t;
+                    }
+                    o.x = pack_bf16x2(f[0], f[1]);
+                    o.y = pack_bf16x2(f[2], f[3]);
+                    o.z = pack_bf16x2(f[4], f[5]);
+                    o.w = pack_bf16x2(f[6], f[7]);
+                  }
+                  *reinterpret_cast<uint4*>(unit + p * kZPlaneBytes + soff[s]) = o;
                 }
-                o.x = pack_bf16x2(r[0], r[1]);
-                o.y = pack_bf16x2(r[2], r[3]);
-                o.z = pack_bf16x2(r[4], r[5]);
-                o.w = pack_bf16x2(r[6], r[7]);
               }
-              *reinterpret_cast<uint4*>(unit + soff[u]) = o;
             }
           }
         }
@@ -376,83 +392,87 @@ __global__ void __launch_bounds__(kThreads, 1) conv3_igemm_kernel(const Conv3Dev
       tc_fence_after_sync();
       const int y = ic.y0 + ry, xq = ic.x0 + rx;
       const bool row_ok = (y < a.H) && (xq < a.W);
+      // flattened (plane, 16-column chunk) iteration space; the residual / mask rows of iteration
+      // i+1 are requested before the TMEM load of iteration i, so their latency overlaps the math.
+      const int nch = a.NT >> 4;
+      const int nplanes = min(PZ, a.D - ic.z0);
+      const int nit = nplanes * nch;
+      const size_t vox0 = ((static_cast<size_t>(ic.n) * a.D + ic.z0) * a.H + (row_ok ? y : 0)) * a.W + (row_ok ? xq : 0);
+      const size_t vox_plane = static_cast<size_t>(a.H) * a.W;
+      Raw16<T> pre_res, pre_mx;
+      pre_res.zero();
+      pre_mx.zero();
+      auto prefetch = [&](int it) {
+        const int p = it / nch;
+        const int cbase = ic.n0 + (it - p * nch) * 16;
+        const int nvalid = a.Cout - cbase;
+        if (row_ok && nvalid > 0) {
+          const size_t vox = vox0 + p * vox_plane;
+          if (rg != nullptr) pre_res.load(rg + vox * a.res_pitch + cbase, nvalid > 8);
+          if (mask_mode) pre_mx.load(mg + vox * a.mask_x_pitch + cbase, nvalid > 8);
+        }
+      };
+      if (nit > 0) prefetch(0);
 #pragma unroll 1
-      for (int p = 0; p < PZ; ++p) {
-        const int z = ic.z0 + p;
-        if (z >= a.D) break;
-        const size_t vox = ((static_cast<size_t>(ic.n) * a.D + z) * a.H + (row_ok ? y : 0)) * a.W +
-                           (row_ok ? xq : 0);
-#pragma unroll 1
-        for (int cc = 0; cc < a.NT; cc += 16) {
-          uint32_t r[16];
-          tmem_ld16(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * acc_cols + p * a.NT + cc, r);
-          tmem_ld_wait();
-          const int cbase = ic.n0 + cc;
-          const int nvalid = a.Cout - cbase;  // multiple of 8 (Cout % 8 == 0)
-          if (nvalid <= 0) continue;
-          float v[16];
+      for (int it = 0; it < nit; ++it) {
+        const int p = it / nch;
+        const int cc = (it - p * nch) * 16;
+        const Raw16<T> cur_res = pre_res, cur_mx = pre_mx;
+        if (it + 1 < nit) prefetch(it + 1);
+        const size_t vox = vox0 + p * vox_plane;
+        uint32_t r[16];
+        __syncwarp();
+        tmem_ld16(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * acc_cols + p * a.NT + cc, r);
+        tmem_ld_wait();
+        const int cbase = ic.n0 + cc;
+        const int nvalid = a.Cout - cbase;  // multiple of 8 (Cout % 8 == 0)
+        if (nvalid <= 0) continue;
+        float v[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-          float xh[16];
-          if (row_ok) {
-            if (rg != nullptr) {
-              float t[8];
-              Vec8<T>::load(rg + vox * a.res_pitch + cbase, t);
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        float xh[16];
+        if (row_ok) {
+          if (rg != nullptr) {
+            float t[16];
+            cur_res.to_float(t);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] += t[j];
-              if (nvalid > 8) {
-                Vec8<T>::load(rg + vox * a.res_pitch + cbase + 8, t);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[8 + j] += t[j];
-              }
-            }
-            if (mask_mode) {
-              float t[8];
-              Vec8<T>::load(mg + vox * a.mask_x_pitch + cbase, t);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) xh[j] = t[j];
-              if (nvalid > 8) {
-                Vec8<T>::load(mg + vox * a.mask_x_pitch + cbase + 8, t);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) xh[8 + j] = t[j];
-              } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) xh[8 + j] = 0.f;
-              }
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float h = (xh[j] - sm.mstat[cc + j][0]) * sm.mstat[cc + j][1];
-                xh[j] = h;
-                v[j] = h > 0.f ? v[j] : v[j] * a.slope;
-              }
-            }
+            for (int j = 0; j < 16; ++j) v[j] += t[j];
           }
-          if (want_stats) {
-            float s1[16], s2[16];
+          if (mask_mode) {
+            cur_mx.to_float(xh);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              const float val = row_ok ? v[j] : 0.f;
-              s1[j] = val;
-              s2[j] = mask_mode ? (row_ok ? val * xh[j] : 0.f) : val * val;
-            }
-            const float t1 = butterfly16(s1, lane);
-            const float t2 = butterfly16(s2, lane);
-            if ((lane & 1) == 0) {
-              const int col = cc + butterfly_col(lane);
-              sm.stat[warp - kEpiWarp0][col][0] += t1;
-              sm.stat[warp - kEpiWarp0][col][1] += t2;
+              const float h = (xh[j] - sm.mstat[cc + j][0]) * sm.mstat[cc + j][1];
+              xh[j] = h;
+              v[j] = h > 0.f ? v[j] : v[j] * a.slope;
             }
           }
-          if (row_ok) {
-            float o[8];
+        }
+        if (want_stats) {
+          float s1[16], s2[16];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = v[j];
-            Vec8<T>::store(yg + vox * a.y_pitch + cbase, o);
-            if (nvalid > 8) {
+          for (int j = 0; j < 16; ++j) {
+            const float val = row_ok ? v[j] : 0.f;
+            s1[j] = val;
+            s2[j] = mask_mode ? (row_ok ? val * xh[j] : 0.f) : val * val;
+          }
+          const float t1 = butterfly16(s1, lane);
+          const float t2 = butterfly16(s2, lane);
+          if ((lane & 1) == 0) {
+            const int col = cc + butterfly_col(lane);
+            sm.stat[warp - kEpiWarp0][col][0] += t1;
+            sm.stat[warp - kEpiWarp0][col][1] += t2;
+          }
+        }
+        if (row_ok) {
+          float o[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) o[j] = v[8 + j];
-              Vec8<T>::store(yg + vox * a.y_pitch + cbase + 8, o);
-            }
+          for (int j = 0; j < 8; ++j) o[j] = v[j];
+          Vec8<T>::store(yg + vox * a.y_pitch + cbase, o);
+          if (nvalid > 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = v[8 + j];
+            Vec8<T>::store(yg + vox * a.y_pitch + cbase + 8, o);
           }
         }
       }

@@ -32,6 +32,7 @@ constexpr int kWgTileY = 16, kWgTileX = 8;
 constexpr int kWgPlaneVox = 180;            // haloed a-plane
 constexpr int kWgAChunkBytes = kWgPlaneVox * 16;  // 2880
 constexpr int kWgDyChunkBytes = 128 * 16;         // 2048
+constexpr int kWgCtrlBytes = 4096;                // barriers + per-sample norm table
 
 struct WgradDev {
   int N, D, H, W, Cin, Cout;
@@ -51,6 +52,7 @@ struct WgradDev {
   int mirrored;            // dy ring written twice
   int dy_slot_bytes;       // CGo * 2048
   int piece_floats;        // 3 * TS * OT * IT
+  int cgi_shift, cgo_shift;  // log2(CGi) / log2(CGo) when a power of two, else -1
   uint32_t idesc;
 };
 
@@ -58,7 +60,10 @@ struct __align__(16) WgradSmem {
   uint64_t full[2], empty[2], done;
   uint32_t tmem_base;
   uint32_t pad_[1];
+  float2 norm[256];  // (scale, shift) of the CTA's IT input channels for the current sample
 };
+
+static_assert(sizeof(WgradSmem) <= kWgCtrlBytes, "control block overflows its smem region");
 
 struct WgUnit {
   int n, y0, x0, zs, ze;
@@ -82,7 +87,7 @@ template <typename T>
 __global__ void __launch_bounds__(kWgThreads, 1) conv3_wgrad_kernel(const WgradDev a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   WgradSmem& sm = *reinterpret_cast<WgradSmem*>(smem_raw);
-  uint8_t* dy_buf = smem_raw + 1024;
+  uint8_t* dy_buf = smem_raw + kWgCtrlBytes;
   const int dy_slots = a.mirrored ? 8 : 4;
   uint8_t* a_buf = dy_buf + dy_slots * a.dy_slot_bytes;
   const int a_slot_bytes = a.CGi * kWgAChunkBytes;
@@ -158,9 +163,29 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3_wgrad_kernel(const WgradD
     const T* __restrict__ xg = reinterpret_cast<const T*>(a.x);
     const T* __restrict__ dyg = reinterpret_cast<const T*>(a.dy);
     const bool has_norm = a.in_stats != nullptr;
+    const long long xplane = static_cast<long long>(a.H) * a.W * a.x_pitch;
+    const long long dplane = static_cast<long long>(a.H) * a.W * a.dy_pitch;
+    constexpr int U = 4;  // independent loads in flight per thread
     uint32_t t = 0;
+    int cur_n = -1;
     for (int u = rank; u < a.n_units; u += a.ranks) {
       const WgUnit un = wg_decode_unit(a, u);
+      if (un.n != cur_n) {
+        // per-sample (scale, shift) of this CTA's input channels: a = act(x * scale + shift)
+        named_bar_sync(2, kWgNumProducerThreads);
+        for (int c = pt; c < a.IT; c += kWgNumProducerThreads) {
+          float2 ns = make_float2(1.f, 0.f);
+          if (has_norm && i0 + c < a.Cin) {
+            const float* st = a.in_stats + (static_cast<size_t>(un.n) * a.x_pitch + i0 + c) * 2;
+            float mean, rstd;
+            stats_to_mean_rstd(st[0], st[1], a.inv_count, a.eps, mean, rstd);
+            ns = make_float2(rstd, -mean * rstd);
+          }
+          sm.norm[c] = ns;
+        }
+        named_bar_sync(2, kWgNumProducerThreads);
+        cur_n = un.n;
+      }
       for (int zb = un.zs; zb < un.ze; ++zb) {
         const uint32_t s = t & 1u;
         mbar_wait(smem_u32(&sm.empty[s]), ((t >> 1) & 1u) ^ 1u);
@@ -173,36 +198,57 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3_wgrad_kernel(const WgradD
         {
           uint8_t* dst = a_buf + s * a_slot_bytes;
           const int ops = 23 * a.CGi * 8;
-          for (int i = pt; i < ops; i += kWgNumProducerThreads) {
-            const int vi = i & 7;
-            const int cj = (i >> 3) % a.CGi;
-            const int g8 = (i >> 3) / a.CGi;
-            const int vox = g8 * 8 + vi;
-            if (vox >= kWgPlaneVox) continue;
-            const int yy = vox / 10, xx = vox - yy * 10;
-            const int y = un.y0 - 1 + yy, xq = un.x0 - 1 + xx;
-            const int ch = i0 + cj * 8;
-            uint4 o = make_uint4(0u, 0u, 0u, 0u);
-            if (ch < a.Cin && y >= 0 && y < a.H && xq >= 0 && xq < a.W) {
-              const size_t v = ((static_cast<size_t>(un.n) * a.D + zb) * a.H + y) * a.W + xq;
-              float f[8];
-              Vec8<T>::load(xg + v * a.x_pitch + ch, f);
-              if (has_norm) {
-                const float* st = a.in_stats + (static_cast<size_t>(un.n) * a.x_pitch + ch) * 2;
+          const long long zbase = (static_cast<long long>(un.n) * a.D + zb) * xplane;
+          for (int ib = pt; ib < ops; ib += kWgNumProducerThreads * U) {
+            Raw8<T> raw[U];
+            int off[U], cjs[U];
+            bool inb[U];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  float mean, rstd;
-                  stats_to_mean_rstd(st[2 * j], st[2 * j + 1], a.inv_count, a.eps, mean, rstd);
-                  float h = (f[j] - mean) * rstd;
-                  f[j] = h > 0.f ? h : h * a.slope;
+            for (int q = 0; q < U; ++q) {
+              const int i = ib + q * kWgNumProducerThreads;
+              off[q] = -1;
+              inb[q] = false;
+              cjs[q] = 0;
+              if (i < ops) {
+                const int vi = i & 7;
+                const int w8 = i >> 3;
+                const int cj = a.cgi_shift >= 0 ? (w8 & (a.CGi - 1)) : (w8 % a.CGi);
+                const int g8 = a.cgi_shift >= 0 ? (w8 >> a.cgi_shift) : (w8 / a.CGi);
+                const int vox = g8 * 8 + vi;
+                if (vox < kWgPlaneVox) {
+                  const int yy = vox / 10, xx = vox - yy * 10;
+                  const int y = un.y0 - 1 + yy, xq = un.x0 - 1 + xx;
+                  const int ch = i0 + cj * 8;
+                  off[q] = (cj * kWgPlaneVox + vox) * 16;
+                  cjs[q] = cj;
+                  inb[q] = ch < a.Cin && y >= 0 && y < a.H && xq >= 0 && xq < a.W;
+                  if (inb[q]) raw[q].load(xg + zbase + (static_cast<long long>(y) * a.W + xq) * a.x_pitch + ch);
                 }
               }
-              o.x = pack_bf16x2(f[0], f[1]);
-              o.y = pack_bf16x2(f[2], f[3]);
-              o.z = pack_bf16x2(f[4], f[5]);
-              o.w = pack_bf16x2(f[6], f[7]);
             }
-            *reinterpret_cast<uint4*>(dst + (cj * kWgPlaneVox + vox) * 16) = o;
+#pragma unroll
+            for (int q = 0; q < U; ++q) {
+              if (off[q] >= 0) {
+                uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                if (inb[q]) {
+                  float f[8];
+                  raw[q].to_float(f);
+                  if (has_norm) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                      const float2 ns = sm.norm[cjs[q] * 8 + j];
+                      const float h = fmaf(f[j], ns.x, ns.y);
+                      f[j] = h > 0.f ? h : h * a.slope;
+                    }
+                  }
+                  o.x = pack_bf16x2(f[0], f[1]);
+                  o.y = pack_bf16x2(f[2], f[3]);
+                  o.z = pack_bf16x2(f[4], f[5]);
+                  o.w = pack_bf16x2(f[6], f[7]);
+                }
+                *reinterpret_cast<uint4*>(dst + off[q]) = o;
+              }
+            }
           }
         }
         // ---- dy planes: zb+1 always, zb-1 and zb at a column start ----
@@ -212,25 +258,44 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3_wgrad_kernel(const WgradD
           uint8_t* dst0 = dy_buf + slot * a.dy_slot_bytes;
           const bool zin = z >= 0 && z < a.D;
           const int ops = 16 * a.CGo * 8;
-          for (int i = pt; i < ops; i += kWgNumProducerThreads) {
-            const int vi = i & 7;
-            const int cj = (i >> 3) % a.CGo;
-            const int g8 = (i >> 3) / a.CGo;
-            const int y = un.y0 + g8, xq = un.x0 + vi;
-            const int ch = o0 + cj * 8;
-            uint4 o = make_uint4(0u, 0u, 0u, 0u);
-            if (zin && ch < a.Cout && y < a.H && xq < a.W) {
-              const size_t v = ((static_cast<size_t>(un.n) * a.D + z) * a.H + y) * a.W + xq;
-              float f[8];
-              Vec8<T>::load(dyg + v * a.dy_pitch + ch, f);
-              o.x = pack_bf16x2(f[0], f[1]);
-              o.y = pack_bf16x2(f[2], f[3]);
-              o.z = pack_bf16x2(f[4], f[5]);
-              o.w = pack_bf16x2(f[6], f[7]);
+          const long long zbase = (static_cast<long long>(un.n) * a.D + z) * dplane;
+          for (int ib = pt; ib < ops; ib += kWgNumProducerThreads * U) {
+            Raw8<T> raw[U];
+            int off[U];
+            bool inb[U];
+#pragma unroll
+            for (int q = 0; q < U; ++q) {
+              const int i = ib + q * kWgNumProducerThreads;
+              off[q] = -1;
+              inb[q] = false;
+              if (i < ops) {
+                const int vi = i & 7;
+                const int w8 = i >> 3;
+                const int cj = a.cgo_shift >= 0 ? (w8 & (a.CGo - 1)) : (w8 % a.CGo);
+                const int g8 = a.cgo_shift >= 0 ? (w8 >> a.cgo_shift) : (w8 / a.CGo);
+                const int y = un.y0 + g8, xq = un.x0 + vi;
+                const int ch = o0 + cj * 8;
+                off[q] = (cj * 128 + g8 * 8 + vi) * 16;
+                inb[q] = zin && ch < a.Cout && y < a.H && xq < a.W;
+                if (inb[q]) raw[q].load(dyg + zbase + (static_cast<long long>(y) * a.W + xq) * a.dy_pitch + ch);
+              }
             }
-            const int off = (cj * 128 + g8 * 8 + vi) * 16;
-            *reinterpret_cast<uint4*>(dst0 + off) = o;
-            if (a.mirrored) *reinterpret_cast<uint4*>(dst0 + 4 * a.dy_slot_bytes + off) = o;
+#pragma unroll
+            for (int q = 0; q < U; ++q) {
+              if (off[q] >= 0) {
+                uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                if (inb[q]) {
+                  float f[8];
+                  raw[q].to_float(f);
+                  o.x = pack_bf16x2(f[0], f[1]);
+                  o.y = pack_bf16x2(f[2], f[3]);
+                  o.z = pack_bf16x2(f[4], f[5]);
+                  o.w = pack_bf16x2(f[6], f[7]);
+                }
+                *reinterpret_cast<uint4*>(dst0 + off[q]) = o;
+                if (a.mirrored) *reinterpret_cast<uint4*>(dst0 + 4 * a.dy_slot_bytes + off[q]) = o;
+              }
+            }
           }
         }
         fence_proxy_async_smem();
@@ -319,7 +384,7 @@ static int wgrad_plan(int Cout, int Cin, int N, int D, int H, int W, int max_cta
   for (int it = 16; it <= 256 && it <= ci_pad; it += 16) {
     if (ci_pad % it) continue;
     const int a_bytes = 2 * (it / 8) * kWgAChunkBytes;
-    if (1024 + dy_bytes + a_bytes > 227 * 1024) continue;
+    if (kWgCtrlBytes + dy_bytes + a_bytes > 227 * 1024) continue;
     for (int ts : {9, 3, 1}) {
       if (d.KS * ts * it > 512) continue;
       const long long score = static_cast<long long>(it < 128 ? it : 128) * 16 + ts;  // IT first, then TS
@@ -354,6 +419,9 @@ static int wgrad_plan(int Cout, int Cin, int N, int D, int H, int W, int max_cta
   if (ranks > d.n_units) ranks = d.n_units;
   d.ranks = ranks;
   d.idesc = make_idesc_bf16(128, d.IT, 1, 1);
+  auto log2_or_neg = [](int v) { int l = 0; while ((1 << l) < v) ++l; return (1 << l) == v ? l : -1; };
+  d.cgi_shift = log2_or_neg(d.CGi);
+  d.cgo_shift = log2_or_neg(d.CGo);
   return 0;
 }
 
@@ -394,7 +462,7 @@ extern "C" int rsb_conv3_wgrad(const RsbConv3WgradArgs* p, void* stream) {
   const size_t need = static_cast<size_t>(grid) * d.piece_floats * sizeof(float);
   RSB_REQUIRE(p->workspace_bytes >= need, "wgrad: workspace too small (%zu < %zu)", p->workspace_bytes, need);
 
-  size_t smem = 1024 + static_cast<size_t>(d.mirrored ? 8 : 4) * d.dy_slot_bytes + 2 * static_cast<size_t>(d.CGi) * kWgAChunkBytes;
+  size_t smem = kWgCtrlBytes + static_cast<size_t>(d.mirrored ? 8 : 4) * d.dy_slot_bytes + 2 * static_cast<size_t>(d.CGi) * kWgAChunkBytes;
   if (smem < 120 * 1024) smem = 120 * 1024;  // 1 CTA / SM (each CTA owns all 512 TMEM columns)
   RSB_REQUIRE(smem <= 227 * 1024, "wgrad: shared memory budget exceeded (%zu)", smem);
   cudaStream_t st = static_cast<cudaStream_t>(stream);

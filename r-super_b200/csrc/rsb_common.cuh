@@ -243,6 +243,54 @@ struct Vec8<float> {
   }
 };
 
+// Unconverted 8 / 16-channel payloads: lets a kernel issue global loads early and convert late
+// (software prefetch without the convert instruction forcing an early wait on the load).
+template <typename T>
+struct Raw8;
+template <>
+struct Raw8<__nv_bfloat16> {
+  uint4 u;
+  RSB_DEVICE void load(const __nv_bfloat16* p) { u = *reinterpret_cast<const uint4*>(p); }
+  RSB_DEVICE void zero() { u = make_uint4(0u, 0u, 0u, 0u); }
+  RSB_DEVICE void to_float(float (&f)[8]) const {
+    f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x);
+    f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+    f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z);
+    f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+  }
+};
+template <>
+struct Raw8<float> {
+  float4 a, b;
+  RSB_DEVICE void load(const float* p) {
+    a = *reinterpret_cast<const float4*>(p);
+    b = *reinterpret_cast<const float4*>(p + 4);
+  }
+  RSB_DEVICE void zero() { a = make_float4(0.f, 0.f, 0.f, 0.f); b = a; }
+  RSB_DEVICE void to_float(float (&f)[8]) const {
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+    f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+};
+template <typename T>
+struct Raw16 {
+  Raw8<T> lo, hi;
+  RSB_DEVICE void load(const T* p, bool both) {
+    lo.load(p);
+    if (both) hi.load(p + 8); else hi.zero();
+  }
+  RSB_DEVICE void zero() { lo.zero(); hi.zero(); }
+  RSB_DEVICE void to_float(float (&f)[16]) const {
+    float t[8];
+    lo.to_float(t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = t[j];
+    hi.to_float(t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[8 + j] = t[j];
+  }
+};
+
 RSB_DEVICE float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

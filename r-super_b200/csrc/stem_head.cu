@@ -155,6 +155,73 @@ __global__ void stem_wgrad_kernel(const float* __restrict__ x, const T* __restri
   for (int j = 0; j < 8; ++j) atomicAdd(&dw[(cg * 8 + j) * 27 + tap], acc[j]);
 }
 
+// Tiled variant (Cout <= 64): a block stages a 1 x 8 x 32 voxel tile of dy (as fp32) and the haloed
+// 3 x 10 x 34 input tile in shared memory; thread (tap, 8-channel group) then walks the 256 voxels
+// with 3 shared loads per 8 FMAs and keeps its 8 partial sums in registers across all its tiles.
+constexpr int kSwTX = 32, kSwTY = 8;
+constexpr int kSwVox = kSwTX * kSwTY;
+template <typename T>
+__global__ void __launch_bounds__(256) stem_wgrad_tiled_kernel(const float* __restrict__ x, const T* __restrict__ dy,
+                                                               long long dyp, float* __restrict__ dw, int N, int D,
+                                                               int H, int W, int Cout, int tiles_x, int tiles_y,
+                                                               long long num_tiles) {
+  extern __shared__ float sm[];
+  float* sx = sm;                         // [3][10][34]
+  float* sdy = sm + 3 * 10 * 34;          // [256][Cout]
+  const int CG = Cout / 8;
+  const int tap = threadIdx.x / CG, cg = threadIdx.x % CG;
+  const bool active = tap < 27;
+  const int dz = tap / 9, dyy = (tap / 3) % 3, dxx = tap % 3;
+  float acc[8] = {0};
+  for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    long long t = tile;
+    const int xt = static_cast<int>(t % tiles_x); t /= tiles_x;
+    const int yt = static_cast<int>(t % tiles_y); t /= tiles_y;
+    const int z = static_cast<int>(t % D);
+    const int n = static_cast<int>(t / D);
+    const int x0 = xt * kSwTX, y0 = yt * kSwTY;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * 10 * 34; i += blockDim.x) {
+      const int xx = i % 34, yy = (i / 34) % 10, zz = i / 340;
+      const int gz = z - 1 + zz, gy = y0 - 1 + yy, gx = x0 - 1 + xx;
+      const bool inb = gz >= 0 && gz < D && gy >= 0 && gy < H && gx >= 0 && gx < W;
+      sx[i] = inb ? x[((static_cast<long long>(n) * D + gz) * H + gy) * W + gx] : 0.f;
+    }
+    for (int i = threadIdx.x; i < kSwVox * CG; i += blockDim.x) {
+      const int c8 = i % CG, v = i / CG;
+      const int gy = y0 + v / kSwTX, gx = x0 + v % kSwTX;
+      float f[8];
+      if (gy < H && gx < W) {
+        Vec8<T>::load(dy + (((static_cast<long long>(n) * D + z) * H + gy) * W + gx) * dyp + c8 * 8, f);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = 0.f;
+      }
+      float4* d4 = reinterpret_cast<float4*>(sdy + v * Cout + c8 * 8);
+      d4[0] = make_float4(f[0], f[1], f[2], f[3]);
+      d4[1] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+    __syncthreads();
+    if (active) {
+#pragma unroll 4
+      for (int v = 0; v < kSwVox; ++v) {
+        const int vy = v / kSwTX, vx = v % kSwTX;
+        const float xv = sx[(dz * 10 + vy + dyy) * 34 + vx + dxx];
+        const float4* d4 = reinterpret_cast<const float4*>(sdy + v * Cout + cg * 8);
+        const float4 a = d4[0], b = d4[1];
+        acc[0] = fmaf(xv, a.x, acc[0]); acc[1] = fmaf(xv, a.y, acc[1]);
+        acc[2] = fmaf(xv, a.z, acc[2]); acc[3] = fmaf(xv, a.w, acc[3]);
+        acc[4] = fmaf(xv, b.x, acc[4]); acc[5] = fmaf(xv, b.y, acc[5]);
+        acc[6] = fmaf(xv, b.z, acc[6]); acc[7] = fmaf(xv, b.w, acc[7]);
+      }
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&dw[(cg * 8 + j) * 27 + tap], acc[j]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // head 1x1x1 + bias
 // ------------------------------------------------------------------------------------------
@@ -316,6 +383,25 @@ extern "C" int rsb_stem_conv_wgrad(const float* x, const void* dy, int dy_pitch,
   const long long total = static_cast<long long>(N) * D * H * W;
   const int sms = rsb_num_sms();
   RSB_REQUIRE(sms > 0, "no CUDA device");
+  if (Cout <= 64) {
+    const int tiles_x = (W + kSwTX - 1) / kSwTX, tiles_y = (H + kSwTY - 1) / kSwTY;
+    const long long num_tiles = static_cast<long long>(N) * D * tiles_y * tiles_x;
+    const size_t smb = sizeof(float) * (3 * 10 * 34 + kSwVox * Cout);
+    const int threads = ((27 * (Cout / 8)) + 31) / 32 * 32;
+    long long blocks = static_cast<long long>(sms) * 4;
+    if (blocks > num_tiles) blocks = num_tiles;
+    cudaError_t ea;
+    if (dtype == RSB_BF16) {
+      ea = cudaFuncSetAttribute(stem_wgrad_tiled_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smb));
+      RSB_REQUIRE(ea == cudaSuccess, "stem_conv_wgrad: smem opt-in failed: %s", cudaGetErrorString(ea));
+      stem_wgrad_tiled_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), threads, smb, st>>>(x, (const __nv_bfloat16*)dy, dy_pitch, dw_oidhw, N, D, H, W, Cout, tiles_x, tiles_y, num_tiles);
+    } else if (dtype == RSB_F32) {
+      ea = cudaFuncSetAttribute(stem_wgrad_tiled_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smb));
+      RSB_REQUIRE(ea == cudaSuccess, "stem_conv_wgrad: smem opt-in failed: %s", cudaGetErrorString(ea));
+      stem_wgrad_tiled_kernel<float><<<static_cast<unsigned>(blocks), threads, smb, st>>>(x, (const float*)dy, dy_pitch, dw_oidhw, N, D, H, W, Cout, tiles_x, tiles_y, num_tiles);
+    } else { set_last_error("bad dtype %d", dtype); return -1; }
+    return check_launch("stem_wgrad_tiled_kernel");
+  }
   long long blocks = static_cast<long long>(sms) * 8;
   long long vpb = (total + blocks - 1) / blocks;
   if (vpb < 64) vpb = 64;
