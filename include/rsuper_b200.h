@@ -99,6 +99,9 @@ typedef struct RsbConv3Args {
 } RsbConv3Args;
 
 int rsb_conv3_forward(const RsbConv3Args* args, void* stream);
+/* profiling aid: per-CTA pipeline wait-cycle counters of subsequent rsb_conv3_forward launches
+ * (16 int64 per CTA; NULL disables).  Not used by the product path. */
+int rsb_debug_set_timing_buffer(void* device_ptr);
 
 /* weight gradient of the same conv: dW[co][ci][tap] = sum_v dy[v][co] * a[v+tap-1][ci],
  * a = act(norm(x)) recomputed in the staging.  tcgen05 with MN-major operands (K = voxels).

@@ -68,6 +68,7 @@ struct Conv3Dev {
   int num_items;
   int acc_stages;
   uint32_t idesc;
+  long long* dbg;  // optional per-CTA wait-cycle counters (rsb_debug_set_timing_buffer)
 };
 
 struct __align__(16) Conv3Smem {
@@ -194,62 +195,93 @@ __global__ void __launch_bounds__(kThreads, 1) conv3_igemm_kernel(const Conv3Dev
 
   if (warp == 0) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    // The whole warp walks the pipeline (waits are warp-converged); one elected lane issues.  Using
+    // elect.sync (instead of `lane == 0`) lets ptxas emit the uniform-datapath UTCHMMA without a
+    // per-instruction ELECT/BRA.U.ANY loop.
+    {
       uint32_t a_it = 0, b_it = 0, acc_it = 0;
+      long long tw_a = 0, tw_b = 0, tw_acc = 0;
+      const long long t_begin = clock64();
       const uint32_t a_hi = ((160u >> 4) & 0x3FFFu) | (1u << 14);  // SBO = 160 B (next y row), version 1
       const uint32_t b_hi = ((512u >> 4) & 0x3FFFu) | (1u << 14);  // SBO = 512 B (next 8 couts)
       const uint32_t a_lbo = ((static_cast<uint32_t>(kChunkPlaneBytes) >> 4) & 0x3FFFu) << 16;
       const uint32_t b_lbo = ((128u >> 4) & 0x3FFFu) << 16;
       for (int item = blockIdx.x; item < a.num_items; item += gridDim.x) {
         const uint32_t as = acc_it % a.acc_stages;
+        long long tq = clock64();
         mbar_wait(smem_u32(&sm.acc_empty[as]), ((acc_it / a.acc_stages) & 1u) ^ 1u);
+        tw_acc += clock64() - tq;
         tc_fence_after_sync();
-        const uint32_t d_base = tmem_base + as * acc_cols;
+        uint32_t d_acc[PZ];
+#pragma unroll
+        for (int p = 0; p < PZ; ++p) d_acc[p] = tmem_base + as * acc_cols + p * a.NT;
         for (int c = 0; c < a.nchunks; ++c) {
           const uint32_t ab = a_it & 1u;
+          tq = clock64();
           mbar_wait(smem_u32(&sm.a_full[ab]), (a_it >> 1) & 1u);
+          tw_a += clock64() - tq;
           tc_fence_after_sync();
-          const int ksteps = (c == a.nchunks - 1) ? a.last_ksteps : 2;
-          const uint32_t a_unit = a_base + ab * a_unit_bytes<PZ>();
+          const bool two_k = (c != a.nchunks - 1) || (a.last_ksteps == 2);
+          // Descriptor low words (start address >> 4, LBO in the upper half) are formed once per
+          // chunk / per tap; every MMA then costs one integer add per operand: the single issuing
+          // thread is the pipeline's critical resource (measured: ~56 cycles per 128xNx16 MMA when
+          // the issue loop is tight vs ~160 with per-MMA descriptor arithmetic).
+          const uint32_t a_unit_lo = a_lbo | ((a_base + ab * a_unit_bytes<PZ>()) >> 4);
+          uint32_t first = (c != 0) ? 1u : 0u;  // accumulate flag of the very first MMA of each accumulator
+#pragma unroll
           for (int tap = 0; tap < 27; ++tap) {
+            constexpr int kPlaneUnits = kPlaneVox;  // one 8-channel plane = 180 x 16 B
             const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
             const uint32_t bs = b_it % kNumBStages;
+            tq = clock64();
             mbar_wait(smem_u32(&sm.b_full[bs]), (b_it / kNumBStages) & 1u);
+            tw_b += clock64() - tq;
             tc_fence_after_sync();
-            const uint32_t b_st = b_base + bs * b_stage_bytes;
+            const uint32_t b_lo = b_lbo | ((b_base + bs * b_stage_bytes) >> 4);
+            const uint32_t a_tap_lo = a_unit_lo + (kd * 4 * kPlaneUnits + kh * kHaloX + kw);
+            if (elect_one()) {
 #pragma unroll
             for (int p = 0; p < PZ; ++p) {
-              for (int s = 0; s < ksteps; ++s) {
-                const uint32_t a_addr =
-                    a_unit + (((p + kd) * 4 + 2 * s) * kPlaneVox + kh * kHaloX + kw) * 16;
-                const uint32_t b_addr = b_st + s * 256;
-                const uint64_t adesc =
-                    (static_cast<uint64_t>(a_hi) << 32) | (a_lbo | ((a_addr >> 4) & 0x3FFFu));
-                const uint64_t bdesc =
-                    (static_cast<uint64_t>(b_hi) << 32) | (b_lbo | ((b_addr >> 4) & 0x3FFFu));
-                umma_bf16_ss(d_base + p * a.NT, adesc, bdesc, a.idesc, (c | tap | s) != 0 ? 1u : 0u);
+              const uint64_t ad0 = (static_cast<uint64_t>(a_hi) << 32) | (a_tap_lo + p * 4 * kPlaneUnits);
+              const uint64_t bd0 = (static_cast<uint64_t>(b_hi) << 32) | b_lo;
+              umma_bf16_ss(d_acc[p], ad0, bd0, a.idesc, tap == 0 ? first : 1u);
+              if (two_k) {
+                const uint64_t ad1 = (static_cast<uint64_t>(a_hi) << 32) | (a_tap_lo + (p * 4 + 2) * kPlaneUnits);
+                const uint64_t bd1 = (static_cast<uint64_t>(b_hi) << 32) | (b_lo + 16);
+                umma_bf16_ss(d_acc[p], ad1, bd1, a.idesc, 1u);
               }
             }
             umma_commit(smem_u32(&sm.b_empty[bs]));
+            if (tap == 26) {
+              umma_commit(smem_u32(&sm.a_empty[ab]));
+              if (c == a.nchunks - 1) umma_commit(smem_u32(&sm.acc_full[as]));
+            }
+            }
+            __syncwarp();
             ++b_it;
           }
-          umma_commit(smem_u32(&sm.a_empty[ab]));
           ++a_it;
         }
-        umma_commit(smem_u32(&sm.acc_full[as]));
         ++acc_it;
+      }
+      if (a.dbg != nullptr && lane == 0) {
+        long long* d = a.dbg + static_cast<size_t>(blockIdx.x) * 16;
+        d[0] = clock64() - t_begin; d[1] = tw_a; d[2] = tw_b; d[3] = tw_acc; d[4] = acc_it;
       }
     }
   } else if (warp == 1) {
     // =========================== weight loader ===========================
     if (lane == 0) {
       uint32_t b_it = 0;
+      long long tw_be = 0;
       for (int item = blockIdx.x; item < a.num_items; item += gridDim.x) {
         const ItemCoord ic = decode_item(a, item, PZ);
         for (int c = 0; c < a.nchunks; ++c) {
           for (int tap = 0; tap < 27; ++tap) {
             const uint32_t bs = b_it % kNumBStages;
+            const long long tq = clock64();
             mbar_wait(smem_u32(&sm.b_empty[bs]), ((b_it / kNumBStages) & 1u) ^ 1u);
+            tw_be += clock64() - tq;
             const uint8_t* src =
                 a.w_packed +
                 (static_cast<size_t>(c * 27 + tap) * a.cout_groups + (ic.n0 >> 3)) * 512;
@@ -259,6 +291,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3_igemm_kernel(const Conv3Dev
           }
         }
       }
+      if (a.dbg != nullptr) a.dbg[static_cast<size_t>(blockIdx.x) * 16 + 9] = tw_be;
     }
   } else if (warp >= kProducerWarp0) {
     // =========================== A producers ===========================
@@ -275,6 +308,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3_igemm_kernel(const Conv3Dev
     const long long plane_stride = static_cast<long long>(a.H) * a.W * a.x_pitch;
     const bool has_norm = a.in_stats != nullptr;
     uint32_t a_it = 0;
+    long long tw_pe = 0;
+    const long long tp_begin = clock64();
     for (int item = blockIdx.x; item < a.num_items; item += gridDim.x) {
       const ItemCoord ic = decode_item(a, item, PZ);
       int soff[kSlots];
@@ -293,7 +328,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3_igemm_kernel(const Conv3Dev
       const long long nbase = static_cast<long long>(ic.n) * a.D * plane_stride;
       for (int c = 0; c < a.nchunks; ++c) {
         const uint32_t ab = a_it & 1u;
+        const long long tq = clock64();
         mbar_wait(smem_u32(&sm.a_empty[ab]), ((a_it >> 1) & 1u) ^ 1u);
+        tw_pe += clock64() - tq;
         uint8_t* unit = a_buf + ab * a_unit_bytes<PZ>();
         const int ch0 = c * kChunk + cj * 8;
         const bool ch_ok = ch0 < a.Cin;
@@ -358,6 +395,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv3_igemm_kernel(const Conv3Dev
         ++a_it;
       }
     }
+    if (a.dbg != nullptr && pw == 0 && lane == 0) {
+      long long* d = a.dbg + static_cast<size_t>(blockIdx.x) * 16;
+      d[5] = clock64() - tp_begin; d[6] = tw_pe;
+    }
   } else {
     // =========================== epilogue ===========================
     const int ew = warp & 3;  // TMEM lane quarter this warp may access
@@ -372,6 +413,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3_igemm_kernel(const Conv3Dev
     float* stat_dst = mask_mode ? a.bwd_sums : a.out_stats;
     const long long stat_pitch = mask_mode ? a.mask_x_pitch : a.y_pitch;
     uint32_t acc_it = 0;
+    long long tw_ef = 0;
+    const long long te_begin = clock64();
     for (int item = blockIdx.x; item < a.num_items; item += gridDim.x) {
       const ItemCoord ic = decode_item(a, item, PZ);
       if (mask_mode) {
@@ -388,7 +431,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3_igemm_kernel(const Conv3Dev
         named_bar_sync(1, 128);
       }
       const uint32_t as = acc_it % a.acc_stages;
+      const long long tq = clock64();
       mbar_wait(smem_u32(&sm.acc_full[as]), (acc_it / a.acc_stages) & 1u);
+      tw_ef += clock64() - tq;
       tc_fence_after_sync();
       const int y = ic.y0 + ry, xq = ic.x0 + rx;
       const bool row_ok = (y < a.H) && (xq < a.W);
@@ -493,6 +538,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv3_igemm_kernel(const Conv3Dev
         __syncwarp();
       }
     }
+    if (a.dbg != nullptr && warp == kEpiWarp0 && lane == 0) {
+      long long* d = a.dbg + static_cast<size_t>(blockIdx.x) * 16;
+      d[7] = clock64() - te_begin; d[8] = tw_ef;
+    }
   }
 
   // ---------------- teardown ----------------
@@ -552,6 +601,16 @@ static int launch_conv3(const Conv3Dev& dev, int grid, size_t smem_bytes, cudaSt
 
 using namespace rsb;
 
+static long long* g_timing_buffer = nullptr;
+// Bring-up / profiling aid: when set (device pointer to >= 16 * grid int64), conv3_forward launches
+// record per-CTA cycle counters: [0] MMA thread total, [1..3] its waits on a_full / b_full / acc_empty,
+// [4] items, [5] producer total, [6] producer wait on a_empty, [7] epilogue total, [8] epilogue wait on
+// acc_full, [9] weight-loader wait on b_empty.
+extern "C" int rsb_debug_set_timing_buffer(void* device_ptr) {
+  g_timing_buffer = reinterpret_cast<long long*>(device_ptr);
+  return 0;
+}
+
 extern "C" size_t rsb_conv3_packed_weight_bytes(int Cout, int Cin) {
   const int nchunks = (Cin + kChunk - 1) / kChunk;
   const int co_pad = round_up(Cout, 16);
@@ -597,6 +656,7 @@ extern "C" int rsb_conv3_forward(const RsbConv3Args* p, void* stream) {
   d.y = p->y; d.y_pitch = p->y_pitch; d.res = p->res; d.res_pitch = p->res_pitch;
   d.out_stats = p->out_stats; d.mask_x = p->mask_x; d.mask_x_pitch = p->mask_x_pitch;
   d.mask_stats = p->mask_stats; d.bwd_sums = p->bwd_sums;
+  d.dbg = g_timing_buffer;
 
   const int co_pad = round_up(p->Cout, 16);
   d.cout_groups = co_pad / 8;

@@ -122,7 +122,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3_wgrad_kernel(const WgradD
 
   if (warp == 0) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    // warp-converged waits; one elected lane issues (see conv3_igemm.cu)
+    {
       const uint32_t a_hi = ((static_cast<uint32_t>(kWgDyChunkBytes) >> 4) & 0x3FFFu) | (1u << 14);  // dy: SBO = next 8 couts
       const uint32_t a_lbo = ((128u >> 4) & 0x3FFFu) << 16;                                           // next 8 voxels (y row)
       const uint32_t b_hi = ((static_cast<uint32_t>(kWgAChunkBytes) >> 4) & 0x3FFFu) | (1u << 14);   // a: SBO = next 8 cins
@@ -134,28 +135,34 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3_wgrad_kernel(const WgradD
           const uint32_t s = t & 1u;
           mbar_wait(smem_u32(&sm.full[s]), (t >> 1) & 1u);
           tc_fence_after_sync();
+          const uint32_t b_slot_lo = b_lbo | ((a_base + s * a_slot_bytes) >> 4);
+          const uint32_t first = t != 0 ? 1u : 0u;
+          if (elect_one()) {
           for (int w = 0; w < a.KS; ++w) {
             const int win = mod4(zb - 1 + w * a.PM);
-            const uint32_t a_win = dy_base + win * a.dy_slot_bytes;
+            const uint32_t a_win_lo = a_lbo | ((dy_base + win * a.dy_slot_bytes) >> 4);
             for (int ti = 0; ti < a.TS; ++ti) {
               const int tap = tapset * a.TS + ti;  // in-plane tap index kh*3+kw
               const int kh = tap / 3, kw = tap % 3;
               const uint32_t d_col = tmem_base + (w * a.TS + ti) * a.IT;
+              const uint32_t b_tap_lo = b_slot_lo + kh * 10 + kw;
+              // 8 K-steps of 16 voxels (2 y-rows): dy advances 256 B, the haloed a-plane 2 * 160 B
 #pragma unroll
               for (int ks = 0; ks < 8; ++ks) {
-                const uint32_t a_addr = a_win + ks * 256;
-                const uint32_t b_addr = a_base + s * a_slot_bytes + ((2 * ks + kh) * 10 + kw) * 16;
-                const uint64_t adesc = (static_cast<uint64_t>(a_hi) << 32) | (a_lbo | ((a_addr >> 4) & 0x3FFFu));
-                const uint64_t bdesc = (static_cast<uint64_t>(b_hi) << 32) | (b_lbo | ((b_addr >> 4) & 0x3FFFu));
-                umma_bf16_ss(d_col, adesc, bdesc, a.idesc, (t | ks) != 0 ? 1u : 0u);
+                const uint64_t adesc = (static_cast<uint64_t>(a_hi) << 32) | (a_win_lo + ks * 16);
+                const uint64_t bdesc = (static_cast<uint64_t>(b_hi) << 32) | (b_tap_lo + ks * 20);
+                umma_bf16_ss(d_col, adesc, bdesc, a.idesc, ks == 0 ? first : 1u);
               }
             }
           }
           umma_commit(smem_u32(&sm.empty[s]));
+          }
+          __syncwarp();
           ++t;
         }
       }
-      umma_commit(smem_u32(&sm.done));
+      if (elect_one()) umma_commit(smem_u32(&sm.done));
+      __syncwarp();
     }
   } else if (warp >= kWgProducerWarp0) {
     // =========================== producers ===========================
