@@ -125,6 +125,7 @@ typedef struct RsbConv3WgradArgs {
 
 size_t rsb_conv3_wgrad_workspace_bytes(int Cout, int Cin, int max_ctas);
 int rsb_conv3_wgrad(const RsbConv3WgradArgs* args, void* stream);
+int rsb_debug_set_wgrad_timing_buffer(void* device_ptr); /* profiling aid, see above */
 
 /* ---------------------------------------------------------------------------------------------
  * stem conv 3x3x3 with Cin = 1 (inconv.conv1, model/dim3/unet_utils.py:15,18) — direct

@@ -54,6 +54,7 @@ struct WgradDev {
   int piece_floats;        // 3 * TS * OT * IT
   int cgi_shift, cgo_shift;  // log2(CGi) / log2(CGo) when a power of two, else -1
   uint32_t idesc;
+  long long* dbg;
 };
 
 struct __align__(16) WgradSmem {
@@ -129,11 +130,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3_wgrad_kernel(const WgradD
       const uint32_t b_hi = ((static_cast<uint32_t>(kWgAChunkBytes) >> 4) & 0x3FFFu) | (1u << 14);   // a: SBO = next 8 cins
       const uint32_t b_lbo = ((160u >> 4) & 0x3FFFu) << 16;                                           // next y row of the halo plane
       uint32_t t = 0;
+      long long tw_full = 0;
+      const long long t_begin = clock64();
       for (int u = rank; u < a.n_units; u += a.ranks) {
         const WgUnit un = wg_decode_unit(a, u);
         for (int zb = un.zs; zb < un.ze; ++zb) {
           const uint32_t s = t & 1u;
+          const long long tq = clock64();
           mbar_wait(smem_u32(&sm.full[s]), (t >> 1) & 1u);
+          tw_full += clock64() - tq;
           tc_fence_after_sync();
           const uint32_t b_slot_lo = b_lbo | ((a_base + s * a_slot_bytes) >> 4);
           const uint32_t first = t != 0 ? 1u : 0u;
@@ -163,6 +168,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3_wgrad_kernel(const WgradD
       }
       if (elect_one()) umma_commit(smem_u32(&sm.done));
       __syncwarp();
+      if (a.dbg != nullptr && lane == 0) {
+        long long* d = a.dbg + static_cast<size_t>(blockIdx.x) * 16;
+        d[0] = clock64() - t_begin; d[1] = tw_full; d[2] = t;
+      }
     }
   } else if (warp >= kWgProducerWarp0) {
     // =========================== producers ===========================
@@ -175,6 +184,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3_wgrad_kernel(const WgradD
     constexpr int U = 4;  // independent loads in flight per thread
     uint32_t t = 0;
     int cur_n = -1;
+    long long tw_empty = 0;
+    const long long tp_begin = clock64();
     for (int u = rank; u < a.n_units; u += a.ranks) {
       const WgUnit un = wg_decode_unit(a, u);
       if (un.n != cur_n) {
@@ -195,7 +206,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3_wgrad_kernel(const WgradD
       }
       for (int zb = un.zs; zb < un.ze; ++zb) {
         const uint32_t s = t & 1u;
+        const long long tq = clock64();
         mbar_wait(smem_u32(&sm.empty[s]), ((t >> 1) & 1u) ^ 1u);
+        tw_empty += clock64() - tq;
         const bool col_start = (zb == un.zs);
         if (col_start && t >= 1) {
           // a new column rewrites every dy slot: the previous step must have drained too
@@ -309,6 +322,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3_wgrad_kernel(const WgradD
         mbar_arrive(smem_u32(&sm.full[s]));
         ++t;
       }
+    }
+    if (a.dbg != nullptr && pt == 0) {
+      long long* d = a.dbg + static_cast<size_t>(blockIdx.x) * 16;
+      d[3] = clock64() - tp_begin; d[4] = tw_empty;
     }
     // =========================== epilogue (warps 2..5) ===========================
     if (warp < kWgProducerWarp0 + 4) {
@@ -436,6 +453,14 @@ static int wgrad_plan(int Cout, int Cin, int N, int D, int H, int W, int max_cta
 
 using namespace rsb;
 
+static long long* g_wgrad_timing_buffer = nullptr;
+// profiling aid (see rsb_debug_set_timing_buffer): [0] MMA warp total cycles, [1] its wait on `full`,
+// [2] steps, [3] producer total, [4] producer wait on `empty`
+extern "C" int rsb_debug_set_wgrad_timing_buffer(void* device_ptr) {
+  g_wgrad_timing_buffer = reinterpret_cast<long long*>(device_ptr);
+  return 0;
+}
+
 extern "C" size_t rsb_conv3_wgrad_workspace_bytes(int Cout, int Cin, int max_ctas) {
   if (max_ctas <= 0) max_ctas = rsb_num_sms();
   if (max_ctas <= 0) max_ctas = 148;
@@ -464,6 +489,7 @@ extern "C" int rsb_conv3_wgrad(const RsbConv3WgradArgs* p, void* stream) {
   d.inv_count = 1.0f / (static_cast<float>(p->D) * p->H * p->W);
   d.dy = p->dy; d.dy_pitch = p->dy_pitch;
   d.ws = reinterpret_cast<float*>(p->workspace);
+  d.dbg = g_wgrad_timing_buffer;
   RSB_REQUIRE(wgrad_plan(p->Cout, p->Cin, p->N, p->D, p->H, p->W, sms, d) == 0, "wgrad: no feasible tiling");
   const int grid = d.ranks * d.n_groups;
   const size_t need = static_cast<size_t>(grid) * d.piece_floats * sizeof(float);

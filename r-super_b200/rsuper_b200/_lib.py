@@ -72,6 +72,7 @@ SIGNATURES = {
     "rsb_conv3_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "rsb_conv3_forward": (c_int, [C.POINTER(RsbConv3Args), c_void_p]),
     "rsb_debug_set_timing_buffer": (c_int, [c_void_p]),
+    "rsb_debug_set_wgrad_timing_buffer": (c_int, [c_void_p]),
     "rsb_conv3_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "rsb_conv3_wgrad": (c_int, [C.POINTER(RsbConv3WgradArgs), c_void_p]),
     "rsb_stem_conv_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
