@@ -48,34 +48,36 @@ int rsb_num_sms(void);
 
 /* ---------------------------------------------------------------------------------------------
  * 3x3x3 convolution, stride 1, pad 1, no bias — nn.Conv3d inside ConvNormAct
- * (model/dim3/conv_layers.py:29-38), with the pre-activation InstanceNorm + (Leaky)ReLU of
- * conv_layers.py:47-49 fused into the operand staging, the residual add of BasicBlock
- * (conv_layers.py:92) and the next layer's InstanceNorm statistics fused into the epilogue.
- * Implicit GEMM on tcgen05 (M = 128 voxels, N = Cout tile, K = 27*Cin), accumulators in TMEM.
- * The same kernel is the data gradient (dgrad) when given flipped/transposed weights.
+ * (model/dim3/conv_layers.py:29-38), with the residual add of BasicBlock (conv_layers.py:92) and the
+ * next layer's InstanceNorm statistics fused into the epilogue.  The operand `a` is the bf16 tensor
+ * a = act(instnorm(x)) produced by rsb_norm_act (the pre-activation of conv_layers.py:47-49).
+ * TMA-fed implicit GEMM on tcgen05 (M = 128 voxels, N = merged (kd, Cout tile), K = 9*Cin per plane),
+ * accumulators in TMEM.  The same kernel is the data gradient (dgrad) when given flipped/transposed
+ * weights; its epilogue then applies act'(xhat) and reduces the InstanceNorm-backward sums.
  * ------------------------------------------------------------------------------------------ */
 
-/* bytes of the packed bf16 weight image for a (Cout, Cin) 3x3x3 conv */
-size_t rsb_conv3_packed_weight_bytes(int Cout, int Cin);
+/* N tile the kernels use for a given Cout (packing and launch agree on it) */
+int rsb_conv3_n_tile(int Cout);
+/* bytes of the packed bf16 weight image for a (Cout, Cin) 3x3x3 conv; parts = 1, or 3 for the
+ * split-precision image [hi | hi | lo] */
+size_t rsb_conv3_packed_weight_bytes(int Cout, int Cin, int parts);
 
 /* fp32 OIDHW [Cout][Cin][3][3][3] (the nn.Parameter layout) -> packed bf16 UMMA tiles.
  * transpose_flip = 0: forward operand.  1: dgrad operand (taps flipped, Cin/Cout swapped: the
  * packed image then describes a conv with Cin' = Cout, Cout' = Cin). */
 int rsb_conv3_pack_weights(const float* w_oidhw, void* packed, int Cout, int Cin,
-                           int transpose_flip, void* stream);
+                           int transpose_flip, int parts, void* stream);
 
 typedef struct RsbConv3Args {
   /* geometry */
   int N, D, H, W;
   int Cin, Cout;
-  int dtype; /* storage dtype of x, y, res, mask_x */
-  /* input (raw, pre-norm) NDHWC */
-  const void* x;
-  int x_pitch;
-  /* prologue: a = act((x - mean) * rstd); in_stats == NULL => identity (no norm, no act) */
-  const float* in_stats; /* [N][x_pitch][2] (sum, sumsq) over D*H*W */
-  float eps;             /* 1e-4 */
-  float slope;           /* 0 => ReLU (reference default), 0.01 => LeakyReLU */
+  int dtype; /* storage dtype of y, res, mask_x */
+  /* conv operand, bf16 NDHWC (see rsb_norm_act); a_lo != NULL selects the 3-pass split-precision
+   * product a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (weights packed with parts = 3) */
+  const void* a;
+  int a_pitch;
+  const void* a_lo;
   /* packed weights from rsb_conv3_pack_weights */
   const void* w_packed;
   /* output */
@@ -92,9 +94,10 @@ typedef struct RsbConv3Args {
   int mask_x_pitch;
   const float* mask_stats;
   float* bwd_sums;
+  float eps;   /* 1e-4 */
+  float slope; /* 0 => ReLU (reference default), 0.01 => LeakyReLU */
   /* tuning (0 = auto) */
   int planes_per_item; /* PZ in {1,2,4} */
-  int n_tile;          /* multiple of 16, <= 256 */
   int max_ctas;        /* 0 => number of SMs */
 } RsbConv3Args;
 
@@ -103,18 +106,15 @@ int rsb_conv3_forward(const RsbConv3Args* args, void* stream);
  * (16 int64 per CTA; NULL disables).  Not used by the product path. */
 int rsb_debug_set_timing_buffer(void* device_ptr);
 
-/* weight gradient of the same conv: dW[co][ci][tap] = sum_v dy[v][co] * a[v+tap-1][ci],
- * a = act(norm(x)) recomputed in the staging.  tcgen05 with MN-major operands (K = voxels).
- * Writes fp32 OIDHW (overwrites or accumulates). */
+/* weight gradient of the same conv: dW[co][ci][tap] = sum_v dy[v][co] * a[v+tap-1][ci], both
+ * operands bf16 NDHWC (a = the rsb_norm_act operand tensor of the forward conv), fetched by TMA and
+ * consumed MN-major by tcgen05 (K = voxels).  Writes fp32 OIDHW (overwrites or accumulates). */
 typedef struct RsbConv3WgradArgs {
   int N, D, H, W;
   int Cin, Cout;
-  int dtype;
-  const void* x;
-  int x_pitch;
-  const float* in_stats;
-  float eps, slope;
-  const void* dy;
+  const void* a;      /* bf16 [N][D][H][W][a_pitch] */
+  int a_pitch;
+  const void* dy;     /* bf16 [N][D][H][W][dy_pitch] */
   int dy_pitch;
   float* dw_oidhw;    /* [Cout][Cin][27] fp32 */
   int accumulate;     /* 0: overwrite, 1: += */
@@ -126,6 +126,17 @@ typedef struct RsbConv3WgradArgs {
 size_t rsb_conv3_wgrad_workspace_bytes(int Cout, int Cin, int max_ctas);
 int rsb_conv3_wgrad(const RsbConv3WgradArgs* args, void* stream);
 int rsb_debug_set_wgrad_timing_buffer(void* device_ptr); /* profiling aid, see above */
+
+/* ---------------------------------------------------------------------------------------------
+ * Conv operand producer: hi = bf16(act((x - mean) * rstd)) — the pre-activation
+ * nn.InstanceNorm3d(eps=1e-4, affine=False) + nn.ReLU of ConvNormAct (conv_layers.py:39-49;
+ * slope = 0 => ReLU, 0.01 => LeakyReLU) as one fused, 128-bit vectorised pass.  stats == NULL =>
+ * plain cast.  lo != NULL additionally writes lo = bf16(value - hi) for the split-precision
+ * (3 x bf16 ~ fp32) parity mode.  x has storage dtype `dtype`; hi / lo are always bf16.
+ * ------------------------------------------------------------------------------------------ */
+int rsb_norm_act(const void* x, int x_pitch, int dtype, const float* stats, float eps, float slope,
+                 void* hi, int hi_pitch, void* lo, int lo_pitch, int N, int D, int H, int W, int C,
+                 void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * stem conv 3x3x3 with Cin = 1 (inconv.conv1, model/dim3/unet_utils.py:15,18) — direct

@@ -1,0 +1,645 @@
+// conv3_fprop.cu — 3x3x3 convolution (stride 1, pad 1, no bias) as a TMA-fed implicit GEMM on tcgen05.
+//
+// Replaces nn.Conv3d inside ConvNormAct (rsuper_train/model/dim3/conv_layers.py:29-38) together with the
+// BasicBlock residual add (conv_layers.py:92) and the statistics the NEXT InstanceNorm needs.  The conv
+// operand a = act(instnorm(x)) (conv_layers.py:39-49) is produced once by rsb_norm_act and consumed here
+// and by the weight-gradient kernel.  With flipped / transposed weights the same kernel is the data gradient,
+// whose epilogue applies act'(xhat) and accumulates the two InstanceNorm-backward reductions.
+//
+// Design (B200 / sm_100a, one persistent CTA per SM, 384 threads):
+//   GEMM view   M = 128 output voxels (16 y x 8 x of one z-plane), N = merged (kd, Cout tile), K = 9 * Cin per plane.
+//   work item   (n, z-block of PZ planes, y-tile, x-tile, N-tile): PZ accumulators of 128 x NT fp32 in TMEM,
+//               double buffered (2 * PZ * NT <= 512 columns) so the epilogue of item i overlaps item i+1.
+//   A operand   ONE TMA box per (item, 32-channel chunk): (32 ch, 10 x, 18 y, PZ+2 z) of the NDHWC operand
+//               lands as 64-byte voxel rows with the hardware 64B swizzle = K-major SWIZZLE_64B.  Zero padding
+//               (per sample, in all three axes) and ragged tiles are the TMA's out-of-bounds zero fill.  Every
+//               filter tap is a row shift of the descriptor start address inside that halo box (the swizzle is
+//               a function of absolute address bits), so the box is staged once and read by all 27 taps.
+//   kd merge    input plane p feeds output planes p-2..p (kd = 2,1,0).  Their accumulators are adjacent TMEM
+//               column ranges and the packed weights keep [kd=2 | kd=1 | kd=0] adjacent, so ONE tcgen05.mma with
+//               N = 3 * NT covers three taps: an MMA costs max(32 + N/4, N/2) cycles at M = 128, K = 16
+//               (operand fetch from shared memory bounds it below N = 128 — profiles/r01_umma_*_probe.log), so
+//               a 32-channel layer goes from 46 cycles per tap to 56 cycles per three taps.
+//   B operand   weights pre-packed (rsb_conv3_pack_weights) into un-swizzled K-major core-matrix tiles so that
+//               one (chunk, kh, kw, N-tile) slice [3 kd][NT][32 k] is a single contiguous bulk copy; ring of stages.
+//   roles       warp 0: A producer (TMA) | warp 1: MMA issuer | warp 2: B producer (bulk copies) | warp 3: TMEM
+//               owner | warps 4-11: epilogue (tcgen05.ld, + residual / act' mask, InstanceNorm (sum, sumsq) or
+//               backward (S1, S2) reductions, NDHWC stores with a channel pitch).
+#include "rsb_common.cuh"
+#include "rsb_tma.cuh"
+
+#include "../../include/rsuper_b200.h"
+
+namespace rsb {
+
+constexpr int kFpThreads = 384;
+constexpr int kFpEpiWarp0 = 4;
+constexpr int kFpEpiWarps = 8;
+constexpr int kFpPlaneRows = 180;                  // haloed plane: 18 x 10 voxels
+constexpr int kFpPlaneBytes = kFpPlaneRows * 64;   // 32 channels (64 B) per voxel row
+constexpr int kFpMaxBStages = 8;
+constexpr int kFpMaxNT = 128;
+
+struct FpropDev {
+  int N, D, H, W, Cin, Cout;
+  const uint8_t* w_packed;
+  void* y;
+  long long y_pitch;
+  const void* aux;  // residual (forward) or the masking tensor x (dgrad), storage dtype
+  long long aux_pitch;
+  int mask_mode;
+  const float* mask_stats;
+  float* stat_dst;  // out_stats (forward) or bwd_sums (dgrad)
+  long long stat_pitch;
+  float eps, slope, inv_count;
+  // derived
+  int NT, ntiles, nchunks, parts, last_ksteps;
+  int tiles_x, tiles_y, zblocks, num_items;
+  int b_stages;
+  uint32_t b_stage_bytes, a_unit_bytes;
+  long long* dbg;
+};
+
+struct __align__(16) FpropSmem {
+  uint64_t a_full[2], a_empty[2];
+  uint64_t b_full[kFpMaxBStages], b_empty[kFpMaxBStages];
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+  uint32_t pad_[3];
+  float stat[kFpEpiWarps][kFpMaxNT][2];  // per epilogue warp partial (sum, sumsq) / (S1, S2)
+  float mstat[kFpMaxNT][2];              // (mean, rstd) of the masking tensor for the current item
+};
+constexpr int kFpCtrlBytes = (sizeof(FpropSmem) + 1023) / 1024 * 1024;
+
+struct FpItem {
+  int n, z0, y0, x0, n0, nt;
+};
+template <int PZ>
+RSB_DEVICE FpItem fp_decode_item(const FpropDev& a, int item) {
+  FpItem c;
+  int t = item;
+  c.nt = t % a.ntiles; t /= a.ntiles;
+  const int xt = t % a.tiles_x; t /= a.tiles_x;
+  const int yt = t % a.tiles_y; t /= a.tiles_y;
+  const int zb = t % a.zblocks; t /= a.zblocks;
+  c.n = t;
+  c.z0 = zb * PZ;
+  c.y0 = yt * 16;
+  c.x0 = xt * 8;
+  c.n0 = c.nt * a.NT;
+  return c;
+}
+
+// Sum 16 per-lane values across the 32 lanes of a warp.  On return, lanes with bit0 == 0 hold the
+// total for column butterfly_col(lane) (lanes with bit0 == 1 hold a duplicate).
+RSB_DEVICE float butterfly16(float (&v)[16], int lane) {
+  float b8[8];
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float send = up ? v[j] : v[j + 8];
+      float keep = up ? v[j + 8] : v[j];
+      b8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  float b4[4];
+  {
+    const bool up = lane & 8;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float send = up ? b8[j] : b8[j + 4];
+      float keep = up ? b8[j + 4] : b8[j];
+      b4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  float b2[2];
+  {
+    const bool up = lane & 4;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      float send = up ? b4[j] : b4[j + 2];
+      float keep = up ? b4[j + 2] : b4[j];
+      b2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  float b1;
+  {
+    const bool up = lane & 2;
+    float send = up ? b2[0] : b2[1];
+    float keep = up ? b2[1] : b2[0];
+    b1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  b1 += __shfl_xor_sync(0xffffffffu, b1, 1);
+  return b1;
+}
+RSB_DEVICE int butterfly_col(int lane) {
+  return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+}
+
+template <typename T, int PZ>
+__global__ void __launch_bounds__(kFpThreads, 1)
+conv3_fprop_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const FpropDev a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  FpropSmem& sm = *reinterpret_cast<FpropSmem*>(smem_raw);
+  const uint32_t a_base = smem_u32(smem_raw) + kFpCtrlBytes;  // 2 units
+  const uint32_t b_base = a_base + 2 * a.a_unit_bytes;        // b_stages stages
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr int NP = PZ + 2;
+
+  // ---------------- one-time setup ----------------
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&sm.a_full[i]), 1);
+      mbar_init(smem_u32(&sm.a_empty[i]), 1);
+      mbar_init(smem_u32(&sm.acc_full[i]), 1);
+      mbar_init(smem_u32(&sm.acc_empty[i]), kFpEpiWarps * 32);
+    }
+    for (int i = 0; i < kFpMaxBStages; ++i) {
+      mbar_init(smem_u32(&sm.b_full[i]), 1);
+      mbar_init(smem_u32(&sm.b_empty[i]), 1);
+    }
+    mbar_fence_init();
+    tma_prefetch_desc(&tm_hi);
+    tma_prefetch_desc(&tm_lo);
+  }
+  for (int i = threadIdx.x; i < kFpEpiWarps * kFpMaxNT * 2; i += kFpThreads) (&sm.stat[0][0][0])[i] = 0.f;
+  if (warp == 3) {
+    tmem_alloc(smem_u32(&sm.tmem_base), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = sm.tmem_base;
+  const uint32_t acc_cols = PZ * a.NT;
+  const int total_chunks = a.parts * a.nchunks;
+
+  if (warp == 0) {
+    // =========================== A producer (TMA) ===========================
+    uint32_t ab = 0, aph = 0;
+    for (int item = blockIdx.x; item < a.num_items; item += gridDim.x) {
+      const FpItem ic = fp_decode_item<PZ>(a, item);
+      for (int c = 0; c < total_chunks; ++c) {
+        const int part = c / a.nchunks, cb = c - part * a.nchunks;
+        mbar_wait(smem_u32(&sm.a_empty[ab]), aph ^ 1u);
+        if (elect_one()) {
+          const uint32_t bar = smem_u32(&sm.a_full[ab]);
+          mbar_arrive_expect_tx(bar, NP * kFpPlaneBytes);
+          tma_load_5d(a_base + ab * a.a_unit_bytes, part == 1 ? &tm_lo : &tm_hi, cb * 32, ic.x0 - 1, ic.y0 - 1, ic.z0 - 1, ic.n, bar);
+        }
+        __syncwarp();
+        if (++ab == 2) { ab = 0; aph ^= 1u; }
+      }
+    }
+  } else if (warp == 2) {
+    // =========================== B producer (bulk copies of packed weight slices) ===========================
+    uint32_t bs = 0, bph = 0;
+    for (int item = blockIdx.x; item < a.num_items; item += gridDim.x) {
+      const FpItem ic = fp_decode_item<PZ>(a, item);
+      const uint8_t* src = a.w_packed + static_cast<size_t>(ic.nt) * a.b_stage_bytes;
+      const size_t step = static_cast<size_t>(a.ntiles) * a.b_stage_bytes;
+      for (int ct = 0; ct < total_chunks * 9; ++ct) {
+        mbar_wait(smem_u32(&sm.b_empty[bs]), bph ^ 1u);
+        if (elect_one()) {
+          const uint32_t bar = smem_u32(&sm.b_full[bs]);
+          mbar_arrive_expect_tx(bar, a.b_stage_bytes);
+          bulk_g2s(b_base + bs * a.b_stage_bytes, src, a.b_stage_bytes, bar);
+        }
+        __syncwarp();
+        src += step;
+        if (++bs == static_cast<uint32_t>(a.b_stages)) { bs = 0; bph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    // Per input plane p of the halo box: output planes q = max(0,p-2) .. min(PZ-1,p)  <->  kd = p - q.
+    // Everything that depends only on p is tabulated once; the issue loop is one add per operand per MMA
+    // (the tensor pipe's queue is shallow: issue-side arithmetic shows up 1:1 as pipe bubbles).
+    uint32_t pl_a[NP], pl_b[NP], pl_d[NP], pl_idesc[NP];
+    const uint32_t slot16 = static_cast<uint32_t>(a.NT / 8) * 512u / 16u;  // one kd slot of a B stage, in 16-byte units
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      const int qlo = p - 2 > 0 ? p - 2 : 0;
+      const int qhi = p < PZ - 1 ? p : PZ - 1;
+      pl_a[p] = static_cast<uint32_t>(p) * (kFpPlaneBytes / 16);
+      pl_b[p] = static_cast<uint32_t>(2 - (p - qlo)) * slot16;
+      pl_d[p] = static_cast<uint32_t>(qlo * a.NT);
+      pl_idesc[p] = make_idesc_bf16(128, (qhi - qlo + 1) * a.NT, 0, 0);
+    }
+    const uint32_t idesc1 = make_idesc_bf16(128, a.NT, 0, 0);
+    const uint32_t a_hi = desc_hi(640, kLayoutSw64);   // 8-row groups (8 x) are one y row = 10 voxel rows apart
+    const uint32_t b_hi = desc_hi(512, kLayoutNone);   // next 8 couts
+    const uint32_t a_lbo = 1u << 16;                   // unused for swizzled K-major
+    const uint32_t b_lbo = ((128u >> 4) & 0x3FFFu) << 16;  // next 8-wide k group
+    uint32_t ab = 0, aph = 0, bs = 0, bph = 0, as = 0, asph = 0;
+    const bool dbg = a.dbg != nullptr;
+    long long tw_a = 0, tw_b = 0, tw_acc = 0, n_items = 0;
+    const long long t_begin = clock64();
+    for (int item = blockIdx.x; item < a.num_items; item += gridDim.x) {
+      long long tq = dbg ? clock64() : 0;
+      mbar_wait(smem_u32(&sm.acc_empty[as]), asph ^ 1u);
+      if (dbg) tw_acc += clock64() - tq;
+      tc_fence_after_sync();
+      const uint32_t d_base = tmem_base + as * acc_cols;
+      for (int c = 0; c < total_chunks; ++c) {
+        tq = dbg ? clock64() : 0;
+        mbar_wait(smem_u32(&sm.a_full[ab]), aph);
+        if (dbg) tw_a += clock64() - tq;
+        const int cb = c % a.nchunks;
+        const int ksteps = (cb == a.nchunks - 1) ? a.last_ksteps : 2;
+        const uint32_t a_unit_lo = a_lbo | ((a_base + ab * a.a_unit_bytes) >> 4);
+#pragma unroll 1
+        for (int t = 0; t < 9; ++t) {
+          const int kh = t / 3, kw = t - kh * 3;
+          tq = dbg ? clock64() : 0;
+          mbar_wait(smem_u32(&sm.b_full[bs]), bph);
+          if (dbg) tw_b += clock64() - tq;
+          tc_fence_after_sync();
+          const uint32_t b_lo = b_lbo | ((b_base + bs * a.b_stage_bytes) >> 4);
+          const uint32_t a_tap_lo = a_unit_lo + static_cast<uint32_t>(kh * 10 + kw) * 4u;  // 64-byte rows
+          if (elect_one()) {
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint32_t a_ks = a_tap_lo + ks * 2u;   // 16 channels = 32 bytes inside the row
+              const uint32_t b_ks = b_lo + ks * 16u;      // two 8-wide k groups = 256 bytes
+              if (c == 0 && t == 0 && ks == 0) {
+                // first touch of every accumulator: plane p initialises output plane q = p (kd = 0)
+#pragma unroll
+                for (int p = 0; p < NP; ++p) {
+                  const uint64_t ad = desc_join(a_hi, a_ks + pl_a[p]);
+                  if (p < PZ) {
+                    if (p > 0) {
+                      const int qlo = p - 2 > 0 ? p - 2 : 0;
+                      umma_bf16_ss(d_base + pl_d[p], ad, desc_join(b_hi, b_ks + pl_b[p]), make_idesc_bf16(128, (p - qlo) * a.NT, 0, 0), 1u);
+                    }
+                    umma_bf16_ss(d_base + p * a.NT, ad, desc_join(b_hi, b_ks + 2 * slot16), idesc1, 0u);
+                  } else {
+                    umma_bf16_ss(d_base + pl_d[p], ad, desc_join(b_hi, b_ks + pl_b[p]), pl_idesc[p], 1u);
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int p = 0; p < NP; ++p)
+                  umma_bf16_ss(d_base + pl_d[p], desc_join(a_hi, a_ks + pl_a[p]), desc_join(b_hi, b_ks + pl_b[p]), pl_idesc[p], 1u);
+              }
+            }
+            umma_commit(smem_u32(&sm.b_empty[bs]));
+            if (t == 8) {
+              umma_commit(smem_u32(&sm.a_empty[ab]));
+              if (c == total_chunks - 1) umma_commit(smem_u32(&sm.acc_full[as]));
+            }
+          }
+          __syncwarp();
+          if (++bs == static_cast<uint32_t>(a.b_stages)) { bs = 0; bph ^= 1u; }
+        }
+        if (++ab == 2) { ab = 0; aph ^= 1u; }
+      }
+      if (++as == 2) { as = 0; asph ^= 1u; }
+      ++n_items;
+    }
+    if (dbg && lane == 0) {
+      long long* d = a.dbg + static_cast<size_t>(blockIdx.x) * 16;
+      d[0] = clock64() - t_begin; d[1] = tw_a; d[2] = tw_b; d[3] = tw_acc; d[4] = n_items;
+    }
+  } else if (warp >= kFpEpiWarp0) {
+    // =========================== epilogue (8 warps) ===========================
+    const int ew = warp & 3;                       // TMEM lane quarter this warp may access
+    const int eset = (warp - kFpEpiWarp0) >> 2;    // two warps share a quarter: they take alternate iterations
+    const int eidx = warp - kFpEpiWarp0;
+    const int et = eidx * 32 + lane;
+    const int row = ew * 32 + lane;
+    const int ry = row >> 3, rx = row & 7;
+    T* __restrict__ yg = reinterpret_cast<T*>(a.y);
+    const T* __restrict__ xg = reinterpret_cast<const T*>(a.aux);
+    const bool want_stats = a.stat_dst != nullptr;
+    const bool mask_mode = a.mask_mode != 0;
+    const bool has_aux = a.aux != nullptr;
+    uint32_t as = 0, asph = 0;
+    const bool dbg = a.dbg != nullptr;
+    long long tw_ef = 0;
+    const long long te_begin = clock64();
+    const int nch = a.NT >> 4;
+    for (int item = blockIdx.x; item < a.num_items; item += gridDim.x) {
+      const FpItem ic = fp_decode_item<PZ>(a, item);
+      if (mask_mode) {
+        named_bar_sync(1, kFpEpiWarps * 32);
+        for (int cidx = et; cidx < a.NT; cidx += kFpEpiWarps * 32) {
+          float mean = 0.f, rstd = 1.f;
+          if (ic.n0 + cidx < a.Cout) {
+            const float* st = a.mask_stats + (static_cast<size_t>(ic.n) * a.aux_pitch + ic.n0 + cidx) * 2;
+            stats_to_mean_rstd(st[0], st[1], a.inv_count, a.eps, mean, rstd);
+          }
+          sm.mstat[cidx][0] = mean;
+          sm.mstat[cidx][1] = rstd;
+        }
+        named_bar_sync(1, kFpEpiWarps * 32);
+      }
+      const int y = ic.y0 + ry, xq = ic.x0 + rx;
+      const bool row_ok = (y < a.H) && (xq < a.W);
+      const int nplanes = min(PZ, a.D - ic.z0);
+      const int nit = nplanes * nch;  // (plane, 16-column chunk) iterations; this warp takes it = eset, eset+2, ...
+      const size_t vox0 = ((static_cast<size_t>(ic.n) * a.D + ic.z0) * a.H + (row_ok ? y : 0)) * a.W + (row_ok ? xq : 0);
+      const size_t vox_plane = static_cast<size_t>(a.H) * a.W;
+      // aux rows (residual / masking tensor) are requested two iterations ahead: their global-memory latency
+      // (~1 us) is paid while the accumulators are still being produced, not per 16 columns.
+      Raw16<T> pre0, pre1;
+      pre0.zero();
+      pre1.zero();
+      auto fetch = [&](int it, Raw16<T>& dst) {
+        dst.zero();
+        if (it < nit && has_aux && row_ok) {
+          const int p = it / nch;
+          const int cbase = ic.n0 + (it - p * nch) * 16;
+          const int nvalid = a.Cout - cbase;
+          if (nvalid > 0) dst.load(xg + (vox0 + p * vox_plane) * a.aux_pitch + cbase, nvalid > 8);
+        }
+      };
+      fetch(eset, pre0);
+      fetch(eset + 2, pre1);
+      const long long tq = dbg ? clock64() : 0;
+      mbar_wait(smem_u32(&sm.acc_full[as]), asph);
+      if (dbg) tw_ef += clock64() - tq;
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int it = eset; it < nit; it += 2) {
+        const int p = it / nch;
+        const int cc = (it - p * nch) * 16;
+        const Raw16<T> cur = pre0;
+        pre0 = pre1;
+        fetch(it + 4, pre1);
+        const size_t vox = vox0 + p * vox_plane;
+        uint32_t r[16];
+        __syncwarp();
+        tmem_ld16(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * acc_cols + p * a.NT + cc, r);
+        tmem_ld_wait();
+        const int cbase = ic.n0 + cc;
+        const int nvalid = a.Cout - cbase;  // multiple of 8 (Cout % 8 == 0)
+        if (nvalid <= 0) continue;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        float xh[16];
+        if (row_ok && has_aux) {
+          cur.to_float(xh);
+          if (!mask_mode) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += xh[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float h = (xh[j] - sm.mstat[cc + j][0]) * sm.mstat[cc + j][1];
+              xh[j] = h;
+              v[j] = h > 0.f ? v[j] : v[j] * a.slope;
+            }
+          }
+        }
+        if (want_stats) {
+          float s1[16], s2[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float val = row_ok ? v[j] : 0.f;
+            s1[j] = val;
+            s2[j] = mask_mode ? (row_ok ? val * xh[j] : 0.f) : val * val;
+          }
+          const float t1 = butterfly16(s1, lane);
+          const float t2 = butterfly16(s2, lane);
+          if ((lane & 1) == 0) {
+            const int col = cc + butterfly_col(lane);
+            sm.stat[eidx][col][0] += t1;
+            sm.stat[eidx][col][1] += t2;
+          }
+        }
+        if (row_ok) {
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = v[j];
+          Vec8<T>::store(yg + vox * a.y_pitch + cbase, o);
+          if (nvalid > 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = v[8 + j];
+            Vec8<T>::store(yg + vox * a.y_pitch + cbase + 8, o);
+          }
+        }
+      }
+      tc_fence_before_sync();
+      mbar_arrive(smem_u32(&sm.acc_empty[as]));
+      if (++as == 2) { as = 0; asph ^= 1u; }
+      if (want_stats) {
+        __syncwarp();
+        for (int col = lane; col < a.NT; col += 32) {
+          const float s1 = sm.stat[eidx][col][0], s2 = sm.stat[eidx][col][1];
+          if (ic.n0 + col < a.Cout && (s1 != 0.f || s2 != 0.f)) {
+            float* dst = a.stat_dst + (static_cast<size_t>(ic.n) * a.stat_pitch + ic.n0 + col) * 2;
+            atomicAdd(dst, s1);
+            atomicAdd(dst + 1, s2);
+          }
+          sm.stat[eidx][col][0] = 0.f;
+          sm.stat[eidx][col][1] = 0.f;
+        }
+        __syncwarp();
+      }
+    }
+    if (dbg && eidx == 0 && lane == 0) {
+      long long* d = a.dbg + static_cast<size_t>(blockIdx.x) * 16;
+      d[7] = clock64() - te_begin; d[8] = tw_ef;
+    }
+  }
+
+  // ---------------- teardown ----------------
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 3) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing: fp32 OIDHW -> bf16 [part][chunk][kh,kw (9)][N-tile][kd slot (3: kd = 2,1,0)][NT/8][4 (k/8)][8 (o%8)][8 (k%8)]
+// parts = 3 writes the split-precision image [hi | hi | lo] along K (pairs with the operand parts [hi | lo | hi]).
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_conv3_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cin, int transpose_flip,
+                                          int co_eff, int ci_eff, int NT, int ntiles, int nchunks, size_t total) {
+  size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  size_t t = i;
+  const int kk = t & 7; t >>= 3;
+  const int orow = t & 7; t >>= 3;
+  const int kc = t & 3; t >>= 2;
+  const int og = t % (NT / 8); t /= (NT / 8);
+  const int slot = t % 3; t /= 3;
+  const int nt = t % ntiles; t /= ntiles;
+  const int khw = t % 9; t /= 9;
+  const int chunk = t % nchunks; t /= nchunks;
+  const int part = static_cast<int>(t);
+  const int o = nt * NT + og * 8 + orow;
+  const int k = chunk * 32 + kc * 8 + kk;
+  const int tap = (2 - slot) * 9 + khw;
+  float v = 0.f;
+  if (o < co_eff && k < ci_eff) {
+    if (!transpose_flip) {
+      v = w[(static_cast<size_t>(o) * Cin + k) * 27 + tap];
+    } else {
+      // effective conv: out channel o = original ci, in channel k = original co, taps flipped
+      v = w[(static_cast<size_t>(k) * Cin + o) * 27 + (26 - tap)];
+    }
+  }
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  out[i] = (part == 2) ? __float2bfloat16_rn(v - __bfloat162float(hi)) : hi;
+}
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// N tile: largest multiple of 16 that divides the padded Cout and is <= 128
+static int pick_nt(int Cout) {
+  const int co_pad = round_up(Cout, 16);
+  int best = 16;
+  for (int nt = 16; nt <= kFpMaxNT && nt <= co_pad; nt += 16)
+    if (co_pad % nt == 0) best = nt;
+  return best;
+}
+
+template <typename T, int PZ>
+static int launch_fprop(const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, const FpropDev& dev, int grid, size_t smem_bytes,
+                        cudaStream_t stream) {
+  auto kern = conv3_fprop_kernel<T, PZ>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes));
+  if (e != cudaSuccess) {
+    set_last_error("conv3: cudaFuncSetAttribute(%zu B smem) failed: %s", smem_bytes, cudaGetErrorString(e));
+    return -2;
+  }
+  kern<<<grid, kFpThreads, smem_bytes, stream>>>(tm_hi, tm_lo, dev);
+  return check_launch("conv3_fprop_kernel");
+}
+
+}  // namespace rsb
+
+using namespace rsb;
+
+static long long* g_timing_buffer = nullptr;
+// Bring-up / profiling aid: when set (device pointer to >= 16 * grid int64), conv3_forward launches record
+// per-CTA cycle counters: [0] MMA warp total, [1..3] its waits on a_full / b_full / acc_empty, [4] items,
+// [7] epilogue total, [8] epilogue wait on acc_full.
+extern "C" int rsb_debug_set_timing_buffer(void* device_ptr) {
+  g_timing_buffer = reinterpret_cast<long long*>(device_ptr);
+  return 0;
+}
+
+extern "C" int rsb_conv3_n_tile(int Cout) { return pick_nt(Cout); }
+
+extern "C" size_t rsb_conv3_packed_weight_bytes(int Cout, int Cin, int parts) {
+  const int nchunks = (Cin + 31) / 32;
+  const int co_pad = round_up(Cout, 16);
+  return static_cast<size_t>(parts) * nchunks * 27 * co_pad * 64;
+}
+
+extern "C" int rsb_conv3_pack_weights(const float* w_oidhw, void* packed, int Cout, int Cin, int transpose_flip, int parts,
+                                      void* stream) {
+  RSB_REQUIRE(w_oidhw && packed, "pack_weights: null pointer");
+  RSB_REQUIRE(Cout > 0 && Cin > 0, "pack_weights: bad channel counts");
+  RSB_REQUIRE(parts == 1 || parts == 3, "pack_weights: parts must be 1 or 3");
+  const int co_eff = transpose_flip ? Cin : Cout;
+  const int ci_eff = transpose_flip ? Cout : Cin;
+  const int NT = pick_nt(co_eff);
+  const int ntiles = round_up(co_eff, 16) / NT;
+  const int nchunks = (ci_eff + 31) / 32;
+  const size_t total = rsb_conv3_packed_weight_bytes(co_eff, ci_eff, parts) / 2;
+  const int threads = 256;
+  const unsigned blocks = static_cast<unsigned>((total + threads - 1) / threads);
+  pack_conv3_weights_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      w_oidhw, reinterpret_cast<__nv_bfloat16*>(packed), Cin, transpose_flip, co_eff, ci_eff, NT, ntiles, nchunks, total);
+  return check_launch("pack_conv3_weights_kernel");
+}
+
+extern "C" int rsb_conv3_forward(const RsbConv3Args* p, void* stream) {
+  RSB_REQUIRE(p != nullptr, "conv3: null args");
+  RSB_REQUIRE(p->a && p->y && p->w_packed, "conv3: null tensor pointer");
+  RSB_REQUIRE(p->N > 0 && p->D > 0 && p->H > 0 && p->W > 0, "conv3: bad geometry");
+  RSB_REQUIRE(p->Cin > 0 && p->Cin % 8 == 0, "conv3: Cin must be a positive multiple of 8 (got %d)", p->Cin);
+  RSB_REQUIRE(p->Cout > 0 && p->Cout % 8 == 0, "conv3: Cout must be a positive multiple of 8 (got %d)", p->Cout);
+  RSB_REQUIRE(p->dtype == RSB_BF16 || p->dtype == RSB_F32, "conv3: bad dtype %d", p->dtype);
+  RSB_REQUIRE(p->a_pitch >= p->Cin && p->a_pitch % 8 == 0, "conv3: bad a_pitch %d", p->a_pitch);
+  RSB_REQUIRE(p->y_pitch >= p->Cout && p->y_pitch % 8 == 0, "conv3: bad y_pitch %d", p->y_pitch);
+  RSB_REQUIRE(!p->res || (p->res_pitch >= p->Cout && p->res_pitch % 8 == 0), "conv3: bad res_pitch");
+  RSB_REQUIRE(!p->mask_x || (p->mask_stats && p->bwd_sums && p->mask_x_pitch % 8 == 0),
+              "conv3: mask_x needs mask_stats and bwd_sums");
+  RSB_REQUIRE(!(p->mask_x && (p->out_stats || p->res)), "conv3: the dgrad mask epilogue excludes out_stats / res");
+
+  FpropDev d{};
+  d.N = p->N; d.D = p->D; d.H = p->H; d.W = p->W; d.Cin = p->Cin; d.Cout = p->Cout;
+  d.w_packed = reinterpret_cast<const uint8_t*>(p->w_packed);
+  d.y = p->y; d.y_pitch = p->y_pitch;
+  d.mask_mode = p->mask_x != nullptr;
+  d.aux = d.mask_mode ? p->mask_x : p->res;
+  d.aux_pitch = d.mask_mode ? p->mask_x_pitch : p->res_pitch;
+  d.mask_stats = p->mask_stats;
+  d.stat_dst = d.mask_mode ? p->bwd_sums : p->out_stats;
+  d.stat_pitch = d.mask_mode ? p->mask_x_pitch : p->y_pitch;
+  d.eps = p->eps; d.slope = p->slope;
+  d.inv_count = 1.0f / (static_cast<float>(p->D) * p->H * p->W);
+  d.dbg = g_timing_buffer;
+  d.parts = p->a_lo != nullptr ? 3 : 1;
+
+  const int co_pad = round_up(p->Cout, 16);
+  d.NT = pick_nt(p->Cout);
+  d.ntiles = co_pad / d.NT;
+  d.nchunks = (p->Cin + 31) / 32;
+  d.last_ksteps = ((p->Cin - 1) % 32) < 16 ? 1 : 2;
+  d.tiles_x = (p->W + 7) / 8;
+  d.tiles_y = (p->H + 15) / 16;
+
+  int sms = p->max_ctas > 0 ? p->max_ctas : rsb_num_sms();
+  RSB_REQUIRE(sms > 0, "conv3: could not query the SM count");
+
+  int PZ = p->planes_per_item;
+  if (PZ == 0) {
+    // as many planes per item as the double-buffered accumulators allow (more planes = wider merged MMAs and
+    // more reuse of every weight slice), but at least ~2 items per SM
+    PZ = d.NT <= 64 ? 4 : 2;
+    while (PZ > 1) {
+      const long long items = static_cast<long long>(p->N) * ((p->D + PZ - 1) / PZ) * d.tiles_y * d.tiles_x * d.ntiles;
+      if (PZ <= p->D && items >= 2LL * sms) break;
+      PZ >>= 1;
+    }
+  }
+  RSB_REQUIRE(PZ == 1 || PZ == 2 || PZ == 4, "conv3: planes_per_item must be 1, 2 or 4 (got %d)", PZ);
+  RSB_REQUIRE(2 * PZ * d.NT <= 512, "conv3: 2*PZ*n_tile = %d exceeds the 512 TMEM columns", 2 * PZ * d.NT);
+  RSB_REQUIRE(3 * d.NT <= 256 || PZ <= 2, "conv3: merged N exceeds 256");
+  d.zblocks = (p->D + PZ - 1) / PZ;
+  const long long items = static_cast<long long>(p->N) * d.zblocks * d.tiles_y * d.tiles_x * d.ntiles;
+  RSB_REQUIRE(items < (1LL << 31), "conv3: too many work items");
+  d.num_items = static_cast<int>(items);
+  d.b_stage_bytes = 3u * d.NT * 64u;
+  d.a_unit_bytes = static_cast<uint32_t>(((PZ + 2) * kFpPlaneBytes + 1023) / 1024 * 1024);
+  const size_t fixed = kFpCtrlBytes + 2 * static_cast<size_t>(d.a_unit_bytes);
+  int stages = static_cast<int>((226 * 1024 - fixed) / d.b_stage_bytes);
+  if (stages > kFpMaxBStages) stages = kFpMaxBStages;
+  RSB_REQUIRE(stages >= 2, "conv3: shared memory budget exceeded (NT=%d PZ=%d)", d.NT, PZ);
+  d.b_stages = stages;
+  size_t smem = fixed + static_cast<size_t>(stages) * d.b_stage_bytes;
+  if (smem < 120 * 1024) smem = 120 * 1024;  // force 1 CTA / SM: each CTA owns all 512 TMEM columns
+
+  CUtensorMap tm_hi, tm_lo;
+  int rc = make_act_tensor_map(&tm_hi, p->a, p->a_pitch, p->Cin, p->N, p->D, p->H, p->W, 32, 10, 18, PZ + 2);
+  if (rc) return rc;
+  rc = make_act_tensor_map(&tm_lo, p->a_lo ? p->a_lo : p->a, p->a_pitch, p->Cin, p->N, p->D, p->H, p->W, 32, 10, 18, PZ + 2);
+  if (rc) return rc;
+
+  const int grid = static_cast<int>(items < sms ? items : sms);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+#define RSB_DISPATCH(TT)                                                          \
+  switch (PZ) {                                                                   \
+    case 1: return launch_fprop<TT, 1>(tm_hi, tm_lo, d, grid, smem, st);          \
+    case 2: return launch_fprop<TT, 2>(tm_hi, tm_lo, d, grid, smem, st);          \
+    default: return launch_fprop<TT, 4>(tm_hi, tm_lo, d, grid, smem, st);         \
+  }
+  if (p->dtype == RSB_BF16) {
+    RSB_DISPATCH(__nv_bfloat16)
+  } else {
+    RSB_DISPATCH(float)
+  }
+#undef RSB_DISPATCH
+}

@@ -358,6 +358,53 @@ __global__ void instnorm_bwd_apply_kernel(const T* __restrict__ g, long long gp,
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// norm_act: the conv operand  a = bf16(act((x - mean) * rstd))  (pre-activation InstanceNorm3d(eps=1e-4,
+// affine=False) + (Leaky)ReLU of ConvNormAct, conv_layers.py:39-49), written once and then read by the TMA
+// units of the fprop and wgrad kernels.  With lo != nullptr the fp32 value is split into hi + lo bf16
+// parts (lo = bf16(a - hi)) for the 3-pass split-precision mode.  stats == nullptr => plain cast / split.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void norm_act_kernel(const T* __restrict__ x, long long xp, const float* __restrict__ stats,
+                                __nv_bfloat16* __restrict__ hi, long long hp, __nv_bfloat16* __restrict__ lo,
+                                long long lp, float eps, float slope, int C, long long V) {
+  const int CG = C / 8;
+  const int n = blockIdx.y;
+  ClMap m = cl_map(CG);
+  const float inv = 1.f / static_cast<float>(V);
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = 1.f;
+    sh[j] = 0.f;
+    if (stats != nullptr) {
+      const long long sidx = (static_cast<long long>(n) * xp + m.cg * 8 + j) * 2;
+      float mean, rstd;
+      stats_to_mean_rstd(stats[sidx], stats[sidx + 1], inv, eps, mean, rstd);
+      sc[j] = rstd;
+      sh[j] = -mean * rstd;
+    }
+  }
+  for (long long e = m.e0; e < V * CG; e += m.stride) {
+    const long long v = static_cast<long long>(n) * V + e / CG;
+    float f[8], h[8];
+    Vec8<T>::load(x + v * xp + m.cg * 8, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = fmaf(f[j], sc[j], sh[j]);
+      if (stats != nullptr) t = t > 0.f ? t : t * slope;
+      f[j] = t;
+      h[j] = __bfloat162float(__float2bfloat16_rn(t));
+    }
+    Vec8<__nv_bfloat16>::store(hi + v * hp + m.cg * 8, f);
+    if (lo != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] -= h[j];
+      Vec8<__nv_bfloat16>::store(lo + v * lp + m.cg * 8, f);
+    }
+  }
+}
+
 }  // namespace rsb
 
 using namespace rsb;
@@ -485,4 +532,18 @@ extern "C" int rsb_instnorm_backward_apply(const void* g, int g_pitch, const voi
                (instnorm_bwd_apply_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)g, g_pitch, (const __nv_bfloat16*)x, x_pitch, x_stats, bwd_sums, (const __nv_bfloat16*)add, add_pitch, (__nv_bfloat16*)dx, dx_pitch, eps, C, V)),
                (instnorm_bwd_apply_kernel<float><<<grid, block, 0, st>>>((const float*)g, g_pitch, (const float*)x, x_pitch, x_stats, bwd_sums, (const float*)add, add_pitch, (float*)dx, dx_pitch, eps, C, V)))
   return check_launch("instnorm_backward_apply");
+}
+
+extern "C" int rsb_norm_act(const void* x, int x_pitch, int dtype, const float* stats, float eps, float slope,
+                            void* hi, int hi_pitch, void* lo, int lo_pitch, int N, int D, int H, int W, int C,
+                            void* stream) {
+  RSB_REQUIRE(x && hi, "norm_act: null pointer");
+  RSB_REQUIRE(x_pitch % 8 == 0 && hi_pitch % 8 == 0 && (!lo || lo_pitch % 8 == 0), "norm_act: pitches must be multiples of 8");
+  RSB_CL_COMMON(C, N)
+  const long long V = static_cast<long long>(D) * H * W;
+  dim3 grid(cl_grid(V * CG, block, sms), N);
+  RSB_BY_DTYPE(dtype,
+               (norm_act_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)x, x_pitch, stats, (__nv_bfloat16*)hi, hi_pitch, (__nv_bfloat16*)lo, lo_pitch, eps, slope, C, V)),
+               (norm_act_kernel<float><<<grid, block, 0, st>>>((const float*)x, x_pitch, stats, (__nv_bfloat16*)hi, hi_pitch, (__nv_bfloat16*)lo, lo_pitch, eps, slope, C, V)))
+  return check_launch("norm_act");
 }

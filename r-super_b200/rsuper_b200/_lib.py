@@ -27,8 +27,7 @@ class RsbConv3Args(C.Structure):
         ("N", c_int), ("D", c_int), ("H", c_int), ("W", c_int),
         ("Cin", c_int), ("Cout", c_int),
         ("dtype", c_int),
-        ("x", c_void_p), ("x_pitch", c_int),
-        ("in_stats", c_void_p), ("eps", c_float), ("slope", c_float),
+        ("a", c_void_p), ("a_pitch", c_int), ("a_lo", c_void_p),
         ("w_packed", c_void_p),
         ("y", c_void_p), ("y_pitch", c_int),
         ("res", c_void_p), ("res_pitch", c_int),
@@ -36,7 +35,8 @@ class RsbConv3Args(C.Structure):
         ("mask_x", c_void_p), ("mask_x_pitch", c_int),
         ("mask_stats", c_void_p),
         ("bwd_sums", c_void_p),
-        ("planes_per_item", c_int), ("n_tile", c_int), ("max_ctas", c_int),
+        ("eps", c_float), ("slope", c_float),
+        ("planes_per_item", c_int), ("max_ctas", c_int),
     ]
 
 
@@ -44,9 +44,7 @@ class RsbConv3WgradArgs(C.Structure):
     _fields_ = [
         ("N", c_int), ("D", c_int), ("H", c_int), ("W", c_int),
         ("Cin", c_int), ("Cout", c_int),
-        ("dtype", c_int),
-        ("x", c_void_p), ("x_pitch", c_int),
-        ("in_stats", c_void_p), ("eps", c_float), ("slope", c_float),
+        ("a", c_void_p), ("a_pitch", c_int),
         ("dy", c_void_p), ("dy_pitch", c_int),
         ("dw_oidhw", c_void_p), ("accumulate", c_int),
         ("workspace", c_void_p), ("workspace_bytes", c_size_t),
@@ -68,13 +66,16 @@ SIGNATURES = {
     "rsb_version": (C.c_char_p, []),
     "rsb_last_error": (C.c_char_p, []),
     "rsb_num_sms": (c_int, []),
-    "rsb_conv3_packed_weight_bytes": (c_size_t, [c_int, c_int]),
-    "rsb_conv3_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "rsb_conv3_n_tile": (c_int, [c_int]),
+    "rsb_conv3_packed_weight_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "rsb_conv3_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "rsb_conv3_forward": (c_int, [C.POINTER(RsbConv3Args), c_void_p]),
     "rsb_debug_set_timing_buffer": (c_int, [c_void_p]),
     "rsb_debug_set_wgrad_timing_buffer": (c_int, [c_void_p]),
     "rsb_conv3_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "rsb_conv3_wgrad": (c_int, [C.POINTER(RsbConv3WgradArgs), c_void_p]),
+    "rsb_norm_act": (c_int, [c_void_p, c_int, c_int, c_void_p, c_float, c_float, c_void_p, c_int, c_void_p, c_int,
+                             c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "rsb_stem_conv_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
                                       c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "rsb_stem_conv_wgrad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p,

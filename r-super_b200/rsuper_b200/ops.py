@@ -90,29 +90,32 @@ def new_stats(n, c, device) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------
 # conv 3x3x3
 # --------------------------------------------------------------------------------------------
-def conv3_pack_weights(w: torch.Tensor, transpose_flip: bool = False) -> torch.Tensor:
-    """fp32 OIDHW [Cout,Cin,3,3,3] -> packed bf16 UMMA image (uint8 buffer)."""
+def conv3_pack_weights(w: torch.Tensor, transpose_flip: bool = False, split: bool = False) -> torch.Tensor:
+    """fp32 OIDHW [Cout,Cin,3,3,3] -> packed bf16 UMMA image (uint8 buffer); split => [hi | hi | lo] parts."""
     assert w.dtype == torch.float32 and w.is_cuda and w.is_contiguous() and w.shape[2:] == (3, 3, 3)
     cout, cin = w.shape[0], w.shape[1]
     co_eff, ci_eff = (cin, cout) if transpose_flip else (cout, cin)
-    nbytes = lib().rsb_conv3_packed_weight_bytes(co_eff, ci_eff)
+    parts = 3 if split else 1
+    nbytes = lib().rsb_conv3_packed_weight_bytes(co_eff, ci_eff, parts)
     out = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
-    _call("pack_weights", 1, 0.0, lib().rsb_conv3_pack_weights, _p(w), _p(out), cout, cin, int(transpose_flip), _stream(), what="conv3_pack_weights")
+    _call("pack_weights", 1, 0.0, lib().rsb_conv3_pack_weights, _p(w), _p(out), cout, cin, int(transpose_flip), parts, _stream(), what="conv3_pack_weights")
     return out
 
 
-def conv3_forward(x, w_packed, y, *, in_stats=None, slope=0.0, res=None, out_stats=None,
-                  mask_x=None, mask_stats=None, bwd_sums=None, planes_per_item=0, n_tile=0,
-                  max_ctas=0, eps=EPS_IN):
-    """y = conv3x3x3(act(instnorm(x))) [+ res]; optional fused statistics / dgrad masking epilogue."""
+def conv3_forward(a_op, w_packed, y, *, a_lo=None, slope=0.0, res=None, out_stats=None,
+                  mask_x=None, mask_stats=None, bwd_sums=None, planes_per_item=0, max_ctas=0, eps=EPS_IN):
+    """y = conv3x3x3(a_op) [+ res]; a_op is the bf16 operand from norm_act (a_lo: its split-precision low part,
+    with weights packed split=True); optional fused output statistics / dgrad masking epilogue."""
     a = _lib.RsbConv3Args()
-    n, d, h, w_, cin = x.shape
+    n, d, h, w_, cin = a_op.shape
     cout = y.shape[4]
-    assert y.shape[:4] == x.shape[:4] and y.dtype == x.dtype
+    assert y.shape[:4] == a_op.shape[:4] and a_op.dtype == torch.bfloat16
     a.N, a.D, a.H, a.W, a.Cin, a.Cout = n, d, h, w_, cin, cout
-    a.dtype = dtype_code(x)
-    a.x, a.x_pitch = _p(x), _check_cl(x, "x")
-    a.in_stats = _st(in_stats, x, "in_stats")
+    a.dtype = dtype_code(y)
+    a.a, a.a_pitch = _p(a_op), _check_cl(a_op, "a")
+    if a_lo is not None:
+        assert a_lo.shape == a_op.shape and a_lo.dtype == torch.bfloat16 and _check_cl(a_lo, "a_lo") == a.a_pitch
+        a.a_lo = _p(a_lo)
     a.eps, a.slope = eps, slope
     a.w_packed = _p(w_packed)
     a.y, a.y_pitch = _p(y), _check_cl(y, "y")
@@ -124,7 +127,7 @@ def conv3_forward(x, w_packed, y, *, in_stats=None, slope=0.0, res=None, out_sta
         assert mask_x.shape == y.shape and mask_x.dtype == y.dtype
         a.mask_x, a.mask_x_pitch = _p(mask_x), _check_cl(mask_x, "mask_x")
         a.mask_stats, a.bwd_sums = _st(mask_stats, mask_x, "mask_stats"), _st(bwd_sums, mask_x, "bwd_sums")
-    a.planes_per_item, a.n_tile, a.max_ctas = planes_per_item, n_tile, max_ctas
+    a.planes_per_item, a.max_ctas = planes_per_item, max_ctas
     _call("conv3_igemm", 1, 2.0 * 27 * cin * cout * n * d * h * w_, lib().rsb_conv3_forward, C.byref(a), _stream(), what="conv3_forward")
     return y
 
@@ -144,25 +147,33 @@ def _wgrad_workspace(cout: int, cin: int, device) -> torch.Tensor:
     return ws
 
 
-def conv3_wgrad(x, dy, dw, *, in_stats=None, slope=0.0, accumulate=False, eps=EPS_IN, max_ctas=0):
-    """dw[Cout,Cin,3,3,3] (fp32) = wgrad(dy, act(instnorm(x)))."""
+def conv3_wgrad(a_op, dy, dw, *, accumulate=False, max_ctas=0):
+    """dw[Cout,Cin,3,3,3] (fp32) (+)= wgrad(dy, a_op); both operands bf16 NDHWC (a_op from norm_act)."""
     a = _lib.RsbConv3WgradArgs()
-    n, d, h, w_, cin = x.shape
+    n, d, h, w_, cin = a_op.shape
     cout = dy.shape[4]
-    assert dy.shape[:4] == x.shape[:4] and dy.dtype == x.dtype
+    assert dy.shape[:4] == a_op.shape[:4] and dy.dtype == torch.bfloat16 and a_op.dtype == torch.bfloat16
     assert dw.dtype == torch.float32 and dw.is_contiguous() and tuple(dw.shape) == (cout, cin, 3, 3, 3)
     a.N, a.D, a.H, a.W, a.Cin, a.Cout = n, d, h, w_, cin, cout
-    a.dtype = dtype_code(x)
-    a.x, a.x_pitch = _p(x), _check_cl(x, "x")
-    a.in_stats = _st(in_stats, x, "in_stats")
-    a.eps, a.slope = eps, slope
+    a.a, a.a_pitch = _p(a_op), _check_cl(a_op, "a")
     a.dy, a.dy_pitch = _p(dy), _check_cl(dy, "dy")
     a.dw_oidhw, a.accumulate = _p(dw), int(accumulate)
-    ws = _wgrad_workspace(cout, cin, x.device)
+    ws = _wgrad_workspace(cout, cin, a_op.device)
     a.workspace, a.workspace_bytes = _p(ws), ws.numel()
     a.max_ctas = max_ctas
     _call("conv3_wgrad", 2, 2.0 * 27 * cin * cout * n * d * h * w_, lib().rsb_conv3_wgrad, C.byref(a), _stream(), what="conv3_wgrad")
     return dw
+
+
+def norm_act(x, stats=None, *, slope=0.0, eps=EPS_IN, split=False, out=None):
+    """Conv operand tensor(s): hi = bf16(act(instnorm(x))) [, lo = bf16(value - hi)]; stats=None => cast/split."""
+    n, d, h, w_, c = x.shape
+    hi = out if out is not None else torch.empty((n, d, h, w_, c), dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty((n, d, h, w_, c), dtype=torch.bfloat16, device=x.device) if split else None
+    _call("norm_act", 1, 0.0, lib().rsb_norm_act, _p(x), _check_cl(x, "x"), dtype_code(x), _st(stats, x, "stats"), eps, slope,
+          _p(hi), _check_cl(hi, "hi"), _p(lo), _check_cl(lo, "lo") if lo is not None else 0, n, d, h, w_, c, _stream(),
+          what="norm_act")
+    return (hi, lo) if split else hi
 
 
 # --------------------------------------------------------------------------------------------

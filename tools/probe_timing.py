@@ -13,21 +13,28 @@ def stats_of(x):
     v = x.reshape(n, -1, c).double()
     return torch.stack([v.sum(1), (v * v).sum(1)], -1).float()
 
-def run(N, D, H, W, Cin, Cout, res=True, pz=0, nt=0):
+def run(N, D, H, W, Cin, Cout, res=True, pz=0):
     g = torch.Generator().manual_seed(0)
     x = torch.randn(N, D, H, W, Cin, generator=g).to(dev).to(torch.bfloat16)
     w = (torch.randn(Cout, Cin, 3, 3, 3, generator=g) / (27 * Cin) ** 0.5).to(dev)
     y = torch.zeros(N, D, H, W, Cout, dtype=torch.bfloat16, device=dev)
     r = torch.randn(N, D, H, W, Cout, generator=g).to(dev).to(torch.bfloat16) if res else None
-    ist, ost = stats_of(x.float()), torch.zeros(N, Cout, 2, device=dev)
+    ost = torch.zeros(N, Cout, 2, device=dev)
     wp = ops.conv3_pack_weights(w)
     buf = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
     for _ in range(2):
-        ops.conv3_forward(x, wp, y, in_stats=ist, res=r, out_stats=ost, planes_per_item=pz, n_tile=nt)
+        ops.conv3_forward(x, wp, y, res=r, out_stats=ost, planes_per_item=pz)
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(5):
+        ops.conv3_forward(x, wp, y, res=r, out_stats=ost, planes_per_item=pz)
+    f1.record()
+    torch.cuda.synchronize()
+    ms_plain = f0.elapsed_time(f1) / 5
     lib().rsb_debug_set_timing_buffer(C.c_void_p(buf.data_ptr()))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    ops.conv3_forward(x, wp, y, in_stats=ist, res=r, out_stats=ost, planes_per_item=pz, n_tile=nt)
+    ops.conv3_forward(x, wp, y, res=r, out_stats=ost, planes_per_item=pz)
     e1.record()
     torch.cuda.synchronize()
     lib().rsb_debug_set_timing_buffer(None)
@@ -35,10 +42,10 @@ def run(N, D, H, W, Cin, Cout, res=True, pz=0, nt=0):
     b = buf.view(148, 16).double()
     m = b.mean(0)
     fl = 2.0 * 27 * Cin * Cout * N * D * H * W
-    print(f"N{N} {D}x{H}x{W} {Cin}->{Cout} pz={pz} nt={nt}: {ms:.3f} ms {fl / ms / 1e9:.0f} TF/s | items/CTA {m[4]:.1f} | "
+    print(f"N{N} {D}x{H}x{W} {Cin}->{Cout} pz={pz}: {ms_plain:.3f} ms {fl / ms_plain / 1e9:.0f} TF/s (instrumented {ms:.3f}) | items/CTA {m[4]:.1f} | "
           f"MMA thread total {m[0]:.0f} cyc: wait a_full {100 * m[1] / m[0]:.0f}% b_full {100 * m[2] / m[0]:.0f}% acc_empty {100 * m[3] / m[0]:.0f}% "
-          f"issue/other {100 * (m[0] - m[1] - m[2] - m[3]) / m[0]:.0f}% | producer wait a_empty {100 * m[6] / m[5]:.0f}% | "
-          f"epilogue wait acc_full {100 * m[8] / m[7]:.0f}% | loader wait b_empty {100 * m[9] / m[0]:.0f}% | cyc/item {m[0] / m[4]:.0f}")
+          f"issue/other {100 * (m[0] - m[1] - m[2] - m[3]) / m[0]:.0f}% | "
+          f"epilogue wait acc_full {100 * m[8] / m[7]:.0f}% | cyc/item {m[0] / m[4]:.0f}")
 
 if __name__ == "__main__":
     run(2, 128, 128, 128, 32, 32)
@@ -50,7 +57,6 @@ if __name__ == "__main__":
     run(2, 64, 64, 64, 192, 128, res=False)
     run(2, 64, 64, 64, 128, 192, res=False)
     run(2, 32, 32, 32, 128, 128)
-    run(2, 32, 32, 32, 128, 128, nt=64)
     run(2, 16, 16, 16, 256, 256)
     run(2, 16, 16, 16, 576, 512, res=False)
     run(2, 8, 8, 8, 320, 320)

@@ -197,6 +197,11 @@ int main() {
       {0, 11, 10, 0, 32, 2, "noswz halo N=32  8 accumulators ", 8},
       {0, 11, 10, 0, 128, 2, "noswz halo N=128 4 accumulators ", 4},
       {4, 11, 10, 0, 32, 2, "sw64  halo N=32  8 accumulators ", 8},
+      {0, 11, 10, 0, 64, 2, "noswz halo N=64                 "},
+      {0, 11, 10, 0, 96, 2, "noswz halo N=96                 "},
+      {0, 11, 10, 0, 192, 2, "noswz halo N=192                "},
+      {0, 11, 10, 0, 256, 2, "noswz halo N=256                "},
+      {0, 11, 10, 0, 96, 2, "noswz halo N=96  4 accumulators ", 4},
   };
   for (const Case& c : cases) {
     Params p{c.mode, c.start, c.group, c.bo, c.N, c.ksteps, 512, a_rows, c.nacc};
