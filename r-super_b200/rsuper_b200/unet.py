@@ -7,7 +7,8 @@ backward run entirely on the hand-written sm_100a kernels of librsuper_b200.so:
   reference op (file:line)                                   kernel
   ---------------------------------------------------------  ---------------------------------
   inconv.conv1  Conv3d(1,b,3)          unet_utils.py:15,18    rsb_stem_conv_forward / _wgrad
-  ConvNormAct preact IN->ReLU->Conv3d  conv_layers.py:47-49   rsb_conv3_forward (fused prologue)
+  ConvNormAct preact IN->ReLU          conv_layers.py:47-49   rsb_norm_act (bf16 conv operand, written once)
+  ConvNormAct Conv3d(k3,p1,no bias)    conv_layers.py:29-38   rsb_conv3_forward (TMA-fed tcgen05 implicit GEMM)
   BasicBlock `out += shortcut(x)`      conv_layers.py:92      rsb_conv3_forward epilogue (res)
   BasicBlock conv1 || shortcut conv    conv_layers.py:85-92   ONE GEMM with N = 2*Cout (same
                                                               IN(x): affine-free norms coincide)
@@ -114,34 +115,57 @@ def _sums_like(a: Act) -> torch.Tensor:
 
 
 class _Engine:
-    """Kernel schedule of one forward / backward pass (pure host logic; all compute is in the .so)."""
+    """Kernel schedule of one forward / backward pass (pure host logic; all compute is in the .so).
+
+    precision 'bf16': bf16 activation storage, bf16 tensor-core operands (one MMA pass), fp32 accumulation.
+    precision 'fp32': fp32 activation storage; every tensor-core product is the 3-pass split
+                      a_hi*w_hi + a_lo*w_hi + a_hi*w_lo of bf16 halves (~2^-17 relative, fp32 accumulation) —
+                      the parity mode measured against the fp32 reference."""
 
     def __init__(self, base_ch: int, slope: float, dtype: torch.dtype):
         self.b = base_ch
         self.slope = float(slope)
         self.dtype = dtype
+        self.split = dtype == torch.float32
+
+    # ---- operand / conv / wgrad helpers ------------------------------------------------------------
+    def _operand(self, t: torch.Tensor, stats=None):
+        """(hi, lo) bf16 conv operand of a stored tensor: act(instnorm(t)) when stats are given, else t itself."""
+        if stats is None and not self.split and t.dtype == torch.bfloat16:
+            return (t, None)
+        r = ops.norm_act(t, stats, slope=self.slope, split=self.split)
+        return r if self.split else (r, None)
+
+    def _conv(self, op, w, y, flip=False, **kw):
+        wp = ops.conv3_pack_weights(w, flip, split=self.split)
+        return ops.conv3_forward(op[0], wp, y, a_lo=op[1], slope=self.slope, **kw)
+
+    def _wgrad(self, a_op, dy_op, dw):
+        ops.conv3_wgrad(a_op[0], dy_op[0], dw)
+        if self.split:
+            ops.conv3_wgrad(a_op[1], dy_op[0], dw, accumulate=True)
+            ops.conv3_wgrad(a_op[0], dy_op[1], dw, accumulate=True)
+        return dw
 
     # ---- forward -------------------------------------------------------------------------------
     def _block_fwd(self, x: Act, w1, w2, wsc, out: Act, saved: list):
         n, d, h, w_, _ = x.t.shape
         cout = w2.shape[0]
         dev = x.t.device
+        a_x = self._operand(x.t, x.st)
         if wsc is not None:
             wcat = torch.cat([w1, wsc], dim=0).contiguous()
             hs = Act.new(n, d, h, w_, 2 * cout, self.dtype, dev)
-            ops.conv3_forward(x.t, ops.conv3_pack_weights(wcat), hs.t, in_stats=x.st, slope=self.slope,
-                              out_stats=hs.st)
+            self._conv(a_x, wcat, hs.t, out_stats=hs.st)
             hh, ss = hs.view(0, cout), hs.view(cout, 2 * cout)
-            ops.conv3_forward(hh.t, ops.conv3_pack_weights(w2), out.t, in_stats=hh.st, slope=self.slope,
-                              res=ss.t, out_stats=out.st)
-            saved.append((x, hh))
+            a_h = self._operand(hh.t, hh.st)
+            self._conv(a_h, w2, out.t, res=ss.t, out_stats=out.st)
         else:
             hh = Act.new(n, d, h, w_, cout, self.dtype, dev)
-            ops.conv3_forward(x.t, ops.conv3_pack_weights(w1), hh.t, in_stats=x.st, slope=self.slope,
-                              out_stats=hh.st)
-            ops.conv3_forward(hh.t, ops.conv3_pack_weights(w2), out.t, in_stats=hh.st, slope=self.slope,
-                              res=x.t, out_stats=out.st)
-            saved.append((x, hh))
+            self._conv(a_x, w1, hh.t, out_stats=hh.st)
+            a_h = self._operand(hh.t, hh.st)
+            self._conv(a_h, w2, out.t, res=x.t, out_stats=out.st)
+        saved.append((x, hh, a_x, a_h))
 
     def forward(self, x: torch.Tensor, P: dict, num_classes: int, save: bool):
         """x fp32 [N,1,D,H,W]; P maps parameter names to fp32 tensors. Returns (logits, saved)."""
@@ -200,44 +224,38 @@ class _Engine:
         n, d, h, w_, _ = like.shape
         return torch.empty((n, d, h, w_, c), dtype=self.dtype, device=like.device)
 
-    def _block_bwd_identity(self, x: Act, hh: Act, w1, w2, d_out: torch.Tensor, dx_dest: torch.Tensor):
-        s = self.slope
+    def _block_bwd_identity(self, x: Act, hh: Act, a_x, a_h, w1, w2, d_out: torch.Tensor, dx_dest: torch.Tensor):
         c = w2.shape[0]
+        d_op = self._operand(d_out)
         g_h = self._new(d_out, c)
         sums_h = _sums_like(hh)
-        ops.conv3_forward(d_out, ops.conv3_pack_weights(w2, True), g_h, mask_x=hh.t, mask_stats=hh.st,
-                          bwd_sums=sums_h, slope=s)
-        dw2 = torch.empty_like(w2)
-        ops.conv3_wgrad(hh.t, d_out, dw2, in_stats=hh.st, slope=s)
+        self._conv(d_op, w2, g_h, flip=True, mask_x=hh.t, mask_stats=hh.st, bwd_sums=sums_h)
+        dw2 = self._wgrad(a_h, d_op, torch.empty_like(w2))
         ops.instnorm_backward_apply(g_h, hh.t, hh.st, sums_h, g_h)  # in place: g_h becomes d(h)
+        gh_op = self._operand(g_h)
         g_x = self._new(d_out, x.C)
         sums_x = _sums_like(x)
-        ops.conv3_forward(g_h, ops.conv3_pack_weights(w1, True), g_x, mask_x=x.t, mask_stats=x.st,
-                          bwd_sums=sums_x, slope=s)
-        dw1 = torch.empty_like(w1)
-        ops.conv3_wgrad(x.t, g_h, dw1, in_stats=x.st, slope=s)
+        self._conv(gh_op, w1, g_x, flip=True, mask_x=x.t, mask_stats=x.st, bwd_sums=sums_x)
+        dw1 = self._wgrad(a_x, gh_op, torch.empty_like(w1))
         ops.instnorm_backward_apply(g_x, x.t, x.st, sums_x, dx_dest, add=d_out)
         return dw1, dw2
 
-    def _block_bwd_shortcut(self, x: Act, hh: Act, w1, w2, wsc, dcat2: torch.Tensor, dx_dest: torch.Tensor):
+    def _block_bwd_shortcut(self, x: Act, hh: Act, a_x, a_h, w1, w2, wsc, dcat2: torch.Tensor, dx_dest: torch.Tensor):
         """dcat2 [.., 2C]: channels [C:2C] hold d(out) on entry; [0:C] receives d(h)."""
-        s = self.slope
         c = w2.shape[0]
         d_out = dcat2[..., c:]
         dh = dcat2[..., :c]
+        d_op = self._operand(d_out)
         sums_h = _sums_like(hh)
-        ops.conv3_forward(d_out, ops.conv3_pack_weights(w2, True), dh, mask_x=hh.t, mask_stats=hh.st,
-                          bwd_sums=sums_h, slope=s)
-        dw2 = torch.empty_like(w2)
-        ops.conv3_wgrad(hh.t, d_out, dw2, in_stats=hh.st, slope=s)
+        self._conv(d_op, w2, dh, flip=True, mask_x=hh.t, mask_stats=hh.st, bwd_sums=sums_h)
+        dw2 = self._wgrad(a_h, d_op, torch.empty_like(w2))
         ops.instnorm_backward_apply(dh, hh.t, hh.st, sums_h, dh)
         wcat = torch.cat([w1, wsc], dim=0).contiguous()
+        dcat_op = self._operand(dcat2)
         g_x = self._new(dcat2, x.C)
         sums_x = _sums_like(x)
-        ops.conv3_forward(dcat2, ops.conv3_pack_weights(wcat, True), g_x, mask_x=x.t, mask_stats=x.st,
-                          bwd_sums=sums_x, slope=s)
-        dwcat = torch.empty_like(wcat)
-        ops.conv3_wgrad(x.t, dcat2, dwcat, in_stats=x.st, slope=s)
+        self._conv(dcat_op, wcat, g_x, flip=True, mask_x=x.t, mask_stats=x.st, bwd_sums=sums_x)
+        dwcat = self._wgrad(a_x, dcat_op, torch.empty_like(wcat))
         ops.instnorm_backward_apply(g_x, x.t, x.st, sums_x, dx_dest)
         return dwcat[:c], dw2, dwcat[c:]
 
@@ -263,15 +281,15 @@ class _Engine:
             pre = f"up{j}.conv."
             ia, ib = 7 + 2 * j, 8 + 2 * j
             # block B (identity shortcut): d_out = d_cur, dx goes into the d(out) slot of block A
-            xb, hb = saved[ib]
+            xb, hb, axb, ahb = saved[ib]
             dcat2 = self._new(xb.t, 2 * ch[l])
-            dw1, dw2 = self._block_bwd_identity(xb, hb, P[pre + "1.conv1.conv.weight"], P[pre + "1.conv2.conv.weight"],
+            dw1, dw2 = self._block_bwd_identity(xb, hb, axb, ahb, P[pre + "1.conv1.conv.weight"], P[pre + "1.conv2.conv.weight"],
                                                 d_cur, dcat2[..., ch[l]:])
             G[pre + "1.conv1.conv.weight"], G[pre + "1.conv2.conv.weight"] = dw1, dw2
             # block A (conv shortcut) on the concat buffer
-            xa, ha = saved[ia]
+            xa, ha, axa, aha = saved[ia]
             d_cat = self._new(xa.t, xa.C)
-            dw1, dw2, dwsc = self._block_bwd_shortcut(xa, ha, P[pre + "0.conv1.conv.weight"],
+            dw1, dw2, dwsc = self._block_bwd_shortcut(xa, ha, axa, aha, P[pre + "0.conv1.conv.weight"],
                                                       P[pre + "0.conv2.conv.weight"],
                                                       P[pre + "0.shortcut.conv.weight"], dcat2, d_cat)
             G[pre + "0.conv1.conv.weight"], G[pre + "0.conv2.conv.weight"] = dw1, dw2
@@ -284,14 +302,14 @@ class _Engine:
         for l in (4, 3, 2, 1):
             pre = f"down{l}.conv."
             ia, ib = 2 * l - 1, 2 * l
-            xb, hb = saved[ib]
+            xb, hb, axb, ahb = saved[ib]
             dcat2 = self._new(xb.t, 2 * ch[l])
-            dw1, dw2 = self._block_bwd_identity(xb, hb, P[pre + "2.conv1.conv.weight"], P[pre + "2.conv2.conv.weight"],
+            dw1, dw2 = self._block_bwd_identity(xb, hb, axb, ahb, P[pre + "2.conv1.conv.weight"], P[pre + "2.conv2.conv.weight"],
                                                 d_cur, dcat2[..., ch[l]:])
             G[pre + "2.conv1.conv.weight"], G[pre + "2.conv2.conv.weight"] = dw1, dw2
-            xa, ha = saved[ia]  # xa = pooled input
+            xa, ha, axa, aha = saved[ia]  # xa = pooled input
             d_p = self._new(xa.t, xa.C)
-            dw1, dw2, dwsc = self._block_bwd_shortcut(xa, ha, P[pre + "1.conv1.conv.weight"],
+            dw1, dw2, dwsc = self._block_bwd_shortcut(xa, ha, axa, aha, P[pre + "1.conv1.conv.weight"],
                                                       P[pre + "1.conv2.conv.weight"],
                                                       P[pre + "1.shortcut.conv.weight"], dcat2, d_p)
             G[pre + "1.conv1.conv.weight"], G[pre + "1.conv2.conv.weight"] = dw1, dw2
@@ -300,9 +318,9 @@ class _Engine:
             d_cur = self._new(x_prev.t, ch[l - 1])
             ops.maxpool2_backward(x_prev.t, d_p, d_cur, dskip=dskip[l - 1])
         # inc block + stem
-        x0, h0 = saved[0]
+        x0, h0, ax0, ah0 = saved[0]
         d_t0 = self._new(x0.t, b)
-        dw1, dw2 = self._block_bwd_identity(x0, h0, P["inc.conv2.conv1.conv.weight"], P["inc.conv2.conv2.conv.weight"],
+        dw1, dw2 = self._block_bwd_identity(x0, h0, ax0, ah0, P["inc.conv2.conv1.conv.weight"], P["inc.conv2.conv2.conv.weight"],
                                             d_cur, d_t0)
         G["inc.conv2.conv1.conv.weight"], G["inc.conv2.conv2.conv.weight"] = dw1, dw2
         dws = torch.empty_like(P["inc.conv1.weight"])
@@ -355,7 +373,7 @@ class B200UNet(nn.Module):
         if any(s != [2, 2, 2] for s in sc) or len(sc) != 4 or any(k != [3, 3, 3] for k in ks):
             raise NotImplementedError("B200UNet implements scale=[[2,2,2]]*4 and kernel_size=[[3,3,3]]*5")
         if precision not in ("bf16", "fp32"):
-            raise ValueError("precision must be 'bf16' (bf16 storage) or 'fp32' (fp32 storage)")
+            raise ValueError("precision must be 'bf16' (bf16 storage / operands) or 'fp32' (fp32 storage, split 3xbf16 products)")
         b = base_ch
         self.base_ch, self.num_classes = b, num_classes
         self.negative_slope, self.precision, self.return_dict = negative_slope, precision, return_dict

@@ -35,11 +35,13 @@ def _truth(x, sd, slope=0.0):
 
 
 def test_logits_vs_reference_golden(cuda_dev, golden):
-    """Against the REAL reference's recorded fp32 logits (32^3, 2^3 voxels at the bottom level, where one
-    bf16 operand rounding is a visible perturbation).  Bound = bf16-operand noise level of this net; the
-    yardstick-based checks below show it equals the oracle's own noise when it rounds at the same points."""
+    """Against the REAL reference's recorded fp32 logits (cfg1: base 8, 32^3).  North-star bar: logits within 1e-3
+    relative fp32 and the argmax mask bit-exact — met by precision='fp32' (split 3xbf16 tensor-core products).
+    The bf16 perf mode is bounded by the bf16-operand noise of this net (2^3 voxels at the bottom level, where one
+    operand rounding is a visible perturbation); the fp64-yardstick tests below show it equals the oracle's own
+    noise when the oracle rounds at the same points."""
     from oracle.unet_ref import synthetic_image
-    for precision, bound, min_agree in (("fp32", 8e-2, 0.985), ("bf16", 6e-1, 0.93)):
+    for precision, bound, min_agree in (("fp32", 1e-3, 1.0), ("bf16", 6e-1, 0.93)):
         net, _ = _make(cuda_dev, precision)
         x = synthetic_image(1, S, S, S, seed=3, device=cuda_dev)
         with torch.no_grad():
@@ -53,23 +55,30 @@ def test_logits_vs_reference_golden(cuda_dev, golden):
 
 @pytest.mark.parametrize("precision,slope,side", [("fp32", 0.0, 64), ("bf16", 0.0, 64), ("fp32", 0.01, 32), ("bf16", 0.0, 32)])
 def test_forward_accuracy_vs_fp64_truth(cuda_dev, precision, slope, side):
-    """Error against the fp64 truth must not exceed that of the oracle evaluated with the same rounding
-    points (bf16 operands [+ bf16 storage]): the kernels add no error of their own."""
+    """fp32 mode: within the north-star 1e-3 of the fp64 truth, argmax bit-exact.  bf16 mode: error against the
+    fp64 truth must not exceed that of the oracle evaluated with the same rounding points (bf16 operands + bf16
+    storage): the kernels add no error of their own."""
     from oracle.unet_ref import synthetic_image, unet_forward
     net, sd = _make(cuda_dev, precision, slope)
     x = synthetic_image(2 if side == 32 else 1, side, side, side, seed=4, device=cuda_dev)
     with torch.no_grad():
         out = net(x)["segmentation"]
         truth = _truth(x, sd, slope)
-        emul = unet_forward(x, sd, slope=slope, emulate=True, storage=precision)
+        emul = unet_forward(x, sd, slope=slope, emulate=True, storage="bf16")
         pure = unet_forward(x, sd, slope=slope)
     e_mine, e_emul, e_pure = rel(out.double(), truth), rel(emul.double(), truth), rel(pure.double(), truth)
     agree = (out.argmax(1) == truth.argmax(1)).float().mean().item()
     agree_emul = (emul.argmax(1) == truth.argmax(1)).float().mean().item()
-    print(f"[fwd] {precision} slope={slope} {side}^3: err vs fp64 truth: kernels {e_mine:.3e} | emulating oracle {e_emul:.3e} | "
+    print(f"[fwd] {precision} slope={slope} {side}^3: err vs fp64 truth: kernels {e_mine:.3e} | bf16-emulating oracle {e_emul:.3e} | "
           f"fp32 oracle {e_pure:.3e}; argmax agreement kernels {agree:.5f} emul {agree_emul:.5f}")
-    assert e_mine <= 2.0 * e_emul + 1e-3
-    assert agree >= agree_emul - 5e-3
+    if precision == "fp32":
+        # reference configuration (ReLU): the north-star 1e-3.  The LeakyReLU variant on the 32^3 toy (InstanceNorm over
+        # 2^3 voxels at the bottom, nothing clamped to zero) amplifies the 2^-17 split-product error up to ~2e-3
+        # depending on the run's atomic-add order in the statistics; it gets a 3e-3 bound.
+        assert e_mine <= (1e-3 if slope == 0.0 else 3e-3) and agree == 1.0
+    else:
+        assert e_mine <= 2.0 * e_emul + 1e-3
+        assert agree >= agree_emul - 5e-3
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
@@ -96,19 +105,28 @@ def test_backward_accuracy_vs_fp64_truth(cuda_dev, precision):
         return l["overall"].item(), {k: v.grad for k, v in sdr.items()}
 
     l64, g64 = oracle_grads(torch.float64, False)
+    l32, g32 = oracle_grads(torch.float32, False)
     lem, gem = oracle_grads(torch.float32, True)
-    print(f"[bwd] {precision}: loss kernels {loss['overall'].item():.6f} | emulating oracle {lem:.6f} | fp64 truth {l64:.6f}")
-    assert abs(loss["overall"].item() - l64) <= 2.0 * abs(lem - l64) + 2e-3 * abs(l64)
-    worst = (0.0, 0.0, "")
+    print(f"[bwd] {precision}: loss kernels {loss['overall'].item():.6f} | fp32 oracle {l32:.6f} | bf16-emulating oracle {lem:.6f} | fp64 truth {l64:.6f}")
+    if precision == "fp32":
+        assert abs(loss["overall"].item() - l64) <= 1e-5 * abs(l64)   # north star: loss within 1e-5
+    else:
+        assert abs(loss["overall"].item() - l64) <= 2.0 * abs(lem - l64) + 2e-3 * abs(l64)
+    worst = (0.0, 0.0, 0.0, "")
     for k, p in net.named_parameters():
         assert p.grad is not None and p.grad.shape == p.shape, k   # DDP: every parameter gets a grad
-        e_mine, e_emul = rel(p.grad.double(), g64[k]), rel(gem[k].double(), g64[k])
+        e_mine, e_emul, e_32 = rel(p.grad.double(), g64[k]), rel(gem[k].double(), g64[k]), rel(g32[k].double(), g64[k])
         if e_mine > worst[0]:
-            worst = (e_mine, e_emul, k)
-        # the emulating oracle rounds forward operands only (autograd backward stays fp32) while the
-        # kernels also round dy / recomputed activations for dgrad & wgrad: allow that extra 2^-8-level term
-        assert e_mine <= 3.0 * e_emul + 2e-2, (k, e_mine, e_emul)
-    print(f"[bwd] {precision}: worst grad err vs fp64 truth {worst[0]:.3e} (emulating oracle {worst[1]:.3e}) at {worst[2]}")
+            worst = (e_mine, e_emul, e_32, k)
+        if precision == "fp32":
+            # split products carry ~2^-17 per operand; this 2^3-bottom toy net amplifies any perturbation of the
+            # forward activations in its gradients (the fp32 oracle's own error is printed for scale)
+            assert e_mine <= 5e-2, (k, e_mine, e_32)
+        else:
+            # the emulating oracle rounds forward operands only (autograd backward stays fp32) while the kernels
+            # also round dy for dgrad & wgrad: allow that extra 2^-8-level term
+            assert e_mine <= 3.0 * e_emul + 2e-2, (k, e_mine, e_emul)
+    print(f"[bwd] {precision}: worst grad err vs fp64 truth {worst[0]:.3e} (fp32 oracle {worst[2]:.3e}, bf16-emulating oracle {worst[1]:.3e}) at {worst[3]}")
 
 
 def test_module_contract(cuda_dev):
