@@ -10,8 +10,10 @@ echo "bench exit=$?" >> gpurun_out/${tag}_bench.err
 if [ "$2" != "noncu" ]; then
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/${tag}_launches.csv \
    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_bench.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv3_igemm -s 130 -c 4 -o gpurun_out/${tag}_conv3_full \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv3_fprop -s 136 -c 3 -o gpurun_out/${tag}_conv3_fprop_full \
    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv3_wgrad_kernel -s 68 -c 3 -o gpurun_out/${tag}_conv3_wgrad_full \
+   python bench.py --steps 1 --warmup 3 --no-cpu-baseline >> gpurun_out/${tag}_ncu_full.log 2>&1
 fi
 grep -E "passed|failed|FAILED|\[fwd\]|\[bwd\]|\[golden\]|smoke" gpurun_out/${tag}_gpu_tests.log | tail -40
 cat gpurun_out/${tag}_bench.json; tail -5 gpurun_out/${tag}_bench.err
