@@ -217,12 +217,15 @@ typedef struct RsbSegLossArgs {
   const uint8_t* label;
   const uint8_t* known; /* NULL => all ones */
   const float* class_weights;
+  const float* bce_weight_map; /* optional fp32 [B][C][V] per-voxel weight of the BCE term (Ball loss: GWRP foreground
+                                  weights + background indicator, losses_foundation.py:1775-1811); NULL => 1 */
   float* partials;  /* [B*C*4] workspace, zeroed by forward */
   float* coef;      /* [B*C*4] workspace (per-(b,c) backward coefficients) */
   float* loss_out;  /* [3]: total, bce, dice */
 } RsbSegLossArgs;
 int rsb_seg_loss_forward(const RsbSegLossArgs* args, void* stream);
-/* dlogits (+)= grad_scale[0] * dL/dlogits ; grad_scale is a device scalar */
+/* dlogits (+)= grad_scale[0] * d(bce term)/dlogits + grad_scale[1] * d(dice term)/dlogits ; grad_scale points to
+ * two device floats (pass the same value twice for the plain segmentation loss) */
 int rsb_seg_loss_backward(const RsbSegLossArgs* args, const float* grad_scale, float* dlogits,
                           int accumulate, void* stream);
 
@@ -233,6 +236,44 @@ int rsb_seg_loss_backward(const RsbSegLossArgs* args, const float* grad_scale, f
  * ------------------------------------------------------------------------------------------ */
 int rsb_dilate_ball(const uint8_t* src, uint8_t* dst, uint8_t* tmp, int n_vol, int D, int H, int W,
                     int kernel_size, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Report-supervised losses (training/losses_foundation.py): Volume loss (:250-395) and Ball loss
+ * (:1336-1864).  Rows are contiguous runs of V = D*H*W elements.  The scalar glue (per-tumour loop,
+ * formulas on [B][L] values) is host code, as in the reference.
+ * ------------------------------------------------------------------------------------------ */
+/* get_lesion_channels (:204-248) for single-channel groups: dst[r] = src[row_map[r]]; and its adjoint */
+int rsb_rows_gather(const void* src, const int* row_map, void* dst, int n_rows, long long V, int elem_bytes, void* stream);
+int rsb_rows_scatter_add(const float* src, const int* row_map, float* dst, int n_rows, long long V, void* stream);
+/* mask algebra on uint8 0/1 volumes; op: 0 a|b, 1 a&b, 2 a&~b, 3 ~(a|b), 4 ~a   (to_penalize :1605, borders :1721-1737) */
+int rsb_u8_binary(const uint8_t* a, const uint8_t* b, uint8_t* out, int op, long long n, void* stream);
+/* counts[r] = number of non-zero voxels of row r (the `.sum() > 0` / `.sum() < t` tests) */
+int rsb_u8_row_count(const uint8_t* a, long long* counts, int n_rows, long long V, void* stream);
+/* Volume loss reduction (:330-340): sums[r] = scale[r] * sum_v sigmoid(x[r][v]) * mask[r][v], and
+ * dx[r][v] (+)= coef[r] * scale[r] * mask * sigmoid'(x) */
+int rsb_masked_sigmoid_sum(const float* x, const uint8_t* mask, const float* scale, float* sums, int n_rows, long long V, void* stream);
+int rsb_masked_sigmoid_grad(const float* x, const uint8_t* mask, const float* scale, const float* coef, float* dx, int accumulate,
+                            int n_rows, long long V, void* stream);
+/* Ball loss (:1680-1719): x_iter = sigmoid(x) * seg ; x_iter *= (1 - mask) */
+int rsb_ball_prepare(const float* x, const uint8_t* seg, float* x_iter, long long V, void* stream);
+int rsb_ball_remove(float* x_iter, const uint8_t* mask, long long V, void* stream);
+/* isolate_tumor (:1387-1420): argmax of the cross-correlation of x_iter with a (Gaussian) ball given as n_taps int4
+ * {dz, dy, dx, float bits of the weight}; argmax_out receives (score bits << 32 | 0xFFFFFFFF - flat index), first
+ * maximum in flattened order */
+size_t rsb_ball_workspace_bytes(int D, int H, int W);
+int rsb_ball_correlate_argmax(const float* x_iter, const void* taps, int n_taps, int kernel_half, void* workspace,
+                              long long* argmax_out, int D, int H, int W, void* stream);
+/* candidates {value bits, voxel index}: mode 0 = voxels of the ball (centre, grid half-width, radius^2 — insert_ball
+ * :1336-1385) with x > 0 (also writes the 0/1 ball volume); mode 1 = voxels with mask != 0, value sigmoid(x) */
+int rsb_ball_candidates(const float* x, const uint8_t* mask, int mode, int cz, int cy, int cx, int half, float radius2,
+                        void* cand, int* n_cand, int max_cand, uint8_t* ball_out, int D, int H, int W, void* stream);
+/* torch.topk membership x3 (:1470-1490) by exact ranking (value desc, index asc): m_i[idx] = rank < k_i */
+int rsb_ball_rank_select(const void* cand, const int* n_cand, int max_cand, int k0, int k1, int k2, uint8_t* m0, uint8_t* m1,
+                         uint8_t* m2, void* stream);
+/* GlobalWeightedRankPooling weights (:442-537, hard cutoff) times N, scattered to voxel order */
+int rsb_ball_rank_gwrp(const void* cand, const int* n_cand, int max_cand, float concentration, float* wmap, void* stream);
+/* wmap = (pseudo ? wmap : 0) + (1 - dilated)   — foreground GWRP weights + background indicator (:1775-1811) */
+int rsb_ball_weight_map(float* wmap, const uint8_t* pseudo, const uint8_t* dilated, long long V, void* stream);
 
 #ifdef __cplusplus
 }

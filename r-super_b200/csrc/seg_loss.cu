@@ -37,12 +37,14 @@ RSB_DEVICE float block_sum(float v, float* red) {
 __global__ void __launch_bounds__(kSegThreads) seg_loss_pass1_kernel(const float* __restrict__ logits,
                                                                      const uint8_t* __restrict__ label,
                                                                      const uint8_t* __restrict__ known,
+                                                                     const float* __restrict__ wmap,
                                                                      float* __restrict__ partials, long long V) {
   __shared__ float red[8];
   const int bc = blockIdx.y;
   const float* r = logits + static_cast<long long>(bc) * V;
   const uint8_t* l = label + static_cast<long long>(bc) * V;
   const uint8_t* k = known ? known + static_cast<long long>(bc) * V : nullptr;
+  const float* wm = wmap ? wmap + static_cast<long long>(bc) * V : nullptr;
   float s_bce = 0.f, s_tp = 0.f, s_fp = 0.f, s_fn = 0.f;
   const long long nvec = V / 16;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
@@ -62,7 +64,7 @@ __global__ void __launch_bounds__(kSegThreads) seg_loss_pass1_kernel(const float
       const float kn = ((kw[j >> 2] >> ((j & 3) * 8)) & 0xFFu) ? 1.f : 0.f;
       const float x = xs[j];
       const float sg = sigmoidf_acc(x);
-      s_bce += kn * bce_logits(x, lab);
+      s_bce += kn * bce_logits(x, lab) * (wm ? wm[i * 16 + j] : 1.f);
       s_tp += kn * lab * sg;
       s_fp += kn * (1.f - lab) * sg;
       s_fn += kn * lab * (1.f - sg);
@@ -75,7 +77,7 @@ __global__ void __launch_bounds__(kSegThreads) seg_loss_pass1_kernel(const float
       const float kn = k ? (k[i] ? 1.f : 0.f) : 1.f;
       const float x = r[i];
       const float sg = sigmoidf_acc(x);
-      s_bce += kn * bce_logits(x, lab);
+      s_bce += kn * bce_logits(x, lab) * (wm ? wm[i] : 1.f);
       s_tp += kn * lab * sg;
       s_fp += kn * (1.f - lab) * sg;
       s_fn += kn * lab * (1.f - sg);
@@ -161,13 +163,16 @@ __global__ void seg_loss_finalize_kernel(const float* __restrict__ partials, con
 __global__ void __launch_bounds__(kSegThreads) seg_loss_pass2_kernel(const float* __restrict__ logits,
                                                                      const uint8_t* __restrict__ label,
                                                                      const uint8_t* __restrict__ known,
+                                                                     const float* __restrict__ wmap,
                                                                      const float* __restrict__ coef,
                                                                      const float* __restrict__ grad_scale,
                                                                      float* __restrict__ dlogits, int accumulate,
                                                                      long long V) {
   const int bc = blockIdx.y;
-  const float gs = grad_scale ? grad_scale[0] : 1.f;
-  const float c0 = coef[bc * 4 + 0] * gs, c1 = coef[bc * 4 + 1] * gs, c2 = coef[bc * 4 + 2] * gs;
+  // grad_scale[0] scales the BCE term, grad_scale[1] the Dice term (separate dict entries in the Ball loss)
+  const float gb = grad_scale ? grad_scale[0] : 1.f, gd = grad_scale ? grad_scale[1] : 1.f;
+  const float c0 = coef[bc * 4 + 0] * gb, c1 = coef[bc * 4 + 1] * gd, c2 = coef[bc * 4 + 2] * gd;
+  const float* wm = wmap ? wmap + static_cast<long long>(bc) * V : nullptr;
   const float* r = logits + static_cast<long long>(bc) * V;
   const uint8_t* l = label + static_cast<long long>(bc) * V;
   const uint8_t* k = known ? known + static_cast<long long>(bc) * V : nullptr;
@@ -190,7 +195,7 @@ __global__ void __launch_bounds__(kSegThreads) seg_loss_pass2_kernel(const float
       const bool lab = ((lw[j >> 2] >> ((j & 3) * 8)) & 0xFFu) != 0;
       const float kn = ((kw[j >> 2] >> ((j & 3) * 8)) & 0xFFu) ? 1.f : 0.f;
       const float sg = sigmoidf_acc(xs[j]);
-      o[j] = kn * (c0 * (sg - (lab ? 1.f : 0.f)) + sg * (1.f - sg) * (lab ? c1 : c2));
+      o[j] = kn * (c0 * (wm ? wm[i * 16 + j] : 1.f) * (sg - (lab ? 1.f : 0.f)) + sg * (1.f - sg) * (lab ? c1 : c2));
     }
     float4* dp = reinterpret_cast<float4*>(d + i * 16);
     if (accumulate) {
@@ -210,7 +215,7 @@ __global__ void __launch_bounds__(kSegThreads) seg_loss_pass2_kernel(const float
       const bool lab = l[i] != 0;
       const float kn = k ? (k[i] ? 1.f : 0.f) : 1.f;
       const float sg = sigmoidf_acc(r[i]);
-      const float v = kn * (c0 * (sg - (lab ? 1.f : 0.f)) + sg * (1.f - sg) * (lab ? c1 : c2));
+      const float v = kn * (c0 * (wm ? wm[i] : 1.f) * (sg - (lab ? 1.f : 0.f)) + sg * (1.f - sg) * (lab ? c1 : c2));
       d[i] = accumulate ? d[i] + v : v;
     }
   }
@@ -245,7 +250,7 @@ extern "C" int rsb_seg_loss_forward(const RsbSegLossArgs* p, void* stream) {
   cudaError_t e = cudaMemsetAsync(p->partials, 0, sizeof(float) * 4 * p->B * p->C, st);
   RSB_REQUIRE(e == cudaSuccess, "seg_loss: memset failed: %s", cudaGetErrorString(e));
   dim3 grid(seg_grid_x(p->V), p->B * p->C);
-  seg_loss_pass1_kernel<<<grid, kSegThreads, 0, st>>>(p->logits, p->label, p->known, p->partials, p->V);
+  seg_loss_pass1_kernel<<<grid, kSegThreads, 0, st>>>(p->logits, p->label, p->known, p->bce_weight_map, p->partials, p->V);
   int rc = check_launch("seg_loss_pass1_kernel");
   if (rc) return rc;
   seg_loss_finalize_kernel<<<1, 256, 0, st>>>(p->partials, p->class_weights, p->coef, p->loss_out, p->B, p->C, p->V);
@@ -259,6 +264,6 @@ extern "C" int rsb_seg_loss_backward(const RsbSegLossArgs* p, const float* grad_
   RSB_REQUIRE(p->V % 16 == 0, "seg_loss: D*H*W must be a multiple of 16 (got %lld)", p->V);
   dim3 grid(seg_grid_x(p->V), p->B * p->C);
   seg_loss_pass2_kernel<<<grid, kSegThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      p->logits, p->label, p->known, p->coef, grad_scale, dlogits, accumulate, p->V);
+      p->logits, p->label, p->known, p->bce_weight_map, p->coef, grad_scale, dlogits, accumulate, p->V);
   return check_launch("seg_loss_pass2_kernel");
 }

@@ -56,7 +56,7 @@ class RsbSegLossArgs(C.Structure):
     _fields_ = [
         ("B", c_int), ("C", c_int), ("V", c_ll),
         ("logits", c_void_p), ("label", c_void_p), ("known", c_void_p),
-        ("class_weights", c_void_p),
+        ("class_weights", c_void_p), ("bce_weight_map", c_void_p),
         ("partials", c_void_p), ("coef", c_void_p), ("loss_out", c_void_p),
     ]
 
@@ -110,6 +110,21 @@ SIGNATURES = {
                                       c_void_p]),
     "rsb_dilate_ball": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                 c_void_p]),
+    "rsb_rows_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p]),
+    "rsb_rows_scatter_add": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_ll, c_void_p]),
+    "rsb_u8_binary": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_ll, c_void_p]),
+    "rsb_u8_row_count": (c_int, [c_void_p, c_void_p, c_int, c_ll, c_void_p]),
+    "rsb_masked_sigmoid_sum": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_void_p]),
+    "rsb_masked_sigmoid_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll, c_void_p]),
+    "rsb_ball_prepare": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
+    "rsb_ball_remove": (c_int, [c_void_p, c_void_p, c_ll, c_void_p]),
+    "rsb_ball_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "rsb_ball_correlate_argmax": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "rsb_ball_candidates": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_int,
+                                    c_void_p, c_int, c_int, c_int, c_void_p]),
+    "rsb_ball_rank_select": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rsb_ball_rank_gwrp": (c_int, [c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p]),
+    "rsb_ball_weight_map": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
 }
 
 _lib = None

@@ -39,7 +39,7 @@ class _SegLoss(torch.autograd.Function):
     def backward(ctx, grad_out):
         st = ctx.state
         dl = torch.empty_like(st.keep[0])
-        ops.seg_loss_backward(st, grad_out.detach().reshape(1).float().contiguous(), dl)
+        ops.seg_loss_backward(st, grad_out.detach().reshape(1).float().repeat(2).contiguous(), dl)
         ctx.state = None
         return dl, None, None, None
 

@@ -295,12 +295,12 @@ def channel_stats(x, stats=None):
 class SegLossState:
     """Device workspaces of one fused BCE+Dice evaluation (kept for the backward pass)."""
 
-    def __init__(self, logits, label_u8, known_u8, class_weights):
+    def __init__(self, logits, label_u8, known_u8, class_weights, wmap=None):
         b, c = logits.shape[:2]
         v = logits[0, 0].numel()
         dev = logits.device
         self.args = _lib.RsbSegLossArgs()
-        self.keep = (logits, label_u8, known_u8, class_weights)
+        self.keep = (logits, label_u8, known_u8, class_weights, wmap)
         self.partials = torch.empty(b * c * 4, dtype=torch.float32, device=dev)
         self.coef = torch.empty(b * c * 4, dtype=torch.float32, device=dev)
         self.loss_out = torch.empty(3, dtype=torch.float32, device=dev)
@@ -308,23 +308,28 @@ class SegLossState:
         a.B, a.C, a.V = b, c, v
         a.logits, a.label, a.known = _p(logits), _p(label_u8), _p(known_u8)
         a.class_weights = _p(class_weights)
+        a.bce_weight_map = _p(wmap)
         a.partials, a.coef, a.loss_out = _p(self.partials), _p(self.coef), _p(self.loss_out)
 
 
-def seg_loss_forward(logits, label_u8, known_u8=None, class_weights=None) -> SegLossState:
+def seg_loss_forward(logits, label_u8, known_u8=None, class_weights=None, wmap=None) -> SegLossState:
     assert logits.dtype == torch.float32 and logits.is_contiguous() and logits.dim() == 5
     assert label_u8.dtype == torch.uint8 and label_u8.is_contiguous() and label_u8.shape == logits.shape
     if known_u8 is not None:
         assert known_u8.dtype == torch.uint8 and known_u8.is_contiguous() and known_u8.shape == logits.shape
     if class_weights is not None:
         assert class_weights.dtype == torch.float32 and class_weights.is_contiguous()
-    st = SegLossState(logits, label_u8, known_u8, class_weights)
+    if wmap is not None:
+        assert wmap.dtype == torch.float32 and wmap.is_contiguous() and wmap.shape == logits.shape
+    st = SegLossState(logits, label_u8, known_u8, class_weights, wmap)
     _call("seg_loss", 2, 0.0, lib().rsb_seg_loss_forward, C.byref(st.args), _stream(), what="seg_loss_forward")
     return st
 
 
 def seg_loss_backward(st: SegLossState, grad_scale, dlogits, accumulate=False):
+    """grad_scale: device fp32 [2] = (scale of the BCE term, scale of the Dice term)."""
     assert dlogits.dtype == torch.float32 and dlogits.is_contiguous()
+    assert grad_scale.dtype == torch.float32 and grad_scale.numel() == 2 and grad_scale.is_contiguous()
     _call("seg_loss", 1, 0.0, lib().rsb_seg_loss_backward, C.byref(st.args), _p(grad_scale), _p(dlogits), int(accumulate),
                                       _stream(), what="seg_loss_backward")
     return dlogits
@@ -339,3 +344,99 @@ def dilate_ball(src_u8, kernel_size: int):
     tmp = torch.empty_like(src_u8)
     _call("dilate", 1, 0.0, lib().rsb_dilate_ball, _p(src_u8), _p(dst), _p(tmp), nvol, d, h, w_, int(kernel_size), _stream(), what="dilate_ball")
     return dst
+
+
+# --------------------------------------------------------------------------------------------
+# report-supervised losses (Volume / Ball): thin wrappers, rows are contiguous [.., V] runs
+# --------------------------------------------------------------------------------------------
+def _rows(t: torch.Tensor, v: int) -> int:
+    assert t.is_contiguous() and t.numel() % v == 0
+    return t.numel() // v
+
+
+def rows_gather(src, row_map, n_rows, v):
+    """dst[r] = src.view(-1, V)[row_map[r]] — lesion-channel selection (get_lesion_channels)."""
+    assert src.is_contiguous() and row_map.dtype == torch.int32 and src.element_size() in (1, 4)
+    dst = torch.empty((n_rows, v), dtype=src.dtype, device=src.device)
+    _call("report", 1, 0.0, lib().rsb_rows_gather, _p(src), _p(row_map), _p(dst), n_rows, v, src.element_size(), _stream(), what="rows_gather")
+    return dst
+
+
+def rows_scatter_add(src, row_map, dst, v):
+    assert src.dtype == torch.float32 and dst.dtype == torch.float32 and src.is_contiguous() and dst.is_contiguous()
+    _call("report", 1, 0.0, lib().rsb_rows_scatter_add, _p(src), _p(row_map), _p(dst), _rows(src, v), v, _stream(), what="rows_scatter_add")
+    return dst
+
+
+U8_OR, U8_AND, U8_ANDNOT, U8_NOR, U8_NOT = 0, 1, 2, 3, 4
+
+
+def u8_binary(a, b, op, out=None):
+    assert a.dtype == torch.uint8 and a.is_contiguous() and (b is None or (b.dtype == torch.uint8 and b.is_contiguous() and b.numel() == a.numel()))
+    out = torch.empty_like(a) if out is None else out
+    _call("report", 1, 0.0, lib().rsb_u8_binary, _p(a), _p(b), _p(out), op, a.numel(), _stream(), what="u8_binary")
+    return out
+
+
+def u8_row_count(a, v):
+    assert a.dtype == torch.uint8 and a.is_contiguous()
+    counts = torch.empty(_rows(a, v), dtype=torch.int64, device=a.device)
+    _call("report", 1, 0.0, lib().rsb_u8_row_count, _p(a), _p(counts), counts.numel(), v, _stream(), what="u8_row_count")
+    return counts
+
+
+def masked_sigmoid_sum(x, mask, scale, v):
+    assert x.dtype == torch.float32 and x.is_contiguous() and mask.dtype == torch.uint8 and mask.is_contiguous()
+    sums = torch.empty(_rows(x, v), dtype=torch.float32, device=x.device)
+    _call("report", 1, 0.0, lib().rsb_masked_sigmoid_sum, _p(x), _p(mask), _p(scale), _p(sums), sums.numel(), v, _stream(), what="masked_sigmoid_sum")
+    return sums
+
+
+def masked_sigmoid_grad(x, mask, scale, coef, dx, v, accumulate=False):
+    assert coef.dtype == torch.float32 and coef.is_contiguous() and dx.dtype == torch.float32 and dx.is_contiguous()
+    _call("report", 1, 0.0, lib().rsb_masked_sigmoid_grad, _p(x), _p(mask), _p(scale), _p(coef), _p(dx), int(accumulate), _rows(x, v), v,
+          _stream(), what="masked_sigmoid_grad")
+    return dx
+
+
+def ball_prepare(x, seg):
+    assert x.dtype == torch.float32 and x.is_contiguous() and seg.dtype == torch.uint8 and seg.is_contiguous()
+    out = torch.empty_like(x)
+    _call("report", 1, 0.0, lib().rsb_ball_prepare, _p(x), _p(seg), _p(out), x.numel(), _stream(), what="ball_prepare")
+    return out
+
+
+def ball_remove(x_iter, mask):
+    _call("report", 1, 0.0, lib().rsb_ball_remove, _p(x_iter), _p(mask), x_iter.numel(), _stream(), what="ball_remove")
+    return x_iter
+
+
+def ball_correlate_argmax(x_iter, taps, kernel_half):
+    """Flat index (device int64 scalar, packed) of the first maximum of corr(x_iter, ball taps)."""
+    d, h, w_ = x_iter.shape
+    ws = torch.empty(lib().rsb_ball_workspace_bytes(d, h, w_), dtype=torch.uint8, device=x_iter.device)
+    out = torch.empty(1, dtype=torch.int64, device=x_iter.device)
+    _call("report", 2, 0.0, lib().rsb_ball_correlate_argmax, _p(x_iter), _p(taps), taps.shape[0], kernel_half, _p(ws), _p(out), d, h, w_,
+          _stream(), what="ball_correlate_argmax")
+    return out
+
+
+def ball_candidates(x, mask, mode, center, half, radius2, cand, n_cand, ball_out):
+    d, h, w_ = x.shape
+    cz, cy, cx = center
+    _call("report", 1, 0.0, lib().rsb_ball_candidates, _p(x), _p(mask), mode, cz, cy, cx, half, float(radius2), _p(cand), _p(n_cand),
+          cand.shape[0], _p(ball_out), d, h, w_, _stream(), what="ball_candidates")
+
+
+def ball_rank_select(cand, n_cand, max_cand, ks, masks):
+    _call("report", 1, 0.0, lib().rsb_ball_rank_select, _p(cand), _p(n_cand), max_cand, ks[0], ks[1], ks[2], _p(masks[0]), _p(masks[1]),
+          _p(masks[2]), _stream(), what="ball_rank_select")
+
+
+def ball_rank_gwrp(cand, n_cand, max_cand, concentration, wmap):
+    _call("report", 1, 0.0, lib().rsb_ball_rank_gwrp, _p(cand), _p(n_cand), max_cand, float(concentration), _p(wmap), _stream(), what="ball_rank_gwrp")
+
+
+def ball_weight_map(wmap, pseudo, dilated):
+    _call("report", 1, 0.0, lib().rsb_ball_weight_map, _p(wmap), _p(pseudo), _p(dilated), wmap.numel(), _stream(), what="ball_weight_map")
+    return wmap

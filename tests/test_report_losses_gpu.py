@@ -1,0 +1,152 @@
+"""GPU parity of the report-supervised losses (Volume loss, Ball loss, calculate_loss dicts) through the
+reference-facing API of rsuper_b200 against the oracle (CPU, fp32) on the same seeded inputs, and against the
+golden values recorded from the REAL reference (tests/golden/reference_outputs.npz).
+
+Tolerances: discrete structures (ball centre, pseudo / dilated / penalize masks) bit-exact; losses 1e-5 (north star);
+gradients 1e-4 relative to their maximum."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return ((a - b).abs().max() / (b.abs().max() + 1e-20)).item()
+
+
+def pack(t):
+    return np.packbits(t.detach().cpu().numpy().astype(bool).reshape(-1))
+
+
+def _seg_inputs():
+    from oracle import synth
+    shp = (16, 24, 32)
+    cls3 = ["liver", "liver_lesion", "pancreas"]
+    lg = synth.synthetic_logits(2, 3, shp, seed=2)
+    b3 = synth.make_batch(["mask", "report"], cls3, shp, seed=11)
+    return lg, b3, cls3
+
+
+def _ball_inputs(shape=(32, 32, 32), seed=21, kinds=("report", "mask"), lseed=6):
+    from oracle import synth
+    cls2 = ["organ", "pancreatic_lesion"]
+    bb = synth.make_batch(list(kinds), cls2, shape, seed=seed)
+    lgb = synth.synthetic_logits(len(kinds), 2, shape, seed=lseed, scale=2.0)
+    return bb, lgb, cls2
+
+
+def test_volume_loss(cuda_dev, golden):
+    from oracle import losses_ref as LR
+    from rsuper_b200 import report_losses as RL
+    lg, b3, cls3 = _seg_inputs()
+    ref_in = lg.clone().requires_grad_(True)
+    ref = LR.volume_loss_basic(ref_in, b3["mask"].float(), b3["volumes"], b3["label"].float(), b3["unk_channels"].float(), cls3,
+                               tolerance=0.2)["dice_volume_loss"]
+    ref.backward()
+    x = lg.to(cuda_dev).requires_grad_(True)
+    out = RL.volume_loss_basic(x, b3["mask"].to(cuda_dev), b3["volumes"].to(cuda_dev), b3["label"].to(cuda_dev),
+                               b3["unk_channels"].to(cuda_dev), cls3, tolerance=0.2)["dice_volume_loss"]
+    out.backward()
+    assert abs(out.item() - ref.item()) <= 1e-6 and abs(out.item() - float(golden["volume_loss"])) <= 1e-6
+    assert rel(x.grad.cpu(), ref_in.grad) <= 1e-4
+    assert abs(x.grad.double().abs().sum().item() / float(golden["volume_grad_sum"]) - 1) <= 1e-4
+    # class weights and the larger tolerance branch
+    cw = torch.tensor([[1.0, 2.0, 0.5], [0.25, 1.5, 3.0]])
+    r2 = LR.volume_loss_basic(lg, b3["mask"].float(), b3["volumes"], b3["label"].float(), b3["unk_channels"].float(), cls3,
+                              tolerance=0.1, class_weights=cw[:, :, None, None, None])["dice_volume_loss"]
+    o2 = RL.volume_loss_basic(lg.to(cuda_dev), b3["mask"].to(cuda_dev), b3["volumes"].to(cuda_dev), b3["label"].to(cuda_dev),
+                              b3["unk_channels"].to(cuda_dev), cls3, tolerance=0.1, class_weights=cw.to(cuda_dev))["dice_volume_loss"]
+    assert abs(o2.item() - r2.item()) <= 1e-6
+
+
+def test_isolate_tumor_bit_exact(cuda_dev, golden):
+    from oracle import losses_ref as LR
+    from rsuper_b200 import report_losses as RL
+    bb, lgb, _ = _ball_inputs()
+    prob = torch.sigmoid(lgb[0, 1]) * LR.dilate_volume(bb["mask"][0, 1].float(), 31)
+    dia, volm = float(golden["isolate_args"][0]), float(golden["isolate_args"][1])
+    m, ms, mb = RL.isolate_tumor(prob.to(cuda_dev).contiguous(), dia, True, 1.5, volm, diameter_margin=0.2, volume_margin=0.2)
+    assert np.array_equal(pack(m), golden["isolate_mask"])
+    assert np.array_equal(pack(ms), golden["isolate_small"])
+    assert np.array_equal(pack(mb), golden["isolate_big"])
+    # second configuration: ball clipped by the volume border, several margins
+    for seed, dia2 in ((5, 9.0), (8, 14.0)):
+        bb2, lg2, _ = _ball_inputs(shape=(32, 48, 40), seed=seed, lseed=seed)
+        p2 = torch.sigmoid(lg2[0, 1]) * LR.dilate_volume(bb2["mask"][0, 1].float(), 31)
+        vol2 = 4.0 / 3.0 * np.pi * (dia2 / 2) ** 3
+        ref = LR.isolate_tumor(p2, dia2, True, 1.5, vol2, diameter_margin=0.5, volume_margin=0.5)
+        got = RL.isolate_tumor(p2.to(cuda_dev).contiguous(), dia2, True, 1.5, vol2, diameter_margin=0.5, volume_margin=0.5)
+        for a, b in zip(got, ref):
+            assert np.array_equal(pack(a), pack(b)), (seed, dia2)
+
+
+def test_gwrp_weights(cuda_dev, golden):
+    from oracle import losses_ref as LR
+    from oracle import synth
+    from rsuper_b200 import ops
+    xl = synth.synthetic_logits(1, 1, (12, 12, 12), seed=4)[0, 0]
+    xv = torch.sigmoid(xl)
+    pm = (xv > 0.6)
+    n = int(pm.sum())
+    ref = LR.gwrp_weights(xv * pm.float() + pm.float(), N=pm.float().sum(), c=0.5, hard_cutoff=True)
+    np.testing.assert_allclose(ref.numpy(), golden["gwrp_weights"], rtol=1e-5, atol=1e-9)
+    x = xl.to(cuda_dev).contiguous()
+    pseudo = pm.to(torch.uint8).to(cuda_dev).reshape(-1).contiguous()
+    wmap = torch.zeros(x.numel(), device=cuda_dev)
+    cand = torch.empty((n, 2), dtype=torch.int32, device=cuda_dev)
+    n_cand = torch.empty(1, dtype=torch.int32, device=cuda_dev)
+    ops.ball_candidates(x, pseudo, 1, (0, 0, 0), 0, 0.0, cand, n_cand, None)
+    ops.ball_rank_gwrp(cand, n_cand, n, 0.5, wmap)
+    assert int(n_cand.item()) == n
+    np.testing.assert_allclose(wmap.cpu().numpy().reshape(12, 12, 12) / n, golden["gwrp_weights"], rtol=2e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("cfg", [dict(), dict(shape=(32, 48, 32), seed=33, kinds=("mask", "report", "report"), lseed=9)])
+def test_ball_loss(cuda_dev, golden, cfg):
+    from oracle import losses_ref as LR
+    from rsuper_b200 import report_losses as RL
+    bb, lgb, cls2 = _ball_inputs(**cfg)
+    ref_in = lgb.clone().requires_grad_(True)
+    dbg_ref, dbg = {}, {}
+    ref = LR.ball_loss(ref_in, bb["label"].float(), bb["unk_channels"].float(), bb["mask"].float(), bb["volumes"], bb["diameters"],
+                       cls2, apply_dice_loss=True, diameter_margin=0.2, volume_margin=0.2, debug=dbg_ref)
+    (ref["ball_loss_bce"] + 0.5 * ref["ball_loss_dice"]).backward()
+    x = lgb.to(cuda_dev).requires_grad_(True)
+    out = RL.ball_loss(x, bb["label"].to(cuda_dev), bb["unk_channels"].to(cuda_dev), bb["mask"].to(cuda_dev), bb["volumes"].to(cuda_dev),
+                       bb["diameters"].to(cuda_dev), cls2, apply_dice_loss=True, diameter_margin=0.2, volume_margin=0.2, debug=dbg)
+    (out["ball_loss_bce"] + 0.5 * out["ball_loss_dice"]).backward()
+    for k in ("pseudo", "dilated", "penalize"):
+        assert len(dbg[k]) == len(dbg_ref[k])
+        for a, b in zip(dbg[k], dbg_ref[k]):
+            assert np.array_equal(pack(a), pack(b)), k
+    assert abs(out["ball_loss_bce"].item() - ref["ball_loss_bce"].item()) <= 1e-5
+    assert abs(out["ball_loss_dice"].item() - ref["ball_loss_dice"].item()) <= 1e-5
+    assert rel(x.grad.cpu(), ref_in.grad) <= 1e-4
+    if not cfg:
+        assert abs(out["ball_loss_bce"].item() - float(golden["ball_loss_bce"])) <= 1e-5
+        assert abs(out["ball_loss_dice"].item() - float(golden["ball_loss_dice"])) <= 1e-5
+
+
+def test_calculate_loss_dicts(cuda_dev, golden):
+    from oracle import losses_ref as LR
+    from rsuper_b200 import losses
+    bb, lgb, cls2 = _ball_inputs()
+    dev = cuda_dev
+    for tag, lossname, deep in (("ball_dice_last_deep", "ball_dice_last", True), ("dice", "dice", False),
+                                ("ball", "ball", False), ("both", "ball_dice_both", False)):
+        a = LR.default_args(loss=lossname)
+        lg = lgb.to(dev).requires_grad_(True)
+        mo = {"segmentation": [lg, lg * 0.5 + 0.1]} if deep else {"segmentation": lg}
+        res = losses.calculate_loss(mo, bb["label"].long().to(dev), bb["unk_channels"].float().to(dev), a, None, bb["mask"].float().to(dev),
+                                    bb["volumes"].to(dev), bb["diameters"].to(dev), cls2, input_tensor=bb["image"].to(dev))
+        assert sorted(res.keys()) == list(golden[f"calc::{tag}::keys"]), tag
+        for k, v in res.items():
+            assert abs(v.item() - float(golden[f"calc::{tag}::{k}"])) <= 1e-5, (tag, k, v.item(), float(golden[f"calc::{tag}::{k}"]))
+        res["overall"].backward()
+        assert abs(lg.grad.double().abs().sum().item() / float(golden[f"calc::{tag}::grad_sum"]) - 1) <= 1e-4, tag
+    # inconsistent report batch raises like the reference (:864-869)
+    with pytest.raises(ValueError):
+        losses.calculate_loss({"segmentation": lgb.to(dev).requires_grad_(True)}, bb["label"].long().to(dev),
+                              torch.zeros_like(bb["unk_channels"]).float().to(dev), LR.default_args(loss="ball"), None,
+                              bb["mask"].float().to(dev), bb["volumes"].to(dev), bb["diameters"].to(dev), cls2)
