@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #ifndef RSB_DEVICE
 #define RSB_DEVICE __device__ __forceinline__
@@ -83,6 +84,7 @@ RSB_DEVICE void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 26)) {
+      printf("rsb mbar_wait timeout: block %d thread %d barrier smem+0x%x parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
       __trap();
     }
   }

@@ -304,7 +304,7 @@ def test_seg_loss_forward_backward_vs_oracle(cuda_dev):
         st = ops.seg_loss_forward(lg, b3["label"], known.to(torch.uint8), cw)
         assert abs(st.loss_out[0].item() - ref.item()) <= 1e-5  # north star: loss within 1e-5
         dl = torch.zeros_like(lg)
-        ops.seg_loss_backward(st, torch.ones(1, device=cuda_dev), dl)
+        ops.seg_loss_backward(st, torch.ones(2, device=cuda_dev), dl)
         assert rel(dl, lz.grad) <= 1e-4
     # known=None path (mask-only batches, train_ddp.py:268-271)
     lz = lg.clone().requires_grad_(True)
@@ -326,7 +326,7 @@ def test_seg_loss_matches_golden(cuda_dev, golden):
     assert abs(st.loss_out[1].item() - float(golden["seg_bce"])) <= 1e-5
     assert abs(st.loss_out[2].item() - float(golden["seg_dice"])) <= 1e-5
     dl = torch.zeros_like(lg)
-    ops.seg_loss_backward(st, torch.ones(1, device=cuda_dev), dl)
+    ops.seg_loss_backward(st, torch.ones(2, device=cuda_dev), dl)
     np.testing.assert_allclose(dl.cpu().numpy()[:, :, ::4, ::4, ::4], golden["seg_grad"], rtol=2e-3, atol=1e-9)
 
 
