@@ -58,8 +58,8 @@ int rsb_num_sms(void);
 
 /* N tile the kernels use for a given Cout (packing and launch agree on it) */
 int rsb_conv3_n_tile(int Cout);
-/* bytes of the packed bf16 weight image for a (Cout, Cin) 3x3x3 conv; parts = 1, or 3 for the
- * split-precision image [hi | hi | lo] */
+/* bytes of the packed bf16 weight image for a (Cout, Cin) 3x3x3 conv; parts = 1, 3 for the split-precision
+ * image [hi | hi | lo], or 6 for the three-piece image [hi | lo | hi | lo2 | hi | lo] */
 size_t rsb_conv3_packed_weight_bytes(int Cout, int Cin, int parts);
 
 /* fp32 OIDHW [Cout][Cin][3][3][3] (the nn.Parameter layout) -> packed bf16 UMMA tiles.
@@ -78,6 +78,7 @@ typedef struct RsbConv3Args {
   const void* a;
   int a_pitch;
   const void* a_lo;
+  const void* a_lo2; /* third piece: 6-pass product carrying ~24 mantissa bits of both operands (weights packed with parts = 6) */
   /* packed weights from rsb_conv3_pack_weights */
   const void* w_packed;
   /* output */
@@ -132,11 +133,12 @@ int rsb_debug_set_wgrad_timing_buffer(void* device_ptr); /* profiling aid, see a
  * nn.InstanceNorm3d(eps=1e-4, affine=False) + nn.ReLU of ConvNormAct (conv_layers.py:39-49;
  * slope = 0 => ReLU, 0.01 => LeakyReLU) as one fused, 128-bit vectorised pass.  stats == NULL =>
  * plain cast.  lo != NULL additionally writes lo = bf16(value - hi) for the split-precision
- * (3 x bf16 ~ fp32) parity mode.  x has storage dtype `dtype`; hi / lo are always bf16.
+ * parity mode; lo2 != NULL (needs lo) a third piece lo2 = bf16(value - hi - lo), together ~24 mantissa bits.
+ * x has storage dtype `dtype`; hi / lo / lo2 are always bf16.
  * ------------------------------------------------------------------------------------------ */
 int rsb_norm_act(const void* x, int x_pitch, int dtype, const float* stats, float eps, float slope,
-                 void* hi, int hi_pitch, void* lo, int lo_pitch, int N, int D, int H, int W, int C,
-                 void* stream);
+                 void* hi, int hi_pitch, void* lo, int lo_pitch, void* lo2, int lo2_pitch, int N, int D, int H,
+                 int W, int C, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * stem conv 3x3x3 with Cin = 1 (inconv.conv1, model/dim3/unet_utils.py:15,18) — direct

@@ -143,7 +143,8 @@ RSB_DEVICE int butterfly_col(int lane) {
 
 template <typename T, int PZ>
 __global__ void __launch_bounds__(kFpThreads, 1)
-conv3_fprop_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const FpropDev a) {
+conv3_fprop_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+                   const __grid_constant__ CUtensorMap tm_lo2, const FpropDev a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   FpropSmem& sm = *reinterpret_cast<FpropSmem*>(smem_raw);
   const uint32_t a_base = smem_u32(smem_raw) + kFpCtrlBytes;  // 2 units
@@ -168,6 +169,7 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_const
     mbar_fence_init();
     tma_prefetch_desc(&tm_hi);
     tma_prefetch_desc(&tm_lo);
+    tma_prefetch_desc(&tm_lo2);
   }
   for (int i = threadIdx.x; i < kFpEpiWarps * kFpMaxNT * 2; i += kFpThreads) (&sm.stat[0][0][0])[i] = 0.f;
   if (warp == 3) {
@@ -192,7 +194,10 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_const
         if (elect_one()) {
           const uint32_t bar = smem_u32(&sm.a_full[ab]);
           mbar_arrive_expect_tx(bar, NP * kFpPlaneBytes);
-          tma_load_5d(a_base + ab * a.a_unit_bytes, part == 1 ? &tm_lo : &tm_hi, cb * 32, ic.x0 - 1, ic.y0 - 1, ic.z0 - 1, ic.n, bar);
+          // operand piece of this K part: 3 parts = [hi | lo | hi], 6 parts = [hi | hi | lo | hi | lo2 | lo]
+          const int piece = a.parts == 3 ? (part == 1 ? 1 : 0) : (a.parts == 6 ? ((0x120100 >> (4 * part)) & 0xF) : 0);
+          const CUtensorMap* tm = piece == 0 ? &tm_hi : (piece == 1 ? &tm_lo : &tm_lo2);
+          tma_load_5d(a_base + ab * a.a_unit_bytes, tm, cb * 32, ic.x0 - 1, ic.y0 - 1, ic.z0 - 1, ic.n, bar);
         }
         __syncwarp();
         if (++ab == 2) { ab = 0; aph ^= 1u; }
@@ -591,10 +596,12 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_const
 
 // ---------------------------------------------------------------------------------------------
 // weight packing: fp32 OIDHW -> bf16 [part][chunk][kh,kw (9)][N-tile][kd slot (3: kd = 2,1,0)][NT/8][4 (k/8)][8 (o%8)][8 (k%8)]
-// parts = 3 writes the split-precision image [hi | hi | lo] along K (pairs with the operand parts [hi | lo | hi]).
+// parts = 3 writes the split-precision image [hi | hi | lo] along K (pairs with the operand parts [hi | lo | hi]);
+// parts = 6 the three-piece image [hi | lo | hi | lo2 | hi | lo] (operand parts [hi | hi | lo | hi | lo2 | lo]):
+// all products down to 2^-24 of the fp32 operands.
 // ---------------------------------------------------------------------------------------------
 __global__ void pack_conv3_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cin, int transpose_flip,
-                                          int co_eff, int ci_eff, int NT, int ntiles, int nchunks, size_t total) {
+                                          int co_eff, int ci_eff, int NT, int ntiles, int nchunks, int parts, size_t total) {
   size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (i >= total) return;
   size_t t = i;
@@ -619,8 +626,14 @@ __global__ void pack_conv3_weights_kernel(const float* __restrict__ w, __nv_bflo
       v = w[(static_cast<size_t>(k) * Cin + o) * 27 + (26 - tap)];
     }
   }
-  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-  out[i] = (part == 2) ? __float2bfloat16_rn(v - __bfloat162float(hi)) : hi;
+  // weight piece of this part: 3 parts -> [0,0,1], 6 parts -> [0,1,0,2,0,1]
+  const int piece = parts == 3 ? (part == 2 ? 1 : 0) : (parts == 6 ? ((0x102010 >> (4 * part)) & 0xF) : 0);
+  __nv_bfloat16 q = __float2bfloat16_rn(v);
+  for (int k = 0; k < piece; ++k) {
+    v -= __bfloat162float(q);
+    q = __float2bfloat16_rn(v);
+  }
+  out[i] = q;
 }
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -635,15 +648,15 @@ static int pick_nt(int Cout) {
 }
 
 template <typename T, int PZ>
-static int launch_fprop(const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, const FpropDev& dev, int grid, size_t smem_bytes,
-                        cudaStream_t stream) {
+static int launch_fprop(const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, const CUtensorMap& tm_lo2, const FpropDev& dev, int grid,
+                        size_t smem_bytes, cudaStream_t stream) {
   auto kern = conv3_fprop_kernel<T, PZ>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes));
   if (e != cudaSuccess) {
     set_last_error("conv3: cudaFuncSetAttribute(%zu B smem) failed: %s", smem_bytes, cudaGetErrorString(e));
     return -2;
   }
-  kern<<<grid, kFpThreads, smem_bytes, stream>>>(tm_hi, tm_lo, dev);
+  kern<<<grid, kFpThreads, smem_bytes, stream>>>(tm_hi, tm_lo, tm_lo2, dev);
   return check_launch("conv3_fprop_kernel");
 }
 
@@ -672,7 +685,7 @@ extern "C" int rsb_conv3_pack_weights(const float* w_oidhw, void* packed, int Co
                                       void* stream) {
   RSB_REQUIRE(w_oidhw && packed, "pack_weights: null pointer");
   RSB_REQUIRE(Cout > 0 && Cin > 0, "pack_weights: bad channel counts");
-  RSB_REQUIRE(parts == 1 || parts == 3, "pack_weights: parts must be 1 or 3");
+  RSB_REQUIRE(parts == 1 || parts == 3 || parts == 6, "pack_weights: parts must be 1, 3 or 6");
   const int co_eff = transpose_flip ? Cin : Cout;
   const int ci_eff = transpose_flip ? Cout : Cin;
   const int NT = pick_nt(co_eff);
@@ -682,7 +695,7 @@ extern "C" int rsb_conv3_pack_weights(const float* w_oidhw, void* packed, int Co
   const int threads = 256;
   const unsigned blocks = static_cast<unsigned>((total + threads - 1) / threads);
   pack_conv3_weights_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
-      w_oidhw, reinterpret_cast<__nv_bfloat16*>(packed), Cin, transpose_flip, co_eff, ci_eff, NT, ntiles, nchunks, total);
+      w_oidhw, reinterpret_cast<__nv_bfloat16*>(packed), Cin, transpose_flip, co_eff, ci_eff, NT, ntiles, nchunks, parts, total);
   return check_launch("pack_conv3_weights_kernel");
 }
 
@@ -713,7 +726,8 @@ extern "C" int rsb_conv3_forward(const RsbConv3Args* p, void* stream) {
   d.eps = p->eps; d.slope = p->slope;
   d.inv_count = 1.0f / (static_cast<float>(p->D) * p->H * p->W);
   d.dbg = g_timing_buffer;
-  d.parts = p->a_lo != nullptr ? 3 : 1;
+  RSB_REQUIRE(!p->a_lo2 || p->a_lo, "conv3: a_lo2 needs a_lo");
+  d.parts = p->a_lo2 != nullptr ? 6 : (p->a_lo != nullptr ? 3 : 1);
 
   const int co_pad = round_up(p->Cout, 16);
   d.NT = pick_nt(p->Cout);
@@ -763,10 +777,12 @@ extern "C" int rsb_conv3_forward(const RsbConv3Args* p, void* stream) {
   size_t smem = fixed + static_cast<size_t>(stages) * d.b_stage_bytes;
   if (smem < 120 * 1024) smem = 120 * 1024;  // force 1 CTA / SM: each CTA owns all 512 TMEM columns
 
-  CUtensorMap tm_hi, tm_lo;
+  CUtensorMap tm_hi, tm_lo, tm_lo2;
   int rc = make_act_tensor_map(&tm_hi, p->a, p->a_pitch, p->Cin, p->N, p->D, p->H, p->W, 32, 10, 18, PZ + 2);
   if (rc) return rc;
   rc = make_act_tensor_map(&tm_lo, p->a_lo ? p->a_lo : p->a, p->a_pitch, p->Cin, p->N, p->D, p->H, p->W, 32, 10, 18, PZ + 2);
+  if (rc) return rc;
+  rc = make_act_tensor_map(&tm_lo2, p->a_lo2 ? p->a_lo2 : p->a, p->a_pitch, p->Cin, p->N, p->D, p->H, p->W, 32, 10, 18, PZ + 2);
   if (rc) return rc;
 
   const int grid = static_cast<int>(items < sms ? items : sms);
@@ -774,9 +790,9 @@ extern "C" int rsb_conv3_forward(const RsbConv3Args* p, void* stream) {
 
 #define RSB_DISPATCH(TT)                                                          \
   switch (PZ) {                                                                   \
-    case 1: return launch_fprop<TT, 1>(tm_hi, tm_lo, d, grid, smem, st);          \
-    case 2: return launch_fprop<TT, 2>(tm_hi, tm_lo, d, grid, smem, st);          \
-    default: return launch_fprop<TT, 4>(tm_hi, tm_lo, d, grid, smem, st);         \
+    case 1: return launch_fprop<TT, 1>(tm_hi, tm_lo, tm_lo2, d, grid, smem, st);          \
+    case 2: return launch_fprop<TT, 2>(tm_hi, tm_lo, tm_lo2, d, grid, smem, st);          \
+    default: return launch_fprop<TT, 4>(tm_hi, tm_lo, tm_lo2, d, grid, smem, st);         \
   }
   if (p->dtype == RSB_BF16) {
     RSB_DISPATCH(__nv_bfloat16)

@@ -27,7 +27,7 @@ class RsbConv3Args(C.Structure):
         ("N", c_int), ("D", c_int), ("H", c_int), ("W", c_int),
         ("Cin", c_int), ("Cout", c_int),
         ("dtype", c_int),
-        ("a", c_void_p), ("a_pitch", c_int), ("a_lo", c_void_p),
+        ("a", c_void_p), ("a_pitch", c_int), ("a_lo", c_void_p), ("a_lo2", c_void_p),
         ("w_packed", c_void_p),
         ("y", c_void_p), ("y_pitch", c_int),
         ("res", c_void_p), ("res_pitch", c_int),
@@ -75,7 +75,7 @@ SIGNATURES = {
     "rsb_conv3_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "rsb_conv3_wgrad": (c_int, [C.POINTER(RsbConv3WgradArgs), c_void_p]),
     "rsb_norm_act": (c_int, [c_void_p, c_int, c_int, c_void_p, c_float, c_float, c_void_p, c_int, c_void_p, c_int,
-                             c_int, c_int, c_int, c_int, c_int, c_void_p]),
+                             c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "rsb_stem_conv_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
                                       c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "rsb_stem_conv_wgrad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p,

@@ -90,19 +90,20 @@ def new_stats(n, c, device) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------
 # conv 3x3x3
 # --------------------------------------------------------------------------------------------
-def conv3_pack_weights(w: torch.Tensor, transpose_flip: bool = False, split: bool = False) -> torch.Tensor:
-    """fp32 OIDHW [Cout,Cin,3,3,3] -> packed bf16 UMMA image (uint8 buffer); split => [hi | hi | lo] parts."""
+def conv3_pack_weights(w: torch.Tensor, transpose_flip: bool = False, split=False) -> torch.Tensor:
+    """fp32 OIDHW [Cout,Cin,3,3,3] -> packed bf16 UMMA image (uint8 buffer); split = True / 3 => [hi | hi | lo] parts,
+    split = 6 => the three-piece image [hi | lo | hi | lo2 | hi | lo]."""
     assert w.dtype == torch.float32 and w.is_cuda and w.is_contiguous() and w.shape[2:] == (3, 3, 3)
     cout, cin = w.shape[0], w.shape[1]
     co_eff, ci_eff = (cin, cout) if transpose_flip else (cout, cin)
-    parts = 3 if split else 1
+    parts = 6 if split == 6 else (3 if split else 1)
     nbytes = lib().rsb_conv3_packed_weight_bytes(co_eff, ci_eff, parts)
     out = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
     _call("pack_weights", 1, 0.0, lib().rsb_conv3_pack_weights, _p(w), _p(out), cout, cin, int(transpose_flip), parts, _stream(), what="conv3_pack_weights")
     return out
 
 
-def conv3_forward(a_op, w_packed, y, *, a_lo=None, slope=0.0, res=None, out_stats=None,
+def conv3_forward(a_op, w_packed, y, *, a_lo=None, a_lo2=None, slope=0.0, res=None, out_stats=None,
                   mask_x=None, mask_stats=None, bwd_sums=None, planes_per_item=0, max_ctas=0, eps=EPS_IN):
     """y = conv3x3x3(a_op) [+ res]; a_op is the bf16 operand from norm_act (a_lo: its split-precision low part,
     with weights packed split=True); optional fused output statistics / dgrad masking epilogue."""
@@ -116,6 +117,9 @@ def conv3_forward(a_op, w_packed, y, *, a_lo=None, slope=0.0, res=None, out_stat
     if a_lo is not None:
         assert a_lo.shape == a_op.shape and a_lo.dtype == torch.bfloat16 and _check_cl(a_lo, "a_lo") == a.a_pitch
         a.a_lo = _p(a_lo)
+    if a_lo2 is not None:
+        assert a_lo is not None and a_lo2.shape == a_op.shape and a_lo2.dtype == torch.bfloat16 and _check_cl(a_lo2, "a_lo2") == a.a_pitch
+        a.a_lo2 = _p(a_lo2)
     a.eps, a.slope = eps, slope
     a.w_packed = _p(w_packed)
     a.y, a.y_pitch = _p(y), _check_cl(y, "y")
@@ -166,13 +170,17 @@ def conv3_wgrad(a_op, dy, dw, *, accumulate=False, max_ctas=0):
 
 
 def norm_act(x, stats=None, *, slope=0.0, eps=EPS_IN, split=False, out=None):
-    """Conv operand tensor(s): hi = bf16(act(instnorm(x))) [, lo = bf16(value - hi)]; stats=None => cast/split."""
+    """Conv operand tensor(s): hi = bf16(act(instnorm(x))) [, lo = bf16(value - hi) [, lo2 = bf16(value - hi - lo)]];
+    split = False | True (hi, lo) | 3 (hi, lo, lo2); stats=None => cast / split only."""
     n, d, h, w_, c = x.shape
     hi = out if out is not None else torch.empty((n, d, h, w_, c), dtype=torch.bfloat16, device=x.device)
     lo = torch.empty((n, d, h, w_, c), dtype=torch.bfloat16, device=x.device) if split else None
+    lo2 = torch.empty((n, d, h, w_, c), dtype=torch.bfloat16, device=x.device) if split == 3 else None
     _call("norm_act", 1, 0.0, lib().rsb_norm_act, _p(x), _check_cl(x, "x"), dtype_code(x), _st(stats, x, "stats"), eps, slope,
-          _p(hi), _check_cl(hi, "hi"), _p(lo), _check_cl(lo, "lo") if lo is not None else 0, n, d, h, w_, c, _stream(),
-          what="norm_act")
+          _p(hi), _check_cl(hi, "hi"), _p(lo), _check_cl(lo, "lo") if lo is not None else 0,
+          _p(lo2), _check_cl(lo2, "lo2") if lo2 is not None else 0, n, d, h, w_, c, _stream(), what="norm_act")
+    if split == 3:
+        return hi, lo, lo2
     return (hi, lo) if split else hi
 
 

@@ -119,8 +119,10 @@ class _Engine:
 
     precision 'bf16': bf16 activation storage, bf16 tensor-core operands (one MMA pass), fp32 accumulation.
     precision 'fp32': fp32 activation storage; every tensor-core product is the 3-pass split
-                      a_hi*w_hi + a_lo*w_hi + a_hi*w_lo of bf16 halves (~2^-17 relative, fp32 accumulation) —
-                      the parity mode measured against the fp32 reference."""
+                      a_hi*w_hi + a_lo*w_hi + a_hi*w_lo of bf16 halves (~2^-17 per operand, fp32 accumulation) — the
+                      parity mode measured against the fp32 reference.  (The kernels also take a third piece / six
+                      products, but the tensor pipe's truncating fp32 accumulation already bounds a conv at ~1e-5 of
+                      its output range, so the third piece buys nothing — tests/test_kernels_gpu.py.)"""
 
     def __init__(self, base_ch: int, slope: float, dtype: torch.dtype):
         self.b = base_ch
@@ -130,15 +132,16 @@ class _Engine:
 
     # ---- operand / conv / wgrad helpers ------------------------------------------------------------
     def _operand(self, t: torch.Tensor, stats=None):
-        """(hi, lo) bf16 conv operand of a stored tensor: act(instnorm(t)) when stats are given, else t itself."""
+        """bf16 conv operand pieces of a stored tensor: (hi,) in bf16 mode, (hi, lo) in fp32 mode;
+        act(instnorm(t)) when stats are given, else t itself."""
         if stats is None and not self.split and t.dtype == torch.bfloat16:
-            return (t, None)
+            return (t,)
         r = ops.norm_act(t, stats, slope=self.slope, split=self.split)
-        return r if self.split else (r, None)
+        return r if self.split else (r,)
 
     def _conv(self, op, w, y, flip=False, **kw):
         wp = ops.conv3_pack_weights(w, flip, split=self.split)
-        return ops.conv3_forward(op[0], wp, y, a_lo=op[1], slope=self.slope, **kw)
+        return ops.conv3_forward(op[0], wp, y, a_lo=op[1] if self.split else None, slope=self.slope, **kw)
 
     def _wgrad(self, a_op, dy_op, dw):
         ops.conv3_wgrad(a_op[0], dy_op[0], dw)

@@ -40,11 +40,12 @@ def test_argument_validation_returns_errors_without_a_gpu():
     assert lib.rsb_dilate_ball(None, None, None, 1, 4, 4, 4, 5, None) != 0
     assert lib.rsb_conv3_packed_weight_bytes(32, 32, 1) == 27 * 32 * 64
     assert lib.rsb_conv3_packed_weight_bytes(40, 24, 3) == 3 * 27 * 48 * 64
+    assert lib.rsb_conv3_packed_weight_bytes(32, 64, 6) == 6 * 2 * 27 * 32 * 64
     assert [lib.rsb_conv3_n_tile(c) for c in (32, 64, 96, 192, 320, 576, 640)] == [32, 64, 96, 96, 80, 96, 128]
     w = _lib.RsbConv3WgradArgs()
     assert lib.rsb_conv3_wgrad(ctypes.byref(w), None) != 0 and b"null" in lib.rsb_last_error()
     assert lib.rsb_conv3_wgrad_workspace_bytes(64, 96, 148) > 0
-    assert lib.rsb_norm_act(None, 8, 0, None, 1e-4, 0.0, None, 8, None, 0, 1, 4, 4, 4, 8, None) != 0
+    assert lib.rsb_norm_act(None, 8, 0, None, 1e-4, 0.0, None, 8, None, 0, None, 0, 1, 4, 4, 4, 8, None) != 0
     with pytest.raises(RuntimeError):
         _lib.check(-1, "unit-test")
 

@@ -95,6 +95,14 @@ def test_conv3_split_precision_matches_fp32(cuda_dev):
         ops.conv3_forward(hi, ops.conv3_pack_weights(w, split=True), y, a_lo=lo)
         ref = cl(F.conv3d(act_ref(nc(x), 0.0), w, padding=1))
         assert rel(y, ref) <= 3e-5
+        # three pieces per operand, six products: the operands are then exact to ~2^-24, but the result is not better —
+        # the floor (~1e-5 of the output range) is the tensor pipe's truncating fp32 accumulation, which is why
+        # precision='fp32' stops at two pieces
+        hi, lo, lo2 = ops.norm_act(x, stats_of(x), split=3)
+        assert rel((hi.double() + lo.double() + lo2.double()).float(), cl(act_ref(nc(x), 0.0))) <= 2e-6
+        ops.conv3_forward(hi, ops.conv3_pack_weights(w, split=6), y, a_lo=lo, a_lo2=lo2)
+        ref64 = cl(F.conv3d(act_ref(nc(x), 0.0).double(), w.double(), padding=1))
+        assert rel(y.double(), ref64) <= 3e-5
 
 
 def test_conv3_channel_slices_and_stats_pitch(cuda_dev):

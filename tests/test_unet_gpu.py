@@ -83,6 +83,7 @@ def test_forward_accuracy_vs_fp64_truth(cuda_dev, precision, slope, side):
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_backward_accuracy_vs_fp64_truth(cuda_dev, precision):
+    S = 64 if precision == "fp32" else 32   # fp32 bars are checked on a patch whose bottom level is 4^3, not 2^3, voxels
     from oracle import losses_ref as LR
     from oracle import synth
     from oracle.unet_ref import synthetic_image, unet_forward
