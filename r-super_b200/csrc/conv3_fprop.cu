@@ -57,8 +57,10 @@ struct FpropDev {
   // derived
   int NT, ntiles, nchunks, parts, last_ksteps;
   int tiles_x, tiles_y, zblocks, num_items;
+  uint32_t mg_nt, mg_tx, mg_ty, mg_zb;  // ceil(2^32 / divisor): exact quotients for dividends < 2^31 / divisor range used here
   int b_stages;
   int issuers;  // 1 or 2 MMA issuer warps
+  int acc_stages;  // TMEM accumulator stages: 2..4 (as many as fit 512 columns)
   int tps;      // filter taps per B stage: 3 (one kh row) for narrow N tiles, else 1
   uint32_t b_tap_bytes, b_stage_bytes, a_unit_bytes;
   long long* dbg;
@@ -67,7 +69,7 @@ struct FpropDev {
 struct __align__(16) FpropSmem {
   uint64_t a_full[2], a_empty[2];
   uint64_t b_full[kFpMaxBStages], b_empty[kFpMaxBStages];
-  uint64_t acc_full[2], acc_empty[2];
+  uint64_t acc_full[4], acc_empty[4];
   uint32_t tmem_base;
   uint32_t pad_[3];
   float stat[kFpEpiWarps][kFpMaxNT][2];  // per epilogue warp partial (sum, sumsq) / (S1, S2)
@@ -78,14 +80,20 @@ constexpr int kFpCtrlBytes = (sizeof(FpropSmem) + 1023) / 1024 * 1024;
 struct FpItem {
   int n, z0, y0, x0, n0, nt;
 };
+// q = t / d for 0 <= t < 2^31 via a precomputed magic m = ceil(2^32 / d) (exact while t * (m*d - 2^32) < 2^32, i.e. for
+// every item index / divisor of this kernel: host-checked); four of these replace ~100 instructions of integer division
+// that every role executed per work item.
+RSB_DEVICE int fast_div(int t, uint32_t magic, int d) {
+  return d == 1 ? t : static_cast<int>(__umulhi(static_cast<uint32_t>(t), magic));
+}
 template <int PZ>
 RSB_DEVICE FpItem fp_decode_item(const FpropDev& a, int item) {
   FpItem c;
-  int t = item;
-  c.nt = t % a.ntiles; t /= a.ntiles;
-  const int xt = t % a.tiles_x; t /= a.tiles_x;
-  const int yt = t % a.tiles_y; t /= a.tiles_y;
-  const int zb = t % a.zblocks; t /= a.zblocks;
+  int t = item, q;
+  q = fast_div(t, a.mg_nt, a.ntiles); c.nt = t - q * a.ntiles; t = q;
+  q = fast_div(t, a.mg_tx, a.tiles_x); const int xt = t - q * a.tiles_x; t = q;
+  q = fast_div(t, a.mg_ty, a.tiles_y); const int yt = t - q * a.tiles_y; t = q;
+  q = fast_div(t, a.mg_zb, a.zblocks); const int zb = t - q * a.zblocks; t = q;
   c.n = t;
   c.z0 = zb * PZ;
   c.y0 = yt * 16;
@@ -159,6 +167,8 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_const
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&sm.a_full[i]), 1);
       mbar_init(smem_u32(&sm.a_empty[i]), a.issuers);   // every MMA issuer warp releases a unit
+    }
+    for (int i = 0; i < 4; ++i) {
       mbar_init(smem_u32(&sm.acc_full[i]), a.issuers);  // ... and publishes an accumulator stage
       mbar_init(smem_u32(&sm.acc_empty[i]), kFpEpiWarps * 32);
     }
@@ -313,7 +323,7 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_const
         }
         if (++ab == 2) { ab = 0; aph ^= 1u; }
       }
-      if (++as == 2) { as = 0; asph ^= 1u; }
+      if (++as == static_cast<uint32_t>(a.acc_stages)) { as = 0; asph ^= 1u; }
       ++n_items;
     }
     if (dbg && lane == 0) {
@@ -420,7 +430,7 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_const
         __syncwarp();
         if (++ab == 2) { ab = 0; aph ^= 1u; }
       }
-      if (++as == 2) { as = 0; asph ^= 1u; }
+      if (++as == static_cast<uint32_t>(a.acc_stages)) { as = 0; asph ^= 1u; }
       ++n_items;
     }
     if (dbg && lane == 0) {
@@ -501,11 +511,6 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_const
         float s1[16], s2[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
-        float mmean[16], mrstd[16];
-        if (mask_mode) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) { mmean[j] = sm.mstat[cc + j][0]; mrstd[j] = sm.mstat[cc + j][1]; }
-        }
 #pragma unroll
         for (int p = 0; p < PZ; ++p) {
           if (p >= nplanes || (p_step == 2 && (p & 1) != eset)) continue;  // warp-uniform
@@ -531,7 +536,7 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_const
             } else {
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                const float h = (xh[j] - mmean[j]) * mrstd[j];
+                const float h = (xh[j] - sm.mstat[cc + j][0]) * sm.mstat[cc + j][1];
                 v[j] = h > 0.f ? v[j] : v[j] * a.slope;
                 s1[j] += v[j];
                 s2[j] = fmaf(v[j], h, s2[j]);
@@ -563,7 +568,7 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_const
       }
       tc_fence_before_sync();
       mbar_arrive(smem_u32(&sm.acc_empty[as]));
-      if (++as == 2) { as = 0; asph ^= 1u; }
+      if (++as == static_cast<uint32_t>(a.acc_stages)) { as = 0; asph ^= 1u; }
       if (want_stats) {
         __syncwarp();
         for (int col = lane; col < a.NT; col += 32) {
@@ -753,6 +758,12 @@ extern "C" int rsb_conv3_forward(const RsbConv3Args* p, void* stream) {
   }
   RSB_REQUIRE(PZ == 1 || PZ == 2 || PZ == 4, "conv3: planes_per_item must be 1, 2 or 4 (got %d)", PZ);
   RSB_REQUIRE(2 * PZ * d.NT <= 512, "conv3: 2*PZ*n_tile = %d exceeds the 512 TMEM columns", 2 * PZ * d.NT);
+  d.acc_stages = 512 / (PZ * d.NT);
+  if (d.acc_stages > 4) d.acc_stages = 4;
+  {
+    const char* e = getenv("RSB_FPROP_ACC_STAGES");
+    if (e && e[0] >= '2' && e[0] <= '4' && (e[0] - '0') <= d.acc_stages) d.acc_stages = e[0] - '0';
+  }
   RSB_REQUIRE(3 * d.NT <= 256 || PZ <= 2, "conv3: merged N exceeds 256");
   {
     // One issuer warp by default.  The two-issuer schedule (alternate taps, see the kernel) is 15-30 % faster on the
@@ -765,6 +776,15 @@ extern "C" int rsb_conv3_forward(const RsbConv3Args* p, void* stream) {
   const long long items = static_cast<long long>(p->N) * d.zblocks * d.tiles_y * d.tiles_x * d.ntiles;
   RSB_REQUIRE(items < (1LL << 31), "conv3: too many work items");
   d.num_items = static_cast<int>(items);
+  {
+    auto magic = [&](int dv, uint32_t& m) {
+      m = dv > 1 ? static_cast<uint32_t>((0x100000000ULL + dv - 1) / dv) : 0u;
+      // exactness bound of the round-up method: t * e < 2^32 with e = m*dv - 2^32 < dv
+      return dv == 1 || static_cast<unsigned long long>(items) * static_cast<unsigned long long>(dv) < 0x100000000ULL;
+    };
+    RSB_REQUIRE(magic(d.ntiles, d.mg_nt) && magic(d.tiles_x, d.mg_tx) && magic(d.tiles_y, d.mg_ty) && magic(d.zblocks, d.mg_zb),
+                "conv3: work-item count too large for the fast index decode");
+  }
   d.b_tap_bytes = 3u * d.NT * 64u;
   d.tps = (d.NT <= 64 && d.issuers == 1) ? 3 : 1;
   d.b_stage_bytes = d.tps * d.b_tap_bytes;

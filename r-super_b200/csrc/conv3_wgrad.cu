@@ -309,46 +309,40 @@ conv3_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_const
   }
 }
 
-// Deterministic reduction of the per-CTA partials into fp32 OIDHW.  A block owns 64 consecutive piece elements; its
-// 256 threads split the ranks four ways (fixed partition => bit-reproducible), with the loads of one thread unrolled
-// so that a whole batch is in flight: the first version walked up to 148 ranks with one dependent load at a time.
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgradDev a, float* __restrict__ dw, int accumulate) {
-  __shared__ float part[4][64];
+// Deterministic reduction of the per-CTA partials into fp32 OIDHW (fixed summation order => bit-reproducible).
+// One thread per element walks the ranks with four independent accumulators so that several loads are in flight.
+__global__ void wgrad_reduce_kernel(const WgradDev a, float* __restrict__ dw, int accumulate) {
   const long long total = static_cast<long long>(a.n_groups) * a.piece_floats;
-  const int ex = threadIdx.x & 63, ry = threadIdx.x >> 6;
-  for (long long base = static_cast<long long>(blockIdx.x) * 64; base < total; base += static_cast<long long>(gridDim.x) * 64) {
-    const long long e = base + ex;
-    float acc = 0.f;
-    if (e < total) {
-      const int group = static_cast<int>(e / a.piece_floats);
-      const size_t pe = static_cast<size_t>(e % a.piece_floats);
-      const float* src = a.ws + static_cast<size_t>(group) * a.piece_floats + pe;
-      const size_t rstride = static_cast<size_t>(a.n_groups) * a.piece_floats;
-#pragma unroll 8
-      for (int rk = ry; rk < a.ranks; rk += 4) acc += src[static_cast<size_t>(rk) * rstride];
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+       e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int group = static_cast<int>(e / a.piece_floats);
+    const size_t pe = static_cast<size_t>(e % a.piece_floats);
+    int r = static_cast<int>(pe);
+    const int ci = r % a.ITc; r /= a.ITc;
+    const int co = r % a.OT; r /= a.OT;
+    const int kh = r % 3; r /= 3;
+    const int ti = r % a.TS; r /= a.TS;
+    const int off = r;  // 0..2
+    const int tapset = group % a.n_tapsets;
+    const int itile = (group / a.n_tapsets) % a.n_itiles;
+    const int otile = group / (a.n_tapsets * a.n_itiles);
+    const int o = otile * a.OT + co, i = itile * a.ITc + ci;
+    if (o >= a.Cout || i >= a.Cin) continue;
+    const int tap = (2 - off) * 9 + kh * 3 + tapset * a.TS + ti;
+    const float* src = a.ws + static_cast<size_t>(group) * a.piece_floats + pe;
+    const size_t rstride = static_cast<size_t>(a.n_groups) * a.piece_floats;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int rk = 0;
+    for (; rk + 4 <= a.ranks; rk += 4) {
+      a0 += src[static_cast<size_t>(rk) * rstride];
+      a1 += src[static_cast<size_t>(rk + 1) * rstride];
+      a2 += src[static_cast<size_t>(rk + 2) * rstride];
+      a3 += src[static_cast<size_t>(rk + 3) * rstride];
     }
-    part[ry][ex] = acc;
-    __syncthreads();
-    if (ry == 0 && e < total) {
-      const float sum = (part[0][ex] + part[1][ex]) + (part[2][ex] + part[3][ex]);
-      const int group = static_cast<int>(e / a.piece_floats);
-      int r = static_cast<int>(e % a.piece_floats);
-      const int ci = r % a.ITc; r /= a.ITc;
-      const int co = r % a.OT; r /= a.OT;
-      const int kh = r % 3; r /= 3;
-      const int ti = r % a.TS; r /= a.TS;
-      const int off = r;  // 0..2
-      const int tapset = group % a.n_tapsets;
-      const int itile = (group / a.n_tapsets) % a.n_itiles;
-      const int otile = group / (a.n_tapsets * a.n_itiles);
-      const int o = otile * a.OT + co, i = itile * a.ITc + ci;
-      if (o < a.Cout && i < a.Cin) {
-        const int tap = (2 - off) * 9 + kh * 3 + tapset * a.TS + ti;
-        float* dst = dw + (static_cast<size_t>(o) * a.Cin + i) * 27 + tap;
-        *dst = accumulate ? (*dst + sum) : sum;
-      }
-    }
-    __syncthreads();
+    for (; rk < a.ranks; ++rk) a0 += src[static_cast<size_t>(rk) * rstride];
+    const float acc = (a0 + a1) + (a2 + a3);
+    float* dst = dw + (static_cast<size_t>(o) * a.Cin + i) * 27 + tap;
+    *dst = accumulate ? (*dst + acc) : acc;
   }
 }
 
@@ -489,8 +483,8 @@ extern "C" int rsb_conv3_wgrad(const RsbConv3WgradArgs* p, void* stream) {
   rc = check_launch("conv3_wgrad_kernel");
   if (rc) return rc;
   const long long total = static_cast<long long>(d.n_groups) * d.piece_floats;
-  int rblocks = static_cast<int>((total + 63) / 64);
+  int rblocks = static_cast<int>((total + 127) / 128);
   if (rblocks > sms * 16) rblocks = sms * 16;
-  wgrad_reduce_kernel<<<rblocks, 256, 0, st>>>(d, p->dw_oidhw, p->accumulate);
+  wgrad_reduce_kernel<<<rblocks, 128, 0, st>>>(d, p->dw_oidhw, p->accumulate);
   return check_launch("wgrad_reduce_kernel");
 }
