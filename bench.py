@@ -210,6 +210,7 @@ def main():
     ap.add_argument("--base", type=int, default=32)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--trace", default=None, help="write the per-launch CUDA-event timeline of the timed region to this file")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -327,9 +328,18 @@ def main():
     if rank == 0:
         peaks = load_peaks()
         fam = {}
-        for name, flops, a, b in prof:
+        for name, flops, a, b, _desc in prof:
             d = fam.setdefault(name, [0.0, 0.0, 0])
             d[0] += a.elapsed_time(b); d[1] += flops; d[2] += 1
+        if args.trace:
+            with open(args.trace, "w") as f:
+                agg = {}
+                for name, flops, a, b, desc in prof:
+                    d = agg.setdefault(desc, [0.0, 0.0, 0])
+                    d[0] += a.elapsed_time(b); d[1] += flops; d[2] += 1
+                for desc, (ms, fl, cnt) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+                    tf = f"{fl / (ms * 1e-3) / 1e12:7.0f} TF/s" if fl > 0 else " " * 12
+                    f.write(f"{ms / args.steps:8.3f} ms/step  {cnt / args.steps:5.1f} launches  {ms / cnt * 1e3:8.1f} us  {tf}  {desc}\n")
         kern = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[2] / args.steps,
                     "tflops": (v[1] / (v[0] * 1e-3) / 1e12) if v[0] > 0 and v[1] > 0 else None} for k, v in fam.items()}
         dom = fam.get("conv3_igemm", [0.0, 0.0, 0])

@@ -23,7 +23,7 @@ LAUNCHES = 0
 PROFILE = None
 
 
-def _call(family: str, nkern: int, flops: float, fn, *args, what: str):
+def _call(family: str, nkern: int, flops: float, fn, *args, what: str, desc: str = ""):
     global LAUNCHES
     LAUNCHES += nkern
     if PROFILE is None:
@@ -33,7 +33,7 @@ def _call(family: str, nkern: int, flops: float, fn, *args, what: str):
     a.record()
     rc = fn(*args)
     b.record()
-    PROFILE.append((family, flops, a, b))
+    PROFILE.append((family, flops, a, b, what + (" " + desc if desc else "")))
     check(rc, what)
 
 
@@ -132,7 +132,8 @@ def conv3_forward(a_op, w_packed, y, *, a_lo=None, a_lo2=None, slope=0.0, res=No
         a.mask_x, a.mask_x_pitch = _p(mask_x), _check_cl(mask_x, "mask_x")
         a.mask_stats, a.bwd_sums = _st(mask_stats, mask_x, "mask_stats"), _st(bwd_sums, mask_x, "bwd_sums")
     a.planes_per_item, a.max_ctas = planes_per_item, max_ctas
-    _call("conv3_igemm", 1, 2.0 * 27 * cin * cout * n * d * h * w_, lib().rsb_conv3_forward, C.byref(a), _stream(), what="conv3_forward")
+    _call("conv3_igemm", 1, 2.0 * 27 * cin * cout * n * d * h * w_, lib().rsb_conv3_forward, C.byref(a), _stream(), what="conv3_forward",
+          desc=f"{cin}->{cout} {n}x{d}x{h}x{w_}{' dgrad' if mask_x is not None else ''}{' res' if res is not None else ''}")
     return y
 
 
@@ -165,7 +166,8 @@ def conv3_wgrad(a_op, dy, dw, *, accumulate=False, max_ctas=0):
     ws = _wgrad_workspace(cout, cin, a_op.device)
     a.workspace, a.workspace_bytes = _p(ws), ws.numel()
     a.max_ctas = max_ctas
-    _call("conv3_wgrad", 2, 2.0 * 27 * cin * cout * n * d * h * w_, lib().rsb_conv3_wgrad, C.byref(a), _stream(), what="conv3_wgrad")
+    _call("conv3_wgrad", 2, 2.0 * 27 * cin * cout * n * d * h * w_, lib().rsb_conv3_wgrad, C.byref(a), _stream(), what="conv3_wgrad",
+          desc=f"{cin}x{cout} {n}x{d}x{h}x{w_}")
     return dw
 
 
@@ -178,7 +180,7 @@ def norm_act(x, stats=None, *, slope=0.0, eps=EPS_IN, split=False, out=None):
     lo2 = torch.empty((n, d, h, w_, c), dtype=torch.bfloat16, device=x.device) if split == 3 else None
     _call("norm_act", 1, 0.0, lib().rsb_norm_act, _p(x), _check_cl(x, "x"), dtype_code(x), _st(stats, x, "stats"), eps, slope,
           _p(hi), _check_cl(hi, "hi"), _p(lo), _check_cl(lo, "lo") if lo is not None else 0,
-          _p(lo2), _check_cl(lo2, "lo2") if lo2 is not None else 0, n, d, h, w_, c, _stream(), what="norm_act")
+          _p(lo2), _check_cl(lo2, "lo2") if lo2 is not None else 0, n, d, h, w_, c, _stream(), what="norm_act", desc=f"{c} {n}x{d}x{h}x{w_}")
     if split == 3:
         return hi, lo, lo2
     return (hi, lo) if split else hi
@@ -232,7 +234,7 @@ def head_backward(x, w, dlogits, dx, dw, db):
 def maxpool2_forward(x, y, out_stats=None):
     n, d, h, w_, c = x.shape
     _call("pool", 1, 0.0, lib().rsb_maxpool2_forward, _p(x), _check_cl(x, "x"), _p(y), _check_cl(y, "y"), dtype_code(x),
-                                     _st(out_stats, y, "out_stats"), n, d, h, w_, c, _stream(), what="maxpool2_forward")
+                                     _st(out_stats, y, "out_stats"), n, d, h, w_, c, _stream(), what="maxpool2_forward", desc=f"{c} {n}x{d}x{h}x{w_}")
     return y
 
 
@@ -240,7 +242,7 @@ def maxpool2_backward(x, dy, dx, dskip=None):
     n, d, h, w_, c = x.shape
     _call("pool", 1, 0.0, lib().rsb_maxpool2_backward, _p(x), _check_cl(x, "x"), _p(dy), _check_cl(dy, "dy"), _p(dskip),
                                       _check_cl(dskip, "dskip") if dskip is not None else 0, _p(dx),
-                                      _check_cl(dx, "dx"), dtype_code(x), n, d, h, w_, c, _stream(), what="maxpool2_backward")
+                                      _check_cl(dx, "dx"), dtype_code(x), n, d, h, w_, c, _stream(), what="maxpool2_backward", desc=f"{c} {n}x{d}x{h}x{w_}")
     return dx
 
 
@@ -249,7 +251,7 @@ def upsample_forward(x, y, out_stats=None):
     _, do, ho, wo, _ = y.shape
     _call("upsample", 1, 0.0, lib().rsb_upsample_trilinear_forward, _p(x), _check_cl(x, "x"), _p(y), _check_cl(y, "y"),
                                                dtype_code(x), _st(out_stats, y, "out_stats"), n, di, hi, wi, do, ho, wo, c,
-                                               _stream(), what="upsample_forward")
+                                               _stream(), what="upsample_forward", desc=f"{c} {n}x{do}x{ho}x{wo}")
     return y
 
 
@@ -257,7 +259,7 @@ def upsample_backward(dy, dx):
     n, do, ho, wo, c = dy.shape
     _, di, hi, wi, _ = dx.shape
     _call("upsample", 1, 0.0, lib().rsb_upsample_trilinear_backward, _p(dy), _check_cl(dy, "dy"), _p(dx), _check_cl(dx, "dx"),
-                                                dtype_code(dy), n, di, hi, wi, do, ho, wo, c, _stream(), what="upsample_backward")
+                                                dtype_code(dy), n, di, hi, wi, do, ho, wo, c, _stream(), what="upsample_backward", desc=f"{c} {n}x{do}x{ho}x{wo}")
     return dx
 
 
@@ -266,7 +268,7 @@ def instnorm_backward_apply(g, x, x_stats, bwd_sums, dx, add=None, eps=EPS_IN):
     _call("instnorm_bwd", 1, 0.0, lib().rsb_instnorm_backward_apply, _p(g), _check_cl(g, "g"), _p(x), _check_cl(x, "x"), _st(x_stats, x, "x_stats"),
                                             _st(bwd_sums, x, "bwd_sums"), _p(add), _check_cl(add, "add") if add is not None else 0,
                                             _p(dx), _check_cl(dx, "dx"), dtype_code(x), eps, n, d, h, w_, c,
-                                            _stream(), what="instnorm_backward_apply")
+                                            _stream(), what="instnorm_backward_apply", desc=f"{c} {n}x{d}x{h}x{w_}")
     return dx
 
 
