@@ -68,6 +68,25 @@ size_t rsb_conv3_packed_weight_bytes(int Cout, int Cin, int parts);
 int rsb_conv3_pack_weights(const float* w_oidhw, void* packed, int Cout, int Cin,
                            int transpose_flip, int parts, void* stream);
 
+/* Batched packing: one launch for every conv of a network (replaces the per-layer rsb_conv3_pack_weights calls and
+ * the torch.cat of the merged conv1 || shortcut weights — conv_layers.py:85-92).  A job's logical OIDHW tensor is
+ * [w_a (rows_a rows) ; w_b (Cout - rows_a rows)].  Fill {w_a, w_b, packed, rows_a, Cout, Cin, transpose_flip, parts}
+ * on the host, call rsb_conv3_pack_plan (fills the derived fields and the block count), copy the table to device
+ * memory once, then launch rsb_conv3_pack_weights_batched on it every step. */
+typedef struct RsbPackJob {
+  const float* w_a;
+  const float* w_b;
+  void* packed;
+  int rows_a, Cout, Cin;
+  int transpose_flip, parts;
+  /* derived (rsb_conv3_pack_plan) */
+  int co_eff, ci_eff, NT, ntiles, nchunks;
+  unsigned int block_begin;
+  unsigned long long total;
+} RsbPackJob;
+int rsb_conv3_pack_plan(RsbPackJob* jobs_host, int n_jobs, unsigned int* total_blocks);
+int rsb_conv3_pack_weights_batched(const RsbPackJob* jobs_device, int n_jobs, unsigned int total_blocks, void* stream);
+
 typedef struct RsbConv3Args {
   /* geometry */
   int N, D, H, W;

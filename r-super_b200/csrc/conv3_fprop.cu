@@ -653,6 +653,57 @@ __global__ void pack_conv3_weights_kernel(const float* __restrict__ w, __nv_bflo
   out[i] = q;
 }
 
+
+// Batched variant: ONE launch packs every conv of a network (forward and dgrad images) from a job table in device
+// memory — 68 launches of ~13 us per train step otherwise.  A job's logical weight tensor is the row-wise concatenation
+// [w_a (rows_a rows) ; w_b] (the merged conv1 || shortcut GEMM of a BasicBlock needs no torch.cat).
+__global__ void pack_conv3_weights_batched_kernel(const RsbPackJob* __restrict__ jobs, int n_jobs) {
+  __shared__ int s_job;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = n_jobs - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (jobs[mid].block_begin <= blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    s_job = lo;
+  }
+  __syncthreads();
+  const RsbPackJob& jb = jobs[s_job];
+  const size_t i = static_cast<size_t>(blockIdx.x - jb.block_begin) * blockDim.x + threadIdx.x;
+  if (i >= jb.total) return;
+  const int NT = jb.NT;
+  size_t t = i;
+  const int kk = t & 7; t >>= 3;
+  const int orow = t & 7; t >>= 3;
+  const int kc = t & 3; t >>= 2;
+  const int og = t % (NT / 8); t /= (NT / 8);
+  const int slot = t % 3; t /= 3;
+  const int nt = t % jb.ntiles; t /= jb.ntiles;
+  const int khw = t % 9; t /= 9;
+  const int chunk = t % jb.nchunks; t /= jb.nchunks;
+  const int part = static_cast<int>(t);
+  const int o = nt * NT + og * 8 + orow;
+  const int k = chunk * 32 + kc * 8 + kk;
+  const int tap = (2 - slot) * 9 + khw;
+  float v = 0.f;
+  if (o < jb.co_eff && k < jb.ci_eff) {
+    // (row, col) of the logical OIDHW tensor and the tap to read
+    const int row = jb.transpose_flip ? k : o, col = jb.transpose_flip ? o : k;
+    const int tp = jb.transpose_flip ? 26 - tap : tap;
+    const float* src = row < jb.rows_a ? jb.w_a + static_cast<size_t>(row) * jb.Cin * 27
+                                       : jb.w_b + static_cast<size_t>(row - jb.rows_a) * jb.Cin * 27;
+    v = src[static_cast<size_t>(col) * 27 + tp];
+  }
+  const int parts = jb.parts;
+  const int piece = parts == 3 ? (part == 2 ? 1 : 0) : (parts == 6 ? ((0x102010 >> (4 * part)) & 0xF) : 0);
+  __nv_bfloat16 q = __float2bfloat16_rn(v);
+  for (int r = 0; r < piece; ++r) {
+    v -= __bfloat162float(q);
+    q = __float2bfloat16_rn(v);
+  }
+  reinterpret_cast<__nv_bfloat16*>(jb.packed)[i] = q;
+}
+
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 // N tile: largest multiple of 16 that divides the padded Cout and is <= 128
@@ -714,6 +765,35 @@ extern "C" int rsb_conv3_pack_weights(const float* w_oidhw, void* packed, int Co
   pack_conv3_weights_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
       w_oidhw, reinterpret_cast<__nv_bfloat16*>(packed), Cin, transpose_flip, co_eff, ci_eff, NT, ntiles, nchunks, parts, total);
   return check_launch("pack_conv3_weights_kernel");
+}
+
+extern "C" int rsb_conv3_pack_plan(RsbPackJob* jobs, int n_jobs, unsigned int* total_blocks) {
+  RSB_REQUIRE(jobs && total_blocks && n_jobs > 0, "pack_plan: bad arguments");
+  unsigned long long blocks = 0;
+  for (int j = 0; j < n_jobs; ++j) {
+    RsbPackJob& jb = jobs[j];
+    RSB_REQUIRE(jb.w_a && jb.packed, "pack_plan: job %d has a null pointer", j);
+    RSB_REQUIRE(jb.Cout > 0 && jb.Cin > 0 && jb.rows_a > 0 && jb.rows_a <= jb.Cout, "pack_plan: job %d has bad channel counts", j);
+    RSB_REQUIRE(jb.rows_a == jb.Cout || jb.w_b, "pack_plan: job %d needs w_b for rows beyond rows_a", j);
+    RSB_REQUIRE(jb.parts == 1 || jb.parts == 3 || jb.parts == 6, "pack_plan: parts must be 1, 3 or 6");
+    jb.co_eff = jb.transpose_flip ? jb.Cin : jb.Cout;
+    jb.ci_eff = jb.transpose_flip ? jb.Cout : jb.Cin;
+    jb.NT = pick_nt(jb.co_eff);
+    jb.ntiles = round_up(jb.co_eff, 16) / jb.NT;
+    jb.nchunks = (jb.ci_eff + 31) / 32;
+    jb.total = rsb_conv3_packed_weight_bytes(jb.co_eff, jb.ci_eff, jb.parts) / 2;
+    jb.block_begin = static_cast<unsigned int>(blocks);
+    blocks += (jb.total + 255) / 256;
+    RSB_REQUIRE(blocks < (1ull << 31), "pack_plan: too many blocks");
+  }
+  *total_blocks = static_cast<unsigned int>(blocks);
+  return 0;
+}
+
+extern "C" int rsb_conv3_pack_weights_batched(const RsbPackJob* jobs_device, int n_jobs, unsigned int total_blocks, void* stream) {
+  RSB_REQUIRE(jobs_device && n_jobs > 0 && total_blocks > 0, "pack_weights_batched: bad arguments");
+  pack_conv3_weights_batched_kernel<<<total_blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(jobs_device, n_jobs);
+  return check_launch("pack_conv3_weights_batched_kernel");
 }
 
 extern "C" int rsb_conv3_forward(const RsbConv3Args* p, void* stream) {

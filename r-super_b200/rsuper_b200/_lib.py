@@ -40,6 +40,17 @@ class RsbConv3Args(C.Structure):
     ]
 
 
+class RsbPackJob(C.Structure):
+    _fields_ = [
+        ("w_a", c_void_p), ("w_b", c_void_p), ("packed", c_void_p),
+        ("rows_a", c_int), ("Cout", c_int), ("Cin", c_int),
+        ("transpose_flip", c_int), ("parts", c_int),
+        ("co_eff", c_int), ("ci_eff", c_int), ("NT", c_int), ("ntiles", c_int), ("nchunks", c_int),
+        ("block_begin", C.c_uint),
+        ("total", C.c_ulonglong),
+    ]
+
+
 class RsbConv3WgradArgs(C.Structure):
     _fields_ = [
         ("N", c_int), ("D", c_int), ("H", c_int), ("W", c_int),
@@ -69,6 +80,8 @@ SIGNATURES = {
     "rsb_conv3_n_tile": (c_int, [c_int]),
     "rsb_conv3_packed_weight_bytes": (c_size_t, [c_int, c_int, c_int]),
     "rsb_conv3_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "rsb_conv3_pack_plan": (c_int, [C.POINTER(RsbPackJob), c_int, C.POINTER(C.c_uint)]),
+    "rsb_conv3_pack_weights_batched": (c_int, [c_void_p, c_int, C.c_uint, c_void_p]),
     "rsb_conv3_forward": (c_int, [C.POINTER(RsbConv3Args), c_void_p]),
     "rsb_debug_set_timing_buffer": (c_int, [c_void_p]),
     "rsb_debug_set_wgrad_timing_buffer": (c_int, [c_void_p]),

@@ -103,6 +103,49 @@ def conv3_pack_weights(w: torch.Tensor, transpose_flip: bool = False, split=Fals
     return out
 
 
+class PackPlan:
+    """Persistent packed-weight images of a set of convs + the device job table that refreshes ALL of them in one launch.
+
+    jobs: list of (key, w_a, w_b | None, transpose_flip); the logical OIDHW tensor of a job is cat([w_a, w_b], 0).
+    The plan holds raw pointers of the parameter tensors: `key()` lets the owner detect re-allocated parameters."""
+
+    def __init__(self, jobs, split=False):
+        parts = 6 if split == 6 else (3 if split else 1)
+        n = len(jobs)
+        arr = (_lib.RsbPackJob * n)()
+        self.images = {}
+        self._keep = []
+        dev = jobs[0][1].device
+        for j, (key, w_a, w_b, flip) in enumerate(jobs):
+            assert w_a.dtype == torch.float32 and w_a.is_cuda and w_a.is_contiguous() and w_a.shape[2:] == (3, 3, 3)
+            cin = w_a.shape[1]
+            cout = w_a.shape[0]
+            if w_b is not None:
+                assert w_b.dtype == torch.float32 and w_b.is_contiguous() and w_b.shape[1:] == w_a.shape[1:]
+                cout += w_b.shape[0]
+            co_eff, ci_eff = (cin, cout) if flip else (cout, cin)
+            img = torch.empty(lib().rsb_conv3_packed_weight_bytes(co_eff, ci_eff, parts), dtype=torch.uint8, device=dev)
+            self.images[key] = img
+            self._keep.append((w_a, w_b))
+            jb = arr[j]
+            jb.w_a, jb.w_b, jb.packed = w_a.data_ptr(), (w_b.data_ptr() if w_b is not None else None), img.data_ptr()
+            jb.rows_a, jb.Cout, jb.Cin, jb.transpose_flip, jb.parts = w_a.shape[0], cout, cin, int(flip), parts
+        nblk = C.c_uint(0)
+        check(lib().rsb_conv3_pack_plan(arr, n, C.byref(nblk)), "conv3_pack_plan")
+        self.n_jobs, self.n_blocks = n, nblk.value
+        self.table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+        self.ptr_key = self.pointer_key([(w_a, w_b) for _, w_a, w_b, _ in jobs])
+
+    @staticmethod
+    def pointer_key(pairs):
+        return tuple((a.data_ptr(), 0 if b is None else b.data_ptr()) for a, b in pairs)
+
+    def refresh(self):
+        """Re-pack every image from the current parameter values (one launch)."""
+        _call("pack_weights", 1, 0.0, lib().rsb_conv3_pack_weights_batched, _p(self.table), self.n_jobs, self.n_blocks, _stream(),
+              what="conv3_pack_weights_batched")
+
+
 def conv3_forward(a_op, w_packed, y, *, a_lo=None, a_lo2=None, slope=0.0, res=None, out_stats=None,
                   mask_x=None, mask_stats=None, bwd_sums=None, planes_per_item=0, max_ctas=0, eps=EPS_IN):
     """y = conv3x3x3(a_op) [+ res]; a_op is the bf16 operand from norm_act (a_lo: its split-precision low part,

@@ -129,6 +129,28 @@ class _Engine:
         self.slope = float(slope)
         self.dtype = dtype
         self.split = dtype == torch.float32
+        self.plan = None  # ops.PackPlan: persistent packed weight images, refreshed by ONE launch per forward
+
+    # ---- packed weights ----------------------------------------------------------------------------
+    BLOCKS = ([("inc.conv2.", False)]
+              + [(f"down{l}.conv.{i}.", i == 1) for l in range(1, 5) for i in (1, 2)]
+              + [(f"up{j}.conv.{i}.", i == 0) for j in range(1, 5) for i in (0, 1)])
+
+    def prepare(self, P: dict):
+        """(Re)build the pack plan when the parameter storage changed, then re-pack every conv (forward and dgrad
+        images; conv1 || shortcut merged row-wise without a torch.cat) from the current values."""
+        pairs = []
+        for pre, has_sc in self.BLOCKS:
+            pairs.append((P[pre + "conv1.conv.weight"], P[pre + "shortcut.conv.weight"] if has_sc else None))
+            pairs.append((P[pre + "conv2.conv.weight"], None))
+        if self.plan is None or self.plan.ptr_key != ops.PackPlan.pointer_key(pairs):
+            jobs = []
+            for (pre, _), k in zip(self.BLOCKS, range(0, len(pairs), 2)):
+                for tag, (wa, wb) in (("c1", pairs[k]), ("c2", pairs[k + 1])):
+                    jobs.append((pre + tag, wa, wb, False))
+                    jobs.append((pre + tag + "T", wa, wb, True))
+            self.plan = ops.PackPlan(jobs, split=self.split)
+        self.plan.refresh()
 
     # ---- operand / conv / wgrad helpers ------------------------------------------------------------
     def _operand(self, t: torch.Tensor, stats=None):
@@ -139,8 +161,8 @@ class _Engine:
         r = ops.norm_act(t, stats, slope=self.slope, split=self.split)
         return r if self.split else (r,)
 
-    def _conv(self, op, w, y, flip=False, **kw):
-        wp = ops.conv3_pack_weights(w, flip, split=self.split)
+    def _conv(self, op, key: str, y, flip=False, **kw):
+        wp = self.plan.images[key + "T" if flip else key]
         return ops.conv3_forward(op[0], wp, y, a_lo=op[1] if self.split else None, slope=self.slope, **kw)
 
     def _wgrad(self, a_op, dy_op, dw):
@@ -151,23 +173,21 @@ class _Engine:
         return dw
 
     # ---- forward -------------------------------------------------------------------------------
-    def _block_fwd(self, x: Act, w1, w2, wsc, out: Act, saved: list):
+    def _block_fwd(self, x: Act, pre: str, has_sc: bool, cout: int, out: Act, saved: list):
         n, d, h, w_, _ = x.t.shape
-        cout = w2.shape[0]
         dev = x.t.device
         a_x = self._operand(x.t, x.st)
-        if wsc is not None:
-            wcat = torch.cat([w1, wsc], dim=0).contiguous()
+        if has_sc:
             hs = Act.new(n, d, h, w_, 2 * cout, self.dtype, dev)
-            self._conv(a_x, wcat, hs.t, out_stats=hs.st)
+            self._conv(a_x, pre + "c1", hs.t, out_stats=hs.st)  # conv1 || shortcut as one GEMM with N = 2*cout
             hh, ss = hs.view(0, cout), hs.view(cout, 2 * cout)
             a_h = self._operand(hh.t, hh.st)
-            self._conv(a_h, w2, out.t, res=ss.t, out_stats=out.st)
+            self._conv(a_h, pre + "c2", out.t, res=ss.t, out_stats=out.st)
         else:
             hh = Act.new(n, d, h, w_, cout, self.dtype, dev)
-            self._conv(a_x, w1, hh.t, out_stats=hh.st)
+            self._conv(a_x, pre + "c1", hh.t, out_stats=hh.st)
             a_h = self._operand(hh.t, hh.st)
-            self._conv(a_h, w2, out.t, res=x.t, out_stats=out.st)
+            self._conv(a_h, pre + "c2", out.t, res=x.t, out_stats=out.st)
         saved.append((x, hh, a_x, a_h))
 
     def forward(self, x: torch.Tensor, P: dict, num_classes: int, save: bool):
@@ -181,6 +201,7 @@ class _Engine:
         ch = [b, 2 * b, 4 * b, 8 * b, 10 * b]
         dims = [(D >> l, H >> l, W >> l) for l in range(5)]
         saved: list = []
+        self.prepare(P)
 
         # skip/concat buffers of decoder levels 0..3: [skip ch[l] | upsampled ch_up[l]]
         up_in = [ch[1], ch[2], ch[3], ch[4]]  # channels arriving from below at level l
@@ -189,8 +210,7 @@ class _Engine:
         # inc: stem conv + BasicBlock(b, b)
         t0 = Act.new(n, *dims[0], b, dt, dev)
         ops.stem_conv_forward(x, P["inc.conv1.weight"], t0.t, t0.st)
-        self._block_fwd(t0, P["inc.conv2.conv1.conv.weight"], P["inc.conv2.conv2.conv.weight"], None,
-                        cat[0].view(0, ch[0]), saved)
+        self._block_fwd(t0, "inc.conv2.", False, b, cat[0].view(0, ch[0]), saved)
         enc_out = [cat[0].view(0, ch[0])]
         pooled = []
         for l in range(1, 5):
@@ -199,10 +219,9 @@ class _Engine:
             pooled.append(p)
             y = Act.new(n, *dims[l], ch[l], dt, dev)
             pre = f"down{l}.conv."
-            self._block_fwd(p, P[pre + "1.conv1.conv.weight"], P[pre + "1.conv2.conv.weight"],
-                            P[pre + "1.shortcut.conv.weight"], y, saved)
+            self._block_fwd(p, pre + "1.", True, ch[l], y, saved)
             out = cat[l].view(0, ch[l]) if l < 4 else Act.new(n, *dims[4], ch[4], dt, dev)
-            self._block_fwd(y, P[pre + "2.conv1.conv.weight"], P[pre + "2.conv2.conv.weight"], None, out, saved)
+            self._block_fwd(y, pre + "2.", False, ch[l], out, saved)
             enc_out.append(out)
         cur = enc_out[4]
         for j, l in enumerate((3, 2, 1, 0), start=1):
@@ -210,10 +229,9 @@ class _Engine:
             ops.upsample_forward(cur.t, upv.t, upv.st)
             y = Act.new(n, *dims[l], ch[l], dt, dev)
             pre = f"up{j}.conv."
-            self._block_fwd(cat[l], P[pre + "0.conv1.conv.weight"], P[pre + "0.conv2.conv.weight"],
-                            P[pre + "0.shortcut.conv.weight"], y, saved)
+            self._block_fwd(cat[l], pre + "0.", True, ch[l], y, saved)
             out = Act.new(n, *dims[l], ch[l], dt, dev, stats=(l != 0))
-            self._block_fwd(y, P[pre + "1.conv1.conv.weight"], P[pre + "1.conv2.conv.weight"], None, out, saved)
+            self._block_fwd(y, pre + "1.", False, ch[l], out, saved)
             cur = out
         logits = torch.empty((n, num_classes, D, H, W), dtype=torch.float32, device=dev)
         w_out = P["outc.weight"].reshape(num_classes, b).contiguous()
@@ -227,38 +245,40 @@ class _Engine:
         n, d, h, w_, _ = like.shape
         return torch.empty((n, d, h, w_, c), dtype=self.dtype, device=like.device)
 
-    def _block_bwd_identity(self, x: Act, hh: Act, a_x, a_h, w1, w2, d_out: torch.Tensor, dx_dest: torch.Tensor):
-        c = w2.shape[0]
+    def _dw(self, like: torch.Tensor, cout: int, cin: int) -> torch.Tensor:
+        return torch.empty((cout, cin, 3, 3, 3), dtype=torch.float32, device=like.device)
+
+    def _block_bwd_identity(self, x: Act, hh: Act, a_x, a_h, pre: str, d_out: torch.Tensor, dx_dest: torch.Tensor):
+        c = hh.C
         d_op = self._operand(d_out)
         g_h = self._new(d_out, c)
         sums_h = _sums_like(hh)
-        self._conv(d_op, w2, g_h, flip=True, mask_x=hh.t, mask_stats=hh.st, bwd_sums=sums_h)
-        dw2 = self._wgrad(a_h, d_op, torch.empty_like(w2))
+        self._conv(d_op, pre + "c2", g_h, flip=True, mask_x=hh.t, mask_stats=hh.st, bwd_sums=sums_h)
+        dw2 = self._wgrad(a_h, d_op, self._dw(d_out, c, c))
         ops.instnorm_backward_apply(g_h, hh.t, hh.st, sums_h, g_h)  # in place: g_h becomes d(h)
         gh_op = self._operand(g_h)
         g_x = self._new(d_out, x.C)
         sums_x = _sums_like(x)
-        self._conv(gh_op, w1, g_x, flip=True, mask_x=x.t, mask_stats=x.st, bwd_sums=sums_x)
-        dw1 = self._wgrad(a_x, gh_op, torch.empty_like(w1))
+        self._conv(gh_op, pre + "c1", g_x, flip=True, mask_x=x.t, mask_stats=x.st, bwd_sums=sums_x)
+        dw1 = self._wgrad(a_x, gh_op, self._dw(d_out, c, x.C))
         ops.instnorm_backward_apply(g_x, x.t, x.st, sums_x, dx_dest, add=d_out)
         return dw1, dw2
 
-    def _block_bwd_shortcut(self, x: Act, hh: Act, a_x, a_h, w1, w2, wsc, dcat2: torch.Tensor, dx_dest: torch.Tensor):
+    def _block_bwd_shortcut(self, x: Act, hh: Act, a_x, a_h, pre: str, dcat2: torch.Tensor, dx_dest: torch.Tensor):
         """dcat2 [.., 2C]: channels [C:2C] hold d(out) on entry; [0:C] receives d(h)."""
-        c = w2.shape[0]
+        c = hh.C
         d_out = dcat2[..., c:]
         dh = dcat2[..., :c]
         d_op = self._operand(d_out)
         sums_h = _sums_like(hh)
-        self._conv(d_op, w2, dh, flip=True, mask_x=hh.t, mask_stats=hh.st, bwd_sums=sums_h)
-        dw2 = self._wgrad(a_h, d_op, torch.empty_like(w2))
+        self._conv(d_op, pre + "c2", dh, flip=True, mask_x=hh.t, mask_stats=hh.st, bwd_sums=sums_h)
+        dw2 = self._wgrad(a_h, d_op, self._dw(dcat2, c, c))
         ops.instnorm_backward_apply(dh, hh.t, hh.st, sums_h, dh)
-        wcat = torch.cat([w1, wsc], dim=0).contiguous()
         dcat_op = self._operand(dcat2)
         g_x = self._new(dcat2, x.C)
         sums_x = _sums_like(x)
-        self._conv(dcat_op, wcat, g_x, flip=True, mask_x=x.t, mask_stats=x.st, bwd_sums=sums_x)
-        dwcat = self._wgrad(a_x, dcat_op, torch.empty_like(wcat))
+        self._conv(dcat_op, pre + "c1", g_x, flip=True, mask_x=x.t, mask_stats=x.st, bwd_sums=sums_x)
+        dwcat = self._wgrad(a_x, dcat_op, self._dw(dcat2, 2 * c, x.C))
         ops.instnorm_backward_apply(g_x, x.t, x.st, sums_x, dx_dest)
         return dwcat[:c], dw2, dwcat[c:]
 
@@ -286,15 +306,12 @@ class _Engine:
             # block B (identity shortcut): d_out = d_cur, dx goes into the d(out) slot of block A
             xb, hb, axb, ahb = saved[ib]
             dcat2 = self._new(xb.t, 2 * ch[l])
-            dw1, dw2 = self._block_bwd_identity(xb, hb, axb, ahb, P[pre + "1.conv1.conv.weight"], P[pre + "1.conv2.conv.weight"],
-                                                d_cur, dcat2[..., ch[l]:])
+            dw1, dw2 = self._block_bwd_identity(xb, hb, axb, ahb, pre + "1.", d_cur, dcat2[..., ch[l]:])
             G[pre + "1.conv1.conv.weight"], G[pre + "1.conv2.conv.weight"] = dw1, dw2
             # block A (conv shortcut) on the concat buffer
             xa, ha, axa, aha = saved[ia]
             d_cat = self._new(xa.t, xa.C)
-            dw1, dw2, dwsc = self._block_bwd_shortcut(xa, ha, axa, aha, P[pre + "0.conv1.conv.weight"],
-                                                      P[pre + "0.conv2.conv.weight"],
-                                                      P[pre + "0.shortcut.conv.weight"], dcat2, d_cat)
+            dw1, dw2, dwsc = self._block_bwd_shortcut(xa, ha, axa, aha, pre + "0.", dcat2, d_cat)
             G[pre + "0.conv1.conv.weight"], G[pre + "0.conv2.conv.weight"] = dw1, dw2
             G[pre + "0.shortcut.conv.weight"] = dwsc
             dskip[l] = d_cat[..., :ch[l]]
@@ -307,14 +324,11 @@ class _Engine:
             ia, ib = 2 * l - 1, 2 * l
             xb, hb, axb, ahb = saved[ib]
             dcat2 = self._new(xb.t, 2 * ch[l])
-            dw1, dw2 = self._block_bwd_identity(xb, hb, axb, ahb, P[pre + "2.conv1.conv.weight"], P[pre + "2.conv2.conv.weight"],
-                                                d_cur, dcat2[..., ch[l]:])
+            dw1, dw2 = self._block_bwd_identity(xb, hb, axb, ahb, pre + "2.", d_cur, dcat2[..., ch[l]:])
             G[pre + "2.conv1.conv.weight"], G[pre + "2.conv2.conv.weight"] = dw1, dw2
             xa, ha, axa, aha = saved[ia]  # xa = pooled input
             d_p = self._new(xa.t, xa.C)
-            dw1, dw2, dwsc = self._block_bwd_shortcut(xa, ha, axa, aha, P[pre + "1.conv1.conv.weight"],
-                                                      P[pre + "1.conv2.conv.weight"],
-                                                      P[pre + "1.shortcut.conv.weight"], dcat2, d_p)
+            dw1, dw2, dwsc = self._block_bwd_shortcut(xa, ha, axa, aha, pre + "1.", dcat2, d_p)
             G[pre + "1.conv1.conv.weight"], G[pre + "1.conv2.conv.weight"] = dw1, dw2
             G[pre + "1.shortcut.conv.weight"] = dwsc
             x_prev = S["enc_out"][l - 1]
@@ -323,8 +337,7 @@ class _Engine:
         # inc block + stem
         x0, h0, ax0, ah0 = saved[0]
         d_t0 = self._new(x0.t, b)
-        dw1, dw2 = self._block_bwd_identity(x0, h0, ax0, ah0, P["inc.conv2.conv1.conv.weight"], P["inc.conv2.conv2.conv.weight"],
-                                            d_cur, d_t0)
+        dw1, dw2 = self._block_bwd_identity(x0, h0, ax0, ah0, "inc.conv2.", d_cur, d_t0)
         G["inc.conv2.conv1.conv.weight"], G["inc.conv2.conv2.conv.weight"] = dw1, dw2
         dws = torch.empty_like(P["inc.conv1.weight"])
         ops.stem_conv_wgrad(S["x"], d_t0, dws)
@@ -391,12 +404,20 @@ class B200UNet(nn.Module):
         self.up4 = _Stage(2 * b + b, b, False)
         self.outc = nn.Conv3d(b, num_classes, kernel_size=1)
 
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st.pop("_engine", None)  # raw device pointers: rebuilt on the next forward
+        return st
+
     def forward(self, x):
         if not x.is_cuda:
             raise RuntimeError("B200UNet has no CPU path: inputs must live on a CUDA (sm_100a) device")
         names, params = zip(*self.named_parameters())
         dtype = torch.bfloat16 if self.precision == "bf16" else torch.float32
-        engine = _Engine(self.base_ch, self.negative_slope, dtype)
+        engine = self.__dict__.get("_engine")
+        if engine is None or engine.dtype != dtype or engine.slope != float(self.negative_slope):
+            engine = _Engine(self.base_ch, self.negative_slope, dtype)
+            self.__dict__["_engine"] = engine  # persistent packed-weight buffers; never pickled / deep-copied
         out = _UNetFunction.apply(x.float(), engine, names, self.num_classes, *params)
         # calculate_loss indexes model_output['segmentation'] (losses_foundation.py:859)
         return {"segmentation": out} if self.return_dict else out

@@ -42,6 +42,17 @@ def test_argument_validation_returns_errors_without_a_gpu():
     assert lib.rsb_conv3_packed_weight_bytes(40, 24, 3) == 3 * 27 * 48 * 64
     assert lib.rsb_conv3_packed_weight_bytes(32, 64, 6) == 6 * 2 * 27 * 32 * 64
     assert [lib.rsb_conv3_n_tile(c) for c in (32, 64, 96, 192, 320, 576, 640)] == [32, 64, 96, 96, 80, 96, 128]
+    jobs = (_lib.RsbPackJob * 2)()
+    nblk = ctypes.c_uint(0)
+    assert lib.rsb_conv3_pack_plan(jobs, 2, ctypes.byref(nblk)) != 0 and b"null" in lib.rsb_last_error()
+    for jb, (co, ci, flip) in zip(jobs, ((64, 32, 0), (64, 32, 1))):
+        jb.w_a, jb.packed, jb.rows_a, jb.Cout, jb.Cin, jb.transpose_flip, jb.parts = 4096, 8192, co, co, ci, flip, 1
+    assert lib.rsb_conv3_pack_plan(jobs, 2, ctypes.byref(nblk)) == 0   # host-only planning: no device access
+    assert (jobs[0].co_eff, jobs[0].ci_eff, jobs[0].NT, jobs[0].nchunks) == (64, 32, 64, 1)
+    assert (jobs[1].co_eff, jobs[1].ci_eff, jobs[1].NT, jobs[1].nchunks) == (32, 64, 32, 2)
+    assert jobs[0].total == 27 * 64 * 32 and jobs[1].block_begin == (jobs[0].total + 255) // 256
+    assert nblk.value == jobs[1].block_begin + (jobs[1].total + 255) // 256
+    assert lib.rsb_conv3_pack_weights_batched(None, 2, nblk, None) != 0
     w = _lib.RsbConv3WgradArgs()
     assert lib.rsb_conv3_wgrad(ctypes.byref(w), None) != 0 and b"null" in lib.rsb_last_error()
     assert lib.rsb_conv3_wgrad_workspace_bytes(64, 96, 148) > 0

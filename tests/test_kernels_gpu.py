@@ -348,3 +348,32 @@ def test_dilation_bit_exact(cuda_dev, golden):
         got = ops.dilate_ball(vol, k)
         assert np.array_equal(np.packbits(got.cpu().numpy().astype(bool).reshape(-1)), golden[f"dilate_{k}"]), k
         assert torch.equal(got.float(), LR.dilate_volume(vol.float(), k))
+
+
+@pytest.mark.parametrize("split", [False, True])
+def test_batched_weight_packing_matches_per_layer_packing(split):
+    """ONE launch over a job table == the per-layer packer, bit for bit: plain, merged rows (conv1 || shortcut) and
+    the flipped / transposed dgrad images."""
+    from rsuper_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    dev = "cuda"
+    w1 = torch.randn(40, 24, 3, 3, 3, generator=g).to(dev)
+    wsc = torch.randn(40, 24, 3, 3, 3, generator=g).to(dev)
+    w2 = torch.randn(96, 64, 3, 3, 3, generator=g).to(dev)
+    w3 = torch.randn(320, 32, 3, 3, 3, generator=g).to(dev)
+    jobs = [("a", w1, wsc, False), ("aT", w1, wsc, True), ("b", w2, None, False), ("bT", w2, None, True), ("c", w3, None, True)]
+    plan = ops.PackPlan(jobs, split=split)
+    for img in plan.images.values():
+        img.fill_(0x5A)
+    plan.refresh()
+    wcat = torch.cat([w1, wsc], 0).contiguous()
+    want = {"a": ops.conv3_pack_weights(wcat, False, split=split), "aT": ops.conv3_pack_weights(wcat, True, split=split),
+            "b": ops.conv3_pack_weights(w2, False, split=split), "bT": ops.conv3_pack_weights(w2, True, split=split),
+            "c": ops.conv3_pack_weights(w3, True, split=split)}
+    for k, ref in want.items():
+        assert plan.images[k].shape == ref.shape and torch.equal(plan.images[k], ref), k
+    # values are re-read on refresh (the optimizer updates parameters in place)
+    w2.mul_(0.5)
+    plan.refresh()
+    assert torch.equal(plan.images["b"], ops.conv3_pack_weights(w2, False, split=split))
+    assert plan.ptr_key == ops.PackPlan.pointer_key([(w1, wsc), (w1, wsc), (w2, None), (w2, None), (w3, None)])
