@@ -657,8 +657,14 @@ __global__ void pack_conv3_weights_kernel(const float* __restrict__ w, __nv_bflo
 // Batched variant: ONE launch packs every conv of a network (forward and dgrad images) from a job table in device
 // memory — 68 launches of ~13 us per train step otherwise.  A job's logical weight tensor is the row-wise concatenation
 // [w_a (rows_a rows) ; w_b] (the merged conv1 || shortcut GEMM of a BasicBlock needs no torch.cat).
-__global__ void pack_conv3_weights_batched_kernel(const RsbPackJob* __restrict__ jobs, int n_jobs) {
+// One block = one (8 output channels, 32 input channels) tile of the effective conv: its 8 x 32 x 27 fp32 source
+// values are contiguous runs of the OIDHW tensor (coalesced loads into shared memory), and every (part, tap) of the
+// tile is one contiguous 512-byte run [k/8 (4)][o%8 (8)][k%8 (8)] of the packed image (coalesced stores).
+constexpr int kPackThreads = 256;
+__global__ void __launch_bounds__(kPackThreads)
+pack_conv3_weights_batched_kernel(const RsbPackJob* __restrict__ jobs, int n_jobs) {
   __shared__ int s_job;
+  __shared__ float sm_w[8 * 32 * 27 + 32];  // [row][col * 27 + tap], row pitch L + 1
   if (threadIdx.x == 0) {
     int lo = 0, hi = n_jobs - 1;
     while (lo < hi) {
@@ -669,39 +675,50 @@ __global__ void pack_conv3_weights_batched_kernel(const RsbPackJob* __restrict__
   }
   __syncthreads();
   const RsbPackJob& jb = jobs[s_job];
-  const size_t i = static_cast<size_t>(blockIdx.x - jb.block_begin) * blockDim.x + threadIdx.x;
-  if (i >= jb.total) return;
-  const int NT = jb.NT;
-  size_t t = i;
-  const int kk = t & 7; t >>= 3;
-  const int orow = t & 7; t >>= 3;
-  const int kc = t & 3; t >>= 2;
-  const int og = t % (NT / 8); t /= (NT / 8);
-  const int slot = t % 3; t /= 3;
-  const int nt = t % jb.ntiles; t /= jb.ntiles;
-  const int khw = t % 9; t /= 9;
-  const int chunk = t % jb.nchunks; t /= jb.nchunks;
-  const int part = static_cast<int>(t);
-  const int o = nt * NT + og * 8 + orow;
-  const int k = chunk * 32 + kc * 8 + kk;
-  const int tap = (2 - slot) * 9 + khw;
-  float v = 0.f;
-  if (o < jb.co_eff && k < jb.ci_eff) {
-    // (row, col) of the logical OIDHW tensor and the tap to read
-    const int row = jb.transpose_flip ? k : o, col = jb.transpose_flip ? o : k;
-    const int tp = jb.transpose_flip ? 26 - tap : tap;
-    const float* src = row < jb.rows_a ? jb.w_a + static_cast<size_t>(row) * jb.Cin * 27
-                                       : jb.w_b + static_cast<size_t>(row - jb.rows_a) * jb.Cin * 27;
-    v = src[static_cast<size_t>(col) * 27 + tp];
+  const int local = static_cast<int>(blockIdx.x - jb.block_begin);
+  const int chunk = local % jb.nchunks, g = local / jb.nchunks;  // g: group of 8 effective output channels
+  const int o0 = g * 8, k0 = chunk * 32;
+  const bool flip = jb.transpose_flip != 0;
+  // source tile: R rows x Cc columns of the logical [Cout][Cin] matrix
+  const int R = flip ? 32 : 8, Cc = flip ? 8 : 32;
+  const int row0 = flip ? k0 : o0, col0 = flip ? o0 : k0;
+  const int L = Cc * 27, pitch = L + 1;
+  const int ncols = min(Cc, jb.Cin - col0);          // valid columns (may be <= 0 for padded groups)
+  const int nvalid = ncols > 0 ? ncols * 27 : 0;
+  for (int e = threadIdx.x; e < R * L; e += kPackThreads) {
+    const int r = e / L, c = e - r * L;
+    const int row = row0 + r;
+    float v = 0.f;
+    if (row < jb.Cout && c < nvalid) {
+      const float* src = row < jb.rows_a ? jb.w_a + static_cast<size_t>(row) * jb.Cin * 27
+                                         : jb.w_b + static_cast<size_t>(row - jb.rows_a) * jb.Cin * 27;
+      v = src[static_cast<size_t>(col0) * 27 + c];
+    }
+    sm_w[r * pitch + c] = v;
   }
-  const int parts = jb.parts;
-  const int piece = parts == 3 ? (part == 2 ? 1 : 0) : (parts == 6 ? ((0x102010 >> (4 * part)) & 0xF) : 0);
-  __nv_bfloat16 q = __float2bfloat16_rn(v);
-  for (int r = 0; r < piece; ++r) {
-    v -= __bfloat162float(q);
-    q = __float2bfloat16_rn(v);
+  __syncthreads();
+  const int t = threadIdx.x;
+  const int kc = t >> 6, orow = (t >> 3) & 7, kk = t & 7;
+  const int kin = kc * 8 + kk;
+  const float* mine = flip ? &sm_w[kin * pitch + orow * 27] : &sm_w[orow * pitch + kin * 27];
+  const int ng = jb.NT / 8;
+  const int nt = g / ng, og = g - nt * ng;
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(jb.packed);
+  for (int part = 0; part < jb.parts; ++part) {
+    const int piece = jb.parts == 3 ? (part == 2 ? 1 : 0) : (jb.parts == 6 ? ((0x102010 >> (4 * part)) & 0xF) : 0);
+#pragma unroll 3
+    for (int tap = 0; tap < 27; ++tap) {
+      const int slot = 2 - tap / 9, khw = tap % 9;
+      float v = mine[flip ? 26 - tap : tap];
+      __nv_bfloat16 q = __float2bfloat16_rn(v);
+      for (int r = 0; r < piece; ++r) {
+        v -= __bfloat162float(q);
+        q = __float2bfloat16_rn(v);
+      }
+      const size_t idx = ((((static_cast<size_t>(part) * jb.nchunks + chunk) * 9 + khw) * jb.ntiles + nt) * 3 + slot) * ng + og;
+      out[idx * 256 + t] = q;
+    }
   }
-  reinterpret_cast<__nv_bfloat16*>(jb.packed)[i] = q;
 }
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -783,7 +800,7 @@ extern "C" int rsb_conv3_pack_plan(RsbPackJob* jobs, int n_jobs, unsigned int* t
     jb.nchunks = (jb.ci_eff + 31) / 32;
     jb.total = rsb_conv3_packed_weight_bytes(jb.co_eff, jb.ci_eff, jb.parts) / 2;
     jb.block_begin = static_cast<unsigned int>(blocks);
-    blocks += (jb.total + 255) / 256;
+    blocks += static_cast<unsigned long long>(round_up(jb.co_eff, 16) / 8) * jb.nchunks;  // one block per (8 co, 32 ci) tile
     RSB_REQUIRE(blocks < (1ull << 31), "pack_plan: too many blocks");
   }
   *total_blocks = static_cast<unsigned int>(blocks);
@@ -792,7 +809,7 @@ extern "C" int rsb_conv3_pack_plan(RsbPackJob* jobs, int n_jobs, unsigned int* t
 
 extern "C" int rsb_conv3_pack_weights_batched(const RsbPackJob* jobs_device, int n_jobs, unsigned int total_blocks, void* stream) {
   RSB_REQUIRE(jobs_device && n_jobs > 0 && total_blocks > 0, "pack_weights_batched: bad arguments");
-  pack_conv3_weights_batched_kernel<<<total_blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(jobs_device, n_jobs);
+  pack_conv3_weights_batched_kernel<<<total_blocks, kPackThreads, 0, static_cast<cudaStream_t>(stream)>>>(jobs_device, n_jobs);
   return check_launch("pack_conv3_weights_batched_kernel");
 }
 

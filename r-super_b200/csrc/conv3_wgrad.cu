@@ -79,6 +79,11 @@ RSB_DEVICE WgUnit wg_decode_unit(const WgradDev& a, int u) {
   return r;
 }
 
+// Template parameters = the tile shape (row bytes of the dy / a tiles, windows, kw taps per group): every descriptor
+// stride of the MMA issue loop is a compile-time constant, and the profiling hooks (Dbg) are compiled out of the
+// production instantiation.  The issuing warp is instruction-bound — the tensor pipe's queue holds ~2 MMAs, so each of
+// its ~17 integer / uniform-move instructions per MMA showed up as pipe idle time (profiles/r01h_wgrad_*).
+template <int RBA, int RBB, int KS, int TS, bool Dbg>
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv3_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CUtensorMap tm_a, const WgradDev a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -176,95 +181,106 @@ conv3_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_const
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     // warp-converged waits; one elected lane issues (uniform-datapath UTCHMMA, no per-instruction branch).
-    // The tensor pipe's instruction queue is shallow: whatever this thread does between two steps is NOT hidden
-    // behind the MMAs in flight, so the loop carries ring positions incrementally (no division, no clock reads
-    // unless the profiling buffer is set) and forms descriptors with one add per operand.
-    const uint32_t lt_a = a.rba == 128 ? kLayoutSw128 : kLayoutSw64;
-    const uint32_t lt_b = a.rbb == 128 ? kLayoutSw128 : kLayoutSw64;
-    const uint32_t a_hi = desc_hi(8 * a.rba, lt_a);    // dy: K groups = 8 voxels (one y row of the tile)
-    const uint32_t b_hi = desc_hi(10 * a.rbb, lt_b);   // a:  K groups = next y row of the haloed plane
-    const uint32_t a_lbo = ((a.dy_sub_bytes >> 4) & 0x3FFFu) << 16;  // M groups: next sub-tile / next plane
-    const uint32_t b_lbo = (((10 * a.rbb) >> 4) & 0x3FFFu) << 16;    // N groups: kh -> next halo row
-    const uint32_t a_kstep = (16 * a.rba) >> 4;        // 16 voxels = 2 y rows of the dy tile
-    const uint32_t b_kstep = (20 * a.rbb) >> 4;        // ... = 2 halo rows
-    const uint32_t dy_slot16 = a.dy_slot_bytes >> 4, a_stage16 = a.a_stage_bytes >> 4;
+    // The tensor pipe's instruction queue is shallow: whatever this thread does between two MMAs is NOT hidden
+    // behind the MMAs in flight, so ring positions are carried incrementally (no division, no multiplication, no
+    // clock reads unless Dbg) and every descriptor is base + compile-time constant.
+    constexpr uint32_t PM = KS == 1 ? 4u : (KS == 2 ? 2u : 1u);
+    constexpr uint32_t WL = PM * KS;
+    constexpr uint32_t S = 128u / (PM * (RBA / 2));            // 64-channel sub-tiles per plane
+    constexpr uint32_t lt_a = RBA == 128 ? kLayoutSw128 : kLayoutSw64;
+    constexpr uint32_t lt_b = RBB == 128 ? kLayoutSw128 : kLayoutSw64;
+    constexpr uint32_t dy_sub_bytes = 128u * RBA;
+    constexpr uint32_t dy_slot16 = (S * dy_sub_bytes) >> 4;
+    constexpr uint32_t a_stage16 = ((180u * RBB + 1023u) / 1024u * 1024u) >> 4;
+    constexpr uint32_t a_kstep = (16u * RBA) >> 4;             // 16 voxels = 2 y rows of the dy tile
+    constexpr uint32_t b_kstep = (20u * RBB) >> 4;             // ... = 2 halo rows
+    constexpr uint32_t b_kw16 = RBB >> 4;
+    constexpr uint32_t Ncols = 3u * (RBB / 2);
+    const uint32_t a_hi = desc_hi(8 * RBA, lt_a);    // dy: K groups = 8 voxels (one y row of the tile)
+    const uint32_t b_hi = desc_hi(10 * RBB, lt_b);   // a:  K groups = next y row of the haloed plane
+    constexpr uint32_t a_lbo = ((dy_sub_bytes >> 4) & 0x3FFFu) << 16;  // M groups: next sub-tile / next plane
+    constexpr uint32_t b_lbo = (((10u * RBB) >> 4) & 0x3FFFu) << 16;   // N groups: kh -> next halo row
     const uint32_t a_ring_lo = a_lbo | (dy_base >> 4);
-    const uint32_t b_ring_lo = b_lbo | ((a_base >> 4) + ((static_cast<uint32_t>(tapset * a.TS) * a.rbb) >> 4));
-    const uint32_t b_kw16 = a.rbb >> 4;
-    const uint32_t R = a.R, SA = a.SA, PM = a.PM, WL = a.WL;
-    const bool dbg = a.dbg != nullptr;
-    const bool no_wait = (a.dbg_mode & 2) != 0, no_commit = (a.dbg_mode & 4) != 0;
-    uint32_t head = 0, head_phase = 0;  // ring position of the oldest dy plane of the current window (offset 0)
+    const uint32_t b_ring_lo = b_lbo | ((a_base >> 4) + ((static_cast<uint32_t>(tapset * TS) * RBB) >> 4));
+    const uint32_t R = a.R, SA = a.SA;
+    const uint32_t idesc = a.idesc;
+    const uint32_t bar_dy_full = smem_u32(&sm.dy_full[0]), bar_dy_empty = smem_u32(&sm.dy_empty[0]);
+    const uint32_t bar_a_full = smem_u32(&sm.a_full[0]), bar_a_empty = smem_u32(&sm.a_empty[0]);
+    const bool no_wait = Dbg && (a.dbg_mode & 2) != 0, no_commit = Dbg && (a.dbg_mode & 4) != 0;
+    uint32_t head = 0;                  // ring position of the oldest dy plane of the current window (offset 0)
+    uint32_t nw = 0, nw_phase = 0;      // ring position / phase of the plane the next wait is for
     uint32_t st = 0, st_phase = 0;      // a-plane stage
+    uint32_t first = 0;                 // 0 until the accumulators have been written once
     uint32_t t = 0;
     long long tw_a = 0, tw_dy = 0;
-    const long long t_begin = clock64();
-    unsigned long long ns_begin;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_begin));
+    const long long t_begin = Dbg ? clock64() : 0;
+    unsigned long long ns_begin = 0;
+    if (Dbg) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_begin));
     for (int u = rank; u < a.n_units; u += a.ranks) {
       const WgUnit un = wg_decode_unit(a, u);
       const int nsteps = un.ze - un.zs;
-      for (int j = 0; j < nsteps; ++j) {
-        long long tq = dbg ? clock64() : 0;
-        if (!no_wait) {
-          // planes head .. head+WL-1 must have landed: all of them at a column start, else only the newest
-          uint32_t s = head, ph = head_phase;
-          for (uint32_t i = 0; i < WL; ++i) {
-            if (j == 0 || i == WL - 1) mbar_wait(smem_u32(&sm.dy_full[s]), ph);
-            if (++s == R) { s = 0; ph ^= 1u; }
-          }
+      // column start: the first WL - 1 planes of the window (afterwards every step waits for ONE new plane)
+      if (!no_wait) {
+        for (uint32_t i = 0; i + 1 < WL; ++i) {
+          mbar_wait(bar_dy_full + 8u * nw, nw_phase);
+          if (++nw == R) { nw = 0; nw_phase ^= 1u; }
         }
-        if (dbg) { const long long now = clock64(); tw_dy += now - tq; tq = now; }
-        if (!no_wait) mbar_wait(smem_u32(&sm.a_full[st]), st_phase);
-        if (dbg) tw_a += clock64() - tq;
+      }
+      for (int j = 0; j < nsteps; ++j) {
+        long long tq = Dbg ? clock64() : 0;
+        if (!no_wait) mbar_wait(bar_dy_full + 8u * nw, nw_phase);
+        if (Dbg) { const long long now = clock64(); tw_dy += now - tq; tq = now; }
+        if (!no_wait) mbar_wait(bar_a_full + 8u * st, st_phase);
+        if (Dbg) tw_a += clock64() - tq;
         tc_fence_after_sync();
-        const uint32_t b_stage_lo = b_ring_lo + st * a_stage16;
-        const uint32_t first = t != 0 ? 1u : 0u;
         if (elect_one()) {
+          const uint32_t b_stage_lo = b_ring_lo + st * a_stage16;
           uint32_t wslot = head;
           uint32_t d_col = tmem_base;
-          for (int w = 0; w < a.KS; ++w) {
+#pragma unroll
+          for (int w = 0; w < KS; ++w) {
             const uint32_t a_win_lo = a_ring_lo + wslot * dy_slot16;
-            uint32_t b_tap_lo = b_stage_lo;
-            for (int ti = 0; ti < a.TS; ++ti) {
+#pragma unroll
+            for (int ti = 0; ti < TS; ++ti) {
 #pragma unroll
               for (int ks = 0; ks < 8; ++ks) {
-                umma_bf16_ss(d_col, desc_join(a_hi, a_win_lo + ks * a_kstep), desc_join(b_hi, b_tap_lo + ks * b_kstep), a.idesc,
-                             ks == 0 ? first : 1u);
+                umma_bf16_ss(d_col, desc_join(a_hi, a_win_lo + ks * a_kstep),
+                             desc_join(b_hi, b_stage_lo + ti * b_kw16 + ks * b_kstep), idesc, ks == 0 ? first : 1u);
               }
-              d_col += a.Ncols;
-              b_tap_lo += b_kw16;
+              d_col += Ncols;
             }
             wslot += PM;
             if (wslot >= R) wslot -= R;
           }
           if (!no_commit) {
-            umma_commit(smem_u32(&sm.a_empty[st]));
-            umma_commit(smem_u32(&sm.dy_empty[head]));
+            umma_commit(bar_a_empty + 8u * st);
+            umma_commit(bar_dy_empty + 8u * head);
             if (j == nsteps - 1) {
-              uint32_t s = head;
+              uint32_t s2 = head;
               for (uint32_t i = 1; i < WL; ++i) {
-                if (++s == R) s = 0;
-                umma_commit(smem_u32(&sm.dy_empty[s]));
+                if (++s2 == R) s2 = 0;
+                umma_commit(bar_dy_empty + 8u * s2);
               }
             }
           }
         }
         __syncwarp();
+        first = 1u;
         ++t;
         if (++st == SA) { st = 0; st_phase ^= 1u; }
-        if (++head == R) { head = 0; head_phase ^= 1u; }
+        if (++head == R) head = 0;
+        if (++nw == R) { nw = 0; nw_phase ^= 1u; }
       }
-      // the WL-1 trailing planes of this column are consumed too
+      // the WL-1 trailing planes of this column are consumed too (nw already points past them)
       head += WL - 1;
-      if (head >= R) { head -= R; head_phase ^= 1u; }
+      if (head >= R) head -= R;
     }
     if (elect_one()) umma_commit(smem_u32(&sm.done));
     __syncwarp();
     // Only this warp polls the final mbarrier; the four epilogue warps sleep in a hardware named barrier meanwhile.
     mbar_wait(smem_u32(&sm.done), 0);
     named_bar_sync(1, 160);
-    if (dbg && lane == 0) {
+    if (Dbg && a.dbg != nullptr && lane == 0) {
       long long* d = a.dbg + static_cast<size_t>(blockIdx.x) * 16;
       unsigned long long ns_end;
       asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_end));
@@ -344,6 +360,18 @@ __global__ void wgrad_reduce_kernel(const WgradDev a, float* __restrict__ dw, in
     float* dst = dw + (static_cast<size_t>(o) * a.Cin + i) * 27 + tap;
     *dst = accumulate ? (*dst + acc) : acc;
   }
+}
+
+template <int RBA, int RBB, int KS, int TS, bool Dbg>
+static int launch_wgrad(const CUtensorMap& tm_dy, const CUtensorMap& tm_a, const WgradDev& d, int grid, size_t smem, cudaStream_t st) {
+  auto kern = conv3_wgrad_kernel<RBA, RBB, KS, TS, Dbg>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) {
+    set_last_error("wgrad: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    return -2;
+  }
+  kern<<<grid, kWgThreads, smem, st>>>(tm_dy, tm_a, d);
+  return check_launch("conv3_wgrad_kernel");
 }
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
@@ -477,10 +505,19 @@ extern "C" int rsb_conv3_wgrad(const RsbConv3WgradArgs* p, void* stream) {
   if (smem < 120 * 1024) smem = 120 * 1024;  // 1 CTA / SM: each CTA owns all 512 TMEM columns
   RSB_REQUIRE(smem <= 227 * 1024, "wgrad: shared memory budget exceeded (%zu)", smem);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  cudaError_t e = cudaFuncSetAttribute(conv3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  RSB_REQUIRE(e == cudaSuccess, "wgrad: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-  conv3_wgrad_kernel<<<grid, kWgThreads, smem, st>>>(tm_dy, tm_a, d);
-  rc = check_launch("conv3_wgrad_kernel");
+  const bool dbg = d.dbg != nullptr;
+  rc = -1;
+#define RSB_WG_CASE(RBA_, RBB_, KS_, TS_)                                                                         \
+  if (rc == -1 && d.rba == RBA_ && d.rbb == RBB_ && d.KS == KS_ && d.TS == TS_)                                    \
+    rc = dbg ? launch_wgrad<RBA_, RBB_, KS_, TS_, true>(tm_dy, tm_a, d, grid, smem, st)                            \
+             : launch_wgrad<RBA_, RBB_, KS_, TS_, false>(tm_dy, tm_a, d, grid, smem, st);
+  RSB_WG_CASE(64, 64, 1, 3)     // A
+  RSB_WG_CASE(64, 128, 1, 1)    // B
+  RSB_WG_CASE(128, 128, 2, 1)   // C
+  RSB_WG_CASE(128, 64, 3, 1)    // D
+  RSB_WG_CASE(128, 64, 2, 1)    // E
+#undef RSB_WG_CASE
+  RSB_REQUIRE(rc != -1, "wgrad: no kernel instantiation for tiling (rba %u rbb %u KS %d TS %d)", d.rba, d.rbb, d.KS, d.TS);
   if (rc) return rc;
   const long long total = static_cast<long long>(d.n_groups) * d.piece_floats;
   int rblocks = static_cast<int>((total + 127) / 128);

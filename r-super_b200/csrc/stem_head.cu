@@ -156,23 +156,31 @@ __global__ void stem_wgrad_kernel(const float* __restrict__ x, const T* __restri
 }
 
 // Tiled variant (Cout <= 64): a block stages a 1 x 8 x 32 voxel tile of dy (as fp32) and the haloed
-// 3 x 10 x 34 input tile in shared memory; thread (tap, 8-channel group) then walks the 256 voxels
-// with 3 shared loads per 8 FMAs and keeps its 8 partial sums in registers across all its tiles.
+// 3 x 10 x 34 input tile in shared memory.  Thread (tile row g, (kd, kh), 8-channel group) walks the 32 voxels of
+// its row with a sliding 3-wide input window and keeps 3 (kw) x 8 (channels) partial sums in registers across all
+// its tiles: 3 shared loads per 24 FMAs (the first tiled version — one tap per thread, 3 loads per 8 FMAs — was
+// bound by shared-memory issue: 650 us at 2 x 128^3 x 32).
 constexpr int kSwTX = 32, kSwTY = 8;
 constexpr int kSwVox = kSwTX * kSwTY;
 template <typename T>
-__global__ void __launch_bounds__(256) stem_wgrad_tiled_kernel(const float* __restrict__ x, const T* __restrict__ dy,
+__global__ void __launch_bounds__(576) stem_wgrad_tiled_kernel(const float* __restrict__ x, const T* __restrict__ dy,
                                                                long long dyp, float* __restrict__ dw, int N, int D,
                                                                int H, int W, int Cout, int tiles_x, int tiles_y,
                                                                long long num_tiles) {
   extern __shared__ float sm[];
   float* sx = sm;                         // [3][10][34]
   float* sdy = sm + 3 * 10 * 34;          // [256][Cout]
+  float* sacc = sdy + kSwVox * Cout;      // [27][Cout] block-level reduction over the 8 row groups
   const int CG = Cout / 8;
-  const int tap = threadIdx.x / CG, cg = threadIdx.x % CG;
-  const bool active = tap < 27;
-  const int dz = tap / 9, dyy = (tap / 3) % 3, dxx = tap % 3;
-  float acc[8] = {0};
+  const int g = threadIdx.x / (9 * CG), r = threadIdx.x % (9 * CG);   // blockDim.x == 8 * 9 * CG
+  const int khd = r / CG, cg = r % CG;
+  const int dz = khd / 3, dyy = khd % 3;
+  for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) sacc[i] = 0.f;
+  float acc[3][8];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
   for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     long long t = tile;
     const int xt = static_cast<int>(t % tiles_x); t /= tiles_x;
@@ -202,23 +210,34 @@ __global__ void __launch_bounds__(256) stem_wgrad_tiled_kernel(const float* __re
       d4[1] = make_float4(f[4], f[5], f[6], f[7]);
     }
     __syncthreads();
-    if (active) {
+    const float* xr = sx + (dz * 10 + g + dyy) * 34;
+    const float* dr = sdy + (g * kSwTX) * Cout + cg * 8;
+    float xa = xr[0], xb = xr[1];
 #pragma unroll 4
-      for (int v = 0; v < kSwVox; ++v) {
-        const int vy = v / kSwTX, vx = v % kSwTX;
-        const float xv = sx[(dz * 10 + vy + dyy) * 34 + vx + dxx];
-        const float4* d4 = reinterpret_cast<const float4*>(sdy + v * Cout + cg * 8);
-        const float4 a = d4[0], b = d4[1];
-        acc[0] = fmaf(xv, a.x, acc[0]); acc[1] = fmaf(xv, a.y, acc[1]);
-        acc[2] = fmaf(xv, a.z, acc[2]); acc[3] = fmaf(xv, a.w, acc[3]);
-        acc[4] = fmaf(xv, b.x, acc[4]); acc[5] = fmaf(xv, b.y, acc[5]);
-        acc[6] = fmaf(xv, b.z, acc[6]); acc[7] = fmaf(xv, b.w, acc[7]);
+    for (int vx = 0; vx < kSwTX; ++vx) {
+      const float xc = xr[vx + 2];
+      const float4* d4 = reinterpret_cast<const float4*>(dr + vx * Cout);
+      const float4 a = d4[0], b = d4[1];
+      const float d[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[0][j] = fmaf(xa, d[j], acc[0][j]);
+        acc[1][j] = fmaf(xb, d[j], acc[1][j]);
+        acc[2][j] = fmaf(xc, d[j], acc[2][j]);
       }
+      xa = xb;
+      xb = xc;
     }
   }
-  if (active) {
+  __syncthreads();
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&dw[(cg * 8 + j) * 27 + tap], acc[j]);
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&sacc[(khd * 3 + k) * Cout + cg * 8 + j], acc[k][j]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) {
+    const int tap = i / Cout, co = i % Cout;
+    atomicAdd(&dw[co * 27 + tap], sacc[i]);
   }
 }
 
@@ -386,9 +405,9 @@ extern "C" int rsb_stem_conv_wgrad(const float* x, const void* dy, int dy_pitch,
   if (Cout <= 64) {
     const int tiles_x = (W + kSwTX - 1) / kSwTX, tiles_y = (H + kSwTY - 1) / kSwTY;
     const long long num_tiles = static_cast<long long>(N) * D * tiles_y * tiles_x;
-    const size_t smb = sizeof(float) * (3 * 10 * 34 + kSwVox * Cout);
-    const int threads = ((27 * (Cout / 8)) + 31) / 32 * 32;
-    long long blocks = static_cast<long long>(sms) * 4;
+    const size_t smb = sizeof(float) * (3 * 10 * 34 + kSwVox * Cout + 27 * Cout);
+    const int threads = 8 * 9 * (Cout / 8);
+    long long blocks = static_cast<long long>(sms) * (Cout <= 32 ? 4 : 2);
     if (blocks > num_tiles) blocks = num_tiles;
     cudaError_t ea;
     if (dtype == RSB_BF16) {

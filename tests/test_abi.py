@@ -50,8 +50,8 @@ def test_argument_validation_returns_errors_without_a_gpu():
     assert lib.rsb_conv3_pack_plan(jobs, 2, ctypes.byref(nblk)) == 0   # host-only planning: no device access
     assert (jobs[0].co_eff, jobs[0].ci_eff, jobs[0].NT, jobs[0].nchunks) == (64, 32, 64, 1)
     assert (jobs[1].co_eff, jobs[1].ci_eff, jobs[1].NT, jobs[1].nchunks) == (32, 64, 32, 2)
-    assert jobs[0].total == 27 * 64 * 32 and jobs[1].block_begin == (jobs[0].total + 255) // 256
-    assert nblk.value == jobs[1].block_begin + (jobs[1].total + 255) // 256
+    assert jobs[0].total == 27 * 64 * 32 and jobs[1].block_begin == (64 // 8) * 1   # one block per (8 co, 32 ci) tile
+    assert nblk.value == jobs[1].block_begin + (32 // 8) * 2
     assert lib.rsb_conv3_pack_weights_batched(None, 2, nblk, None) != 0
     w = _lib.RsbConv3WgradArgs()
     assert lib.rsb_conv3_wgrad(ctypes.byref(w), None) != 0 and b"null" in lib.rsb_last_error()

@@ -244,7 +244,8 @@ def test_maxpool_forward_backward_with_ties(cuda_dev):
     assert torch.equal(dx, cl(xz.grad) + dskip)  # bit-exact routing
 
 
-@pytest.mark.parametrize("dims", [((4, 4, 4), (8, 8, 8)), ((2, 2, 2), (4, 4, 4)), ((8, 6, 4), (16, 12, 8))])
+@pytest.mark.parametrize("dims", [((4, 4, 4), (8, 8, 8)), ((2, 2, 2), (4, 4, 4)), ((8, 6, 4), (16, 12, 8)),
+                                  ((5, 4, 3), (9, 8, 7)), ((32, 16, 16), (64, 32, 32)), ((1, 3, 3), (2, 6, 6))])
 def test_upsample_trilinear(cuda_dev, dims):
     from rsuper_b200 import ops
     (di, hi, wi), (do, ho, wo) = dims
