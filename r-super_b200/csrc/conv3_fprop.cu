@@ -857,11 +857,14 @@ extern "C" int rsb_conv3_forward(const RsbConv3Args* p, void* stream) {
   int PZ = p->planes_per_item;
   if (PZ == 0) {
     // as many planes per item as the double-buffered accumulators allow (more planes = wider merged MMAs and
-    // more reuse of every weight slice), but at least ~2 items per SM
+    // more reuse of every weight slice: an item streams the whole packed weight tensor of its N tile from L2, so the
+    // deep layers are L2-bandwidth bound at PZ = 1), as long as ~3/4 of the SMs still get an item
+    // (measured, tools/probe_pz.py: 128->128 @32^3 88 -> 66 us and 576->512 @16^3 170 -> 115 us at PZ = 2;
+    // 256->256 @16^3 with only 64 items at PZ = 2 is slower than 128 items at PZ = 1).
     PZ = d.NT <= 64 ? 4 : 2;
     while (PZ > 1) {
       const long long items = static_cast<long long>(p->N) * ((p->D + PZ - 1) / PZ) * d.tiles_y * d.tiles_x * d.ntiles;
-      if (PZ <= p->D && items >= 2LL * sms) break;
+      if (PZ <= p->D && items * 4 >= 3LL * sms) break;
       PZ >>= 1;
     }
   }

@@ -18,15 +18,16 @@ namespace rsb {
 // element id e = voxel * CG + cg (CG = C/8 channel groups); blockDim.x is a multiple of CG so a
 // thread keeps the same channel group over its grid-stride loop.
 struct ClMap {
-  int cg;        // channel group of this thread
-  long long e0;  // first element id
-  long long stride;
+  int cg;         // channel group of this thread
+  long long v0;   // first voxel
+  long long vstride;  // voxels per grid sweep (blockDim.x % CG == 0, so a thread keeps its channel group)
 };
 RSB_DEVICE ClMap cl_map(int CG) {
   ClMap m;
-  m.e0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  m.stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  m.cg = static_cast<int>(m.e0 % CG);
+  const unsigned vpb = blockDim.x / CG;  // voxels per block
+  m.cg = static_cast<int>(threadIdx.x % CG);
+  m.v0 = static_cast<long long>(blockIdx.x) * vpb + threadIdx.x / CG;
+  m.vstride = static_cast<long long>(gridDim.x) * vpb;
   return m;
 }
 
@@ -67,8 +68,7 @@ __global__ void ncdhw_to_ndhwc_kernel(const float* __restrict__ src, T* __restri
   const int CG = C / 8;
   const int n = blockIdx.y;
   ClMap m = cl_map(CG);
-  for (long long e = m.e0; e < V * CG; e += m.stride) {
-    const long long v = e / CG;
+  for (long long v = m.v0; v < V; v += m.vstride) {
     float f[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) f[j] = src[(static_cast<long long>(n) * C + m.cg * 8 + j) * V + v];
@@ -82,8 +82,7 @@ __global__ void ndhwc_to_ncdhw_kernel(const T* __restrict__ src, long long pitch
   const int CG = C / 8;
   const int n = blockIdx.y;
   ClMap m = cl_map(CG);
-  for (long long e = m.e0; e < V * CG; e += m.stride) {
-    const long long v = e / CG;
+  for (long long v = m.v0; v < V; v += m.vstride) {
     float f[8];
     Vec8<T>::load(src + (static_cast<long long>(n) * V + v) * pitch + m.cg * 8, f);
 #pragma unroll
@@ -99,8 +98,7 @@ __global__ void channel_stats_kernel(const T* __restrict__ x, long long pitch, f
   const int n = blockIdx.y;
   ClMap m = cl_map(CG);
   float s1[8] = {0}, s2[8] = {0};
-  for (long long e = m.e0; e < V * CG; e += m.stride) {
-    const long long v = e / CG;
+  for (long long v = m.v0; v < V; v += m.vstride) {
     float f[8];
     Vec8<T>::load(x + (static_cast<long long>(n) * V + v) * pitch + m.cg * 8, f);
 #pragma unroll
@@ -122,11 +120,12 @@ __global__ void maxpool2_fwd_kernel(const T* __restrict__ x, long long xp, T* __
   const long long Vo = static_cast<long long>(Do) * Ho * Wo;
   ClMap m = cl_map(CG);
   float s1[8] = {0}, s2[8] = {0};
-  for (long long e = m.e0; e < Vo * CG; e += m.stride) {
-    const long long v = e / CG;
-    const int xo = static_cast<int>(v % Wo);
-    const int yo = static_cast<int>((v / Wo) % Ho);
-    const int zo = static_cast<int>(v / (static_cast<long long>(Wo) * Ho));
+  for (long long v = m.v0; v < Vo; v += m.vstride) {
+    const unsigned vu = static_cast<unsigned>(v);   // per-sample voxel index: host checks Vo < 2^31
+    const unsigned row = vu / static_cast<unsigned>(Wo);
+    const int xo = static_cast<int>(vu - row * Wo);
+    const int zo = static_cast<int>(row / static_cast<unsigned>(Ho));
+    const int yo = static_cast<int>(row - static_cast<unsigned>(zo) * Ho);
     float best[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) best[j] = -INFINITY;
@@ -157,11 +156,12 @@ __global__ void maxpool2_bwd_kernel(const T* __restrict__ x, long long xp, const
   const int Do = D / 2, Ho = H / 2, Wo = W / 2;
   const long long Vo = static_cast<long long>(Do) * Ho * Wo;
   ClMap m = cl_map(CG);
-  for (long long e = m.e0; e < Vo * CG; e += m.stride) {
-    const long long v = e / CG;
-    const int xo = static_cast<int>(v % Wo);
-    const int yo = static_cast<int>((v / Wo) % Ho);
-    const int zo = static_cast<int>(v / (static_cast<long long>(Wo) * Ho));
+  for (long long v = m.v0; v < Vo; v += m.vstride) {
+    const unsigned vu = static_cast<unsigned>(v);   // per-sample voxel index: host checks Vo < 2^31
+    const unsigned row = vu / static_cast<unsigned>(Wo);
+    const int xo = static_cast<int>(vu - row * Wo);
+    const int zo = static_cast<int>(row / static_cast<unsigned>(Ho));
+    const int yo = static_cast<int>(row - static_cast<unsigned>(zo) * Ho);
     float best[8];
     int arg[8];
 #pragma unroll
@@ -289,60 +289,58 @@ __global__ void upsample_fwd_kernel(const T* __restrict__ x, long long xp, T* __
   if (stats != nullptr) block_stats_flush(sm_acc, s1, s2, cg, C, stats + static_cast<long long>(n) * yp * 2);
 }
 
-// Adjoint as a deterministic gather: for input index i, candidate outputs o with src(o) in (i-1, i+1).
-struct Taps {
-  int o[6];
+// Adjoint as a deterministic gather: input index i receives from the outputs o whose source coordinate lies in
+// (i-1, i+1).  They are consecutive, so the taps are a dense window o0 .. o0+5 with zero weights outside the support
+// (at most ceil(2 / scale) <= 6 outputs for ratios up to 2.5); dense + compile-time indexing keeps everything in
+// registers (a compacted {index, weight} list needs dynamic indexing => local memory: that version ran at 710 us).
+struct Win {
+  int o0;
   float w[6];
-  int cnt;
 };
-RSB_DEVICE Taps adjoint_taps(int i, float scale, int in_size, int out_size) {
-  Taps t;
-  t.cnt = 0;
-  int lo, hi;
+RSB_DEVICE float adjoint_weight(int o, int i, float scale, int in_size) {
+  const Lerp l = lerp_src(o, scale, in_size);
+  return (l.i0 == i ? l.w0 : 0.f) + (l.i1 == i ? l.w1 : 0.f);
+}
+RSB_DEVICE Win adjoint_window(int i, float scale, int in_size, int out_size) {
+  Win t;
+  int lo = 0;
   if (scale > 0.f) {
     lo = static_cast<int>(floorf((static_cast<float>(i) - 1.f) / scale)) - 1;
-    hi = static_cast<int>(ceilf((static_cast<float>(i) + 1.f) / scale)) + 1;
-  } else {
-    lo = 0;
-    hi = out_size - 1;
+    if (lo < 0) lo = 0;
+    for (int k = 0; k < 4 && lo < out_size - 1 && adjoint_weight(lo, i, scale, in_size) == 0.f; ++k) ++lo;
   }
-  if (lo < 0) lo = 0;
-  if (hi > out_size - 1) hi = out_size - 1;
+  t.o0 = lo;
 #pragma unroll
-  for (int k = 0; k < 6; ++k) { t.o[k] = 0; t.w[k] = 0.f; }
-  for (int o = lo; o <= hi; ++o) {
-    const Lerp l = lerp_src(o, scale, in_size);
-    float w = 0.f;
-    if (l.i0 == i) w += l.w0;
-    if (l.i1 == i) w += l.w1;
-    if (w != 0.f && t.cnt < 6) {
-      t.o[t.cnt] = o;
-      t.w[t.cnt] = w;
-      ++t.cnt;
-    }
-  }
+  for (int k = 0; k < 6; ++k) t.w[k] = (lo + k < out_size) ? adjoint_weight(lo + k, i, scale, in_size) : 0.f;
   return t;
 }
 
 // Adjoint, z-walking: a thread owns one input column (yi, xi, 8 channels) of a z-chunk [za, zb) of input planes and walks
-// the output planes that touch it.  Per output plane it gathers the (y, x) adjoint Q(zo) (cnt_y * cnt_x vector loads, all
-// independent) and adds lz.w0 * Q / lz.w1 * Q to the two open input-plane accumulators; a finished input plane is
-// stored once.  Deterministic (no atomics); ~4 loads per output element instead of the ~8 of the per-voxel 3-D gather.
+// the output planes that touch it.  Per output plane it gathers the (y, x) adjoint Q(zo) (independent vector loads) and
+// adds lz.w0 * Q / lz.w1 * Q to the two open input-plane accumulators; a finished input plane is stored once.
+// Deterministic (no atomics).
+// A block covers an (xt x yt) patch of input columns: the output rows / columns its threads gather from overlap, so
+// the patch shape sets the L2 -> L1 traffic (19 x 19 output voxels per 8 x 8 inputs: 1.4x the output tensor; a single
+// input row per block reads it 2.7x and was L2-bandwidth bound).
 template <typename T>
-__global__ void upsample_bwd_kernel(const T* __restrict__ dy, long long dyp, T* __restrict__ dx, long long dxp,
-                                    int Di, int Hi, int Wi, int Do, int Ho, int Wo, int C, float sd,
-                                    float sh, float sw, int zchunk) {
+__global__ void __launch_bounds__(512)
+upsample_bwd_kernel(const T* __restrict__ dy, long long dyp, T* __restrict__ dx, long long dxp,
+                    int Di, int Hi, int Wi, int Do, int Ho, int Wo, int C, float sd,
+                    float sh, float sw, int zchunk, int xt) {
   const int CG = C / 8;
-  const int n = blockIdx.z / zchunk_count(Di, zchunk);
-  const int zc = blockIdx.z % zchunk_count(Di, zchunk);
-  const int yi = blockIdx.y;
+  const int nzc = zchunk_count(Di, zchunk);
+  const int n = blockIdx.z / nzc;
+  const int zc = blockIdx.z % nzc;
   const int cg = threadIdx.x % CG;
-  const int xi = blockIdx.x * (blockDim.x / CG) + threadIdx.x / CG;
-  if (xi >= Wi) return;
+  const int col = threadIdx.x / CG;
+  const int xi = blockIdx.x * xt + col % xt;
+  const int yi = blockIdx.y * (blockDim.x / (CG * xt)) + col / xt;
+  if (xi >= Wi || yi >= Hi) return;
   const int za = zc * zchunk, zb = min(Di, za + zchunk);
-  const Taps ty = adjoint_taps(yi, sh, Hi, Ho), tx = adjoint_taps(xi, sw, Wi, Wo);
+  const Win ty = adjoint_window(yi, sh, Hi, Ho), tx = adjoint_window(xi, sw, Wi, Wo);
   const long long oplane = static_cast<long long>(Ho) * Wo * dyp;
-  const T* db = dy + static_cast<long long>(n) * Do * oplane + cg * 8;
+  const T* db = dy + static_cast<long long>(n) * Do * oplane + (static_cast<long long>(ty.o0) * Wo + tx.o0) * dyp + cg * 8;
+  const long long orow = static_cast<long long>(Wo) * dyp;
   T* xc = dx + ((static_cast<long long>(n) * Di * Hi + yi) * Wi + xi) * dxp + cg * 8;
   const long long xstep = static_cast<long long>(Hi) * Wi * dxp;
   // first output plane whose upper source plane reaches za
@@ -365,20 +363,25 @@ __global__ void upsample_bwd_kernel(const T* __restrict__ dy, long long dyp, T* 
     }
     float q[8] = {0};
     const T* pz = db + zo * oplane;
-    for (int b = 0; b < ty.cnt; ++b) {
-      const T* prow = pz + static_cast<long long>(ty.o[b]) * Wo * dyp;
-      float r[8] = {0};
+    // rows one at a time (weight recomputed, not indexed: a fully unrolled 6 x 6 gather hoists 36 loads and spills)
+#pragma unroll 1
+    for (int b = 0; b < 6; ++b) {
+      const float wyb = (ty.o0 + b < Ho) ? adjoint_weight(ty.o0 + b, yi, sh, Hi) : 0.f;
+      if (wyb != 0.f) {
+        const T* prow = pz + b * orow;
+        float r[8] = {0};
 #pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        if (c < tx.cnt) {
-          float f[8];
-          Vec8<T>::load(prow + static_cast<long long>(tx.o[c]) * dyp, f);
+        for (int c = 0; c < 6; ++c) {
+          if (tx.w[c] != 0.f) {
+            float f[8];
+            Vec8<T>::load(prow + c * dyp, f);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) r[j] = fmaf(tx.w[c], f[j], r[j]);
+            for (int j = 0; j < 8; ++j) r[j] = fmaf(tx.w[c], f[j], r[j]);
+          }
         }
-      }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) q[j] = fmaf(ty.w[b], r[j], q[j]);
+        for (int j = 0; j < 8; ++j) q[j] = fmaf(wyb, r[j], q[j]);
+      }
     }
     // lz.i0 == cur or (lz.i0 < za: only its upper plane belongs to this chunk)
     const float wa = (lz.i0 == cur ? lz.w0 : 0.f) + (lz.i1 == cur ? lz.w1 : 0.f);
@@ -393,6 +396,56 @@ __global__ void upsample_bwd_kernel(const T* __restrict__ dy, long long dyp, T* 
     Vec8<T>::store(xc + cur * xstep, accA);
 #pragma unroll
     for (int j = 0; j < 8; ++j) { accA[j] = accB[j]; accB[j] = 0.f; }
+  }
+}
+
+// Two-pass adjoint, pass 1: the z-adjoint at output (y, x) resolution.  A thread owns one output pixel column
+// (p = yo * Wo + xo, 8 channels) of a chunk [za, zb) of input planes and walks zo with ONE vector load per output
+// element, keeping the two open input-plane accumulators in registers.  The expensive (y, x) gather (up to 5 x 5
+// taps) then runs on Di planes instead of Do: half the loads and FMAs for a x2 upsampling.
+template <typename T>
+__global__ void upsample_bwd_z_kernel(const T* __restrict__ dy, long long dyp, T* __restrict__ tmp, int Di, int Do,
+                                      long long HW, int C, float sd, int zchunk) {
+  const int CG = C / 8;
+  const int nzc = zchunk_count(Di, zchunk);
+  const int n = blockIdx.y / nzc, zc = blockIdx.y % nzc;
+  const int za = zc * zchunk, zb = min(Di, za + zchunk);
+  ClMap m = cl_map(CG);
+  int zo_first = 0;
+  if (za > 0 && sd > 0.f) {
+    zo_first = static_cast<int>(floorf((static_cast<float>(za) - 1.f) / sd)) - 1;
+    if (zo_first < 0) zo_first = 0;
+  }
+  for (long long p = m.v0; p < HW; p += m.vstride) {
+    const T* src = dy + (static_cast<long long>(n) * Do * HW + p) * dyp + m.cg * 8;
+    T* dst = tmp + (static_cast<long long>(n) * Di * HW + p) * C + m.cg * 8;
+    float accA[8] = {0}, accB[8] = {0};
+    int cur = za;
+    for (int zo = zo_first; zo < Do; ++zo) {
+      const Lerp lz = lerp_src(zo, sd, Di);
+      if (lz.i1 < za) continue;
+      if (lz.i0 >= zb) break;
+      while (cur < lz.i0) {
+        Vec8<T>::store(dst + cur * HW * C, accA);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { accA[j] = accB[j]; accB[j] = 0.f; }
+        ++cur;
+      }
+      float q[8];
+      Vec8<T>::load(src + zo * HW * dyp, q);
+      const float wa = (lz.i0 == cur ? lz.w0 : 0.f) + (lz.i1 == cur ? lz.w1 : 0.f);
+      const float wb = (lz.i1 == cur + 1) ? lz.w1 : 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        accA[j] = fmaf(wa, q[j], accA[j]);
+        accB[j] = fmaf(wb, q[j], accB[j]);
+      }
+    }
+    for (; cur < zb; ++cur) {
+      Vec8<T>::store(dst + cur * HW * C, accA);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { accA[j] = accB[j]; accB[j] = 0.f; }
+    }
   }
 }
 
@@ -417,8 +470,8 @@ __global__ void instnorm_bwd_apply_kernel(const T* __restrict__ g, long long gp,
     m1[j] = bwd_sums[sidx] * inv;
     m2[j] = bwd_sums[sidx + 1] * inv;
   }
-  for (long long e = m.e0; e < V * CG; e += m.stride) {
-    const long long v = static_cast<long long>(n) * V + e / CG;
+  for (long long vl = m.v0; vl < V; vl += m.vstride) {
+    const long long v = static_cast<long long>(n) * V + vl;
     float gv[8], xv[8], o[8];
     Vec8<T>::load(g + v * gp + m.cg * 8, gv);
     Vec8<T>::load(x + v * xp + m.cg * 8, xv);
@@ -465,8 +518,8 @@ __global__ void norm_act_kernel(const T* __restrict__ x, long long xp, const flo
       sh[j] = -mean * rstd;
     }
   }
-  for (long long e = m.e0; e < V * CG; e += m.stride) {
-    const long long v = static_cast<long long>(n) * V + e / CG;
+  for (long long vl = m.v0; vl < V; vl += m.vstride) {
+    const long long v = static_cast<long long>(n) * V + vl;
     float f[8], h[8];
     Vec8<T>::load(x + v * xp + m.cg * 8, f);
 #pragma unroll
@@ -552,7 +605,8 @@ extern "C" int rsb_maxpool2_forward(const void* x, int x_pitch, void* y, int y_p
   RSB_REQUIRE(D % 2 == 0 && H % 2 == 0 && W % 2 == 0 && D > 0, "maxpool2: spatial dims must be even (%d,%d,%d)", D, H, W);
   RSB_CL_COMMON(C, N)
   const long long Vo = static_cast<long long>(D / 2) * (H / 2) * (W / 2);
-  dim3 grid(cl_grid(Vo * CG, block, sms, 4), N);
+  RSB_REQUIRE(Vo < (1LL << 31), "maxpool2: volume too large");
+  dim3 grid(cl_grid(Vo * CG, block, sms, 8), N);
   const size_t sm = sizeof(float) * 2 * C;
   RSB_BY_DTYPE(dtype,
                (maxpool2_fwd_kernel<__nv_bfloat16><<<grid, block, sm, st>>>((const __nv_bfloat16*)x, x_pitch, (__nv_bfloat16*)y, y_pitch, out_stats, D, H, W, C)),
@@ -567,6 +621,7 @@ extern "C" int rsb_maxpool2_backward(const void* x, int x_pitch, const void* dy,
   RSB_REQUIRE(D % 2 == 0 && H % 2 == 0 && W % 2 == 0 && D > 0, "maxpool2: spatial dims must be even (%d,%d,%d)", D, H, W);
   RSB_CL_COMMON(C, N)
   const long long Vo = static_cast<long long>(D / 2) * (H / 2) * (W / 2);
+  RSB_REQUIRE(Vo < (1LL << 31), "maxpool2: volume too large");
   dim3 grid(cl_grid(Vo * CG, block, sms), N);
   RSB_BY_DTYPE(dtype,
                (maxpool2_bwd_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)x, x_pitch, (const __nv_bfloat16*)dy, dy_pitch, (const __nv_bfloat16*)dskip, dskip_pitch, (__nv_bfloat16*)dx, dx_pitch, D, H, W, C)),
@@ -594,25 +649,52 @@ extern "C" int rsb_upsample_trilinear_forward(const void* x, int x_pitch, void* 
 
 extern "C" int rsb_upsample_trilinear_backward(const void* dy, int dy_pitch, void* dx, int dx_pitch, int dtype,
                                                int N, int Di, int Hi, int Wi, int Do, int Ho, int Wo, int C,
-                                               void* stream) {
+                                               void* workspace, void* stream) {
   RSB_REQUIRE(dy && dx, "upsample_backward: null pointer");
   RSB_REQUIRE(Di > 0 && Hi > 0 && Wi > 0 && Do > 0 && Ho > 0 && Wo > 0, "upsample: bad geometry");
   RSB_CL_COMMON(C, N)
-  RSB_REQUIRE(Hi <= 65535, "upsample: input height too large");
-  RSB_REQUIRE(Do >= Di, "upsample_backward: output depth must not be smaller than the input depth");
-  const int xt = block / CG;
+  RSB_REQUIRE(Do >= Di && Ho >= Hi && Wo >= Wi, "upsample_backward: output must not be smaller than the input");
+  RSB_REQUIRE(2 * Ho <= 5 * Hi + 1 && 2 * Wo <= 5 * Wi + 1, "upsample_backward: y / x ratios above 2.5 are not supported");
+  const float sd_full = ac_scale(Di, Do);
+  if (workspace != nullptr && Do > Di) {
+    // pass 1: z-adjoint into the workspace [N][Di][Ho][Wo][C]; pass 2 below then sees Do == Di (identity in z)
+    const long long HW = static_cast<long long>(Ho) * Wo;
+    int nz1 = 1;
+    while (nz1 < 8 && (HW * CG / block) * N * nz1 < sms * 4LL && (Di + nz1 * 2 - 1) / (nz1 * 2) >= 4) nz1 *= 2;
+    const int zchunk1 = (Di + nz1 - 1) / nz1;
+    const int nzc1 = (Di + zchunk1 - 1) / zchunk1;
+    RSB_REQUIRE(static_cast<long long>(N) * nzc1 <= 65535, "upsample_backward: grid too large");
+    dim3 g1(cl_grid(HW * CG, block, sms, 16), N * nzc1);
+    RSB_BY_DTYPE(dtype,
+                 (upsample_bwd_z_kernel<__nv_bfloat16><<<g1, block, 0, st>>>((const __nv_bfloat16*)dy, dy_pitch, (__nv_bfloat16*)workspace, Di, Do, HW, C, sd_full, zchunk1)),
+                 (upsample_bwd_z_kernel<float><<<g1, block, 0, st>>>((const float*)dy, dy_pitch, (float*)workspace, Di, Do, HW, C, sd_full, zchunk1)))
+    const int rc1 = check_launch("upsample_bwd_z_kernel");
+    if (rc1) return rc1;
+    dy = workspace;
+    dy_pitch = C;
+    Do = Di;
+  }
+  // patch of input columns per block: xt x yt with CG * xt * yt <= 512 threads
+  int xt = 8;
+  while (xt > 1 && CG * xt > 512) xt >>= 1;
+  RSB_REQUIRE(CG * xt <= 512, "upsample_backward: too many channels (%d)", C);
+  int yt = 512 / (CG * xt);
+  if (yt > 8) yt = 8;
+  if (yt > Hi) yt = Hi;
+  const int threads = CG * xt * yt;
+  const int gx = (Wi + xt - 1) / xt, gy = (Hi + yt - 1) / yt;
   // z chunks: enough threads to fill the machine (each thread walks ~Do / nz output planes)
-  const long long cols = static_cast<long long>(N) * Hi * ((Wi + xt - 1) / xt);
+  const long long blocks = static_cast<long long>(N) * gx * gy;
   int nz = 1;
-  while (nz < 8 && cols * nz < sms * 6LL && (Di + nz * 2 - 1) / (nz * 2) >= 4) nz *= 2;
+  while (nz < 16 && blocks * nz < sms * 3LL && (Di + nz * 2 - 1) / (nz * 2) >= 2) nz *= 2;
   const int zchunk = (Di + nz - 1) / nz;
   const int nzc = (Di + zchunk - 1) / zchunk;
-  RSB_REQUIRE(static_cast<long long>(N) * nzc <= 65535, "upsample_backward: batch too large");
-  dim3 grid(static_cast<unsigned>((Wi + xt - 1) / xt), Hi, N * nzc);
+  RSB_REQUIRE(static_cast<long long>(N) * nzc <= 65535 && gy <= 65535, "upsample_backward: grid too large");
+  dim3 grid(gx, gy, N * nzc);
   const float sd = ac_scale(Di, Do), sh = ac_scale(Hi, Ho), sw = ac_scale(Wi, Wo);
   RSB_BY_DTYPE(dtype,
-               (upsample_bwd_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)dy, dy_pitch, (__nv_bfloat16*)dx, dx_pitch, Di, Hi, Wi, Do, Ho, Wo, C, sd, sh, sw, zchunk)),
-               (upsample_bwd_kernel<float><<<grid, block, 0, st>>>((const float*)dy, dy_pitch, (float*)dx, dx_pitch, Di, Hi, Wi, Do, Ho, Wo, C, sd, sh, sw, zchunk)))
+               (upsample_bwd_kernel<__nv_bfloat16><<<grid, threads, 0, st>>>((const __nv_bfloat16*)dy, dy_pitch, (__nv_bfloat16*)dx, dx_pitch, Di, Hi, Wi, Do, Ho, Wo, C, sd, sh, sw, zchunk, xt)),
+               (upsample_bwd_kernel<float><<<grid, threads, 0, st>>>((const float*)dy, dy_pitch, (float*)dx, dx_pitch, Di, Hi, Wi, Do, Ho, Wo, C, sd, sh, sw, zchunk, xt)))
   return check_launch("upsample_trilinear_backward");
 }
 

@@ -108,7 +108,7 @@ SIGNATURES = {
                                                c_int, c_void_p]),
     "rsb_upsample_trilinear_backward": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int,
                                                 c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                                                c_int, c_void_p]),
+                                                c_int, c_void_p, c_void_p]),
     "rsb_instnorm_backward_apply": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,
                                             c_void_p, c_int, c_void_p, c_int, c_int, c_float,
                                             c_int, c_int, c_int, c_int, c_int, c_void_p]),

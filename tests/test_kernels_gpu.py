@@ -261,9 +261,10 @@ def test_upsample_trilinear(cuda_dev, dims):
     assert rel(st, stats_of(cl(ref))) <= 1e-4
     dy = torch.randn(N, do, ho, wo, C, generator=g).to(cuda_dev)
     ref.backward(nc(dy))
-    dx = torch.zeros_like(x)
-    ops.upsample_backward(dy, dx)
-    assert rel(dx, cl(xz.grad)) <= 1e-5
+    for two_pass in (True, False):   # z-adjoint into a scratch + (y, x) gather  |  single-pass 3-D gather
+        dx = torch.full_like(x, float("nan"))
+        ops.upsample_backward(dy, dx, two_pass=two_pass)
+        assert rel(dx, cl(xz.grad)) <= 1e-5
 
 
 def test_instnorm_backward_apply(cuda_dev):
