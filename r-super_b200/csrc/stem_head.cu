@@ -370,6 +370,147 @@ __global__ void head_bwd_weight_kernel(const T* __restrict__ x, long long xp, co
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// head, (voxel, 8-channel group) thread mapping: every global access is a fully coalesced 128-bit access (the
+// one-voxel-per-thread kernels above read 64-byte-strided 16-byte pieces and ran at ~1.7 TB/s); the Cin reduction of
+// the forward finishes with CGC-lane shuffles, the backward fuses dX, dW and db into one pass over (x, dlogits).
+// ------------------------------------------------------------------------------------------
+constexpr int kHeadCgMaxC = 8;
+
+template <typename T, int CGC>
+__global__ void __launch_bounds__(256) head_fwd_cg_kernel(const T* __restrict__ x, long long xp, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, float* __restrict__ logits,
+                                                          long long V, int C) {
+  extern __shared__ float sm[];  // [C][Cin] + [C]
+  constexpr int Cin = CGC * 8;
+  for (int i = threadIdx.x; i < C * Cin; i += blockDim.x) sm[i] = w[i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sm[C * Cin + i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const int n = blockIdx.y;
+  const int cg = threadIdx.x % CGC, vl = threadIdx.x / CGC;
+  constexpr int vpw = 32 / CGC;                      // voxels per warp
+  const long long vstride = static_cast<long long>(gridDim.x) * (256 / CGC);
+  // warp-uniform trip count: the shuffles below need all 32 lanes
+  for (long long vb = static_cast<long long>(blockIdx.x) * (256 / CGC) + (vl / vpw) * vpw; vb < V; vb += vstride) {
+    const long long v = vb + vl % vpw;
+    const bool ok = v < V;
+    float f[8] = {0};
+    if (ok) Vec8<T>::load(x + (static_cast<long long>(n) * V + v) * xp + cg * 8, f);
+    for (int c = 0; c < C; ++c) {
+      const float* wr = sm + c * Cin + cg * 8;
+      float p = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) p = fmaf(f[j], wr[j], p);
+#pragma unroll
+      for (int o = CGC / 2; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+      if (ok && cg == 0) logits[(static_cast<long long>(n) * C + c) * V + v] = p + sm[C * Cin + c];
+    }
+  }
+}
+
+template <typename T, int CGC, int CMAX>
+__global__ void __launch_bounds__(256) head_bwd_cg_kernel(const T* __restrict__ x, long long xp, const float* __restrict__ w,
+                                                          const float* __restrict__ dl, T* __restrict__ dx, long long dxp,
+                                                          float* __restrict__ dw, float* __restrict__ db, long long V, int C) {
+  extern __shared__ float sm[];  // w [C][Cin] | dW partial [C][Cin] | db partial [C]
+  constexpr int Cin = CGC * 8;
+  constexpr int U = 4;           // voxels in flight per thread (memory-level parallelism)
+  float* sw = sm;
+  float* sacc = sm + C * Cin;
+  for (int i = threadIdx.x; i < C * Cin; i += blockDim.x) { sw[i] = w[i]; sacc[i] = 0.f; }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sacc[C * Cin + i] = 0.f;
+  __syncthreads();
+  const int n = blockIdx.y;
+  const int cg = threadIdx.x % CGC;
+  const long long vstride = static_cast<long long>(gridDim.x) * (256 / CGC);
+  float aw[CMAX][8], ab[CMAX];
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) {
+    ab[c] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) aw[c][j] = 0.f;
+  }
+  for (long long v0 = static_cast<long long>(blockIdx.x) * (256 / CGC) + threadIdx.x / CGC; v0 < V; v0 += U * vstride) {
+    Raw8<T> fx[U];
+    float g[U][CMAX];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long v = v0 + u * vstride;
+      if (v < V) {
+        fx[u].load(x + (static_cast<long long>(n) * V + v) * xp + cg * 8);
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) g[u][c] = c < C ? dl[(static_cast<long long>(n) * C + c) * V + v] : 0.f;
+      } else {
+        fx[u].zero();
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) g[u][c] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long v = v0 + u * vstride;
+      float f[8], o[8] = {0};
+      fx[u].to_float(f);
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c) {
+        if (c < C) {
+          const float* wr = sw + c * Cin + cg * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            o[j] = fmaf(g[u][c], wr[j], o[j]);
+            aw[c][j] = fmaf(g[u][c], f[j], aw[c][j]);
+          }
+          ab[c] += g[u][c];
+        }
+      }
+      if (v < V) Vec8<T>::store(dx + (static_cast<long long>(n) * V + v) * dxp + cg * 8, o);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) {
+    if (c < C) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&sacc[c * Cin + cg * 8 + j], aw[c][j]);
+      if (cg == 0) atomicAdd(&sacc[C * Cin + c], ab[c]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * Cin; i += blockDim.x) atomicAdd(&dw[i], sacc[i]);
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&db[i], sacc[C * Cin + i]);
+}
+
+template <typename T>
+static int launch_head_fwd_cg(int CG, dim3 grid, size_t smb, cudaStream_t st, const T* x, long long xp, const float* w,
+                              const float* bias, float* logits, long long V, int C) {
+  switch (CG) {
+    case 1: head_fwd_cg_kernel<T, 1><<<grid, 256, smb, st>>>(x, xp, w, bias, logits, V, C); break;
+    case 2: head_fwd_cg_kernel<T, 2><<<grid, 256, smb, st>>>(x, xp, w, bias, logits, V, C); break;
+    case 4: head_fwd_cg_kernel<T, 4><<<grid, 256, smb, st>>>(x, xp, w, bias, logits, V, C); break;
+    case 8: head_fwd_cg_kernel<T, 8><<<grid, 256, smb, st>>>(x, xp, w, bias, logits, V, C); break;
+    default: return 1;
+  }
+  return 0;
+}
+template <typename T, int CMAX>
+static int launch_head_bwd_cg2(int CG, dim3 grid, size_t smb, cudaStream_t st, const T* x, long long xp, const float* w,
+                               const float* dl, T* dx, long long dxp, float* dw, float* db, long long V, int C) {
+  switch (CG) {
+    case 1: head_bwd_cg_kernel<T, 1, CMAX><<<grid, 256, smb, st>>>(x, xp, w, dl, dx, dxp, dw, db, V, C); break;
+    case 2: head_bwd_cg_kernel<T, 2, CMAX><<<grid, 256, smb, st>>>(x, xp, w, dl, dx, dxp, dw, db, V, C); break;
+    case 4: head_bwd_cg_kernel<T, 4, CMAX><<<grid, 256, smb, st>>>(x, xp, w, dl, dx, dxp, dw, db, V, C); break;
+    case 8: head_bwd_cg_kernel<T, 8, CMAX><<<grid, 256, smb, st>>>(x, xp, w, dl, dx, dxp, dw, db, V, C); break;
+    default: return 1;
+  }
+  return 0;
+}
+template <typename T>
+static int launch_head_bwd_cg(int CG, dim3 grid, size_t smb, cudaStream_t st, const T* x, long long xp, const float* w,
+                              const float* dl, T* dx, long long dxp, float* dw, float* db, long long V, int C) {
+  if (C <= 2) return launch_head_bwd_cg2<T, 2>(CG, grid, smb, st, x, xp, w, dl, dx, dxp, dw, db, V, C);
+  if (C <= 4) return launch_head_bwd_cg2<T, 4>(CG, grid, smb, st, x, xp, w, dl, dx, dxp, dw, db, V, C);
+  return launch_head_bwd_cg2<T, 8>(CG, grid, smb, st, x, xp, w, dl, dx, dxp, dw, db, V, C);
+}
+
 }  // namespace rsb
 
 using namespace rsb;
@@ -442,11 +583,21 @@ extern "C" int rsb_head_forward(const void* x, int x_pitch, int dtype, const flo
   const long long V = static_cast<long long>(D) * H * W;
   const int sms = rsb_num_sms();
   RSB_REQUIRE(sms > 0, "no CUDA device");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t sm = sizeof(float) * (C * Cin + C);
+  const int CG = Cin / 8;
+  if ((CG == 1 || CG == 2 || CG == 4 || CG == 8) && (dtype == RSB_BF16 || dtype == RSB_F32)) {
+    const int vpb = 256 / CG;
+    long long gx = (V + vpb - 1) / vpb;
+    if (gx > sms * 8LL) gx = sms * 8LL;
+    dim3 g(static_cast<unsigned>(gx), N);
+    if (dtype == RSB_BF16) launch_head_fwd_cg<__nv_bfloat16>(CG, g, sm, st, (const __nv_bfloat16*)x, x_pitch, w, bias, logits_ncdhw, V, C);
+    else launch_head_fwd_cg<float>(CG, g, sm, st, (const float*)x, x_pitch, w, bias, logits_ncdhw, V, C);
+    return check_launch("head_fwd_cg_kernel");
+  }
   long long bx = (V + 255) / 256;
   if (bx > sms * 16LL) bx = sms * 16LL;
   dim3 grid(static_cast<unsigned>(bx), N);
-  const size_t sm = sizeof(float) * (C * Cin + C);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == RSB_BF16)
     head_fwd_kernel<__nv_bfloat16><<<grid, 256, sm, st>>>((const __nv_bfloat16*)x, x_pitch, w, bias, logits_ncdhw, V, Cin, C);
   else if (dtype == RSB_F32)
@@ -470,6 +621,19 @@ extern "C" int rsb_head_backward(const void* x, int x_pitch, int dtype, const fl
   RSB_REQUIRE(e == cudaSuccess, "head_backward: memset failed: %s", cudaGetErrorString(e));
   e = cudaMemsetAsync(db, 0, sizeof(float) * C, st);
   RSB_REQUIRE(e == cudaSuccess, "head_backward: memset failed: %s", cudaGetErrorString(e));
+  {
+    const int CG = Cin / 8;
+    if ((CG == 1 || CG == 2 || CG == 4 || CG == 8) && C <= kHeadCgMaxC && (dtype == RSB_BF16 || dtype == RSB_F32)) {
+      const int vpb = 256 / CG;
+      long long gx = (V + vpb - 1) / vpb;
+      if (gx > sms * 6LL) gx = sms * 6LL;
+      dim3 g(static_cast<unsigned>(gx), N);
+      const size_t smb = sizeof(float) * (2 * C * Cin + C);
+      if (dtype == RSB_BF16) launch_head_bwd_cg<__nv_bfloat16>(CG, g, smb, st, (const __nv_bfloat16*)x, x_pitch, w, dlogits_ncdhw, (__nv_bfloat16*)dx, dx_pitch, dw, db, V, C);
+      else launch_head_bwd_cg<float>(CG, g, smb, st, (const float*)x, x_pitch, w, dlogits_ncdhw, (float*)dx, dx_pitch, dw, db, V, C);
+      return check_launch("head_bwd_cg_kernel");
+    }
+  }
   {
     long long bx = (V + 255) / 256;
     if (bx > sms * 16LL) bx = sms * 16LL;

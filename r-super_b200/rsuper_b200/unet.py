@@ -129,7 +129,30 @@ class _Engine:
         self.slope = float(slope)
         self.dtype = dtype
         self.split = dtype == torch.float32
+        self._zp, self._zp_off = None, 0
         self.plan = None  # ops.PackPlan: persistent packed weight images, refreshed by ONE launch per forward
+
+    # ---- zeroed statistics storage: one fill per pass instead of ~50 tiny ones --------------------------
+    def _zeros(self, numel: int, device) -> torch.Tensor:
+        zp = self._zp
+        if zp is None or self._zp_off + numel > zp.numel():
+            zp = self._zp = torch.zeros(max(1 << 16, numel), dtype=torch.float32, device=device)
+            self._zp_off = 0
+        out = zp[self._zp_off:self._zp_off + numel]
+        self._zp_off += (numel + 3) // 4 * 4
+        return out
+
+    def _new_act(self, n, d, h, w, c, dtype, device, stats=True) -> Act:
+        t = torch.empty((n, d, h, w, c), dtype=dtype, device=device)
+        return Act(t, self._zeros(n * c * 2, device).view(n, c, 2) if stats else None)
+
+    def _sums_like(self, a: Act) -> torch.Tensor:
+        """Zeroed (S1,S2) buffer indexed like a's statistics (same pitch, same channel offset)."""
+        pitch = a.t.stride(3)
+        n = a.t.shape[0]
+        full = self._zeros(n * pitch * 2, a.t.device).view(n, pitch, 2)
+        c0 = (a.t.storage_offset() % pitch) if pitch > 0 else 0
+        return full[:, c0:c0 + a.C]
 
     # ---- packed weights ----------------------------------------------------------------------------
     BLOCKS = ([("inc.conv2.", False)]
@@ -178,13 +201,13 @@ class _Engine:
         dev = x.t.device
         a_x = self._operand(x.t, x.st)
         if has_sc:
-            hs = Act.new(n, d, h, w_, 2 * cout, self.dtype, dev)
+            hs = self._new_act(n, d, h, w_, 2 * cout, self.dtype, dev)
             self._conv(a_x, pre + "c1", hs.t, out_stats=hs.st)  # conv1 || shortcut as one GEMM with N = 2*cout
             hh, ss = hs.view(0, cout), hs.view(cout, 2 * cout)
             a_h = self._operand(hh.t, hh.st)
             self._conv(a_h, pre + "c2", out.t, res=ss.t, out_stats=out.st)
         else:
-            hh = Act.new(n, d, h, w_, cout, self.dtype, dev)
+            hh = self._new_act(n, d, h, w_, cout, self.dtype, dev)
             self._conv(a_x, pre + "c1", hh.t, out_stats=hh.st)
             a_h = self._operand(hh.t, hh.st)
             self._conv(a_h, pre + "c2", out.t, res=x.t, out_stats=out.st)
@@ -201,36 +224,37 @@ class _Engine:
         ch = [b, 2 * b, 4 * b, 8 * b, 10 * b]
         dims = [(D >> l, H >> l, W >> l) for l in range(5)]
         saved: list = []
+        self._zp = None  # fresh zero pool: the statistics of this pass live in it until backward is done
         self.prepare(P)
 
         # skip/concat buffers of decoder levels 0..3: [skip ch[l] | upsampled ch_up[l]]
         up_in = [ch[1], ch[2], ch[3], ch[4]]  # channels arriving from below at level l
-        cat = [Act.new(n, *dims[l], ch[l] + up_in[l], dt, dev) for l in range(4)]
+        cat = [self._new_act(n, *dims[l], ch[l] + up_in[l], dt, dev) for l in range(4)]
 
         # inc: stem conv + BasicBlock(b, b)
-        t0 = Act.new(n, *dims[0], b, dt, dev)
+        t0 = self._new_act(n, *dims[0], b, dt, dev)
         ops.stem_conv_forward(x, P["inc.conv1.weight"], t0.t, t0.st)
         self._block_fwd(t0, "inc.conv2.", False, b, cat[0].view(0, ch[0]), saved)
         enc_out = [cat[0].view(0, ch[0])]
         pooled = []
         for l in range(1, 5):
-            p = Act.new(n, *dims[l], ch[l - 1], dt, dev)
+            p = self._new_act(n, *dims[l], ch[l - 1], dt, dev)
             ops.maxpool2_forward(enc_out[l - 1].t, p.t, p.st)
             pooled.append(p)
-            y = Act.new(n, *dims[l], ch[l], dt, dev)
+            y = self._new_act(n, *dims[l], ch[l], dt, dev)
             pre = f"down{l}.conv."
             self._block_fwd(p, pre + "1.", True, ch[l], y, saved)
-            out = cat[l].view(0, ch[l]) if l < 4 else Act.new(n, *dims[4], ch[4], dt, dev)
+            out = cat[l].view(0, ch[l]) if l < 4 else self._new_act(n, *dims[4], ch[4], dt, dev)
             self._block_fwd(y, pre + "2.", False, ch[l], out, saved)
             enc_out.append(out)
         cur = enc_out[4]
         for j, l in enumerate((3, 2, 1, 0), start=1):
             upv = cat[l].view(ch[l], ch[l] + up_in[l])
             ops.upsample_forward(cur.t, upv.t, upv.st)
-            y = Act.new(n, *dims[l], ch[l], dt, dev)
+            y = self._new_act(n, *dims[l], ch[l], dt, dev)
             pre = f"up{j}.conv."
             self._block_fwd(cat[l], pre + "0.", True, ch[l], y, saved)
-            out = Act.new(n, *dims[l], ch[l], dt, dev, stats=(l != 0))
+            out = self._new_act(n, *dims[l], ch[l], dt, dev, stats=(l != 0))
             self._block_fwd(y, pre + "1.", False, ch[l], out, saved)
             cur = out
         logits = torch.empty((n, num_classes, D, H, W), dtype=torch.float32, device=dev)
@@ -252,13 +276,13 @@ class _Engine:
         c = hh.C
         d_op = self._operand(d_out)
         g_h = self._new(d_out, c)
-        sums_h = _sums_like(hh)
+        sums_h = self._sums_like(hh)
         self._conv(d_op, pre + "c2", g_h, flip=True, mask_x=hh.t, mask_stats=hh.st, bwd_sums=sums_h)
         dw2 = self._wgrad(a_h, d_op, self._dw(d_out, c, c))
         ops.instnorm_backward_apply(g_h, hh.t, hh.st, sums_h, g_h)  # in place: g_h becomes d(h)
         gh_op = self._operand(g_h)
         g_x = self._new(d_out, x.C)
-        sums_x = _sums_like(x)
+        sums_x = self._sums_like(x)
         self._conv(gh_op, pre + "c1", g_x, flip=True, mask_x=x.t, mask_stats=x.st, bwd_sums=sums_x)
         dw1 = self._wgrad(a_x, gh_op, self._dw(d_out, c, x.C))
         ops.instnorm_backward_apply(g_x, x.t, x.st, sums_x, dx_dest, add=d_out)
@@ -270,13 +294,13 @@ class _Engine:
         d_out = dcat2[..., c:]
         dh = dcat2[..., :c]
         d_op = self._operand(d_out)
-        sums_h = _sums_like(hh)
+        sums_h = self._sums_like(hh)
         self._conv(d_op, pre + "c2", dh, flip=True, mask_x=hh.t, mask_stats=hh.st, bwd_sums=sums_h)
         dw2 = self._wgrad(a_h, d_op, self._dw(dcat2, c, c))
         ops.instnorm_backward_apply(dh, hh.t, hh.st, sums_h, dh)
         dcat_op = self._operand(dcat2)
         g_x = self._new(dcat2, x.C)
-        sums_x = _sums_like(x)
+        sums_x = self._sums_like(x)
         self._conv(dcat_op, pre + "c1", g_x, flip=True, mask_x=x.t, mask_stats=x.st, bwd_sums=sums_x)
         dwcat = self._wgrad(a_x, dcat_op, self._dw(dcat2, 2 * c, x.C))
         ops.instnorm_backward_apply(g_x, x.t, x.st, sums_x, dx_dest)
@@ -285,6 +309,7 @@ class _Engine:
     def backward(self, S: dict, P: dict, dlogits: torch.Tensor) -> dict:
         ch, up_in, cat = S["ch"], S["up_in"], S["cat"]
         saved = S["saved"]
+        self._zp = None
         b = self.b
         G = {}
         num_classes = dlogits.shape[1]

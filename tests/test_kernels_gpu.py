@@ -205,22 +205,23 @@ def test_stem_and_head(cuda_dev):
     dw = torch.zeros_like(w)
     ops.stem_conv_wgrad(x, dy, dw)
     assert rel(dw, wz.grad) <= 1e-4
-    # head
-    f = torch.randn(N, D, H, W, Co, generator=g).to(cuda_dev)
-    hw = (torch.randn(C, Co, generator=g) / 6).to(cuda_dev).requires_grad_(True)
-    hb = torch.randn(C, generator=g).to(cuda_dev).requires_grad_(True)
-    fz = f.clone().requires_grad_(True)
-    ref = F.conv3d(nc(fz), hw[:, :, None, None, None], hb)
-    logits = torch.zeros(N, C, D, H, W, device=cuda_dev)
-    ops.head_forward(f, hw.detach(), hb.detach(), logits)
-    assert rel(logits, ref) <= 1e-5
-    dl = torch.randn(N, C, D, H, W, generator=g).to(cuda_dev)
-    ref.backward(dl)
-    dx = torch.zeros_like(f)
-    dw_, db_ = torch.zeros(C, Co, device=cuda_dev), torch.zeros(C, device=cuda_dev)
-    ops.head_backward(f, hw.detach(), dl, dx, dw_, db_)
-    assert rel(dx, fz.grad) <= 1e-5
-    assert rel(dw_, hw.grad) <= 1e-4 and rel(db_, hb.grad) <= 1e-4
+    # head: C <= 8 takes the coalesced (voxel, channel-group) kernels, C = 10 the one-voxel-per-thread ones
+    for C in (3, 10):
+        f = torch.randn(N, D, H, W, Co, generator=g).to(cuda_dev)
+        hw = (torch.randn(C, Co, generator=g) / 6).to(cuda_dev).requires_grad_(True)
+        hb = torch.randn(C, generator=g).to(cuda_dev).requires_grad_(True)
+        fz = f.clone().requires_grad_(True)
+        ref = F.conv3d(nc(fz), hw[:, :, None, None, None], hb)
+        logits = torch.zeros(N, C, D, H, W, device=cuda_dev)
+        ops.head_forward(f, hw.detach(), hb.detach(), logits)
+        assert rel(logits, ref) <= 1e-5
+        dl = torch.randn(N, C, D, H, W, generator=g).to(cuda_dev)
+        ref.backward(dl)
+        dx = torch.zeros_like(f)
+        dw_, db_ = torch.zeros(C, Co, device=cuda_dev), torch.zeros(C, device=cuda_dev)
+        ops.head_backward(f, hw.detach(), dl, dx, dw_, db_)
+        assert rel(dx, fz.grad) <= 1e-5
+        assert rel(dw_, hw.grad) <= 1e-4 and rel(db_, hb.grad) <= 1e-4
 
 
 def test_maxpool_forward_backward_with_ties(cuda_dev):

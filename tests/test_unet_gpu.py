@@ -157,3 +157,58 @@ def test_input_validation(cuda_dev):
         net(torch.zeros(1, 1, 32, 32, 32))                      # CPU tensor: no fallback path
     with pytest.raises(NotImplementedError):
         B200UNet(1, 8, num_classes=2, block="SingleConv")
+
+
+# BASELINE.json configs[2..4], scaled down to sizes the CPU oracle finishes in seconds: the same class lists, mixed
+# mask / report batches, a non-cubic PanTS-shaped patch and the 7-tumor 8-class head.
+CONFIG_CASES = [
+    ("cfg3", ["organ", "pancreatic_lesion"], (32, 32, 32), ("report", "mask")),
+    ("cfg4", ["pancreas", "pancreatic_lesion", "veins"], (32, 64, 48), ("mask", "report")),
+    ("cfg5", ["organ"] + sorted(f"{o}_lesion" for o in ("adrenal", "bladder", "colon", "esophagus", "kidney", "liver", "spleen")),
+     (32, 32, 48), ("report", "mask")),
+]
+
+
+@pytest.mark.parametrize("name,classes,shape,kinds", CONFIG_CASES)
+def test_train_step_configs_vs_oracle(cuda_dev, name, classes, shape, kinds):
+    """UNet forward -> calculate_loss (BCE + Dice + Volume + Ball on report samples) -> backward through the
+    reference-facing API in the parity mode, against the fp32 oracle on the same seeded batch.  The pseudo-mask
+    construction of the Ball loss is discrete (argmax / top-k on the logits), so the loss terms are compared at the
+    oracle's own logits too: that isolates the loss kernels (1e-5) from the network's 1e-4-level logit noise."""
+    from oracle import losses_ref as LR
+    from oracle import synth
+    from oracle.unet_ref import unet_forward
+    from rsuper_b200 import losses
+    C = len(classes)
+    net, sd = _make(cuda_dev, "fp32", classes=C)
+    batch = synth.make_batch(list(kinds), classes, shape, seed=17, device=cuda_dev)
+    args = LR.default_args()
+    x = batch["image"]
+    out = net(x)
+    with torch.no_grad():
+        ref_logits = unet_forward(x, sd)
+    assert out["segmentation"].shape == (len(kinds), C) + tuple(shape)
+    assert rel(out["segmentation"], ref_logits) <= 1e-3
+    assert torch.equal(out["segmentation"].argmax(1), ref_logits.argmax(1))
+
+    def call(mod, logits, lab_long):
+        lab = batch["label"].long() if lab_long else batch["label"]
+        return mod.calculate_loss({"segmentation": logits}, lab, batch["unk_channels"].float(), args, None, batch["mask"].float(),
+                                  batch["volumes"], batch["diameters"], classes, input_tensor=x)
+
+    # (1) loss kernels at identical logits: every term within 1e-5 of the oracle
+    lg = ref_logits.clone().requires_grad_(True)
+    lr = ref_logits.clone().requires_grad_(True)
+    mine, ref = call(losses, lg, False), call(LR, lr, True)
+    assert sorted(mine.keys()) == sorted(ref.keys())
+    for k in ref:
+        assert abs(mine[k].item() - ref[k].item()) <= 1e-5 * max(1.0, abs(ref[k].item())), (name, k, mine[k].item(), ref[k].item())
+    mine["overall"].backward()
+    ref["overall"].backward()
+    assert rel(lg.grad, lr.grad) <= 1e-4
+    # (2) the whole step through the module: finite, every parameter receives a gradient, loss close to the oracle's
+    full = call(losses, out["segmentation"], False)
+    full["overall"].backward()
+    assert abs(full["segmentation"].item() - ref["segmentation"].item()) <= 1e-4 * abs(ref["segmentation"].item())
+    for k, p in net.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), (name, k)
