@@ -149,7 +149,11 @@ RSB_DEVICE int butterfly_col(int lane) {
   return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 }
 
-template <typename T, int PZ>
+// NTC > 0: the N tile (and with it taps-per-stage) is a compile-time constant for the MMA issuer, whose loop is
+// instruction-bound on the narrow layers (the tensor pipe queues ~2 MMAs; a 32-channel MMA lasts 40-56 cycles and the
+// generic loop spends ~12 integer / uniform-move instructions per MMA: 7.9k cycles per item against 5.2k of MMA time).
+// NTC == 0: generic runtime N tile.
+template <typename T, int PZ, int NTC>
 __global__ void __launch_bounds__(kFpThreads, 1)
 conv3_fprop_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                    const __grid_constant__ CUtensorMap tm_lo2, const FpropDev a) {
@@ -232,6 +236,95 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_const
         src += a.tps * step;
         if (++bs == static_cast<uint32_t>(a.b_stages)) { bs = 0; bph ^= 1u; }
       }
+    }
+  } else if (NTC > 0 && warp == 1 && a.issuers == 1) {
+    // =========================== MMA issuer, compile-time N tile ===========================
+    // Same schedule as the generic issuer below; every per-plane quantity (accumulator column, weight slot, instruction
+    // descriptor) and the tap geometry are immediates, the first-touch test is hoisted out of the (tap, k-step) loops.
+    constexpr int NT = NTC > 0 ? NTC : 16;
+    constexpr int TP = NT <= 64 ? 3 : 1;                           // taps per B stage (host: d.tps)
+    constexpr uint32_t slot16 = static_cast<uint32_t>(NT / 8) * 512u / 16u;
+    constexpr uint32_t tap16 = 3u * slot16;                        // one tap = 3 kd slots
+    constexpr uint32_t acc_cols_c = PZ * NT;
+    const uint32_t a_hi = desc_hi(640, kLayoutSw64);
+    const uint32_t b_hi = desc_hi(512, kLayoutNone);
+    constexpr uint32_t a_lbo = 1u << 16;
+    constexpr uint32_t b_lbo = ((128u >> 4) & 0x3FFFu) << 16;
+    const uint32_t bar_a_full = smem_u32(&sm.a_full[0]), bar_a_empty = smem_u32(&sm.a_empty[0]);
+    const uint32_t bar_b_full = smem_u32(&sm.b_full[0]), bar_b_empty = smem_u32(&sm.b_empty[0]);
+    const uint32_t bar_acc_full = smem_u32(&sm.acc_full[0]), bar_acc_empty = smem_u32(&sm.acc_empty[0]);
+    const uint32_t a_unit16 = a.a_unit_bytes >> 4, b_stage16 = a.b_stage_bytes >> 4;
+    const uint32_t b_stages = static_cast<uint32_t>(a.b_stages), acc_stages = static_cast<uint32_t>(a.acc_stages);
+    const int nchunks = a.nchunks, last_ksteps = a.last_ksteps;
+    uint32_t ab = 0, aph = 0, bs = 0, bph = 0, as = 0, asph = 0;
+    for (int item = blockIdx.x; item < a.num_items; item += gridDim.x) {
+      mbar_wait(bar_acc_empty + 8u * as, asph ^ 1u);
+      tc_fence_after_sync();
+      const uint32_t d_base = tmem_base + as * acc_cols_c;
+      int cb = 0;
+      for (int c = 0; c < total_chunks; ++c) {
+        mbar_wait(bar_a_full + 8u * ab, aph);
+        const int ksteps = (cb == nchunks - 1) ? last_ksteps : 2;
+        const uint32_t a_unit_lo = a_lbo | ((a_base >> 4) + ab * a_unit16);
+#pragma unroll 1
+        for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll 1
+          for (int kw0 = 0; kw0 < 3; kw0 += TP) {
+            mbar_wait(bar_b_full + 8u * bs, bph);
+            tc_fence_after_sync();
+            if (elect_one()) {
+              const uint32_t b_stage_lo = b_lbo | ((b_base >> 4) + bs * b_stage16);
+              const bool first = (c == 0) && (kh == 0) && (kw0 == 0);
+#pragma unroll
+              for (int tt = 0; tt < TP; ++tt) {
+                const uint32_t b_lo = b_stage_lo + tt * tap16;
+                const uint32_t a_tap_lo = a_unit_lo + static_cast<uint32_t>(kh * 10 + kw0 + tt) * 4u;  // 64-byte rows
+                for (int ks = 0; ks < ksteps; ++ks) {
+                  const uint32_t a_ks = a_tap_lo + ks * 2u;   // 16 channels = 32 bytes inside the row
+                  const uint32_t b_ks = b_lo + ks * 16u;      // two 8-wide k groups = 256 bytes
+                  if (tt == 0 && first && ks == 0) {
+                    // first touch of every accumulator: plane p initialises output plane q = p (kd = 0)
+#pragma unroll
+                    for (int p = 0; p < NP; ++p) {
+                      const int qlo = p - 2 > 0 ? p - 2 : 0;
+                      const int qhi = p < PZ - 1 ? p : PZ - 1;
+                      const uint64_t ad = desc_join(a_hi, a_ks + static_cast<uint32_t>(p) * (kFpPlaneBytes / 16));
+                      if (p < PZ) {
+                        if (p > 0)
+                          umma_bf16_ss(d_base + qlo * NT, ad, desc_join(b_hi, b_ks + static_cast<uint32_t>(2 - (p - qlo)) * slot16),
+                                       make_idesc_bf16(128, (p - qlo) * NT, 0, 0), 1u);
+                        umma_bf16_ss(d_base + p * NT, ad, desc_join(b_hi, b_ks + 2 * slot16), make_idesc_bf16(128, NT, 0, 0), 0u);
+                      } else {
+                        umma_bf16_ss(d_base + qlo * NT, ad, desc_join(b_hi, b_ks + static_cast<uint32_t>(2 - (p - qlo)) * slot16),
+                                     make_idesc_bf16(128, (qhi - qlo + 1) * NT, 0, 0), 1u);
+                      }
+                    }
+                  } else {
+#pragma unroll
+                    for (int p = 0; p < NP; ++p) {
+                      const int qlo = p - 2 > 0 ? p - 2 : 0;
+                      const int qhi = p < PZ - 1 ? p : PZ - 1;
+                      umma_bf16_ss(d_base + qlo * NT, desc_join(a_hi, a_ks + static_cast<uint32_t>(p) * (kFpPlaneBytes / 16)),
+                                   desc_join(b_hi, b_ks + static_cast<uint32_t>(2 - (p - qlo)) * slot16),
+                                   make_idesc_bf16(128, (qhi - qlo + 1) * NT, 0, 0), 1u);
+                    }
+                  }
+                }
+              }
+              umma_commit(bar_b_empty + 8u * bs);
+              if (kh == 2 && kw0 + TP >= 3) {
+                umma_commit(bar_a_empty + 8u * ab);
+                if (c == total_chunks - 1) umma_commit(bar_acc_full + 8u * as);
+              }
+            }
+            __syncwarp();
+            if (++bs == b_stages) { bs = 0; bph ^= 1u; }
+          }
+        }
+        if (++ab == 2) { ab = 0; aph ^= 1u; }
+        if (++cb == nchunks) cb = 0;
+      }
+      if (++as == acc_stages) { as = 0; asph ^= 1u; }
     }
   } else if (warp == 1 && a.issuers == 1) {
     // =========================== MMA issuer (single warp: the default) ===========================
@@ -732,10 +825,10 @@ static int pick_nt(int Cout) {
   return best;
 }
 
-template <typename T, int PZ>
+template <typename T, int PZ, int NTC>
 static int launch_fprop(const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, const CUtensorMap& tm_lo2, const FpropDev& dev, int grid,
                         size_t smem_bytes, cudaStream_t stream) {
-  auto kern = conv3_fprop_kernel<T, PZ>;
+  auto kern = conv3_fprop_kernel<T, PZ, NTC>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes));
   if (e != cudaSuccess) {
     set_last_error("conv3: cudaFuncSetAttribute(%zu B smem) failed: %s", smem_bytes, cudaGetErrorString(e));
@@ -920,11 +1013,21 @@ extern "C" int rsb_conv3_forward(const RsbConv3Args* p, void* stream) {
   const int grid = static_cast<int>(items < sms ? items : sms);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
+  // compile-time N tile instantiations (bf16 storage, single issuer, no profiling hooks); everything else is generic
+  if (p->dtype == RSB_BF16 && d.issuers == 1 && d.dbg == nullptr && getenv("RSB_FPROP_GENERIC") == nullptr) {
+#define RSB_SPEC(PZ_, NT_) if (PZ == PZ_ && d.NT == NT_) return launch_fprop<__nv_bfloat16, PZ_, NT_>(tm_hi, tm_lo, tm_lo2, d, grid, smem, st);
+    RSB_SPEC(4, 32) RSB_SPEC(2, 32) RSB_SPEC(1, 32)
+    RSB_SPEC(4, 64) RSB_SPEC(2, 64) RSB_SPEC(1, 64)
+    RSB_SPEC(2, 96) RSB_SPEC(1, 96)
+    RSB_SPEC(2, 128) RSB_SPEC(1, 128)
+    RSB_SPEC(2, 80) RSB_SPEC(1, 80)
+#undef RSB_SPEC
+  }
 #define RSB_DISPATCH(TT)                                                          \
   switch (PZ) {                                                                   \
-    case 1: return launch_fprop<TT, 1>(tm_hi, tm_lo, tm_lo2, d, grid, smem, st);          \
-    case 2: return launch_fprop<TT, 2>(tm_hi, tm_lo, tm_lo2, d, grid, smem, st);          \
-    default: return launch_fprop<TT, 4>(tm_hi, tm_lo, tm_lo2, d, grid, smem, st);         \
+    case 1: return launch_fprop<TT, 1, 0>(tm_hi, tm_lo, tm_lo2, d, grid, smem, st);          \
+    case 2: return launch_fprop<TT, 2, 0>(tm_hi, tm_lo, tm_lo2, d, grid, smem, st);          \
+    default: return launch_fprop<TT, 4, 0>(tm_hi, tm_lo, tm_lo2, d, grid, smem, st);         \
   }
   if (p->dtype == RSB_BF16) {
     RSB_DISPATCH(__nv_bfloat16)
