@@ -199,8 +199,8 @@ int rsb_maxpool2_backward(const void* x, int x_pitch, const void* dy, int dy_pit
 int rsb_upsample_trilinear_forward(const void* x, int x_pitch, void* y, int y_pitch, int dtype,
                                    float* out_stats, int N, int Di, int Hi, int Wi, int Do, int Ho,
                                    int Wo, int C, void* stream);
-/* workspace: N*Di*Ho*Wo*C elements of the storage dtype (the z-adjoint at output (y, x) resolution; the (y, x)
- * gather then runs on Di planes instead of Do), or NULL for the single-pass 3-D gather. */
+/* workspace: N*Di*(Ho + Hi)*Wo*C elements of the storage dtype for the separable adjoint (z pass -> [N][Di][Ho][Wo][C],
+ * y pass -> [N][Di][Hi][Wo][C], x pass -> dx), or NULL for the single-pass 3-D gather. */
 int rsb_upsample_trilinear_backward(const void* dy, int dy_pitch, void* dx, int dx_pitch,
                                     int dtype, int N, int Di, int Hi, int Wi, int Do, int Ho,
                                     int Wo, int C, void* workspace, void* stream);

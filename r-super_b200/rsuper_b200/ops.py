@@ -299,11 +299,12 @@ def upsample_forward(x, y, out_stats=None):
 
 
 def upsample_backward(dy, dx, two_pass=True):
-    """Adjoint of upsample_forward.  two_pass: z-adjoint into a [N, Di, Ho, Wo, C] scratch first, then the (y, x) gather."""
+    """Adjoint of upsample_forward.  two_pass (default): separable z / y / x adjoint passes through a scratch buffer;
+    False: the single-pass 3-D gather."""
     n, do, ho, wo, c = dy.shape
     _, di, hi, wi, _ = dx.shape
-    ws = torch.empty((n, di, ho, wo, c), dtype=dy.dtype, device=dy.device) if two_pass and do > di else None
-    _call("upsample", 2 if ws is not None else 1, 0.0, lib().rsb_upsample_trilinear_backward, _p(dy), _check_cl(dy, "dy"), _p(dx),
+    ws = torch.empty(n * di * (ho + hi) * wo * c, dtype=dy.dtype, device=dy.device) if two_pass else None
+    _call("upsample", 3 if ws is not None else 1, 0.0, lib().rsb_upsample_trilinear_backward, _p(dy), _check_cl(dy, "dy"), _p(dx),
           _check_cl(dx, "dx"), dtype_code(dy), n, di, hi, wi, do, ho, wo, c, _p(ws), _stream(), what="upsample_backward",
           desc=f"{c} {n}x{do}x{ho}x{wo}")
     return dx
