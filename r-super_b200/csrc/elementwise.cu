@@ -46,14 +46,31 @@ static inline int cl_grid(long long elems, int block, int sms, int waves = 8) {
 // Block-level accumulation of per-channel (a, b) pairs into global stats[(n*C + c)*2 + {0,1}].
 // sm_acc must hold 2*C floats, zeroed before use (done here) — one shared atomic per value per
 // thread, one global atomic per value per block.
-RSB_DEVICE void block_stats_flush(float* sm_acc, const float (&s1)[8], const float (&s2)[8], int cg,
+RSB_DEVICE void block_stats_flush(float* sm_acc, float (&s1)[8], float (&s2)[8], int cg,
                                   int C, float* stats_n) {
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm_acc[i] = 0.f;
-  __syncthreads();
+  // Lanes l, l + CG, l + 2 CG, ... of a warp hold partials of the SAME channels: reduce them with shuffles first.  Going
+  // straight to shared-memory atomics makes every atomic an 8-way same-address conflict at C = 32 — ncu showed that
+  // serialisation (short-scoreboard + barrier stalls), not HBM, bounding maxpool / channel_stats / upsample forward.
+  const int CG = C / 8;
+  bool owner = true;
+  if (CG < 32 && (CG & (CG - 1)) == 0) {
+    for (int o = 16; o >= CG; o >>= 1) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    atomicAdd(&sm_acc[(cg * 8 + j) * 2 + 0], s1[j]);
-    atomicAdd(&sm_acc[(cg * 8 + j) * 2 + 1], s2[j]);
+      for (int j = 0; j < 8; ++j) {
+        s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o);
+        s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o);
+      }
+    }
+    owner = (threadIdx.x & 31) < CG;
+  }
+  __syncthreads();
+  if (owner) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sm_acc[(cg * 8 + j) * 2 + 0], s1[j]);
+      atomicAdd(&sm_acc[(cg * 8 + j) * 2 + 1], s2[j]);
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&stats_n[i], sm_acc[i]);

@@ -521,10 +521,10 @@ extern "C" int rsb_stem_conv_forward(const float* x, const float* w_oidhw, void*
   RSB_REQUIRE(Cout > 0 && Cout % 8 == 0 && Cout <= 256, "stem_conv: Cout must be a multiple of 8 <= 256 (got %d)", Cout);
   RSB_REQUIRE(N > 0 && N <= 65535 && D > 0 && H > 0 && W > 0, "stem_conv: bad geometry");
   const long long V = static_cast<long long>(D) * H * W;
-  dim3 grid(static_cast<unsigned>((V + kStemThreads - 1) / kStemThreads), N);
   const int cpad = (Cout + 15) / 16 * 16;
   const size_t sm = sizeof(float) * (27 * cpad + 2 * Cout);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid(static_cast<unsigned>((V + kStemThreads - 1) / kStemThreads), N);
   if (dtype == RSB_BF16)
     stem_fwd_kernel<__nv_bfloat16><<<grid, kStemThreads, sm, st>>>(x, w_oidhw, (__nv_bfloat16*)y, y_pitch, out_stats, D, H, W, Cout);
   else if (dtype == RSB_F32)

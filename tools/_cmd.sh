@@ -1,7 +1,7 @@
 mkdir -p gpurun_out
 {
-timeout 300 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -p no:cacheprovider -k "upsample or pool or stem" 2>&1 | tail -3
-timeout 300 python tools/probe_sat.py
-} > gpurun_out/run_r.log 2>&1
-timeout 600 ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --section Occupancy --section WarpStateStats --section LaunchStats --clock-control none -k regex:"maxpool|upsample|stem_|pack_conv3" -c 24 --csv --page raw --log-file gpurun_out/sat_ncu.csv python tools/probe_sat.py > /dev/null 2>&1
-cat gpurun_out/run_r.log | cut -c1-200; ls -la gpurun_out/sat_ncu.csv
+timeout 600 python -m pytest tests -m gpu -x -q -p no:cacheprovider 2>&1 | tail -3
+timeout 300 python tools/probe_sat.py stem
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline --trace gpurun_out/trace_t.txt
+} > gpurun_out/run_t.log 2>&1
+cat gpurun_out/run_t.log | cut -c1-250

@@ -13,7 +13,12 @@ g = torch.Generator().manual_seed(0)
 def rnd(*shape, dtype=bf):
     return torch.randn(*shape, generator=g).to(dev).to(dtype)
 
+ONLY = sys.argv[1] if len(sys.argv) > 1 else ""
+
+
 def timed(name, fn, bytes_moved, reps=5):
+    if ONLY and ONLY not in name:
+        return
     for _ in range(2):
         fn()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
