@@ -27,6 +27,8 @@ from __future__ import annotations
 
 from typing import List, Optional, Sequence
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -130,6 +132,11 @@ class _Engine:
         self.dtype = dtype
         self.split = dtype == torch.float32
         self._zp, self._zp_off = None, 0
+        # Second stream: the weight gradients (tensor-bound, 52 registers x 192 threads per SM) run beside the main
+        # backward chain, whose HBM-bound InstanceNorm-backward / pooling / upsampling passes fit on the same SMs, and
+        # their persistent CTAs fill the tails of the dgrad launches; the per-step weight packing overlaps the stem.
+        self.use_side = os.environ.get("RSB_SIDE_STREAM", "1") != "0"
+        self._side = None
         self.plan = None  # ops.PackPlan: persistent packed weight images, refreshed by ONE launch per forward
 
     # ---- zeroed statistics storage: one fill per pass instead of ~50 tiny ones --------------------------
@@ -188,12 +195,30 @@ class _Engine:
         wp = self.plan.images[key + "T" if flip else key]
         return ops.conv3_forward(op[0], wp, y, a_lo=op[1] if self.split else None, slope=self.slope, **kw)
 
+    def _side_stream(self, device):
+        if not self.use_side:
+            return None
+        if self._side is None or self._side.device != device:
+            self._side = torch.cuda.Stream(device=device)
+        return self._side
+
     def _wgrad(self, a_op, dy_op, dw):
+        side = self._side_stream(dw.device)
+        if side is None:
+            self._wgrad_launch(a_op, dy_op, dw)
+            return dw
+        side.wait_stream(torch.cuda.current_stream())   # operands were produced by work already enqueued on the main stream
+        with torch.cuda.stream(side):
+            self._wgrad_launch(a_op, dy_op, dw)
+        for t in (*a_op, *dy_op, dw):
+            t.record_stream(side)                        # the caching allocator must not recycle them before the wgrad ran
+        return dw
+
+    def _wgrad_launch(self, a_op, dy_op, dw):
         ops.conv3_wgrad(a_op[0], dy_op[0], dw)
         if self.split:
             ops.conv3_wgrad(a_op[1], dy_op[0], dw, accumulate=True)
             ops.conv3_wgrad(a_op[0], dy_op[1], dw, accumulate=True)
-        return dw
 
     # ---- forward -------------------------------------------------------------------------------
     def _block_fwd(self, x: Act, pre: str, has_sc: bool, cout: int, out: Act, saved: list):
@@ -225,7 +250,13 @@ class _Engine:
         dims = [(D >> l, H >> l, W >> l) for l in range(5)]
         saved: list = []
         self._zp = None  # fresh zero pool: the statistics of this pass live in it until backward is done
-        self.prepare(P)
+        side = self._side_stream(dev)
+        if side is None:
+            self.prepare(P)
+        else:
+            side.wait_stream(torch.cuda.current_stream())   # the previous step's convs still read the packed images
+            with torch.cuda.stream(side):
+                self.prepare(P)
 
         # skip/concat buffers of decoder levels 0..3: [skip ch[l] | upsampled ch_up[l]]
         up_in = [ch[1], ch[2], ch[3], ch[4]]  # channels arriving from below at level l
@@ -234,6 +265,8 @@ class _Engine:
         # inc: stem conv + BasicBlock(b, b)
         t0 = self._new_act(n, *dims[0], b, dt, dev)
         ops.stem_conv_forward(x, P["inc.conv1.weight"], t0.t, t0.st)
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)   # packed weights ready before the first tensor-core conv
         self._block_fwd(t0, "inc.conv2.", False, b, cat[0].view(0, ch[0]), saved)
         enc_out = [cat[0].view(0, ch[0])]
         pooled = []
@@ -367,6 +400,8 @@ class _Engine:
         dws = torch.empty_like(P["inc.conv1.weight"])
         ops.stem_conv_wgrad(S["x"], d_t0, dws)
         G["inc.conv1.weight"] = dws
+        if self._side is not None and self.use_side:
+            torch.cuda.current_stream().wait_stream(self._side)   # all weight gradients done before autograd hands them on
         return G
 
 
