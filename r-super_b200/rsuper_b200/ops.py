@@ -37,7 +37,14 @@ def _call(family: str, nkern: int, flops: float, fn, *args, what: str, desc: str
     check(rc, what)
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream() -> C.c_void_p:
+    """Current CUDA stream of the current device as a raw handle (the private getter is ~10x cheaper than building a
+    torch.cuda.Stream object per launch: ~300 launches per train step)."""
+    if _raw_stream is not None:
+        return C.c_void_p(_raw_stream(torch.cuda.current_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
