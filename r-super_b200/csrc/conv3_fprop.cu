@@ -906,6 +906,8 @@ extern "C" int rsb_conv3_pack_weights_batched(const RsbPackJob* jobs_device, int
   return check_launch("pack_conv3_weights_batched_kernel");
 }
 
+int rsb_conv3_stream_try(const RsbConv3Args* p, void* stream);  // conv3_stream.cu: 0 = launched, 1 = not eligible, < 0 = error
+
 extern "C" int rsb_conv3_forward(const RsbConv3Args* p, void* stream) {
   RSB_REQUIRE(p != nullptr, "conv3: null args");
   RSB_REQUIRE(p->a && p->y && p->w_packed, "conv3: null tensor pointer");
@@ -919,6 +921,11 @@ extern "C" int rsb_conv3_forward(const RsbConv3Args* p, void* stream) {
   RSB_REQUIRE(!p->mask_x || (p->mask_stats && p->bwd_sums && p->mask_x_pitch % 8 == 0),
               "conv3: mask_x needs mask_stats and bwd_sums");
   RSB_REQUIRE(!(p->mask_x && (p->out_stats || p->res)), "conv3: the dgrad mask epilogue excludes out_stats / res");
+
+  if (g_timing_buffer == nullptr) {
+    const int rs = rsb_conv3_stream_try(p, stream);   // plane-streaming kernel for the 32-channel layers
+    if (rs <= 0) return rs;
+  }
 
   FpropDev d{};
   d.N = p->N; d.D = p->D; d.H = p->H; d.W = p->W; d.Cin = p->Cin; d.Cout = p->Cout;

@@ -116,6 +116,16 @@ def _sums_like(a: Act) -> torch.Tensor:
     return full[:, c0:c0 + a.C]
 
 
+SIDE_STREAM = os.environ.get("RSB_SIDE_STREAM", "1") != "0"
+
+
+def set_side_stream(enabled: bool) -> None:
+    """Run weight gradients / weight packing on a second stream (default) or serialise everything on the caller's
+    stream (per-kernel timing with CUDA events, debugging)."""
+    global SIDE_STREAM
+    SIDE_STREAM = bool(enabled)
+
+
 class _Engine:
     """Kernel schedule of one forward / backward pass (pure host logic; all compute is in the .so).
 
@@ -135,7 +145,6 @@ class _Engine:
         # Second stream: the weight gradients (tensor-bound, 52 registers x 192 threads per SM) run beside the main
         # backward chain, whose HBM-bound InstanceNorm-backward / pooling / upsampling passes fit on the same SMs, and
         # their persistent CTAs fill the tails of the dgrad launches; the per-step weight packing overlaps the stem.
-        self.use_side = os.environ.get("RSB_SIDE_STREAM", "1") != "0"
         self._side = None
         self.plan = None  # ops.PackPlan: persistent packed weight images, refreshed by ONE launch per forward
 
@@ -196,7 +205,7 @@ class _Engine:
         return ops.conv3_forward(op[0], wp, y, a_lo=op[1] if self.split else None, slope=self.slope, **kw)
 
     def _side_stream(self, device):
-        if not self.use_side:
+        if not SIDE_STREAM:
             return None
         if self._side is None or self._side.device != device:
             self._side = torch.cuda.Stream(device=device)
@@ -400,7 +409,7 @@ class _Engine:
         dws = torch.empty_like(P["inc.conv1.weight"])
         ops.stem_conv_wgrad(S["x"], d_t0, dws)
         G["inc.conv1.weight"] = dws
-        if self._side is not None and self.use_side:
+        if self._side is not None:
             torch.cuda.current_stream().wait_stream(self._side)   # all weight gradients done before autograd hands them on
         return G
 

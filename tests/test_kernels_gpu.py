@@ -380,3 +380,59 @@ def test_batched_weight_packing_matches_per_layer_packing(split):
     plan.refresh()
     assert torch.equal(plan.images["b"], ops.conv3_pack_weights(w2, False, split=split))
     assert plan.ptr_key == ops.PackPlan.pointer_key([(w1, wsc), (w1, wsc), (w2, None), (w2, None), (w3, None)])
+
+
+STREAM_CASES = [
+    # N, D, H, W, Cin, Cout, storage dtype, mode ('res' | 'plain' | 'mask'), CTAs
+    (2, 40, 20, 12, 32, 32, torch.bfloat16, "res", 4),     # ragged last z-chunk (32 + 8), ragged y / x tiles, sample change inside a CTA
+    (1, 70, 16, 8, 32, 32, torch.bfloat16, "plain", 1),    # one CTA walks 3 chunks: the 16-slot accumulator ring wraps inside units
+    (1, 33, 16, 16, 24, 24, torch.float32, "res", 3),      # padded channels (Cout 24 -> N tile 32), fp32 storage, a 1-plane chunk
+    (2, 32, 16, 16, 16, 32, torch.bfloat16, "mask", 5),    # dgrad epilogue, Cin = 16 (one k-step)
+    (1, 64, 32, 16, 32, 32, torch.float32, "mask", 2),
+]
+
+
+@pytest.mark.parametrize("case", STREAM_CASES)
+def test_conv3_plane_streaming_kernel(cuda_dev, case, monkeypatch):
+    """The plane-streaming kernel of the 32-channel layers (conv3_stream.cu) against F.conv3d on identical bf16
+    operands; max_ctas forces it at test sizes (it needs >= 3 units per CTA)."""
+    from rsuper_b200 import ops
+    monkeypatch.setenv("RSB_FPROP_STREAM", "1")   # opt-in kernel (see conv3_stream.cu)
+    N, D, H, W, Cin, Cout, dt, mode, ctas = case
+    g = torch.Generator().manual_seed(31)
+    w = (torch.randn(Cout, Cin, 3, 3, 3, generator=g) / (27 * Cin) ** 0.5).to(cuda_dev)
+    if mode != "mask":
+        x = torch.randn(N, D, H, W, Cin, generator=g).to(cuda_dev).to(dt)
+        r = torch.randn(N, D, H, W, Cout, generator=g).to(cuda_dev).to(dt) if mode == "res" else None
+        y = torch.full((N, D, H, W, Cout), float("nan"), dtype=dt, device=cuda_dev)
+        ost = torch.zeros(N, Cout, 2, device=cuda_dev)
+        a_op = ops.norm_act(x, stats_of(x.float()))
+        ops.conv3_forward(a_op, ops.conv3_pack_weights(w), y, res=r, out_stats=ost, max_ctas=ctas)
+        ref = cl(F.conv3d(nc(a_op.float()), bf16r(w), padding=1))
+        if r is not None:
+            ref = ref + r.float()
+        assert rel(y.float(), ref) <= (2e-5 if dt == torch.float32 else 4e-3)
+        assert rel(ost, stats_of(ref)) <= 1e-4
+        # and it is the same result as the item-based kernel (planes_per_item given => not eligible for streaming)
+        y2 = torch.zeros_like(y)
+        ops.conv3_forward(a_op, ops.conv3_pack_weights(w), y2, res=r, planes_per_item=2)
+        assert rel(y.float(), y2.float()) <= (2e-5 if dt == torch.float32 else 4e-3)
+    else:
+        # dgrad: effective conv has Cin' = Cout, Cout' = Cin
+        x = torch.randn(N, D, H, W, Cin, generator=g).to(cuda_dev).to(dt)
+        dy = torch.randn(N, D, H, W, Cout, generator=g).to(cuda_dev)
+        xhat = F.instance_norm(nc(x.float()), eps=1e-4)
+        da = F.conv_transpose3d(bf16r(nc(dy)), bf16r(w), padding=1)
+        gref = torch.where(xhat > 0, da, torch.zeros_like(da))
+        gout = torch.full((N, D, H, W, Cin), float("nan"), dtype=dt, device=cuda_dev)
+        sums = torch.zeros(N, Cin, 2, device=cuda_dev)
+        ops.conv3_forward(ops.norm_act(dy), ops.conv3_pack_weights(w, True), gout, mask_x=x, mask_stats=stats_of(x.float()), bwd_sums=sums,
+                          max_ctas=ctas)
+        if dt == torch.float32:
+            assert rel(gout, cl(gref)) <= 2e-5
+        else:
+            # bf16 x: a handful of voxels sit within rounding of the ReLU threshold; compare where |xhat| is clear of it
+            clear = (xhat.abs() > 1e-2)
+            assert rel(torch.where(clear, nc(gout.float()), gref), gref) <= 4e-3
+        assert rel(sums[..., 0], gref.sum(dim=(2, 3, 4))) <= 2e-3
+        assert rel(sums[..., 1], (gref * xhat).sum(dim=(2, 3, 4))) <= 2e-3
