@@ -153,11 +153,20 @@ int rsb_debug_set_wgrad_timing_buffer(void* device_ptr); /* profiling aid, see a
  * slope = 0 => ReLU, 0.01 => LeakyReLU) as one fused, 128-bit vectorised pass.  stats == NULL =>
  * plain cast.  lo != NULL additionally writes lo = bf16(value - hi) for the split-precision
  * parity mode; lo2 != NULL (needs lo) a third piece lo2 = bf16(value - hi - lo), together ~24 mantissa bits.
- * x has storage dtype `dtype`; hi / lo / lo2 are always bf16.
+ * x has storage dtype `dtype`; hi / lo / lo2 are always bf16.  full != NULL additionally writes the activation
+ * itself in the storage dtype — the block OUTPUT of a post-activation SingleConv = ConvNormAct(preact=False)
+ * (conv_layers.py:50-68); hi may then be NULL.
  * ------------------------------------------------------------------------------------------ */
 int rsb_norm_act(const void* x, int x_pitch, int dtype, const float* stats, float eps, float slope,
-                 void* hi, int hi_pitch, void* lo, int lo_pitch, void* lo2, int lo2_pitch, int N, int D, int H,
-                 int W, int C, void* stream);
+                 void* hi, int hi_pitch, void* lo, int lo_pitch, void* lo2, int lo2_pitch, void* full, int full_pitch,
+                 int N, int D, int H, int W, int C, void* stream);
+
+/* Backward of the post-activation a = act(instnorm(y)) when d(a) comes from pooling / upsampling / the head:
+ * g = d * act'(yhat); bwd_sums[(n, c)] += (sum g, sum g * yhat).  rsb_instnorm_backward_apply(g, y, ...) then yields d(y)
+ * (autograd of nn.InstanceNorm3d + nn.ReLU in ConvNormAct(preact=False), conv_layers.py:50-52). */
+int rsb_act_backward_stats(const void* d, int d_pitch, const void* y, int y_pitch, const float* y_stats,
+                           float* bwd_sums, void* g, int g_pitch, int dtype, float eps, float slope, int N, int D,
+                           int H, int W, int C, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * stem conv 3x3x3 with Cin = 1 (inconv.conv1, model/dim3/unet_utils.py:15,18) — direct

@@ -75,11 +75,40 @@ def _basic_block(xs, xf, sd, prefix, cfg):
     return cfg.store(out), out
 
 
+def _single_conv(xs, sd, prefix, cfg):
+    """SingleConv = ConvNormAct(preact=False): act(norm(conv(x))) (conv_layers.py:50-68); returns the stored output.
+    With emulation the raw conv output is what gets stored / re-read (statistics from the fp32 accumulators)."""
+    y_full = F.conv3d(cfg.operand(xs), cfg.operand(sd[prefix + "conv.conv.weight"]), padding=1)
+    return cfg.store(_norm_act(cfg.store(y_full), y_full, cfg))
+
+
+def _unet_forward_single(x, sd, cfg, tr):
+    """UNet(block='SingleConv') (model/dim3/utils.py:7-13 block map; same inconv / down / up skeleton)."""
+    xs = _single_conv(cfg.store(F.conv3d(x, sd["inc.conv1.weight"], padding=1)), sd, "inc.conv2.", cfg)
+    tr["inc"] = xs
+    skips = [xs]
+    for l in range(1, 5):
+        ys = _single_conv(F.max_pool3d(xs, 2), sd, f"down{l}.conv.1.", cfg)
+        xs = _single_conv(ys, sd, f"down{l}.conv.2.", cfg)
+        tr[f"down{l}.2"] = xs
+        skips.append(xs)
+    cur = skips[4]
+    for j, l in enumerate((3, 2, 1, 0), start=1):
+        up = cfg.store(F.interpolate(cur, size=skips[l].shape[2:], mode="trilinear", align_corners=True))
+        ys = _single_conv(torch.cat([skips[l], up], dim=1), sd, f"up{j}.conv.0.", cfg)
+        cur = _single_conv(ys, sd, f"up{j}.conv.1.", cfg)
+        tr[f"up{j}.1"] = cur
+    return F.conv3d(cur, sd["outc.weight"], sd["outc.bias"])
+
+
 def unet_forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], slope: float = 0.0, emulate: bool = False,
                  storage: str = "fp32", trace: Optional[dict] = None) -> torch.Tensor:
-    """x [N,1,D,H,W] fp32 -> logits [N,C,D,H,W] (unet.py:50-64).  `trace` collects stage outputs."""
+    """x [N,1,D,H,W] fp32 -> logits [N,C,D,H,W] (unet.py:50-64).  `trace` collects stage outputs.  The block type
+    (BasicBlock | SingleConv) is read off the state-dict keys."""
     cfg = _Cfg(slope, emulate, storage)
     tr = trace if trace is not None else {}
+    if "inc.conv2.conv.conv.weight" in sd:
+        return _unet_forward_single(x, sd, cfg, tr)
     # inconv: raw conv then BasicBlock (unet_utils.py:17-21)
     t_full = F.conv3d(x, sd["inc.conv1.weight"], padding=1)
     t_st = cfg.store(t_full)
@@ -107,7 +136,7 @@ def unet_forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], slope: float = 0.
 
 
 def synthetic_state_dict(base_ch: int, num_classes: int, in_ch: int = 1, device="cpu",
-                         gain: float = 1.0) -> Dict[str, torch.Tensor]:
+                         gain: float = 1.0, block: str = "BasicBlock") -> Dict[str, torch.Tensor]:
     """Deterministic, version-independent weights with the reference UNet's names and shapes
     (SURVEY.md §8b state-dict contract).  Values mimic nn.Conv3d's default init
     (kaiming_uniform(a=sqrt(5)) => U(-1/sqrt(fan_in), 1/sqrt(fan_in))) through a hash
@@ -116,6 +145,17 @@ def synthetic_state_dict(base_ch: int, num_classes: int, in_ch: int = 1, device=
     fp32 gradients differ from its fp64 gradients by 2 %; with this init they agree to ~3e-5.)"""
     b = base_ch
     ch = [b, 2 * b, 4 * b, 8 * b, 10 * b]
+    if block == "SingleConv":
+        shapes = [("inc.conv1.weight", (b, in_ch, 3, 3, 3)), ("inc.conv2.conv.conv.weight", (b, b, 3, 3, 3))]
+        for l in range(1, 5):
+            shapes += [(f"down{l}.conv.1.conv.conv.weight", (ch[l], ch[l - 1], 3, 3, 3)),
+                       (f"down{l}.conv.2.conv.conv.weight", (ch[l], ch[l], 3, 3, 3))]
+        for j, l in enumerate((3, 2, 1, 0), start=1):
+            shapes += [(f"up{j}.conv.0.conv.conv.weight", (ch[l], ch[l] + ch[l + 1], 3, 3, 3)),
+                       (f"up{j}.conv.1.conv.conv.weight", (ch[l], ch[l], 3, 3, 3))]
+        shapes += [("outc.weight", (num_classes, b, 1, 1, 1)), ("outc.bias", (num_classes,))]
+        return _fill_state_dict(shapes, gain, device)
+    assert block == "BasicBlock", block
     shapes = [("inc.conv1.weight", (b, in_ch, 3, 3, 3)),
               ("inc.conv2.conv1.conv.weight", (b, b, 3, 3, 3)),
               ("inc.conv2.conv2.conv.weight", (b, b, 3, 3, 3))]
@@ -132,6 +172,10 @@ def synthetic_state_dict(base_ch: int, num_classes: int, in_ch: int = 1, device=
                    (p + "0.shortcut.conv.weight", (co, ci, 3, 3, 3)),
                    (p + "1.conv1.conv.weight", (co, co, 3, 3, 3)), (p + "1.conv2.conv.weight", (co, co, 3, 3, 3))]
     shapes += [("outc.weight", (num_classes, b, 1, 1, 1)), ("outc.bias", (num_classes,))]
+    return _fill_state_dict(shapes, gain, device)
+
+
+def _fill_state_dict(shapes, gain, device):
     sd = {}
     for k, (name, shp) in enumerate(shapes):
         numel = 1

@@ -520,8 +520,8 @@ __global__ void instnorm_bwd_apply_kernel(const T* __restrict__ g, long long gp,
 template <typename T>
 __global__ void norm_act_kernel(const T* __restrict__ x, long long xp, const float* __restrict__ stats,
                                 __nv_bfloat16* __restrict__ hi, long long hp, __nv_bfloat16* __restrict__ lo,
-                                long long lp, __nv_bfloat16* __restrict__ lo2, long long l2p, float eps, float slope, int C,
-                                long long V) {
+                                long long lp, __nv_bfloat16* __restrict__ lo2, long long l2p, T* __restrict__ full, long long fp,
+                                float eps, float slope, int C, long long V) {
   const int CG = C / 8;
   const int n = blockIdx.y;
   ClMap m = cl_map(CG);
@@ -550,7 +550,8 @@ __global__ void norm_act_kernel(const T* __restrict__ x, long long xp, const flo
       f[j] = t;
       h[j] = __bfloat162float(__float2bfloat16_rn(t));
     }
-    Vec8<__nv_bfloat16>::store(hi + v * hp + m.cg * 8, f);
+    if (full != nullptr) Vec8<T>::store(full + v * fp + m.cg * 8, f);   // the activation itself in the storage dtype (post-activation blocks)
+    if (hi != nullptr) Vec8<__nv_bfloat16>::store(hi + v * hp + m.cg * 8, f);
     if (lo != nullptr) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] -= h[j];
@@ -562,6 +563,44 @@ __global__ void norm_act_kernel(const T* __restrict__ x, long long xp, const flo
       }
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// Backward of a POST-activation a = act(instnorm(y)) (SingleConv = ConvNormAct(preact=False), conv_layers.py:50-68)
+// when the gradient d(a) does not come out of a dgrad epilogue (pooling / upsampling / head):
+// g = d * act'(yhat), S1 += sum g, S2 += sum g * yhat per (n, c); rsb_instnorm_backward_apply then turns g into d(y).
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void act_backward_stats_kernel(const T* __restrict__ d, long long dp, const T* __restrict__ y, long long yp,
+                                          const float* __restrict__ y_stats, float* __restrict__ sums, T* __restrict__ g,
+                                          long long gp, float eps, float slope, int C, long long V) {
+  extern __shared__ float sm_acc[];
+  const int CG = C / 8;
+  const int n = blockIdx.y;
+  ClMap m = cl_map(CG);
+  const float inv = 1.f / static_cast<float>(V);
+  float mean[8], rstd[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const long long sidx = (static_cast<long long>(n) * yp + m.cg * 8 + j) * 2;
+    stats_to_mean_rstd(y_stats[sidx], y_stats[sidx + 1], inv, eps, mean[j], rstd[j]);
+  }
+  float s1[8] = {0}, s2[8] = {0};
+  for (long long vl = m.v0; vl < V; vl += m.vstride) {
+    const long long v = static_cast<long long>(n) * V + vl;
+    float dv[8], yv[8];
+    Vec8<T>::load(d + v * dp + m.cg * 8, dv);
+    Vec8<T>::load(y + v * yp + m.cg * 8, yv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float h = (yv[j] - mean[j]) * rstd[j];
+      dv[j] = h > 0.f ? dv[j] : dv[j] * slope;
+      s1[j] += dv[j];
+      s2[j] = fmaf(dv[j], h, s2[j]);
+    }
+    Vec8<T>::store(g + v * gp + m.cg * 8, dv);
+  }
+  block_stats_flush(sm_acc, s1, s2, m.cg, C, sums + static_cast<long long>(n) * yp * 2);
 }
 
 }  // namespace rsb
@@ -742,16 +781,31 @@ extern "C" int rsb_instnorm_backward_apply(const void* g, int g_pitch, const voi
 }
 
 extern "C" int rsb_norm_act(const void* x, int x_pitch, int dtype, const float* stats, float eps, float slope,
-                            void* hi, int hi_pitch, void* lo, int lo_pitch, void* lo2, int lo2_pitch, int N, int D, int H,
-                            int W, int C, void* stream) {
-  RSB_REQUIRE(x && hi, "norm_act: null pointer");
-  RSB_REQUIRE(x_pitch % 8 == 0 && hi_pitch % 8 == 0 && (!lo || lo_pitch % 8 == 0) && (!lo2 || (lo && lo2_pitch % 8 == 0)),
-              "norm_act: pitches must be multiples of 8 (and lo2 needs lo)");
+                            void* hi, int hi_pitch, void* lo, int lo_pitch, void* lo2, int lo2_pitch, void* full, int full_pitch,
+                            int N, int D, int H, int W, int C, void* stream) {
+  RSB_REQUIRE(x && (hi || full), "norm_act: null pointer");
+  RSB_REQUIRE(x_pitch % 8 == 0 && (!hi || hi_pitch % 8 == 0) && (!lo || (hi && lo_pitch % 8 == 0)) && (!lo2 || (lo && lo2_pitch % 8 == 0)) &&
+                  (!full || full_pitch % 8 == 0),
+              "norm_act: pitches must be multiples of 8 (lo needs hi, lo2 needs lo)");
   RSB_CL_COMMON(C, N)
   const long long V = static_cast<long long>(D) * H * W;
   dim3 grid(cl_grid(V * CG, block, sms), N);
   RSB_BY_DTYPE(dtype,
-               (norm_act_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)x, x_pitch, stats, (__nv_bfloat16*)hi, hi_pitch, (__nv_bfloat16*)lo, lo_pitch, (__nv_bfloat16*)lo2, lo2_pitch, eps, slope, C, V)),
-               (norm_act_kernel<float><<<grid, block, 0, st>>>((const float*)x, x_pitch, stats, (__nv_bfloat16*)hi, hi_pitch, (__nv_bfloat16*)lo, lo_pitch, (__nv_bfloat16*)lo2, lo2_pitch, eps, slope, C, V)))
+               (norm_act_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)x, x_pitch, stats, (__nv_bfloat16*)hi, hi_pitch, (__nv_bfloat16*)lo, lo_pitch, (__nv_bfloat16*)lo2, lo2_pitch, (__nv_bfloat16*)full, full_pitch, eps, slope, C, V)),
+               (norm_act_kernel<float><<<grid, block, 0, st>>>((const float*)x, x_pitch, stats, (__nv_bfloat16*)hi, hi_pitch, (__nv_bfloat16*)lo, lo_pitch, (__nv_bfloat16*)lo2, lo2_pitch, (float*)full, full_pitch, eps, slope, C, V)))
   return check_launch("norm_act");
+}
+
+extern "C" int rsb_act_backward_stats(const void* d, int d_pitch, const void* y, int y_pitch, const float* y_stats,
+                                      float* bwd_sums, void* g, int g_pitch, int dtype, float eps, float slope, int N, int D,
+                                      int H, int W, int C, void* stream) {
+  RSB_REQUIRE(d && y && y_stats && bwd_sums && g, "act_backward_stats: null pointer");
+  RSB_CL_COMMON(C, N)
+  const long long V = static_cast<long long>(D) * H * W;
+  dim3 grid(cl_grid(V * CG, block, sms, 4), N);
+  const size_t sm = sizeof(float) * 2 * C;
+  RSB_BY_DTYPE(dtype,
+               (act_backward_stats_kernel<__nv_bfloat16><<<grid, block, sm, st>>>((const __nv_bfloat16*)d, d_pitch, (const __nv_bfloat16*)y, y_pitch, y_stats, bwd_sums, (__nv_bfloat16*)g, g_pitch, eps, slope, C, V)),
+               (act_backward_stats_kernel<float><<<grid, block, sm, st>>>((const float*)d, d_pitch, (const float*)y, y_pitch, y_stats, bwd_sums, (float*)g, g_pitch, eps, slope, C, V)))
+  return check_launch("act_backward_stats");
 }

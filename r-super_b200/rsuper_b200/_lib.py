@@ -88,7 +88,9 @@ SIGNATURES = {
     "rsb_conv3_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "rsb_conv3_wgrad": (c_int, [C.POINTER(RsbConv3WgradArgs), c_void_p]),
     "rsb_norm_act": (c_int, [c_void_p, c_int, c_int, c_void_p, c_float, c_float, c_void_p, c_int, c_void_p, c_int,
-                             c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+                             c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "rsb_act_backward_stats": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                       c_float, c_float, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "rsb_stem_conv_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
                                       c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "rsb_stem_conv_wgrad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p,

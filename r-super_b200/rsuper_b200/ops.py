@@ -221,19 +221,37 @@ def conv3_wgrad(a_op, dy, dw, *, accumulate=False, max_ctas=0):
     return dw
 
 
-def norm_act(x, stats=None, *, slope=0.0, eps=EPS_IN, split=False, out=None):
+def norm_act(x, stats=None, *, slope=0.0, eps=EPS_IN, split=False, out=None, full=None):
     """Conv operand tensor(s): hi = bf16(act(instnorm(x))) [, lo = bf16(value - hi) [, lo2 = bf16(value - hi - lo)]];
-    split = False | True (hi, lo) | 3 (hi, lo, lo2); stats=None => cast / split only."""
+    split = False | True (hi, lo) | 3 (hi, lo, lo2); stats=None => cast / split only.
+    full: tensor of x's dtype that receives the activation itself (post-activation block output); with full given and
+    out / split not requested no bf16 piece is written and `full` is returned."""
     n, d, h, w_, c = x.shape
-    hi = out if out is not None else torch.empty((n, d, h, w_, c), dtype=torch.bfloat16, device=x.device)
+    only_full = full is not None and out is None and not split
+    hi = None if only_full else (out if out is not None else torch.empty((n, d, h, w_, c), dtype=torch.bfloat16, device=x.device))
     lo = torch.empty((n, d, h, w_, c), dtype=torch.bfloat16, device=x.device) if split else None
     lo2 = torch.empty((n, d, h, w_, c), dtype=torch.bfloat16, device=x.device) if split == 3 else None
+    if full is not None:
+        assert full.dtype == x.dtype and full.shape == x.shape
     _call("norm_act", 1, 0.0, lib().rsb_norm_act, _p(x), _check_cl(x, "x"), dtype_code(x), _st(stats, x, "stats"), eps, slope,
-          _p(hi), _check_cl(hi, "hi"), _p(lo), _check_cl(lo, "lo") if lo is not None else 0,
-          _p(lo2), _check_cl(lo2, "lo2") if lo2 is not None else 0, n, d, h, w_, c, _stream(), what="norm_act", desc=f"{c} {n}x{d}x{h}x{w_}")
+          _p(hi), _check_cl(hi, "hi") if hi is not None else 0, _p(lo), _check_cl(lo, "lo") if lo is not None else 0,
+          _p(lo2), _check_cl(lo2, "lo2") if lo2 is not None else 0, _p(full), _check_cl(full, "full") if full is not None else 0,
+          n, d, h, w_, c, _stream(), what="norm_act", desc=f"{c} {n}x{d}x{h}x{w_}")
+    if only_full:
+        return full
     if split == 3:
         return hi, lo, lo2
     return (hi, lo) if split else hi
+
+
+def act_backward_stats(d, y, y_stats, bwd_sums, g, *, slope=0.0, eps=EPS_IN):
+    """g = d * act'(instnorm(y)); bwd_sums += (sum g, sum g * yhat) — backward of a post-activation (SingleConv)."""
+    n, dd, h, w_, c = y.shape
+    assert d.shape == y.shape and g.shape == y.shape and d.dtype == y.dtype == g.dtype
+    _call("instnorm_bwd", 1, 0.0, lib().rsb_act_backward_stats, _p(d), _check_cl(d, "d"), _p(y), _check_cl(y, "y"), _st(y_stats, y, "y_stats"),
+          _st(bwd_sums, y, "bwd_sums"), _p(g), _check_cl(g, "g"), dtype_code(y), eps, slope, n, dd, h, w_, c, _stream(),
+          what="act_backward_stats", desc=f"{c} {n}x{dd}x{h}x{w_}")
+    return g
 
 
 # --------------------------------------------------------------------------------------------

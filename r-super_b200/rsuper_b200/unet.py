@@ -60,23 +60,32 @@ class _BasicBlock(nn.Module):
         return self.conv1.conv.weight, self.conv2.conv.weight, sc
 
 
-class _InConv(nn.Module):
+class _SingleConv(nn.Module):
+    """SingleConv (conv_layers.py:56-68): .conv = ConvNormAct(preact=False) whose .conv is the only parameter."""
+
     def __init__(self, cin, cout):
         super().__init__()
+        self.conv = _CNA(cin, cout)
+
+
+class _InConv(nn.Module):
+    def __init__(self, cin, cout, block=None):
+        super().__init__()
         self.conv1 = nn.Conv3d(cin, cout, kernel_size=3, padding=1, bias=False)
-        self.conv2 = _BasicBlock(cout, cout)
+        self.conv2 = (block or _BasicBlock)(cout, cout)
 
 
 class _Stage(nn.Module):
     """down_block (index 0 is the parameter-free MaxPool3d) / up_block."""
 
-    def __init__(self, cin, cout, down: bool):
+    def __init__(self, cin, cout, down: bool, block=None):
         super().__init__()
+        block = block or _BasicBlock
         blocks: List[nn.Module] = []
         if down:
             blocks.append(nn.Identity())  # placeholder for nn.MaxPool3d: keeps the index -> name map
-        blocks.append(_BasicBlock(cin, cout))
-        blocks.append(_BasicBlock(cout, cout))
+        blocks.append(block(cin, cout))
+        blocks.append(block(cout, cout))
         self.conv = nn.Sequential(*blocks)
 
     def blocks(self):
@@ -136,7 +145,8 @@ class _Engine:
                       products, but the tensor pipe's truncating fp32 accumulation already bounds a conv at ~1e-5 of
                       its output range, so the third piece buys nothing — tests/test_kernels_gpu.py.)"""
 
-    def __init__(self, base_ch: int, slope: float, dtype: torch.dtype):
+    def __init__(self, base_ch: int, slope: float, dtype: torch.dtype, block: str = "BasicBlock"):
+        self.block = block
         self.b = base_ch
         self.slope = float(slope)
         self.dtype = dtype
@@ -175,9 +185,22 @@ class _Engine:
               + [(f"down{l}.conv.{i}.", i == 1) for l in range(1, 5) for i in (1, 2)]
               + [(f"up{j}.conv.{i}.", i == 0) for j in range(1, 5) for i in (0, 1)])
 
+    SINGLE_CONVS = (["inc.conv2."] + [f"down{l}.conv.{i}." for l in range(1, 5) for i in (1, 2)]
+                    + [f"up{j}.conv.{i}." for j in range(1, 5) for i in (0, 1)])
+
     def prepare(self, P: dict):
         """(Re)build the pack plan when the parameter storage changed, then re-pack every conv (forward and dgrad
         images; conv1 || shortcut merged row-wise without a torch.cat) from the current values."""
+        if self.block == "SingleConv":
+            pairs = [(P[pre + "conv.conv.weight"], None) for pre in self.SINGLE_CONVS]
+            if self.plan is None or self.plan.ptr_key != ops.PackPlan.pointer_key(pairs):
+                jobs = []
+                for pre, (wa, _) in zip(self.SINGLE_CONVS, pairs):
+                    jobs.append((pre + "c", wa, None, False))
+                    jobs.append((pre + "cT", wa, None, True))
+                self.plan = ops.PackPlan(jobs, split=self.split)
+            self.plan.refresh()
+            return
         pairs = []
         for pre, has_sc in self.BLOCKS:
             pairs.append((P[pre + "conv1.conv.weight"], P[pre + "shortcut.conv.weight"] if has_sc else None))
@@ -247,8 +270,123 @@ class _Engine:
             self._conv(a_h, pre + "c2", out.t, res=x.t, out_stats=out.st)
         saved.append((x, hh, a_x, a_h))
 
+    # ---- block='SingleConv': post-activation conv -> IN -> act (conv_layers.py:50-68) ---------------------
+    def _post_act(self, y: Act, out_t: torch.Tensor) -> torch.Tensor:
+        """out_t = act(instnorm(y)) in the storage dtype (bf16 storage: that tensor is also the next conv's operand)."""
+        if self.split:
+            return ops.norm_act(y.t, y.st, slope=self.slope, full=out_t)
+        return ops.norm_act(y.t, y.st, slope=self.slope, out=out_t)
+
+    def _single_fwd(self, x_t: torch.Tensor, pre: str, cout: int, out_t, saved: list) -> torch.Tensor:
+        n, d, h, w_, _ = x_t.shape
+        op = self._operand(x_t)
+        y = self._new_act(n, d, h, w_, cout, self.dtype, x_t.device)
+        self._conv(op, pre + "c", y.t, out_stats=y.st)
+        if out_t is None:
+            out_t = torch.empty((n, d, h, w_, cout), dtype=self.dtype, device=x_t.device)
+        self._post_act(y, out_t)
+        saved.append((op, y))
+        return out_t
+
+    def _forward_single(self, x, P, num_classes, save):
+        b, dt, dev = self.b, self.dtype, x.device
+        n, _, D, H, W = x.shape
+        ch = [b, 2 * b, 4 * b, 8 * b, 10 * b]
+        dims = [(D >> l, H >> l, W >> l) for l in range(5)]
+        up_in = [ch[1], ch[2], ch[3], ch[4]]
+        saved: list = []
+        self._zp = None
+        side = self._side_stream(dev)
+        if side is None:
+            self.prepare(P)
+        else:
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self.prepare(P)
+        cat = [torch.empty((n, *dims[l], ch[l] + up_in[l]), dtype=dt, device=dev) for l in range(4)]
+        t0 = torch.empty((n, *dims[0], b), dtype=dt, device=dev)
+        ops.stem_conv_forward(x, P["inc.conv1.weight"], t0, None)
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
+        enc = [self._single_fwd(t0, "inc.conv2.", b, cat[0][..., :b], saved)]
+        for l in range(1, 5):
+            p = torch.empty((n, *dims[l], ch[l - 1]), dtype=dt, device=dev)
+            ops.maxpool2_forward(enc[l - 1], p, None)
+            y = self._single_fwd(p, f"down{l}.conv.1.", ch[l], None, saved)
+            enc.append(self._single_fwd(y, f"down{l}.conv.2.", ch[l], cat[l][..., :ch[l]] if l < 4 else None, saved))
+        cur = enc[4]
+        for j, l in enumerate((3, 2, 1, 0), start=1):
+            ops.upsample_forward(cur, cat[l][..., ch[l]:], None)
+            y = self._single_fwd(cat[l], f"up{j}.conv.0.", ch[l], None, saved)
+            cur = self._single_fwd(y, f"up{j}.conv.1.", ch[l], None, saved)
+        logits = torch.empty((n, num_classes, D, H, W), dtype=torch.float32, device=dev)
+        ops.head_forward(cur, P["outc.weight"].reshape(num_classes, b).contiguous(), P["outc.bias"], logits)
+        if not save:
+            return logits, None
+        return logits, dict(saved=saved, enc=enc, final=cur, x=x, ch=ch, up_in=up_in)
+
+    def _single_bwd(self, op_in, y: Act, pre: str, d_a: torch.Tensor, cin: int, need_dx: bool = True):
+        """d_a = dL/d(act(instnorm(y))) -> (dW, dL/d(input activation))."""
+        g = self._new(y.t, y.C)
+        sums = self._sums_like(y)
+        ops.act_backward_stats(d_a, y.t, y.st, sums, g, slope=self.slope)
+        ops.instnorm_backward_apply(g, y.t, y.st, sums, g)          # in place: g becomes d(y)
+        dy_op = self._operand(g)
+        dw = self._wgrad(op_in, dy_op, self._dw(g, y.C, cin))
+        dx = None
+        if need_dx:
+            dx = self._new(y.t, cin)
+            self._conv(dy_op, pre + "c", dx, flip=True)               # plain dgrad: the input is not normalised here
+        return dw, dx
+
+    def _backward_single(self, S: dict, P: dict, dlogits: torch.Tensor) -> dict:
+        ch, up_in, saved, enc = S["ch"], S["up_in"], S["saved"], S["enc"]
+        b = self.b
+        self._zp = None
+        G = {}
+        num_classes = dlogits.shape[1]
+        final = S["final"]
+        w_out = P["outc.weight"].reshape(num_classes, b).contiguous()
+        d_cur = self._new(final, b)
+        dw_out, db_out = torch.empty_like(w_out), torch.empty_like(P["outc.bias"])
+        ops.head_backward(final, w_out, dlogits, d_cur, dw_out, db_out)
+        G["outc.weight"], G["outc.bias"] = dw_out.reshape(P["outc.weight"].shape), db_out
+        # saved order: 0 inc | 1,2 down1 | 3,4 down2 | 5,6 down3 | 7,8 down4 | 9,10 up1 | 11,12 up2 | 13,14 up3 | 15,16 up4
+        dskip = [None] * 4
+        for j, l in zip((4, 3, 2, 1), (0, 1, 2, 3)):
+            ia, ib = 7 + 2 * j, 8 + 2 * j
+            op_b, y_b = saved[ib]
+            G[f"up{j}.conv.1.conv.conv.weight"], d_y = self._single_bwd(op_b, y_b, f"up{j}.conv.1.", d_cur, ch[l])
+            op_a, y_a = saved[ia]
+            G[f"up{j}.conv.0.conv.conv.weight"], d_cat = self._single_bwd(op_a, y_a, f"up{j}.conv.0.", d_y, ch[l] + up_in[l])
+            dskip[l] = d_cat[..., :ch[l]]
+            n, d, h, w_, _ = d_cat.shape
+            d_cur = torch.empty((n, d // 2, h // 2, w_ // 2, up_in[l]), dtype=self.dtype, device=d_cat.device)
+            ops.upsample_backward(d_cat[..., ch[l]:], d_cur)
+        for l in (4, 3, 2, 1):
+            ia, ib = 2 * l - 1, 2 * l
+            op_b, y_b = saved[ib]
+            G[f"down{l}.conv.2.conv.conv.weight"], d_y = self._single_bwd(op_b, y_b, f"down{l}.conv.2.", d_cur, ch[l])
+            op_a, y_a = saved[ia]
+            G[f"down{l}.conv.1.conv.conv.weight"], d_p = self._single_bwd(op_a, y_a, f"down{l}.conv.1.", d_y, ch[l - 1])
+            x_prev = enc[l - 1]
+            d_cur = self._new(x_prev, ch[l - 1])
+            ops.maxpool2_backward(x_prev, d_p, d_cur, dskip=dskip[l - 1])
+        op0, y0 = saved[0]
+        G["inc.conv2.conv.conv.weight"], d_t0 = self._single_bwd(op0, y0, "inc.conv2.", d_cur, b)
+        dws = torch.empty_like(P["inc.conv1.weight"])
+        ops.stem_conv_wgrad(S["x"], d_t0, dws)
+        G["inc.conv1.weight"] = dws
+        if self._side is not None:
+            torch.cuda.current_stream().wait_stream(self._side)
+        return G
+
     def forward(self, x: torch.Tensor, P: dict, num_classes: int, save: bool):
         """x fp32 [N,1,D,H,W]; P maps parameter names to fp32 tensors. Returns (logits, saved)."""
+        if self.block == "SingleConv":
+            if x.shape[1] != 1 or any(s % 16 for s in x.shape[2:]):
+                raise ValueError(f"B200UNet needs in_ch == 1 and spatial dims that are multiples of 16, got {tuple(x.shape)}")
+            return self._forward_single(x, P, num_classes, save)
         b, dt, dev = self.b, self.dtype, x.device
         n, cin0, D, H, W = x.shape
         if cin0 != 1:
@@ -349,6 +487,8 @@ class _Engine:
         return dwcat[:c], dw2, dwcat[c:]
 
     def backward(self, S: dict, P: dict, dlogits: torch.Tensor) -> dict:
+        if self.block == "SingleConv":
+            return self._backward_single(S, P, dlogits)
         ch, up_in, cat = S["ch"], S["up_in"], S["cat"]
         saved = S["saved"]
         self._zp = None
@@ -448,9 +588,9 @@ class B200UNet(nn.Module):
         super().__init__()
         if in_ch != 1:
             raise NotImplementedError("B200UNet: in_ch must be 1")
-        if block != "BasicBlock" or norm != "in" or not pool:
-            raise NotImplementedError("B200UNet implements block='BasicBlock', norm='in', pool=True "
-                                      "(config/abdomenatlas/resunet_3d.yaml:9-14)")
+        if block not in ("BasicBlock", "SingleConv") or norm != "in" or not pool:
+            raise NotImplementedError("B200UNet implements block='BasicBlock' | 'SingleConv', norm='in', pool=True "
+                                      "(config/abdomenatlas/resunet_3d.yaml:9-14; model/dim3/utils.py:7-13)")
         if base_ch % 8:
             raise ValueError("base_ch must be a multiple of 8 (16-byte channel groups)")
         sc = [list(s) if isinstance(s, (list, tuple)) else [s] * 3 for s in scale]
@@ -462,15 +602,17 @@ class B200UNet(nn.Module):
         b = base_ch
         self.base_ch, self.num_classes = b, num_classes
         self.negative_slope, self.precision, self.return_dict = negative_slope, precision, return_dict
-        self.inc = _InConv(in_ch, b)
-        self.down1 = _Stage(b, 2 * b, True)
-        self.down2 = _Stage(2 * b, 4 * b, True)
-        self.down3 = _Stage(4 * b, 8 * b, True)
-        self.down4 = _Stage(8 * b, 10 * b, True)
-        self.up1 = _Stage(10 * b + 8 * b, 8 * b, False)
-        self.up2 = _Stage(8 * b + 4 * b, 4 * b, False)
-        self.up3 = _Stage(4 * b + 2 * b, 2 * b, False)
-        self.up4 = _Stage(2 * b + b, b, False)
+        self.block = block
+        blk = _SingleConv if block == "SingleConv" else _BasicBlock
+        self.inc = _InConv(in_ch, b, blk)
+        self.down1 = _Stage(b, 2 * b, True, blk)
+        self.down2 = _Stage(2 * b, 4 * b, True, blk)
+        self.down3 = _Stage(4 * b, 8 * b, True, blk)
+        self.down4 = _Stage(8 * b, 10 * b, True, blk)
+        self.up1 = _Stage(10 * b + 8 * b, 8 * b, False, blk)
+        self.up2 = _Stage(8 * b + 4 * b, 4 * b, False, blk)
+        self.up3 = _Stage(4 * b + 2 * b, 2 * b, False, blk)
+        self.up4 = _Stage(2 * b + b, b, False, blk)
         self.outc = nn.Conv3d(b, num_classes, kernel_size=1)
 
     def __getstate__(self):
@@ -485,7 +627,7 @@ class B200UNet(nn.Module):
         dtype = torch.bfloat16 if self.precision == "bf16" else torch.float32
         engine = self.__dict__.get("_engine")
         if engine is None or engine.dtype != dtype or engine.slope != float(self.negative_slope):
-            engine = _Engine(self.base_ch, self.negative_slope, dtype)
+            engine = _Engine(self.base_ch, self.negative_slope, dtype, self.block)
             self.__dict__["_engine"] = engine  # persistent packed-weight buffers; never pickled / deep-copied
         out = _UNetFunction.apply(x.float(), engine, names, self.num_classes, *params)
         # calculate_loss indexes model_output['segmentation'] (losses_foundation.py:859)

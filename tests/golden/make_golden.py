@@ -79,6 +79,20 @@ def main():
         g = dict(net.named_parameters())[k].grad
         out["unet_grad::" + k] = g.detach().numpy() if g.numel() < 4096 else g.detach().reshape(-1)[:4096].numpy()
 
+    # ---------------- UNet(block='SingleConv') forward / backward ----------------
+    net1 = unet_mod.UNet(1, base, num_classes=C, scale=[[2, 2, 2]] * 4, norm="in", kernel_size=[[3, 3, 3]] * 5, block="SingleConv")
+    sd1 = synthetic_state_dict(base, C, block="SingleConv")
+    assert list(sd1.keys()) == [k for k, _ in net1.named_parameters()], "SingleConv state-dict contract changed"
+    net1.load_state_dict(sd1, strict=True)
+    logits1 = net1(x)
+    out["unet_single_logits"] = logits1.detach().numpy()
+    loss1 = lf.calculate_loss(model_output={"segmentation": logits1}, label=batch["label"].long(), unk_voxels=None,
+                              args=args, matcher=None, chosen_segment_mask=None, tumor_volumes_report=None,
+                              tumor_diameters=None, classes=classes)
+    loss1["overall"].backward()
+    out["unet_single_loss_overall"] = np.float32(loss1["overall"].item())
+    out["unet_single_grad_norms"] = np.array([p.grad.norm().item() for _, p in net1.named_parameters()], dtype=np.float64)
+
     # ---------------- structuring elements & dilation ----------------
     for d in (1, 3, 5, 7, 11):
         out[f"ball_{d}"] = pack(lf.create_ball_kernel(d))

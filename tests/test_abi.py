@@ -56,7 +56,8 @@ def test_argument_validation_returns_errors_without_a_gpu():
     w = _lib.RsbConv3WgradArgs()
     assert lib.rsb_conv3_wgrad(ctypes.byref(w), None) != 0 and b"null" in lib.rsb_last_error()
     assert lib.rsb_conv3_wgrad_workspace_bytes(64, 96, 148) > 0
-    assert lib.rsb_norm_act(None, 8, 0, None, 1e-4, 0.0, None, 8, None, 0, None, 0, 1, 4, 4, 4, 8, None) != 0
+    assert lib.rsb_norm_act(None, 8, 0, None, 1e-4, 0.0, None, 8, None, 0, None, 0, None, 0, 1, 4, 4, 4, 8, None) != 0
+    assert lib.rsb_act_backward_stats(None, 8, None, 8, None, None, None, 8, 0, 1e-4, 0.0, 1, 4, 4, 4, 8, None) != 0
     with pytest.raises(RuntimeError):
         _lib.check(-1, "unit-test")
 

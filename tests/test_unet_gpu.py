@@ -156,7 +156,7 @@ def test_input_validation(cuda_dev):
     with pytest.raises(RuntimeError):
         net(torch.zeros(1, 1, 32, 32, 32))                      # CPU tensor: no fallback path
     with pytest.raises(NotImplementedError):
-        B200UNet(1, 8, num_classes=2, block="SingleConv")
+        B200UNet(1, 8, num_classes=2, block="Bottleneck")
 
 
 # BASELINE.json configs[2..4], scaled down to sizes the CPU oracle finishes in seconds: the same class lists, mixed
@@ -215,3 +215,61 @@ def test_train_step_configs_vs_oracle(cuda_dev, name, classes, shape, kinds):
     assert abs(full["segmentation"].item() - ref["segmentation"].item()) <= 1e-4 * abs(ref["segmentation"].item())
     for k, p in net.named_parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all(), (name, k)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_singleconv_unet_vs_reference_and_oracle(cuda_dev, golden, precision):
+    """block='SingleConv' (post-activation conv -> IN -> ReLU, conv_layers.py:56-68): same state-dict
+    names as the reference, logits against the REAL reference's recorded output (32^3) and against the fp64 oracle
+    (64^3: north-star 1e-3 / bit-exact argmax in the parity mode), loss and every weight gradient against autograd."""
+    from oracle import losses_ref as LR
+    from oracle import synth
+    from oracle.unet_ref import synthetic_image, synthetic_state_dict, unet_forward
+    from rsuper_b200 import losses
+    from rsuper_b200.unet import B200UNet
+    net = B200UNet(1, BASE, num_classes=C, scale=[[2, 2, 2]] * 4, norm="in", kernel_size=[[3, 3, 3]] * 5, block="SingleConv",
+                   precision=precision).to(cuda_dev)
+    sd = synthetic_state_dict(BASE, C, device=cuda_dev, block="SingleConv")
+    assert list(sd.keys()) == [k for k, _ in net.named_parameters()] and len(sd) == 20
+    net.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        out32 = net(synthetic_image(1, 32, 32, 32, seed=3, device=cuda_dev))["segmentation"]
+    ref32 = torch.from_numpy(golden["unet_single_logits"]).to(cuda_dev)
+    e32 = rel(out32, ref32)
+    agree32 = (out32.argmax(1) == ref32.argmax(1)).float().mean().item()
+    import os
+    S = int(os.environ.get("RSB_TEST_SINGLE_S", "64"))
+    x = synthetic_image(2, S, S, S, seed=6, device=cuda_dev)
+    classes = ["organ", "pancreatic_lesion"]
+    batch = synth.make_batch(["mask", "mask"], classes, (S, S, S), seed=8, device=cuda_dev)
+    args = LR.default_args(report_volume_loss_basic=0.0)
+    out = net(x)
+    loss = losses.calculate_loss(out, batch["label"], None, args, None, None, None, None, classes)
+    loss["overall"].backward()
+    sd64 = {k: v.double().clone().requires_grad_(True) for k, v in sd.items()}
+    truth = unet_forward(x.double(), sd64)
+    l64 = LR.calculate_loss({"segmentation": truth}, batch["label"].long(), None, args, None, None, None, None, classes)
+    l64["overall"].backward()
+    with torch.no_grad():
+        emul = unet_forward(x, sd, emulate=True, storage="bf16")
+    e_mine, e_emul = rel(out["segmentation"].double(), truth), rel(emul.double(), truth)
+    agree = (out["segmentation"].argmax(1) == truth.argmax(1)).float().mean().item()
+    errs = {k: rel(p.grad.double(), sd64[k].grad) for k, p in net.named_parameters()}
+    worst = max(errs.values())
+    print("[single] grad errs " + " ".join(f"{k.replace('.conv.conv.weight', '')}={v:.1e}" for k, v in errs.items()))
+    print(f"[single] {precision}: golden 32^3 rel {e32:.3e} argmax {agree32:.5f} | 64^3 vs fp64 truth {e_mine:.3e} (bf16-emulating oracle "
+          f"{e_emul:.3e}) argmax {agree:.5f} | loss {loss['overall'].item():.6f} vs {l64['overall'].item():.6f} | worst grad err {worst:.3e}")
+    for k, p in net.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
+    if precision == "fp32":
+        assert e32 <= 3e-3 and agree32 >= 0.9999          # 2^3-voxel bottom level: see test_logits_vs_reference_golden
+        assert e_mine <= 1e-3 and agree == 1.0
+        assert abs(loss["overall"].item() - l64["overall"].item()) <= 1e-5 * abs(l64["overall"].item())
+        # Without residual paths a ReLU whose pre-activation sits within the 2^-17 split-product noise of zero flips against
+        # the fp64 truth, and at the 4^3-voxel bottom level ONE flip moves a gradient by ~1/64 of its scale: the error is
+        # quantised and varies run to run with the atomic-add order of the statistics (observed worst 1.4e-3 .. 8e-2 on the
+        # same inputs).  The typical parameter is held tight, the worst one loosely.
+        assert float(np.median(list(errs.values()))) <= 5e-3 and worst <= 0.25
+    else:
+        assert e_mine <= 2.0 * e_emul + 1e-3
+        assert abs(loss["overall"].item() - l64["overall"].item()) <= 2e-2 * abs(l64["overall"].item())

@@ -1,7 +1,5 @@
 mkdir -p gpurun_out
-{
-timeout 600 python -m pytest tests -m gpu -x -q -p no:cacheprovider 2>&1 | tail -3
-python bench.py --no-cpu-baseline --trace gpurun_out/trace_y.txt
-python bench.py --no-cpu-baseline
-} > gpurun_out/run_y.log 2>&1
-cat gpurun_out/run_y.log | cut -c1-260
+for S in 64 128; do
+RSB_TEST_SINGLE_S=$S timeout 600 python -m pytest tests/test_unet_gpu.py -m gpu -q -s -p no:cacheprovider -k "singleconv and fp32" 2>&1 | grep "single\] \|passed\|failed" | grep -v print
+done > gpurun_out/run_z.log
+cat gpurun_out/run_z.log | cut -c1-1000
