@@ -60,8 +60,15 @@ def dtype_code(t: torch.Tensor) -> int:
     raise TypeError(f"unsupported storage dtype {t.dtype}")
 
 
+_CL_OK = {}   # (shape, strides, offset mod 8) -> channel pitch of layouts that already passed validation
+
+
 def _check_cl(t: torch.Tensor, name: str) -> int:
     """Validate an NDHWC (possibly channel-sliced) activation view and return its channel pitch."""
+    key = (t.shape, t.stride(), t.storage_offset() & 7, t.is_cuda)
+    pitch = _CL_OK.get(key)
+    if pitch is not None:
+        return pitch
     if t.dim() != 5 or not t.is_cuda:
         raise ValueError(f"{name}: expected a 5-D CUDA tensor [N,D,H,W,C], got {tuple(t.shape)}")
     n, d, h, w, c = t.shape
@@ -72,6 +79,8 @@ def _check_cl(t: torch.Tensor, name: str) -> int:
             raise ValueError(f"{name}: not a dense NDHWC view with a channel pitch (strides {t.stride()})")
     if pitch % 8 or (t.storage_offset() % 8) or c % 8:
         raise ValueError(f"{name}: channel count/pitch/offset must be multiples of 8")
+    if len(_CL_OK) < 4096:
+        _CL_OK[key] = pitch
     return pitch
 
 
