@@ -386,7 +386,10 @@ static int wgrad_plan(int Cout, int Cin, int N, int D, int H, int W, int max_cta
   struct Cand { int OTc, S, ITc, TS; };
   const Cand cands[5] = {{32, 1, 32, 3}, {32, 1, 64, 1}, {64, 1, 64, 1}, {64, 2, 32, 1}, {64, 1, 32, 1}};
   double best_cost = -1;
-  for (const Cand& c : cands) {
+  const char* force = getenv("RSB_WGRAD_CAND");   // experiments: restrict the search to one candidate (0..4)
+  for (int ci = 0; ci < 5; ++ci) {
+    const Cand& c = cands[ci];
+    if (force != nullptr && force[0] >= '0' && force[0] <= '4' && ci != force[0] - '0') continue;
     WgradDev d = best;
     d.OTc = c.OTc; d.S = c.S; d.ITc = c.ITc; d.TS = c.TS;
     d.OT = d.S * d.OTc;
