@@ -310,30 +310,13 @@ def main():
     ms_dev = e0.elapsed_time(e1) / args.steps
 
     # ---- timed region 2: end to end through the module API with host buffers ----
-    # Every step's inputs are copied from pinned host memory inside the timed region; the copy of step k+1 runs on a
-    # copy stream while step k computes (double buffering, what a prefetching loader does), the loss is read back
-    # (.item()) every step like train_ddp.py:363 does.
-    copy_stream = torch.cuda.Stream(device=dev)
-
-    def prefetch():
-        with torch.cuda.stream(copy_stream):
-            i_d = img_h.to(dev, non_blocking=True)
-            l_d = lab_h.to(dev, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        return i_d, l_d, ev
-
+    # every step: H2D of that step's image + label from pinned host memory, the train step, D2H of the loss (.item(),
+    # like train_ddp.py:363)
     barrier()
     t0 = time.perf_counter()
-    nxt = prefetch()
-    for k in range(args.steps):
-        img, lab, ev = nxt
-        if k + 1 < args.steps:
-            nxt = prefetch()
-        main = torch.cuda.current_stream()
-        main.wait_event(ev)
-        img.record_stream(main)
-        lab.record_stream(main)
+    for _ in range(args.steps):
+        img = img_h.to(dev, non_blocking=True)
+        lab = lab_h.to(dev, non_blocking=True)
         lv = train_step(img, lab).item()
     torch.cuda.synchronize()
     ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
@@ -345,7 +328,7 @@ def main():
     # weight gradients serialised on the main stream so that a kernel's events measure that kernel alone ----
     from rsuper_b200 import unet as unet_mod
     barrier()
-    unet_mod.set_side_stream(False)
+    prev_side = unet_mod.set_side_stream(False)
     train_step(img_d, lab_d)
     barrier()
     ops.PROFILE = []
@@ -357,7 +340,7 @@ def main():
     barrier()
     prof, ops.PROFILE = ops.PROFILE, None
     ms_prof = p0.elapsed_time(p1) / args.steps
-    unet_mod.set_side_stream(True)
+    unet_mod.set_side_stream(prev_side)
 
     t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
     if dist is not None:

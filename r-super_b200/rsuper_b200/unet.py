@@ -125,14 +125,19 @@ def _sums_like(a: Act) -> torch.Tensor:
     return full[:, c0:c0 + a.C]
 
 
-SIDE_STREAM = os.environ.get("RSB_SIDE_STREAM", "1") != "0"
+# Opt-in (RSB_SIDE_STREAM=1 / set_side_stream(True)).  Measured on B200: 21.8-22.3 ms/step against 22.7-23 ms serialised when
+# the host enqueues far ahead of the GPU, but 27-30 ms on boxes whose host cores were slower or shared (the enqueue order
+# of the two streams then lets a persistent wgrad grab the SMs ahead of the dgrad on the critical path): the serialised
+# schedule is the robust default.
+SIDE_STREAM = os.environ.get("RSB_SIDE_STREAM", "0") == "1"
 
 
-def set_side_stream(enabled: bool) -> None:
-    """Run weight gradients / weight packing on a second stream (default) or serialise everything on the caller's
-    stream (per-kernel timing with CUDA events, debugging)."""
+def set_side_stream(enabled: bool) -> bool:
+    """Run weight gradients / weight packing on a second stream, or serialise everything on the caller's stream
+    (default; also what per-kernel timing with CUDA events needs).  Returns the previous setting."""
     global SIDE_STREAM
-    SIDE_STREAM = bool(enabled)
+    prev, SIDE_STREAM = SIDE_STREAM, bool(enabled)
+    return prev
 
 
 class _Engine:
@@ -152,10 +157,11 @@ class _Engine:
         self.dtype = dtype
         self.split = dtype == torch.float32
         self._zp, self._zp_off = None, 0
-        # Second stream: the weight gradients (tensor-bound, 52 registers x 192 threads per SM) run beside the main
-        # backward chain, whose HBM-bound InstanceNorm-backward / pooling / upsampling passes fit on the same SMs, and
-        # their persistent CTAs fill the tails of the dgrad launches; the per-step weight packing overlaps the stem.
+        # Optional second stream (see SIDE_STREAM): the weight gradients (tensor-bound, 52 registers x 192 threads per SM)
+        # run beside the main backward chain, whose HBM-bound InstanceNorm-backward / pooling / upsampling passes fit on
+        # the same SMs, and their persistent CTAs fill the tails of the dgrad launches; the weight packing overlaps the stem.
         self._side = None
+        self._side_keep = []
         self.plan = None  # ops.PackPlan: persistent packed weight images, refreshed by ONE launch per forward
 
     # ---- zeroed statistics storage: one fill per pass instead of ~50 tiny ones --------------------------
@@ -242,8 +248,11 @@ class _Engine:
         side.wait_stream(torch.cuda.current_stream())   # operands were produced by work already enqueued on the main stream
         with torch.cuda.stream(side):
             self._wgrad_launch(a_op, dy_op, dw)
-        for t in (*a_op, *dy_op, dw):
-            t.record_stream(side)                        # the caching allocator must not recycle them before the wgrad ran
+        # The operands must outlive the side-stream kernel.  They are simply kept referenced until backward() has made the
+        # main stream wait for the side stream (tensor.record_stream would also do, but blocks with pending cross-stream
+        # uses cannot be recycled by the caching allocator when freed: the pool then grows through synchronising
+        # cudaMallocs at unpredictable steps — measured as 27-30 ms steps on some boxes against 22 ms).
+        self._side_keep.append((a_op, dy_op))
         return dw
 
     def _wgrad_launch(self, a_op, dy_op, dw):
@@ -379,6 +388,7 @@ class _Engine:
         G["inc.conv1.weight"] = dws
         if self._side is not None:
             torch.cuda.current_stream().wait_stream(self._side)
+        self._side_keep.clear()
         return G
 
     def forward(self, x: torch.Tensor, P: dict, num_classes: int, save: bool):
@@ -551,6 +561,7 @@ class _Engine:
         G["inc.conv1.weight"] = dws
         if self._side is not None:
             torch.cuda.current_stream().wait_stream(self._side)   # all weight gradients done before autograd hands them on
+        self._side_keep.clear()
         return G
 
 
