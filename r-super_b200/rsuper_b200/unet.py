@@ -248,10 +248,9 @@ class _Engine:
         side.wait_stream(torch.cuda.current_stream())   # operands were produced by work already enqueued on the main stream
         with torch.cuda.stream(side):
             self._wgrad_launch(a_op, dy_op, dw)
-        # The operands must outlive the side-stream kernel.  They are simply kept referenced until backward() has made the
-        # main stream wait for the side stream (tensor.record_stream would also do, but blocks with pending cross-stream
-        # uses cannot be recycled by the caching allocator when freed: the pool then grows through synchronising
-        # cudaMallocs at unpredictable steps — measured as 27-30 ms steps on some boxes against 22 ms).
+        # The operands must outlive the side-stream kernel: they are kept referenced until backward() has made the main
+        # stream wait for the side stream (simpler for the caching allocator than tensor.record_stream, whose blocks
+        # cannot be recycled while cross-stream uses are pending).
         self._side_keep.append((a_op, dy_op))
         return dw
 
