@@ -27,6 +27,15 @@ from oracle import synth  # noqa: E402
 from oracle.unet_ref import synthetic_image, synthetic_state_dict  # noqa: E402
 
 
+# (tag, class names, patch shape, sample kinds): scaled-down versions of BASELINE.json configs[3] (PanTS-shaped, 3 classes,
+# non-cubic) and configs[4] (7 tumour channels + 1 organ channel), mixed mask / report batches
+CONFIG_LOSS_CASES = [
+    ("cfg4", ["pancreas", "pancreatic_lesion", "veins"], (24, 48, 32), ("mask", "report")),
+    ("cfg5", ["organ"] + sorted(f"{o}_lesion" for o in ("adrenal", "bladder", "colon", "esophagus", "kidney", "liver", "spleen")),
+     (32, 32, 32), ("report", "mask")),
+]
+
+
 def import_reference():
     for name in ("nibabel", "matplotlib", "matplotlib.pyplot", "SimpleITK"):
         m = types.ModuleType(name)
@@ -172,6 +181,20 @@ def main():
         for k, v in res.items():
             out[f"calc::{tag}::{k}"] = np.float32(v.item())
         out[f"calc::{tag}::grad_sum"] = np.float64(lgc.grad.double().abs().sum().item())
+
+    # ---------------- calculate_loss on the class lists of BASELINE.json configs[3..4] (PanTS 3-class, 7-tumour 8-class) ----------------
+    for tag, classes_c, shape_c, kinds_c in CONFIG_LOSS_CASES:
+        bc = synth.make_batch(list(kinds_c), classes_c, shape_c, seed=17)
+        lgc = synth.synthetic_logits(len(kinds_c), len(classes_c), shape_c, seed=13, scale=2.0).requires_grad_(True)
+        res = lf.calculate_loss(model_output={"segmentation": lgc}, label=bc["label"].long(), unk_voxels=bc["unk_channels"].float(),
+                                args=LR.default_args(), matcher=None, chosen_segment_mask=bc["mask"].float(),
+                                tumor_volumes_report=bc["volumes"], tumor_diameters=bc["diameters"], classes=classes_c,
+                                input_tensor=bc["image"])
+        res["overall"].backward()
+        out[f"cfgloss::{tag}::keys"] = np.array(sorted(res.keys()))
+        for k, v in res.items():
+            out[f"cfgloss::{tag}::{k}"] = np.float32(v.item())
+        out[f"cfgloss::{tag}::grad_sum"] = np.float64(lgc.grad.double().abs().sum().item())
 
     np.savez_compressed(os.path.join(HERE, "reference_outputs.npz"), **out)
     sz = os.path.getsize(os.path.join(HERE, "reference_outputs.npz"))

@@ -150,3 +150,4 @@ def test_calculate_loss_dicts(cuda_dev, golden):
         losses.calculate_loss({"segmentation": lgb.to(dev).requires_grad_(True)}, bb["label"].long().to(dev),
                               torch.zeros_like(bb["unk_channels"]).float().to(dev), LR.default_args(loss="ball"), None,
                               bb["mask"].float().to(dev), bb["volumes"].to(dev), bb["diameters"].to(dev), cls2)
+
