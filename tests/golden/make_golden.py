@@ -53,6 +53,17 @@ def import_reference():
     return unet, lf
 
 
+def reference_medformer(cfg, num_classes):
+    """The real MedFormer (model/dim3/medformer.py) in the yaml configuration (config/abdomenatlas_ufo/medformer_3d.yaml)
+    scaled by cfg; import_reference() must have run."""
+    mf = importlib.import_module("model.dim3.medformer")
+    return mf.MedFormer(1, num_classes, base_chan=cfg["base_chan"], map_size=cfg["map_size"], conv_block="BasicBlock",
+                        conv_num=cfg["conv_num"], trans_num=cfg["trans_num"], chan_num=cfg["chan_num"], num_heads=cfg["num_heads"],
+                        fusion_depth=cfg["fusion_depth"], fusion_dim=cfg["fusion_dim"], fusion_heads=cfg["fusion_heads"],
+                        expansion=cfg["expansion"], proj_type="depthwise", norm="in", act="relu", kernel_size=[[3, 3, 3]] * 5,
+                        scale=[[2, 2, 2]] * 4, aux_loss=cfg["aux_loss"])
+
+
 def pack(t: torch.Tensor) -> np.ndarray:
     return np.packbits(t.detach().cpu().numpy().astype(bool).reshape(-1))
 
@@ -101,6 +112,23 @@ def main():
     loss1["overall"].backward()
     out["unet_single_loss_overall"] = np.float32(loss1["overall"].item())
     out["unet_single_grad_norms"] = np.array([p.grad.norm().item() for _, p in net1.named_parameters()], dtype=np.float64)
+
+    # ---------------- MedFormer forward / deep-supervision loss / backward (oracle groundwork) ----------------
+    from oracle.medformer_ref import SMALL_CFG, fill_like
+    mnet = reference_medformer(SMALL_CFG, C)
+    msd = fill_like([(k, tuple(v.shape)) for k, v in mnet.named_parameters()])
+    mnet.load_state_dict(msd, strict=True)
+    out["medformer_param_names"] = np.array([k for k, _ in mnet.named_parameters()])
+    out["medformer_param_shapes"] = np.array([",".join(str(d) for d in v.shape) for _, v in mnet.named_parameters()])
+    mo = mnet(x)
+    out["medformer_logits"] = mo["segmentation"][0].detach().numpy()[:, :, ::2, ::2, ::2].copy()
+    out["medformer_aux"] = mo["segmentation"][1].detach().numpy()[:, :, ::2, ::2, ::2].copy()
+    out["medformer_logits_abs_sum"] = np.float64(mo["segmentation"][0].double().abs().sum().item())
+    mloss = lf.calculate_loss(model_output=mo, label=batch["label"].long(), unk_voxels=None, args=args, matcher=None,
+                              chosen_segment_mask=None, tumor_volumes_report=None, tumor_diameters=None, classes=classes)
+    mloss["overall"].backward()
+    out["medformer_loss_overall"] = np.float32(mloss["overall"].item())
+    out["medformer_grad_norms"] = np.array([p.grad.norm().item() for _, p in mnet.named_parameters()], dtype=np.float64)
 
     # ---------------- structuring elements & dilation ----------------
     for d in (1, 3, 5, 7, 11):
