@@ -53,6 +53,21 @@ def import_reference():
     return unet, lf
 
 
+# (tag, volume shape, window): ragged last windows, volume smaller than the window (padding path), exact multiples
+SLIDING_CASES = [("ragged", (40, 48, 56), (16, 16, 32)), ("small", (12, 20, 16), (16, 16, 32)), ("exact", (32, 32, 32), (16, 16, 16))]
+
+
+def sliding_test_net():
+    """A tiny deterministic 'network' for the window logic: 3 output channels from fixed 3x3x3 filters (so window borders
+    matter, like with a real conv net)."""
+    w = torch.frac(torch.sin(torch.arange(3 * 27, dtype=torch.float64) * 12.9898) * 43758.5453).float().reshape(3, 1, 3, 3, 3) - 0.5
+    net = torch.nn.Conv3d(1, 3, 3, padding=1, bias=True)
+    with torch.no_grad():
+        net.weight.copy_(w)
+        net.bias.copy_(torch.tensor([0.1, -0.2, 0.05]))
+    return net.eval()
+
+
 def reference_medformer(cfg, num_classes):
     """The real MedFormer (model/dim3/medformer.py) in the yaml configuration (config/abdomenatlas_ufo/medformer_3d.yaml)
     scaled by cfg; import_reference() must have run."""
@@ -129,6 +144,22 @@ def main():
     mloss["overall"].backward()
     out["medformer_loss_overall"] = np.float32(mloss["overall"].item())
     out["medformer_grad_norms"] = np.array([p.grad.norm().item() for _, p in mnet.named_parameters()], dtype=np.float64)
+
+    # ---------------- sliding-window inference (SURVEY §8f N3 groundwork): the real inference3d.inference_sliding_window ----------------
+    inf3d = importlib.import_module("inference.inference3d")
+    tiny = sliding_test_net()
+    for tag, shp, win in SLIDING_CASES:
+        vol = synthetic_image(1, *shp, seed=9)
+        a = types.SimpleNamespace(window_size=list(win), classes=3)
+        full = inf3d.inference_sliding_window(tiny, vol, a)
+        out[f"sliding_{tag}"] = full.numpy()[:, :, 1::3, 1::3, 1::3].copy()       # every 3rd voxel + a checksum of all of them
+        out[f"sliding_{tag}_sum"] = np.float64(full.double().sum().item())
+    gate = torch.zeros(1, 1, 40, 48, 56)
+    gate[:, :, 4:20, 8:30, 10:20] = 1
+    a = types.SimpleNamespace(window_size=[16, 16, 32], classes=3)
+    full = inf3d.inference_sliding_window(tiny, synthetic_image(1, 40, 48, 56, seed=9), a, pancreas=gate)
+    out["sliding_gated"] = full.numpy()[:, :, 1::3, 1::3, 1::3].copy()
+    out["sliding_gated_sum"] = np.float64(full.double().sum().item())
 
     # ---------------- structuring elements & dilation ----------------
     for d in (1, 3, 5, 7, 11):
