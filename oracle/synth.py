@@ -112,3 +112,30 @@ def synthetic_logits(B: int, C: int, shape, seed: int = 0, scale: float = 3.0, d
                 + 0.3 * torch.sin(7.13 * zz + 3.71 * yy + 5.37 * xx + 0.5 * k)
             out[b, c] = v.to(torch.float32)
     return out.to(device)
+
+
+# ------------------------------------------------------------------------------------------------
+# On-disk crop format of the reference loader (SURVEY §8f N2 groundwork): masks are stored bit-packed along the
+# CHANNEL axis — np.packbits(bool[C, D, H, W], axis=0) -> uint8[ceil(C / 8), D, H, W]
+# (dataset_abdomenatlas_UFO.py:952-975) and unpacked + truncated to C on load (:1006-1015, 1071-1090).
+# numpy packs big-endian: channel c lives in byte c // 8, bit 7 - (c % 8).  A GPU batch-assembly kernel can therefore
+# read label[c][v] = (packed[c >> 3][v] >> (7 - (c & 7))) & 1 straight from the packed bytes (8x less H2D than uint8,
+# 64x less than the int64 labels train_ddp.py uploads today).
+# ------------------------------------------------------------------------------------------------
+def pack_masks(mask: torch.Tensor):
+    """[C, D, H, W] 0/1 -> numpy uint8 [ceil(C/8), D, H, W], the reference's storage format."""
+    import numpy as np
+    return np.packbits(mask.cpu().numpy().astype(np.bool_), axis=0)
+
+
+def unpack_masks(packed, num_classes: int) -> torch.Tensor:
+    """Inverse of pack_masks as the reference loads it: unpack along axis 0, keep the first num_classes channels."""
+    import numpy as np
+    full = np.unpackbits(packed, axis=0)
+    assert num_classes <= full.shape[0] < num_classes + 10          # the reference's own sanity asserts (:1010-1011)
+    return torch.from_numpy(full[:num_classes].copy())
+
+
+def packed_bit(packed, c: int):
+    """Channel c of a packed mask without unpacking (what a kernel would compute per voxel)."""
+    return (packed[c >> 3] >> (7 - (c & 7))) & 1
