@@ -307,6 +307,70 @@ int rsb_ball_rank_gwrp(const void* cand, const int* n_cand, int max_cand, float 
 /* wmap = (pseudo ? wmap : 0) + (1 - dilated)   — foreground GWRP weights + background indicator (:1775-1811) */
 int rsb_ball_weight_map(float* wmap, const uint8_t* pseudo, const uint8_t* dilated, long long V, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Optimizer end of the train step as two multi-tensor launches over a device table of
+ * tensors:  torch.nn.utils.clip_grad_norm_(net.parameters(), max_norm)      (train_ddp.py:352)
+ *           torch.optim.AdamW(lr, betas, eps = 1e-5, weight_decay).step()   (training/utils.py:46-51, train_ddp.py:353)
+ *           update_ema_variables: ema = a * ema + (1 - a) * param           (training/utils.py:154-158)
+ * Launch 1 reduces every gradient to per-block partial sums of squares (fixed order, no atomics); launch 2 re-sums
+ * them in every block, derives clip = min(1, max_norm / (norm + 1e-6)) and updates g (clipped in place, like
+ * clip_grad_norm_), p, exp_avg, exp_avg_sq and the EMA copy in one pass (40 B per parameter).
+ * The table lives in device memory; chunk_begin[i] = sum_{j<i} ceil(n_j / rsb_opt_chunk_elems()).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct RsbOptTensor {
+  float* p;     /* parameter (fp32) */
+  float* g;     /* gradient; multiplied by the clip coefficient in place */
+  float* m;     /* exp_avg */
+  float* v;     /* exp_avg_sq */
+  float* ema;   /* EMA copy of the parameter, or NULL when has_ema = 0 */
+  long long n;  /* elements */
+  long long chunk_begin;
+} RsbOptTensor;
+long long rsb_opt_chunk_elems(void);
+/* upper bound of the grid (= floats the `partials` workspace must hold) */
+int rsb_opt_max_blocks(void);
+/* step counts from 1 (bias corrections 1 - beta^step); max_norm <= 0 disables clipping (partials may then be NULL and
+ * norm_out receives 0); norm_out (optional) receives the total gradient norm BEFORE clipping, the return value of
+ * clip_grad_norm_.  Scalars are doubles like the python floats torch's AdamW computes with. */
+int rsb_clip_adamw_ema_step(const RsbOptTensor* table_device, int n_tensors, long long total_chunks, int has_ema,
+                            float* partials, float* norm_out, double max_norm, double lr, double beta1, double beta2,
+                            double eps, double weight_decay, long long step, double ema_alpha, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Sliding-window inference post-processing: inference/inference3d.py:28-107 and
+ * predict_abdomenatlas.py:637-710.  Volumes are fp32 / uint8 NCDHW like the reference's tensors.
+ * ------------------------------------------------------------------------------------------ */
+/* out[:, :, win] += sigmoid(pred) ; count[:, 0, win] += 1  for the window at (d0, h0, w0) of size (wd, wh, ww)
+ * (inference3d.py:80-100).  pred = fp32 [B][C][wd][wh][ww] logits; pred == NULL: a gated-out window — zeros are added,
+ * only the count moves (:92-100).  out fp32 [B][C][D][H][W], count fp32 [B][D][H][W]. */
+int rsb_sigmoid_window_accumulate(const float* pred, float* out, float* count, int B, int C, int D, int H, int W, int wd,
+                                  int wh, int ww, int d0, int h0, int w0, void* stream);
+/* prob = acc / count (inference3d.py:102; prob may alias acc or be NULL) ; mask = prob > threshold (uint8 0/1, may be
+ * NULL) — the `> 0.5` of predict_abdomenatlas.py:672 */
+int rsb_blend_finalize(const float* acc, const float* count, float* prob, uint8_t* mask, float threshold, int B, int C,
+                       long long V, void* stream);
+/* ndi.binary_dilation(organ, structure = np.ones((3, 3, 3))) with border value 0 (predict_abdomenatlas.py:675) */
+int rsb_dilate_box3(const uint8_t* src, uint8_t* dst, int n_vol, int D, int H, int W, void* stream);
+/* prob *= organ (0/1)   (predict_abdomenatlas.py:678-680) */
+int rsb_gate_by_mask(float* prob, const uint8_t* organ, long long n, void* stream);
+/* Face-connected (6-neighbour) components of one uint8 volume — sitk.ConnectedComponentImageFilter with its default
+ * FullyConnected = off (predict_abdomenatlas.py:690-695).  labels[v] = smallest linear index of v's component, -1 for
+ * background (sorting the distinct roots reproduces the raster-scan numbering 1..n); *n_components = their number.
+ * largest != NULL additionally writes keep_largest_component (:686-710): the first component (raster order) of maximal
+ * size, all zeros when there is none; that needs `workspace` of rsb_cc_workspace_bytes(). */
+size_t rsb_cc_workspace_bytes(int D, int H, int W);
+int rsb_cc_label(const uint8_t* mask, int* labels, int* n_components, uint8_t* largest, void* workspace, int D, int H, int W,
+                 void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Batch assembly from the on-disk crop format: label / unknown / chosen-segment masks are stored
+ * np.packbits(bool[C][D][H][W], axis = 0) (dataset_abdomenatlas_UFO.py:952-975) and loaded with
+ * np.unpackbits(...)[:C] (:1006-1015).  packed = uint8 [B][ceil(C/8)][V] uploaded as stored (8x fewer bytes than uint8
+ * masks, 64x fewer than the int64 labels of train_ddp.py:262); out = uint8 [B][C][V] 0/1 (channel c = bit 7 - (c & 7)
+ * of byte plane c >> 3), complemented when invert != 0.
+ * ------------------------------------------------------------------------------------------ */
+int rsb_unpack_masks(const uint8_t* packed, uint8_t* out, int B, int C, long long V, int invert, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

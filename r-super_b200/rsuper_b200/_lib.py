@@ -72,6 +72,15 @@ class RsbSegLossArgs(C.Structure):
     ]
 
 
+class RsbOptTensor(C.Structure):
+    _fields_ = [
+        ("p", c_void_p), ("g", c_void_p), ("m", c_void_p), ("v", c_void_p), ("ema", c_void_p),
+        ("n", c_ll), ("chunk_begin", c_ll),
+    ]
+
+
+c_double = C.c_double
+
 # name -> (restype, argtypes); every symbol include/rsuper_b200.h declares
 SIGNATURES = {
     "rsb_version": (C.c_char_p, []),
@@ -140,6 +149,18 @@ SIGNATURES = {
     "rsb_ball_rank_select": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rsb_ball_rank_gwrp": (c_int, [c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p]),
     "rsb_ball_weight_map": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
+    "rsb_opt_chunk_elems": (c_ll, []),
+    "rsb_opt_max_blocks": (c_int, []),
+    "rsb_clip_adamw_ema_step": (c_int, [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_double, c_double, c_double, c_double,
+                                        c_double, c_double, c_ll, c_double, c_void_p]),
+    "rsb_sigmoid_window_accumulate": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                              c_int, c_int, c_int, c_void_p]),
+    "rsb_blend_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_ll, c_void_p]),
+    "rsb_dilate_box3": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "rsb_gate_by_mask": (c_int, [c_void_p, c_void_p, c_ll, c_void_p]),
+    "rsb_cc_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "rsb_cc_label": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "rsb_unpack_masks": (c_int, [c_void_p, c_void_p, c_int, c_int, c_ll, c_int, c_void_p]),
 }
 
 _lib = None

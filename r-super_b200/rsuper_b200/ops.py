@@ -531,3 +531,82 @@ def ball_rank_gwrp(cand, n_cand, max_cand, concentration, wmap):
 def ball_weight_map(wmap, pseudo, dilated):
     _call("report", 1, 0.0, lib().rsb_ball_weight_map, _p(wmap), _p(pseudo), _p(dilated), wmap.numel(), _stream(), what="ball_weight_map")
     return wmap
+
+
+# --------------------------------------------------------------------------------------------
+# sliding-window inference post-processing, connected components, bit-packed masks
+# --------------------------------------------------------------------------------------------
+def _need(t: torch.Tensor, dtype, name: str):
+    if not (t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+        raise ValueError(f"{name}: expected a contiguous CUDA {dtype} tensor, got {t.dtype} {tuple(t.shape)} on {t.device}")
+
+
+def sigmoid_window_accumulate(pred: Optional[torch.Tensor], out: torch.Tensor, count: torch.Tensor, start, window):
+    """out[:, :, win] += sigmoid(pred); count[:, 0, win] += 1 (inference3d.py:80-100).  pred None = gated-out window."""
+    _need(out, torch.float32, "out"); _need(count, torch.float32, "count")
+    b, c, d, h, w_ = out.shape
+    assert count.numel() == b * d * h * w_
+    wd, wh, ww = window
+    if pred is not None:
+        _need(pred, torch.float32, "pred")
+        assert tuple(pred.shape) == (b, c, wd, wh, ww), f"window logits {tuple(pred.shape)} != {(b, c, wd, wh, ww)}"
+    _call("infer", 1, 0.0, lib().rsb_sigmoid_window_accumulate, _p(pred), _p(out), _p(count), b, c, d, h, w_, wd, wh, ww,
+          int(start[0]), int(start[1]), int(start[2]), _stream(), what="sigmoid_window_accumulate")
+
+
+def blend_finalize(acc: torch.Tensor, count: torch.Tensor, threshold: Optional[float] = None, in_place: bool = True):
+    """prob = acc / count (in place by default); with a threshold also returns the uint8 mask prob > threshold."""
+    _need(acc, torch.float32, "acc"); _need(count, torch.float32, "count")
+    b, c = acc.shape[0], acc.shape[1]
+    v = acc[0, 0].numel()
+    prob = acc if in_place else torch.empty_like(acc)
+    mask = torch.empty(acc.shape, dtype=torch.uint8, device=acc.device) if threshold is not None else None
+    _call("infer", 1, 0.0, lib().rsb_blend_finalize, _p(acc), _p(count), _p(prob), _p(mask), float(threshold if threshold is not None else 0.5),
+          b, c, v, _stream(), what="blend_finalize")
+    return prob, mask
+
+
+def dilate_box3(mask: torch.Tensor) -> torch.Tensor:
+    """ndi.binary_dilation(mask, structure=np.ones((3, 3, 3))) per [D, H, W] volume of a uint8 [..., D, H, W] tensor."""
+    _need(mask, torch.uint8, "mask")
+    d, h, w_ = mask.shape[-3:]
+    out = torch.empty_like(mask)
+    _call("infer", 1, 0.0, lib().rsb_dilate_box3, _p(mask), _p(out), mask.numel() // (d * h * w_), d, h, w_, _stream(), what="dilate_box3")
+    return out
+
+
+def gate_by_mask(prob: torch.Tensor, organ: torch.Tensor) -> torch.Tensor:
+    """prob *= organ (uint8 0/1), in place (predict_abdomenatlas.py:678-680)."""
+    _need(prob, torch.float32, "prob"); _need(organ, torch.uint8, "organ")
+    assert prob.numel() == organ.numel()
+    _call("infer", 1, 0.0, lib().rsb_gate_by_mask, _p(prob), _p(organ), prob.numel(), _stream(), what="gate_by_mask")
+    return prob
+
+
+def cc_label(mask: torch.Tensor, keep_largest: bool = False):
+    """Face-connected components of one uint8 [D, H, W] volume.  Returns (labels int32 [D, H, W] = smallest linear index of the
+    voxel's component or -1, n_components int32[1] on the device, largest uint8 [D, H, W] or None)."""
+    _need(mask, torch.uint8, "mask")
+    if mask.dim() != 3:
+        raise ValueError(f"cc_label: expected one [D, H, W] volume, got {tuple(mask.shape)}")
+    d, h, w_ = mask.shape
+    labels = torch.empty((d, h, w_), dtype=torch.int32, device=mask.device)
+    n = torch.empty(1, dtype=torch.int32, device=mask.device)
+    ws = largest = None
+    if keep_largest:
+        ws = torch.empty((lib().rsb_cc_workspace_bytes(d, h, w_) + 7) // 8, dtype=torch.int64, device=mask.device)
+        largest = torch.empty_like(mask)
+    _call("infer", 5 if keep_largest else 3, 0.0, lib().rsb_cc_label, _p(mask), _p(labels), _p(n), _p(largest), _p(ws), d, h, w_, _stream(),
+          what="cc_label")
+    return labels, n, largest
+
+
+def unpack_masks(packed: torch.Tensor, num_classes: int, invert: bool = False) -> torch.Tensor:
+    """np.unpackbits(packed, axis=0)[:C] per sample on the device: uint8 [B, ceil(C/8), D, H, W] -> uint8 [B, C, D, H, W]."""
+    _need(packed, torch.uint8, "packed")
+    if packed.dim() != 5 or packed.shape[1] != (num_classes + 7) // 8:
+        raise ValueError(f"unpack_masks: expected [B, {(num_classes + 7) // 8}, D, H, W] for {num_classes} classes, got {tuple(packed.shape)}")
+    b, _, d, h, w_ = packed.shape
+    out = torch.empty((b, num_classes, d, h, w_), dtype=torch.uint8, device=packed.device)
+    _call("assemble", 1, 0.0, lib().rsb_unpack_masks, _p(packed), _p(out), b, num_classes, d * h * w_, int(invert), _stream(), what="unpack_masks")
+    return out

@@ -1,0 +1,131 @@
+"""B200AdamW — the optimizer end of the reference train step as two multi-tensor kernel launches.
+
+Mirrors what `train_epoch` does between `loss.backward()` and the next iteration
+(rsuper_train/train_ddp.py:352-357):
+
+    torch.nn.utils.clip_grad_norm_(net.parameters(), 1.0)          # train_ddp.py:352
+    optimizer.step()                                                # AdamW(eps=1e-5), training/utils.py:46-51
+    update_ema_variables(net, ema_net, args.ema_alpha, step)        # training/utils.py:154-158
+
+`B200AdamW` is a `torch.optim.Optimizer` (param_groups / state_dict / zero_grad / LR schedulers such as
+`exp_lr_scheduler_with_warmup` keep working; the per-parameter state uses torch's AdamW keys `step`, `exp_avg`,
+`exp_avg_sq`, so checkpoints are interchangeable with `training.utils.get_optimizer`'s AdamW), whose `step()` runs
+`rsb_clip_adamw_ema_step` (csrc/train_glue.cu): gradient norm -> clip -> AdamW -> EMA in one pass over
+(g, p, exp_avg, exp_avg_sq, ema).  No CPU / PyTorch fallback: CPU parameters raise.
+
+Usage in place of the three reference lines above:
+
+    opt = B200AdamW(net.parameters(), lr=args.base_lr, betas=args.betas, weight_decay=args.weight_decay,
+                    max_norm=1.0, ema_params=list(ema_net.parameters()), ema_alpha=args.ema_alpha)
+    ...
+    loss.backward(); opt.step()          # opt.last_grad_norm = what clip_grad_norm_ would have returned
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, Optional, Sequence
+
+import torch
+
+from . import ops
+from ._lib import check, lib
+
+
+class B200AdamW(torch.optim.Optimizer):
+    def __init__(self, params: Iterable, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-5, weight_decay: float = 1e-2,
+                 max_norm: Optional[float] = None, ema_params: Optional[Sequence[torch.Tensor]] = None, ema_alpha: float = 0.99):
+        if lr < 0 or eps < 0 or weight_decay < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1):
+            raise ValueError(f"B200AdamW: invalid hyper-parameters lr={lr} betas={betas} eps={eps} weight_decay={weight_decay}")
+        super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
+        self.max_norm = max_norm
+        self.ema_alpha = ema_alpha
+        self.ema_params = list(ema_params) if ema_params is not None else None
+        flat = [p for g in self.param_groups for p in g["params"]]
+        if self.ema_params is not None and (len(self.ema_params) != len(flat) or
+                                            any(e.shape != p.shape for e, p in zip(self.ema_params, flat))):
+            raise ValueError("B200AdamW: ema_params must mirror the parameters one to one")
+        self.global_step = 0          # update_ema_variables' global_step (train_ddp.py:308)
+        self.last_grad_norm = None    # device scalar: total gradient norm before clipping
+        self._tables = {}             # group index -> (pointer signature, device table, n_tensors, total_chunks)
+        self._partials = None
+
+    # -- device table of one param group --------------------------------------------------------------------------
+    def _table(self, gi: int, group, ema_of):
+        chunk = lib().rsb_opt_chunk_elems()
+        rows, sig = [], []
+        begin = 0
+        for p in group["params"]:
+            if p.grad is None:
+                continue
+            if not p.is_cuda:
+                raise RuntimeError("B200AdamW has no CPU path: parameters must live on a CUDA (sm_100a) device")
+            if p.dtype != torch.float32 or p.grad.dtype != torch.float32 or not p.is_contiguous() or not p.grad.is_contiguous() \
+                    or p.grad.is_sparse:
+                raise RuntimeError("B200AdamW: parameters and gradients must be dense contiguous fp32")
+            st = self.state[p]
+            if len(st) == 0:
+                st["step"] = torch.tensor(0.0)  # host scalar tensor like torch's non-capturable AdamW
+                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            e = ema_of.get(id(p))
+            if e is not None and not (e.is_cuda and e.dtype == torch.float32 and e.is_contiguous()):
+                raise RuntimeError("B200AdamW: EMA tensors must be contiguous CUDA fp32")
+            n = p.numel()
+            if n == 0:
+                continue
+            rows.append((p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
+                         e.data_ptr() if e is not None else 0, n, begin))
+            sig.append(rows[-1][:5])
+            begin += (n + chunk - 1) // chunk
+        if not rows:
+            return None
+        cached = self._tables.get(gi)
+        if cached is not None and cached[0] == sig:
+            return cached
+        # 7 x int64 per row == struct RsbOptTensor (5 pointers, n, chunk_begin); uploaded only when a pointer changed
+        dev = group["params"][0].device
+        host = torch.tensor(rows, dtype=torch.int64).pin_memory()
+        table = host.to(dev, non_blocking=True)
+        cached = (sig, table, len(rows), begin, host)   # keep the pinned source alive until the copy has run
+        self._tables[gi] = cached
+        return cached
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        ema_of = {}
+        if self.ema_params is not None:
+            flat = [p for g in self.param_groups for p in g["params"]]
+            ema_of = {id(p): e for p, e in zip(flat, self.ema_params)}
+        if self.max_norm is not None and len(self.param_groups) != 1:
+            raise NotImplementedError("B200AdamW: gradient clipping spans one param group (training/utils.py:29-33 builds one)")
+        alpha = min(1.0 - 1.0 / (self.global_step + 1), self.ema_alpha)   # training/utils.py:156
+        for gi, group in enumerate(self.param_groups):
+            tab = self._table(gi, group, ema_of)
+            if tab is None:
+                continue
+            _, table, n_tensors, total_chunks, _ = tab
+            dev = table.device
+            steps = {int(self.state[p]["step"].item()) for p in group["params"] if p.grad is not None and p.numel()}
+            if len(steps) != 1:
+                raise RuntimeError("B200AdamW: parameters of a group must share their step count")
+            t = steps.pop() + 1
+            if self._partials is None or self._partials.device != dev:
+                self._partials = torch.empty(lib().rsb_opt_max_blocks() + 1, dtype=torch.float32, device=dev)
+            norm_out = self._partials[-1:]
+            clip = float(self.max_norm) if self.max_norm is not None else 0.0
+            b1, b2 = group["betas"]
+            with torch.cuda.device(dev):
+                ops._call("train_glue", 2 if clip > 0 else 1, 0.0, lib().rsb_clip_adamw_ema_step, C.c_void_p(table.data_ptr()),
+                          n_tensors, total_chunks, int(bool(ema_of)), ops._p(self._partials) if clip > 0 else None, ops._p(norm_out),
+                          clip, float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]), t,
+                          float(alpha), ops._stream(), what="clip_adamw_ema_step")
+            self.last_grad_norm = norm_out if clip > 0 else None
+            for p in group["params"]:
+                if p.grad is not None and p.numel():
+                    self.state[p]["step"] += 1
+        self.global_step += 1
+        return loss

@@ -98,3 +98,110 @@ def test_engine_layer_tables_match_the_state_dict_names():
     for pre in _Engine.SINGLE_CONVS:
         w = sd1[pre + "conv.conv.weight"]
         assert w.shape[2:] == (3, 3, 3) and w.shape[0] % 8 == 0 and w.shape[1] % 8 == 0
+
+
+def _header_prototypes():
+    """name -> (return type, [parameter types]) parsed from include/rsuper_b200.h."""
+    txt = open(os.path.join(ROOT, "include", "rsuper_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    protos = {}
+    for ret, name, params in re.findall(r"\b(const char\*|int|size_t|long long)\s+(rsb_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", txt):
+        params = " ".join(params.split())
+        plist = [] if params in ("", "void") else [p.strip() for p in params.split(",")]
+        protos[name] = (ret, plist)
+    return protos
+
+
+def _kind(ctype_param: str) -> str:
+    if "*" in ctype_param:
+        return "ptr"
+    for key, kind in (("double", "f64"), ("float", "f32"), ("long long", "i64"), ("size_t", "size"), ("unsigned int", "u32"), ("int", "i32")):
+        if key in ctype_param:
+            return kind
+    raise AssertionError(f"unparsed parameter type: {ctype_param!r}")
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every ctypes argtypes list has the arity and the scalar/pointer kinds of its C prototype (ctypes itself never
+    checks this; a mismatch would silently corrupt the arguments on the GPU box)."""
+    from rsuper_b200 import _lib
+    kinds = {ctypes.c_void_p: "ptr", ctypes.c_char_p: "ptr", ctypes.c_int: "i32", ctypes.c_uint: "u32", ctypes.c_float: "f32",
+             ctypes.c_double: "f64", ctypes.c_longlong: "i64", ctypes.c_size_t: "size", ctypes.c_ulonglong: "u64"}
+    protos = _header_prototypes()
+    assert sorted(protos) == sorted(_lib.SIGNATURES)
+    rets = {"const char*": ctypes.c_char_p, "int": ctypes.c_int, "size_t": ctypes.c_size_t, "long long": ctypes.c_longlong}
+    for name, (ret, params) in protos.items():
+        res, argtypes = _lib.SIGNATURES[name]
+        assert res is rets[ret], name
+        assert len(argtypes) == len(params), f"{name}: {len(argtypes)} ctypes arguments vs {len(params)} in the header"
+        for i, (a, p) in enumerate(zip(argtypes, params)):
+            got = kinds.get(a, "ptr" if hasattr(a, "contents") or issubclass(a, ctypes._Pointer) else None)
+            assert got == _kind(p), f"{name}: argument {i} is {a} in _lib.py but `{p}` in the header"
+
+
+def test_struct_layouts_match_the_header():
+    """ctypes Structures mirror the header's structs field by field (names and order)."""
+    from rsuper_b200 import _lib
+    txt = open(os.path.join(ROOT, "include", "rsuper_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    for cname, cls in (("RsbPackJob", _lib.RsbPackJob), ("RsbConv3Args", _lib.RsbConv3Args), ("RsbConv3WgradArgs", _lib.RsbConv3WgradArgs),
+                       ("RsbSegLossArgs", _lib.RsbSegLossArgs), ("RsbOptTensor", _lib.RsbOptTensor)):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), txt, flags=re.S).group(1)
+        names = []
+        for decl in body.split(";"):
+            decl = " ".join(decl.split())
+            if not decl:
+                continue
+            first, *rest = decl.split(",")
+            names.append(re.findall(r"[A-Za-z_0-9]+", first)[-1])
+            names += [re.findall(r"[A-Za-z_0-9]+", r)[-1] for r in rest]
+        assert names == [f for f, _ in cls._fields_], cname
+
+
+def test_widened_entry_points_validate_arguments_without_a_gpu():
+    """SURVEY §8f rows (N2 / N3 / N4): null pointers, empty shapes and windows outside the volume are refused with an error
+    code + message before any launch."""
+    from rsuper_b200 import _lib
+    lib = _lib.lib()
+    assert lib.rsb_opt_chunk_elems() == 4096 and lib.rsb_opt_max_blocks() >= 148
+    assert lib.rsb_clip_adamw_ema_step(None, 0, 0, 1, None, None, 1.0, 6e-4, 0.9, 0.999, 1e-5, 0.05, 1, 0.99, None) != 0
+    assert b"empty tensor table" in lib.rsb_last_error()
+    assert lib.rsb_clip_adamw_ema_step(4096, 1, 1, 1, None, None, 1.0, 6e-4, 0.9, 0.999, 1e-5, 0.05, 0, 0.99, None) != 0
+    assert b"step counts from 1" in lib.rsb_last_error()
+    assert lib.rsb_clip_adamw_ema_step(4096, 1, 1, 1, None, None, 1.0, 6e-4, 0.9, 0.999, 1e-5, 0.05, 1, 0.99, None) != 0
+    assert b"partials" in lib.rsb_last_error()
+    assert lib.rsb_sigmoid_window_accumulate(None, 4096, 4096, 1, 2, 16, 16, 16, 8, 8, 8, 9, 0, 0, None) != 0
+    assert b"leaves the volume" in lib.rsb_last_error()
+    assert lib.rsb_blend_finalize(None, None, None, None, 0.5, 1, 1, 8, None) != 0
+    assert lib.rsb_dilate_box3(4096, 4096, 1, 4, 4, 4, None) != 0 and b"distinct" in lib.rsb_last_error()
+    assert lib.rsb_gate_by_mask(None, None, 8, None) != 0
+    assert lib.rsb_cc_workspace_bytes(4, 5, 6) == 4 * 5 * 6 * 4 + 16
+    assert lib.rsb_cc_label(4096, 4096, 4096, 4096, None, 4, 4, 4, None) != 0 and b"workspace" in lib.rsb_last_error()
+    assert lib.rsb_cc_label(4096, 4096, 4096, None, None, 2048, 2048, 2048, None) != 0
+    assert lib.rsb_unpack_masks(None, None, 1, 2, 8, 0, None) != 0
+
+
+def test_widened_host_wrappers_marshal_their_arguments(monkeypatch):
+    """Dry run of the new Python wrappers on CPU tensors with the device checks patched out: every call must get through
+    ctypes marshalling and the C-side validation and fail only at the kernel LAUNCH (there is no GPU here) — a wrong
+    argument count / order would raise ctypes.ArgumentError or a validation message instead."""
+    import torch
+    from rsuper_b200 import ops
+    if torch.cuda.is_available():
+        pytest.skip("dry run is for the GPU-less container")
+    monkeypatch.setattr(ops, "_need", lambda t, dtype, name: None)
+    monkeypatch.setattr(ops, "_stream", lambda: None)
+    out, cnt = torch.zeros(1, 2, 16, 16, 16), torch.zeros(1, 1, 16, 16, 16)
+    calls = [
+        lambda: ops.sigmoid_window_accumulate(torch.zeros(1, 2, 8, 8, 8), out, cnt, (8, 0, 4), (8, 8, 8)),
+        lambda: ops.sigmoid_window_accumulate(None, out, cnt, (8, 0, 4), (8, 8, 8)),
+        lambda: ops.blend_finalize(out, cnt, threshold=0.5),
+        lambda: ops.dilate_box3(torch.zeros(2, 4, 5, 6, dtype=torch.uint8)),
+        lambda: ops.gate_by_mask(torch.zeros(4, 5, 6), torch.zeros(4, 5, 6, dtype=torch.uint8)),
+        lambda: ops.cc_label(torch.zeros(4, 5, 6, dtype=torch.uint8), keep_largest=True),
+        lambda: ops.cc_label(torch.zeros(4, 5, 6, dtype=torch.uint8)),
+        lambda: ops.unpack_masks(torch.zeros(2, 2, 4, 5, 6, dtype=torch.uint8), 11),
+    ]
+    for i, fn in enumerate(calls):
+        with pytest.raises(RuntimeError, match="launch failed"):
+            fn()

@@ -1,0 +1,394 @@
+"""GPU tests of the rows SURVEY §8(f) widens into (N2 batch assembly from bit-packed masks, N3 sliding-window inference +
+connected components, N4 fused clip/AdamW/EMA) and the FULL-SIZE property tests of the hot path at BASELINE.json
+configs[1] (2 x 128^3, base 32).
+
+Everything here calls through the C-ABI and is checked against the oracle (oracle/*.py), the committed golden vectors of
+the REAL reference (tests/golden) or plain torch.  The file sorts after the established suites on purpose: its kernels
+(csrc/train_glue.cu, csrc/infer.cu) and its full-size tolerances were written after round 1's GPU budget was spent, so the
+whole file is marked `staged` (tests/conftest.py: non-strict xfail until the first run on a B200 — an XPASS in the report
+is that first run; the marker comes off once it has been seen green).
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.staged, pytest.mark.timeout(600)]
+
+
+def rel(a, b):
+    return ((a - b).abs().max() / (b.abs().max() + 1e-20)).item()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# N4: clip_grad_norm_ + AdamW + EMA in two launches
+# ------------------------------------------------------------------------------------------------------------------
+def _param_set(dev, seed):
+    """Tensors of awkward sizes: several 4096-element chunks + ragged tail, tiny, 2-D, and one whose storage is offset by
+    one float (not 16-byte aligned: the scalar path, as for DDP bucket views)."""
+    g = torch.Generator().manual_seed(seed)
+    shapes = [(3 * 4096 + 5,), (1000,), (37, 5), (8197,), (4096,), (1,)]
+    out = []
+    for i, s in enumerate(shapes):
+        n = int(np.prod(s))
+        buf = torch.randn(n + 1, generator=g).to(dev)
+        out.append(buf[1:1 + n].view(s) if i == 3 else buf[:n].view(s).clone())
+    return out
+
+
+@pytest.mark.parametrize("with_ema,max_norm", [(True, 1.0), (False, 1.0), (True, None)])
+def test_fused_clip_adamw_ema_matches_torch(cuda_dev, with_ema, max_norm):
+    """Four steps (large gradients: clipping active; small ones: inactive) against torch.nn.utils.clip_grad_norm_ +
+    torch.optim.AdamW(eps=1e-5) + update_ema_variables' formula (train_ddp.py:352-357, training/utils.py:46-51,154-158)."""
+    from rsuper_b200.optim import B200AdamW
+    init = _param_set(cuda_dev, 0)
+    ours = [torch.nn.Parameter(t) for t in init]                      # keeps the misaligned view
+    ref = [torch.nn.Parameter(t.clone()) for t in init]
+    assert ours[3].data_ptr() % 16 != 0
+    ema_o = [p.detach().clone() for p in ours] if with_ema else None
+    ema_r = [p.detach().clone() for p in ref]
+    hyper = dict(lr=6e-4, betas=(0.9, 0.999), eps=1e-5, weight_decay=0.05)
+    opt_o = B200AdamW(ours, max_norm=max_norm, ema_params=ema_o, ema_alpha=0.99, **hyper)
+    opt_r = torch.optim.AdamW(ref, foreach=False, fused=False, **hyper)
+    for step in range(4):
+        grads = [t * (3.0 if step < 2 else 1e-3) for t in _param_set(cuda_dev, 10 + step)]
+        for p, q, g in zip(ours, ref, grads):
+            p.grad = g.clone() if p.data_ptr() % 16 == 0 else torch.cat([g.new_zeros(1), g.reshape(-1)])[1:].view(g.shape)
+            q.grad = g.clone()
+        norm_r = torch.nn.utils.clip_grad_norm_(ref, max_norm) if max_norm is not None else None
+        opt_r.step()
+        alpha = min(1 - 1 / (step + 1), 0.99)
+        with torch.no_grad():
+            for e, q in zip(ema_r, ref):
+                e.mul_(alpha).add_(q.detach(), alpha=1 - alpha)
+        opt_o.step()
+        torch.cuda.synchronize()
+        if max_norm is not None:
+            torch.testing.assert_close(opt_o.last_grad_norm.reshape(()), norm_r.reshape(()), rtol=1e-5, atol=0)
+        for i, (p, q) in enumerate(zip(ours, ref)):
+            torch.testing.assert_close(p.detach(), q.detach(), rtol=2e-6, atol=2e-7, msg=lambda m: f"step {step} param {i}: {m}")
+            torch.testing.assert_close(p.grad, q.grad, rtol=2e-6, atol=1e-9, msg=lambda m: f"step {step} grad {i}: {m}")
+            so, sr = opt_o.state[p], opt_r.state[q]
+            torch.testing.assert_close(so["exp_avg"], sr["exp_avg"], rtol=1e-5, atol=1e-9)
+            torch.testing.assert_close(so["exp_avg_sq"], sr["exp_avg_sq"], rtol=1e-5, atol=1e-12)
+            assert float(so["step"]) == float(sr["step"]) == step + 1
+            if with_ema:
+                torch.testing.assert_close(ema_o[i], ema_r[i], rtol=2e-6, atol=2e-7)
+    # checkpoints are interchangeable with torch's AdamW (same per-parameter state keys)
+    assert set(opt_o.state_dict()["state"][0].keys()) == set(opt_r.state_dict()["state"][0].keys())
+
+
+def test_fused_optimizer_rejects_cpu_parameters():
+    from rsuper_b200.optim import B200AdamW
+    p = torch.nn.Parameter(torch.zeros(8))
+    p.grad = torch.ones(8)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        B200AdamW([p], max_norm=1.0).step()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# N2: bit-packed masks -> device uint8 masks
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("C,shape", [(2, (16, 16, 16)), (3, (8, 12, 20)), (8, (4, 6, 10)), (9, (5, 7, 9)), (42, (6, 5, 7))])
+def test_unpack_masks_bit_exact(cuda_dev, C, shape):
+    from oracle import synth
+    from rsuper_b200 import ops
+    g = torch.Generator().manual_seed(C)
+    masks = (torch.rand((2, C) + shape, generator=g) < 0.3).to(torch.uint8)
+    packed = np.stack([synth.pack_masks(masks[b]) for b in range(2)])          # the reference's storage format
+    assert packed.shape == (2, (C + 7) // 8) + shape
+    want = torch.stack([synth.unpack_masks(packed[b], C) for b in range(2)])
+    assert torch.equal(want, masks)
+    dev_packed = torch.from_numpy(packed).to(cuda_dev)
+    assert torch.equal(ops.unpack_masks(dev_packed, C).cpu(), want)
+    assert torch.equal(ops.unpack_masks(dev_packed, C, invert=True).cpu(), 1 - want)
+    with pytest.raises(ValueError):
+        ops.unpack_masks(dev_packed, C + 8)
+
+
+def test_assemble_batch_feeds_calculate_loss(cuda_dev):
+    """Batch assembled from the packed on-disk format == the batch uploaded as plain tensors, down to the loss values."""
+    from oracle import losses_ref as LR
+    from oracle import synth
+    from rsuper_b200 import batch as B
+    from rsuper_b200 import losses
+    classes = ["organ", "pancreatic_lesion", "veins"]
+    shape = (32, 32, 48)
+    kinds = ["mask", "report"]
+    ref = synth.make_batch(kinds, classes, shape, seed=5)
+    got = B.assemble_batch(
+        images=[ref["image"][b, 0].numpy() for b in range(2)],
+        labels_packed=[synth.pack_masks(ref["label"][b]) for b in range(2)], num_classes=len(classes), device=cuda_dev,
+        unk_packed=[None, synth.pack_masks(ref["unk_channels"][1])],
+        chosen_packed=[None, synth.pack_masks(ref["mask"][1])],
+        volumes=[None, ref["volumes"][1].numpy()], diameters=[None, ref["diameters"][1].numpy()])
+    for k in ("image", "label", "unk_channels", "mask", "volumes", "diameters"):
+        assert got[k].is_cuda and tuple(got[k].shape) == tuple(ref[k].shape), k
+        assert torch.equal(got[k].cpu().float(), ref[k].float()), k
+    assert got["label"].dtype == torch.uint8
+    logits = synth.synthetic_logits(2, len(classes), shape, seed=2, device=cuda_dev)
+    args = LR.default_args()
+    res = []
+    for bt in (got, {k: v.to(cuda_dev) for k, v in ref.items()}):
+        lg = logits.clone().requires_grad_(True)
+        out = losses.calculate_loss({"segmentation": lg}, bt["label"], bt["unk_channels"], args, None, bt["mask"], bt["volumes"],
+                                    bt["diameters"], classes, input_tensor=bt["image"])
+        res.append({k: v.item() for k, v in out.items()})
+    assert res[0].keys() == res[1].keys()
+    for k in res[0]:
+        assert abs(res[0][k] - res[1][k]) <= 1e-6 * max(1.0, abs(res[1][k])), (k, res[0][k], res[1][k])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# N3: sliding-window inference, organ gating, connected components
+# ------------------------------------------------------------------------------------------------------------------
+def _sliding_net(dev):
+    """The tiny deterministic net tests/golden/make_golden.py ran through the REAL inference_sliding_window."""
+    w = torch.frac(torch.sin(torch.arange(3 * 27, dtype=torch.float64) * 12.9898) * 43758.5453).float().reshape(3, 1, 3, 3, 3) - 0.5
+    net = torch.nn.Conv3d(1, 3, 3, padding=1, bias=True)
+    with torch.no_grad():
+        net.weight.copy_(w)
+        net.bias.copy_(torch.tensor([0.1, -0.2, 0.05]))
+    return net.to(dev).eval()
+
+
+def test_sliding_window_blend_matches_reference_golden(cuda_dev, golden):
+    """Window placement, padding of small volumes, gated windows, sigmoid + mean blend — against outputs recorded from the
+    REAL inference3d.inference_sliding_window (same net, same volumes), and against the oracle on the full volume."""
+    from types import SimpleNamespace
+    from oracle.inference_ref import inference_sliding_window as oracle_sw
+    from oracle.unet_ref import synthetic_image
+    from rsuper_b200.inference import inference_sliding_window
+    net = _sliding_net(cuda_dev)
+    gate = torch.zeros(1, 1, 40, 48, 56)
+    gate[:, :, 4:20, 8:30, 10:20] = 1
+    cases = [("ragged", (40, 48, 56), (16, 16, 32), None), ("small", (12, 20, 16), (16, 16, 32), None),
+             ("exact", (32, 32, 32), (16, 16, 16), None), ("gated", (40, 48, 56), (16, 16, 32), gate)]
+    for tag, shp, win, g in cases:
+        vol = synthetic_image(1, *shp, seed=9)
+        a = SimpleNamespace(window_size=list(win), classes=3)
+        out = inference_sliding_window(net, vol.to(cuda_dev), a, pancreas=None if g is None else g.to(cuda_dev))
+        assert not out.is_cuda and out.shape == (1, 3) + shp                 # CPU tensor, like the reference returns
+        np.testing.assert_allclose(out.numpy()[:, :, 1::3, 1::3, 1::3], golden[f"sliding_{tag}"], rtol=0, atol=2e-6)
+        assert abs(out.double().sum().item() - float(golden[f"sliding_{tag}_sum"])) <= 2e-6 * abs(float(golden[f"sliding_{tag}_sum"]))
+        want = oracle_sw(_sliding_net("cpu"), vol, win, 3, gate=g)
+        assert (out - want).abs().max().item() <= 2e-6
+        prob, mask = inference_sliding_window(net, vol.to(cuda_dev), a, pancreas=None if g is None else g.to(cuda_dev),
+                                              keep_on_device=True, threshold=0.5)
+        assert prob.is_cuda and mask.dtype == torch.uint8 and torch.equal(mask.bool(), prob > 0.5)
+        resolved = (want - 0.5).abs() > 4e-6                                  # threshold decisions the tolerance resolves
+        assert torch.equal(mask.cpu().bool()[resolved], (want > 0.5)[resolved])
+
+
+def test_sliding_window_with_b200_unet(cuda_dev):
+    """The windows go through B200UNet (eval, no grad): blended probabilities vs the oracle UNet blended by the oracle."""
+    from types import SimpleNamespace
+    from oracle.inference_ref import inference_sliding_window as oracle_sw
+    from oracle.unet_ref import synthetic_image, synthetic_state_dict, unet_forward
+    from rsuper_b200.inference import inference_sliding_window
+    from rsuper_b200.unet import B200UNet
+    net = B200UNet(1, 8, num_classes=2, precision="fp32").to(cuda_dev)
+    sd = synthetic_state_dict(8, 2, device=cuda_dev)
+    net.load_state_dict(sd)
+    vol = synthetic_image(1, 64, 96, 64, seed=4, device=cuda_dev)
+    a = SimpleNamespace(window_size=[64, 64, 64], classes=2)
+    got = inference_sliding_window(net, vol, a, keep_on_device=True)
+    want = oracle_sw(lambda x: unet_forward(x.to(cuda_dev), sd), vol.cpu(), (64, 64, 64), 2)
+    err = (got.cpu() - want).abs().max().item()
+    print(f"[sliding/unet] max abs prob error {err:.3e}")
+    assert err <= 2e-3                                                        # logits within 1e-3 relative -> probabilities
+
+
+def _np_cc(mask_np):
+    from oracle.inference_ref import connected_components
+    return connected_components(mask_np)
+
+
+@pytest.mark.parametrize("case", ["hand", "random_sparse", "random_dense", "blobs", "empty", "full", "snake"])
+def test_connected_components_bit_exact(cuda_dev, case):
+    """Component COUNT, the partition itself (raster-order numbering) and keep_largest_component — against the oracle
+    (scipy face connectivity == SimpleITK's default)."""
+    from oracle import synth
+    from oracle.inference_ref import keep_largest_component as oracle_largest
+    from rsuper_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    if case == "hand":
+        m = np.zeros((6, 6, 6), dtype=np.uint8)
+        m[0, 0, 0] = 1; m[1, 1, 1] = 1; m[3:5, 3:5, 3:5] = 1; m[3, 3, 5] = 1
+    elif case == "random_sparse":
+        m = (torch.rand((24, 20, 28), generator=g) < 0.12).numpy().astype(np.uint8)
+    elif case == "random_dense":
+        m = (torch.rand((17, 23, 19), generator=g) < 0.45).numpy().astype(np.uint8)     # near the percolation threshold: long merges
+    elif case == "blobs":
+        m = synth.make_batch(["mask"], ["organ", "a_lesion", "b_lesion"], (48, 40, 56), seed=21)["label"][0].amax(0).numpy().astype(np.uint8)
+    elif case == "empty":
+        m = np.zeros((5, 6, 7), dtype=np.uint8)
+    elif case == "full":
+        m = np.ones((9, 8, 7), dtype=np.uint8)
+    else:  # one long serpentine component: the worst case for pointer chains
+        m = np.zeros((1, 32, 33), dtype=np.uint8)
+        m[0, ::2, :] = 1
+        m[0, 1::4, -1] = 1
+        m[0, 3::4, 0] = 1
+    want_labels, want_n = _np_cc(m)
+    labels, n, largest = ops.cc_label(torch.from_numpy(m).to(cuda_dev), keep_largest=True)
+    assert int(n.item()) == want_n
+    lab = labels.cpu().numpy()
+    assert np.array_equal(lab >= 0, m > 0)
+    roots = np.unique(lab[lab >= 0])                       # ascending root index == raster order of first voxels
+    assert len(roots) == want_n
+    dense = np.zeros_like(lab)
+    dense[lab >= 0] = np.searchsorted(roots, lab[lab >= 0]) + 1
+    assert np.array_equal(dense, want_labels)              # same numbering as scipy.ndimage.label / SimpleITK
+    assert np.array_equal(largest.cpu().numpy().astype(bool), oracle_largest(m))
+    labels2, n2, none = ops.cc_label(torch.from_numpy(m).to(cuda_dev))
+    assert none is None and int(n2.item()) == want_n and torch.equal(labels2, labels)
+
+
+def test_organ_gating_matches_oracle(cuda_dev):
+    from types import SimpleNamespace
+    from oracle.inference_ref import gate_lesion_by_organ
+    from rsuper_b200.inference import postprocess_npz
+    g = torch.Generator().manual_seed(3)
+    classes = ["pancreas", "pancreatic_lesion", "kidney_right", "kidney_left", "kidney_lesion"]
+    prob = torch.rand((1, 5, 12, 14, 16), generator=g)
+    prob[0, 0] *= (torch.rand((12, 14, 16), generator=g) < 0.05)        # sparse organs: the dilation matters
+    prob[0, 2] *= (torch.rand((12, 14, 16), generator=g) < 0.03)
+    prob[0, 3] *= (torch.rand((12, 14, 16), generator=g) < 0.03)
+    out = postprocess_npz(prob.to(cuda_dev), classes, SimpleNamespace(organ_mask_on_lesion=True))
+    p = prob[0].numpy()
+    assert np.array_equal(out["pancreatic_lesion"].cpu().numpy(), gate_lesion_by_organ(p[1], p[0]))
+    assert np.array_equal(out["kidney_lesion"].cpu().numpy(), gate_lesion_by_organ(p[4], p[2] + p[3]))
+    assert np.array_equal(out["pancreas"].cpu().numpy(), p[0])
+    plain = postprocess_npz(prob.to(cuda_dev), classes, SimpleNamespace(organ_mask_on_lesion=False))
+    assert np.array_equal(plain["kidney_lesion"].cpu().numpy(), p[4])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Full size (BASELINE.json configs[1]: 2 x 128^3, base 32): size-independent properties of the hot path
+# ------------------------------------------------------------------------------------------------------------------
+def _full_net(cuda_dev, precision):
+    from oracle.unet_ref import synthetic_state_dict
+    from rsuper_b200.unet import B200UNet
+    net = B200UNet(1, 32, num_classes=2, precision=precision).to(cuda_dev)
+    sd = synthetic_state_dict(32, 2, device=cuda_dev)
+    net.load_state_dict(sd)
+    return net, sd
+
+
+def test_full_size_samples_are_independent_and_runs_repeat(cuda_dev):
+    """InstanceNorm is per sample and nothing else couples the batch: a sample's logits in a batch of two equal
+    its logits alone; a second run of the same batch reproduces the first (only the order of the fp32 statistics atomics
+    differs).  fp32 parity mode, 128^3."""
+    from oracle.unet_ref import synthetic_image
+    net, _ = _full_net(cuda_dev, "fp32")
+    x = synthetic_image(2, 128, 128, 128, seed=5, device=cuda_dev)
+    with torch.no_grad():
+        both = net(x)["segmentation"].clone()
+        again = net(x)["segmentation"].clone()
+        solo = net(x[1:2].contiguous())["segmentation"].clone()
+    assert torch.isfinite(both).all()
+    e_rep, e_solo = rel(again, both), rel(solo, both[1:2])
+    print(f"[full-size] repeat rel {e_rep:.2e}, batch-of-2 vs alone rel {e_solo:.2e}")
+    assert e_rep <= 1e-3 and e_solo <= 1e-3
+
+
+def test_full_size_logits_mask_and_component_count_vs_oracle(cuda_dev):
+    """North-star bars at full size, against the oracle run in fp32 on the same GPU (cuDNN, TF32 off): logits within 1e-3
+    relative; the argmax mask identical wherever the oracle's own margin exceeds that tolerance; and — when the masks are
+    identical — the face-connected component count of the lesion mask identical (it is a function of the mask)."""
+    from oracle.inference_ref import connected_components
+    from oracle.unet_ref import synthetic_image, unet_forward
+    net, sd = _full_net(cuda_dev, "fp32")
+    x = synthetic_image(1, 128, 128, 128, seed=6, device=cuda_dev)
+    with torch.no_grad():
+        got = net(x)["segmentation"]
+        want = unet_forward(x, sd)
+    e = rel(got, want)
+    tol = 1e-3 * want.abs().max().item()
+    margin = (want[:, 0] - want[:, 1]).abs()
+    differ = got.argmax(1) != want.argmax(1)
+    print(f"[full-size] logits rel-to-max {e:.3e}; argmax differs at {int(differ.sum())} of {differ.numel()} voxels, "
+          f"{int((differ & (margin > 2 * tol)).sum())} of them outside the tolerance band")
+    assert e <= 1e-3
+    assert int((differ & (margin > 2 * tol)).sum()) == 0
+    if int(differ.sum()) == 0:
+        a = connected_components(got.argmax(1)[0].cpu().numpy())[1]
+        b = connected_components(want.argmax(1)[0].cpu().numpy())[1]
+        assert a == b
+
+
+def test_full_size_seg_loss_vs_oracle_at_identical_logits(cuda_dev):
+    """Loss within 1e-5 and d(logits) within 1e-4 of the oracle at 2 x 2 x 128^3 (the reductions run over 4.2 M voxels)."""
+    from oracle import losses_ref as LR
+    from oracle import synth
+    from rsuper_b200 import losses
+    classes = ["organ", "pancreatic_lesion"]
+    lab = synth.make_batch(["mask", "mask"], classes, (128, 128, 128), seed=8, device=cuda_dev)["label"]
+    logits = synth.synthetic_logits(2, 2, (128, 128, 128), seed=1, device=cuda_dev)
+    a = logits.clone().requires_grad_(True)
+    b = logits.clone().requires_grad_(True)
+    args = LR.default_args(report_volume_loss_basic=0.0)
+    ours = losses.calculate_loss({"segmentation": a}, lab, None, args, None, None, None, None, classes)["overall"]
+    ref = LR.seg_loss(b, lab.float(), torch.ones_like(b))
+    ours.backward(); ref.backward()
+    dl = abs(ours.item() - ref.item()) / abs(ref.item())
+    dg = rel(a.grad, b.grad)
+    print(f"[full-size] seg loss {ours.item():.7f} vs oracle {ref.item():.7f} (rel {dl:.2e}); dlogits rel-to-max {dg:.2e}")
+    assert dl <= 1e-5 and dg <= 1e-4
+
+
+def test_full_size_train_steps_with_fused_optimizer(cuda_dev):
+    """Three full-size bf16 train steps (forward, loss, backward, B200AdamW = clip + AdamW + EMA) against the same steps
+    with the stock torch glue (clip_grad_norm_, fused AdamW, foreach EMA) from identical initial state: identical losses
+    at step 0, parameters and EMA within optimizer rounding after the steps, finite everywhere, loss not increasing."""
+    from oracle import losses_ref as LR
+    from oracle import synth
+    from oracle.unet_ref import synthetic_image
+    from rsuper_b200 import losses
+    from rsuper_b200.optim import B200AdamW
+    classes = ["organ", "pancreatic_lesion"]
+    x = synthetic_image(2, 128, 128, 128, seed=5, device=cuda_dev)
+    lab = synth.make_batch(["mask", "mask"], classes, (128, 128, 128), seed=8, device=cuda_dev)["label"]
+    args = LR.default_args(report_volume_loss_basic=0.0)
+    hyper = dict(lr=6e-4, betas=(0.9, 0.999), eps=1e-5, weight_decay=0.05)
+    runs = []
+    for fused in (True, False):
+        net, _ = _full_net(cuda_dev, "bf16")
+        params = list(net.parameters())
+        ema = [p.detach().clone() for p in params]
+        opt = B200AdamW(params, max_norm=1.0, ema_params=ema, ema_alpha=0.99, **hyper) if fused else \
+            torch.optim.AdamW(params, fused=True, **hyper)
+        ls = []
+        for step in range(3):
+            opt.zero_grad(set_to_none=True)
+            loss = losses.calculate_loss(net(x), lab, None, args, None, None, None, None, classes)["overall"]
+            loss.backward()
+            if not fused:
+                torch.nn.utils.clip_grad_norm_(params, 1.0)
+            opt.step()
+            if not fused:
+                alpha = min(1 - 1 / (step + 1), 0.99)
+                with torch.no_grad():
+                    torch._foreach_mul_(ema, alpha)
+                    torch._foreach_add_(ema, [p.detach() for p in params], alpha=1 - alpha)
+            ls.append(loss.item())
+        runs.append((ls, [p.detach().clone() for p in params], ema))
+        del net, opt
+    (l_f, p_f, e_f), (l_s, p_s, e_s) = runs
+    print(f"[full-size] losses fused {l_f} stock {l_s}")
+    assert all(np.isfinite(l_f)) and abs(l_f[0] - l_s[0]) <= 1e-4 * abs(l_s[0])
+    assert all(abs(a - b) <= 2e-2 * abs(b) for a, b in zip(l_f, l_s))            # the two runs track each other
+    # one AdamW step moves a weight by about lr at most; the two runs see gradients that differ by bf16 / atomics noise, so
+    # compare at the scale of the update, not at fp32 resolution: worst case (opposite signs every step) 2 x 3 x lr
+    lr = hyper["lr"]
+    tot = cnt = 0.0
+    for a, b in zip(p_f + e_f, p_s + e_s):
+        assert torch.isfinite(a).all()
+        d = (a - b).abs()
+        assert d.max().item() <= 2 * 3 * lr * 1.05
+        tot += d.sum().item(); cnt += d.numel()
+    print(f"[full-size] mean |fused - stock| over params + EMA = {tot / cnt:.3e} (lr {lr})")
+    assert tot / cnt <= 0.25 * lr
+    fresh = list(_full_net(cuda_dev, "bf16")[0].parameters())
+    moved = max((a - b.detach()).abs().max().item() for a, b in zip(p_f, fresh))
+    assert moved > 1e-4                                   # the steps really updated the weights
