@@ -77,6 +77,33 @@ def test_fused_clip_adamw_ema_matches_torch(cuda_dev, with_ema, max_norm):
     assert set(opt_o.state_dict()["state"][0].keys()) == set(opt_r.state_dict()["state"][0].keys())
 
 
+def test_fused_clip_adamw_ema_matches_reference_golden(cuda_dev):
+    """Same four steps the REAL reference's get_optimizer / update_ema_variables ran for tests/golden/reference_train_glue.npz
+    (inputs regenerated from oracle/train_glue_ref.glue_inputs)."""
+    import os
+    from oracle.train_glue_ref import glue_inputs
+    from rsuper_b200.optim import B200AdamW
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_train_glue.npz"))
+    params = [torch.nn.Parameter(t) for t in glue_inputs(-1, device=cuda_dev)]
+    ema = [t.clone() for t in glue_inputs(-1, device=cuda_dev)]
+    opt = B200AdamW(params, lr=6e-4, betas=(0.9, 0.999), eps=1e-5, weight_decay=0.05, max_norm=1.0, ema_params=ema, ema_alpha=0.99)
+    for step in range(4):
+        opt.zero_grad()
+        for p, g in zip(params, glue_inputs(step, device=cuda_dev)):
+            p.grad = g.clone()
+        opt.step()
+        assert abs(opt.last_grad_norm.item() - float(gold[f"norm_{step}"])) <= 2e-6 * float(gold[f"norm_{step}"])
+        if f"p_{step}_0" not in gold:
+            continue
+        for i, p in enumerate(params):
+            np.testing.assert_allclose(p.detach().cpu().numpy(), gold[f"p_{step}_{i}"], rtol=2e-6, atol=2e-7)
+            np.testing.assert_allclose(ema[i].cpu().numpy(), gold[f"ema_{step}_{i}"], rtol=2e-6, atol=2e-7)
+            np.testing.assert_allclose(p.grad.cpu().numpy(), gold[f"g_{step}_{i}"], rtol=2e-6, atol=1e-9)
+    for i, p in enumerate(params):
+        np.testing.assert_allclose(opt.state[p]["exp_avg"].cpu().numpy(), gold[f"exp_avg_{i}"], rtol=1e-5, atol=1e-9)
+        np.testing.assert_allclose(opt.state[p]["exp_avg_sq"].cpu().numpy(), gold[f"exp_avg_sq_{i}"], rtol=1e-5, atol=1e-12)
+
+
 def test_fused_optimizer_rejects_cpu_parameters():
     from rsuper_b200.optim import B200AdamW
     p = torch.nn.Parameter(torch.zeros(8))
