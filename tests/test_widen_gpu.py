@@ -419,3 +419,49 @@ def test_full_size_train_steps_with_fused_optimizer(cuda_dev):
     fresh = list(_full_net(cuda_dev, "bf16")[0].parameters())
     moved = max((a - b.detach()).abs().max().item() for a, b in zip(p_f, fresh))
     assert moved > 1e-4                                   # the steps really updated the weights
+
+
+# BASELINE.json configs[2..4] at their FULL patch sizes (the oracle-sized versions are tests/test_unet_gpu.py::CONFIG_CASES)
+FULL_CONFIGS = [
+    ("cfg3", ["organ", "pancreatic_lesion"], (128, 128, 128), ("report", "mask")),
+    ("cfg4", ["pancreas", "pancreatic_lesion", "veins"], (96, 192, 192), ("mask", "report")),
+    ("cfg5", ["organ"] + sorted(f"{o}_lesion" for o in ("adrenal", "bladder", "colon", "esophagus", "kidney", "liver", "spleen")),
+     (160, 160, 160), ("report", "mask")),
+]
+
+
+@pytest.mark.parametrize("name,classes,shape,kinds", FULL_CONFIGS)
+def test_full_size_config_train_step_properties(cuda_dev, name, classes, shape, kinds):
+    """The whole step (base-32 UNet bf16 -> calculate_loss with Volume + Ball terms on the mixed batch -> backward) at the
+    full patch size of each BASELINE.json config.  No oracle finishes these sizes in seconds, so the checks are the
+    size-independent ones: the reference's dict keys, finite non-negative terms, 'overall' = sum of the terms, every
+    parameter receives a finite gradient (the DDP find_unused_parameters=False contract), and the
+    mask-supervised part equals the oracle's segmentation loss evaluated on the SAME logits (torch ops on the GPU)."""
+    from oracle import losses_ref as LR
+    from oracle import synth
+    from rsuper_b200 import losses
+    from rsuper_b200.unet import B200UNet
+    from oracle.unet_ref import synthetic_state_dict
+    C = len(classes)
+    net = B200UNet(1, 32, num_classes=C, precision="bf16").to(cuda_dev)
+    net.load_state_dict(synthetic_state_dict(32, C, device=cuda_dev))
+    batch = synth.make_batch(list(kinds), classes, shape, seed=17, device=cuda_dev)
+    args = LR.default_args()
+    out = net(batch["image"])
+    assert out["segmentation"].shape == (len(kinds), C) + tuple(shape)
+    res = losses.calculate_loss(out, batch["label"], batch["unk_channels"], args, None, batch["mask"], batch["volumes"],
+                                batch["diameters"], classes, input_tensor=batch["image"])
+    vals = {k: v.item() for k, v in res.items()}
+    print(f"[full-size] {name} {shape}: {({k: round(v, 6) for k, v in vals.items()})}")
+    assert {"segmentation", "overall"} <= set(vals) and all(np.isfinite(v) and v >= 0 for v in vals.values())
+    assert abs(vals["overall"] - sum(v for k, v in vals.items() if k != "overall")) <= 1e-5 * max(1.0, vals["overall"])
+    res["overall"].backward()
+    for k, p in net.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all() and p.grad.abs().max() > 0, (name, k)
+    # mask-only batch at the same size: our loss == the oracle's formula on identical logits
+    lab = batch["label"]
+    lg = out["segmentation"].detach()
+    mine = losses.calculate_loss({"segmentation": lg.clone().requires_grad_(True)}, lab, None,
+                                 LR.default_args(report_volume_loss_basic=0.0), None, None, None, None, classes)["overall"].item()
+    ref = LR.seg_loss(lg, lab.float(), torch.ones_like(lg)).item()
+    assert abs(mine - ref) <= 1e-5 * abs(ref), (name, mine, ref)
