@@ -22,9 +22,11 @@ import torch
 from . import ops
 
 
-def _stack_pinned(arrays: Sequence[np.ndarray], dtype) -> torch.Tensor:
+def _stack_pinned(arrays: Sequence[np.ndarray], dtype, device) -> torch.Tensor:
     first = np.asarray(arrays[0])
-    host = torch.empty((len(arrays),) + tuple(first.shape), dtype=dtype).pin_memory()
+    host = torch.empty((len(arrays),) + tuple(first.shape), dtype=dtype)
+    if torch.device(device).type == "cuda":
+        host = host.pin_memory()      # asynchronous H2D needs page-locked staging
     for i, a in enumerate(arrays):
         a = np.asarray(a)
         if a.shape != first.shape:
@@ -44,7 +46,7 @@ def upload_packed_masks(packed: Sequence[np.ndarray], num_classes: int, device) 
         assert a.shape[0] * 8 < num_classes + 10 and a.shape[0] * 8 >= num_classes, \
             f"packed mask {i} has {a.shape[0]} byte planes for {num_classes} classes"
         assert a.shape[0] == cp
-    host = _stack_pinned(packed, torch.uint8)
+    host = _stack_pinned(packed, torch.uint8, device)
     return ops.unpack_masks(host.to(device, non_blocking=True), num_classes)
 
 
@@ -56,12 +58,12 @@ def assemble_batch(images: Sequence[np.ndarray], labels_packed: Sequence[np.ndar
     """One training batch on `device` from per-sample crop files.  A sample without `_gt_unk` / `_chosen_tumor_segment`
     files (fully annotated CT: None entries) gets all-zero masks, volumes and diameters (:1072-1077)."""
     device = torch.device(device)
-    if device.type != "cuda":
+    if not ops._on_device(device):
         raise RuntimeError("rsuper_b200.batch has no CPU path: device must be a CUDA (sm_100a) device")
     B = len(images)
     if B == 0 or len(labels_packed) != B:
         raise ValueError("assemble_batch: need one packed label per image")
-    img = _stack_pinned([np.asarray(a, dtype=np.float32) for a in images], torch.float32)
+    img = _stack_pinned([np.asarray(a, dtype=np.float32) for a in images], torch.float32, device)
     if img.dim() != 4:
         raise ValueError(f"assemble_batch: images must be [D, H, W], got {tuple(img.shape[1:])}")
     out = {"image": img.to(device, non_blocking=True).unsqueeze(1),

@@ -45,7 +45,7 @@ def inference_sliding_window(net, img: torch.Tensor, args, pancreas: Optional[to
     Returns a CPU tensor like the reference unless keep_on_device=True.  With `threshold` set, returns
     (prob, mask uint8 = prob > threshold) from the same finalize pass."""
     net.eval()
-    if not img.is_cuda:
+    if not ops._on_device(img):
         raise RuntimeError("rsuper_b200.inference has no CPU path: img must live on a CUDA (sm_100a) device")
     if pancreas is not None:
         while pancreas.dim() < img.dim():
@@ -96,7 +96,7 @@ _RENAMED = {"uterus": "prostate", "gallbladder": "gall_bladder"}
 def postprocess_npz(pred: torch.Tensor, classes: Sequence[str], args) -> Dict[str, torch.Tensor]:
     """pred [1, C, D, H, W] probabilities (CUDA) -> {class: [D, H, W]} with every lesion channel multiplied by its
     organ's (> 0.5, 3x3x3-dilated) mask when args.organ_mask_on_lesion (predict_abdomenatlas.py:636-684)."""
-    if not pred.is_cuda:
+    if not ops._on_device(pred):
         raise RuntimeError("rsuper_b200.inference has no CPU path")
     pred = pred.squeeze(0).float().contiguous()
     out: Dict[str, torch.Tensor] = {}

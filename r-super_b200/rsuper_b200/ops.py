@@ -48,6 +48,12 @@ def _stream() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _on_device(t) -> bool:
+    """Single place that decides whether a tensor (or a device) may be handed to a kernel; tests/dryrun.py patches it for
+    the host-logic dry run in the GPU-less container."""
+    return t.is_cuda if isinstance(t, torch.Tensor) else torch.device(t).type == "cuda"
+
+
 def _p(t: Optional[torch.Tensor]) -> Optional[C.c_void_p]:
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -65,11 +71,11 @@ _CL_OK = {}   # (shape, strides, offset mod 8) -> channel pitch of layouts that 
 
 def _check_cl(t: torch.Tensor, name: str) -> int:
     """Validate an NDHWC (possibly channel-sliced) activation view and return its channel pitch."""
-    key = (t.shape, t.stride(), t.storage_offset() & 7, t.is_cuda)
+    key = (t.shape, t.stride(), t.storage_offset() & 7, _on_device(t))
     pitch = _CL_OK.get(key)
     if pitch is not None:
         return pitch
-    if t.dim() != 5 or not t.is_cuda:
+    if t.dim() != 5 or not _on_device(t):
         raise ValueError(f"{name}: expected a 5-D CUDA tensor [N,D,H,W,C], got {tuple(t.shape)}")
     n, d, h, w, c = t.shape
     pitch = t.stride(3) if w > 1 else (t.stride(2) // max(w, 1) if h > 1 else t.stride(3))
@@ -109,7 +115,7 @@ def new_stats(n, c, device) -> torch.Tensor:
 def conv3_pack_weights(w: torch.Tensor, transpose_flip: bool = False, split=False) -> torch.Tensor:
     """fp32 OIDHW [Cout,Cin,3,3,3] -> packed bf16 UMMA image (uint8 buffer); split = True / 3 => [hi | hi | lo] parts,
     split = 6 => the three-piece image [hi | lo | hi | lo2 | hi | lo]."""
-    assert w.dtype == torch.float32 and w.is_cuda and w.is_contiguous() and w.shape[2:] == (3, 3, 3)
+    assert w.dtype == torch.float32 and _on_device(w) and w.is_contiguous() and w.shape[2:] == (3, 3, 3)
     cout, cin = w.shape[0], w.shape[1]
     co_eff, ci_eff = (cin, cout) if transpose_flip else (cout, cin)
     parts = 6 if split == 6 else (3 if split else 1)
@@ -133,7 +139,7 @@ class PackPlan:
         self._keep = []
         dev = jobs[0][1].device
         for j, (key, w_a, w_b, flip) in enumerate(jobs):
-            assert w_a.dtype == torch.float32 and w_a.is_cuda and w_a.is_contiguous() and w_a.shape[2:] == (3, 3, 3)
+            assert w_a.dtype == torch.float32 and _on_device(w_a) and w_a.is_contiguous() and w_a.shape[2:] == (3, 3, 3)
             cin = w_a.shape[1]
             cout = w_a.shape[0]
             if w_b is not None:
@@ -537,7 +543,7 @@ def ball_weight_map(wmap, pseudo, dilated):
 # sliding-window inference post-processing, connected components, bit-packed masks
 # --------------------------------------------------------------------------------------------
 def _need(t: torch.Tensor, dtype, name: str):
-    if not (t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+    if not (_on_device(t) and t.dtype == dtype and t.is_contiguous()):
         raise ValueError(f"{name}: expected a contiguous CUDA {dtype} tensor, got {t.dtype} {tuple(t.shape)} on {t.device}")
 
 

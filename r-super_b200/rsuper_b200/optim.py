@@ -22,13 +22,13 @@ Usage in place of the three reference lines above:
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 from typing import Iterable, Optional, Sequence
 
 import torch
 
 from . import ops
-from ._lib import check, lib
 
 
 class B200AdamW(torch.optim.Optimizer):
@@ -51,13 +51,13 @@ class B200AdamW(torch.optim.Optimizer):
 
     # -- device table of one param group --------------------------------------------------------------------------
     def _table(self, gi: int, group, ema_of):
-        chunk = lib().rsb_opt_chunk_elems()
+        chunk = ops.lib().rsb_opt_chunk_elems()
         rows, sig = [], []
         begin = 0
         for p in group["params"]:
             if p.grad is None:
                 continue
-            if not p.is_cuda:
+            if not ops._on_device(p):
                 raise RuntimeError("B200AdamW has no CPU path: parameters must live on a CUDA (sm_100a) device")
             if p.dtype != torch.float32 or p.grad.dtype != torch.float32 or not p.is_contiguous() or not p.grad.is_contiguous() \
                     or p.grad.is_sparse:
@@ -68,7 +68,7 @@ class B200AdamW(torch.optim.Optimizer):
                 st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
             e = ema_of.get(id(p))
-            if e is not None and not (e.is_cuda and e.dtype == torch.float32 and e.is_contiguous()):
+            if e is not None and not (ops._on_device(e) and e.dtype == torch.float32 and e.is_contiguous()):
                 raise RuntimeError("B200AdamW: EMA tensors must be contiguous CUDA fp32")
             n = p.numel()
             if n == 0:
@@ -84,7 +84,9 @@ class B200AdamW(torch.optim.Optimizer):
             return cached
         # 7 x int64 per row == struct RsbOptTensor (5 pointers, n, chunk_begin); uploaded only when a pointer changed
         dev = group["params"][0].device
-        host = torch.tensor(rows, dtype=torch.int64).pin_memory()
+        host = torch.tensor(rows, dtype=torch.int64)
+        if dev.type == "cuda":
+            host = host.pin_memory()
         table = host.to(dev, non_blocking=True)
         cached = (sig, table, len(rows), begin, host)   # keep the pinned source alive until the copy has run
         self._tables[gi] = cached
@@ -114,12 +116,12 @@ class B200AdamW(torch.optim.Optimizer):
                 raise RuntimeError("B200AdamW: parameters of a group must share their step count")
             t = steps.pop() + 1
             if self._partials is None or self._partials.device != dev:
-                self._partials = torch.empty(lib().rsb_opt_max_blocks() + 1, dtype=torch.float32, device=dev)
+                self._partials = torch.empty(ops.lib().rsb_opt_max_blocks() + 1, dtype=torch.float32, device=dev)
             norm_out = self._partials[-1:]
             clip = float(self.max_norm) if self.max_norm is not None else 0.0
             b1, b2 = group["betas"]
-            with torch.cuda.device(dev):
-                ops._call("train_glue", 2 if clip > 0 else 1, 0.0, lib().rsb_clip_adamw_ema_step, C.c_void_p(table.data_ptr()),
+            with torch.cuda.device(dev) if dev.type == "cuda" else contextlib.nullcontext():
+                ops._call("train_glue", 2 if clip > 0 else 1, 0.0, ops.lib().rsb_clip_adamw_ema_step, C.c_void_p(table.data_ptr()),
                           n_tensors, total_chunks, int(bool(ema_of)), ops._p(self._partials) if clip > 0 else None, ops._p(norm_out),
                           clip, float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]), t,
                           float(alpha), ops._stream(), what="clip_adamw_ema_step")
