@@ -371,6 +371,30 @@ int rsb_cc_label(const uint8_t* mask, int* labels, int* n_components, uint8_t* l
  * ------------------------------------------------------------------------------------------ */
 int rsb_unpack_masks(const uint8_t* packed, uint8_t* out, int B, int C, long long V, int invert, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Online intensity augmentations of the loader: training/augmentation.py:17-168 as applied by
+ * training/dataset/dim3/dataset_abdomenatlas_UFO.py:1048-1061.  One fp32 volume of n voxels; the random draws
+ * (factor, offset, gamma, sigma, noise) are made by the host exactly as the reference makes them.
+ * ------------------------------------------------------------------------------------------ */
+size_t rsb_aug_workspace_bytes(void);
+/* stats4 = {min, max, mean, unbiased std} of the volume (augmentation.py:118-126, 152-158): deterministic two-stage
+ * reduction in double */
+int rsb_aug_stats(const float* x, long long n, void* workspace, float* stats4, void* stream);
+/* y = ((x * mul) + add) + noise * noise_std with torch's separate roundings; each stage optional:
+ * brightness_multiply (:86-103), brightness_additive (:69-83), gaussian_noise (:17-19; noise = N(0,1) samples or NULL) */
+int rsb_aug_affine(const float* x, float* y, long long n, float mul, int has_mul, float add, int has_add,
+                   const float* noise, float noise_std, void* stream);
+/* gamma (:106-138): y = pow((x - min) / (max - min), gamma) * (max - min) + min with stats4 = rsb_aug_stats(x); then
+ * (retain_stats) rsb_aug_renorm(y, stats(y), stats(x)): y = (y - mean_y) / std_y * std_x + mean_x, in place */
+int rsb_aug_gamma(const float* x, float* y, long long n, const float* stats4, float gamma, void* stream);
+int rsb_aug_renorm(float* y, long long n, const float* stats_y, const float* stats_x, void* stream);
+/* contrast (:140-168): y = clamp((x - mean) * factor + mean, min, max) */
+int rsb_aug_contrast(const float* x, float* y, long long n, const float* stats4, float factor, void* stream);
+/* gaussian_blur (:48-66): one axis (0 = D, 1 = H, 2 = W) of the separable form of the reference's normalised 3-D
+ * Gaussian, zero padding; taps_host = ntaps (odd, <= 33) weights in HOST memory (passed to the kernel by value) */
+int rsb_aug_blur_axis(const float* x, float* y, int n_vol, int D, int H, int W, int axis, const float* taps_host,
+                      int ntaps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -271,7 +271,7 @@ extern "C" size_t rsb_cc_workspace_bytes(int D, int H, int W) {
 extern "C" int rsb_cc_label(const uint8_t* mask, int* labels, int* n_components, uint8_t* largest, void* workspace, int D, int H, int W,
                             void* stream) {
   RSB_REQUIRE(mask != nullptr && labels != nullptr && n_components != nullptr, "cc_label: null pointer");
-  RSB_REQUIRE(D > 0 && H > 0 && W > 0 && static_cast<long long>(D) * H * W < (1LL << 31), "cc_label: volume must have 1 .. 2^31-1 voxels");
+  RSB_REQUIRE(D > 0 && H > 0 && W > 0 && static_cast<long long>(D) * H * W <= (1LL << 30), "cc_label: volume must have 1 .. 2^30 voxels (32-bit labels)");
   RSB_REQUIRE(largest == nullptr || workspace != nullptr, "cc_label: keep-largest needs the workspace (rsb_cc_workspace_bytes)");
   RSB_REQUIRE(workspace == nullptr || (reinterpret_cast<uintptr_t>(workspace) & 7) == 0, "cc_label: workspace must be 8-byte aligned");
   const int V = D * H * W;

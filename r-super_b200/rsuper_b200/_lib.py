@@ -161,6 +161,13 @@ SIGNATURES = {
     "rsb_cc_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "rsb_cc_label": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "rsb_unpack_masks": (c_int, [c_void_p, c_void_p, c_int, c_int, c_ll, c_int, c_void_p]),
+    "rsb_aug_workspace_bytes": (c_size_t, []),
+    "rsb_aug_stats": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p]),
+    "rsb_aug_affine": (c_int, [c_void_p, c_void_p, c_ll, c_float, c_int, c_float, c_int, c_void_p, c_float, c_void_p]),
+    "rsb_aug_gamma": (c_int, [c_void_p, c_void_p, c_ll, c_void_p, c_float, c_void_p]),
+    "rsb_aug_renorm": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p]),
+    "rsb_aug_contrast": (c_int, [c_void_p, c_void_p, c_ll, c_void_p, c_float, c_void_p]),
+    "rsb_aug_blur_axis": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, C.POINTER(c_float), c_int, c_void_p]),
 }
 
 _lib = None

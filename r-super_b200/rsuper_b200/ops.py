@@ -616,3 +616,60 @@ def unpack_masks(packed: torch.Tensor, num_classes: int, invert: bool = False) -
     out = torch.empty((b, num_classes, d, h, w_), dtype=torch.uint8, device=packed.device)
     _call("assemble", 1, 0.0, lib().rsb_unpack_masks, _p(packed), _p(out), b, num_classes, d * h * w_, int(invert), _stream(), what="unpack_masks")
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# online intensity augmentations: deterministic kernels, the draws come from the host mirror
+# --------------------------------------------------------------------------------------------
+def aug_stats(x: torch.Tensor) -> torch.Tensor:
+    """Device float32[4] = (min, max, mean, unbiased std) of the whole tensor."""
+    _need(x, torch.float32, "x")
+    ws = torch.empty((lib().rsb_aug_workspace_bytes() + 7) // 8, dtype=torch.int64, device=x.device)
+    out = torch.empty(4, dtype=torch.float32, device=x.device)
+    _call("augment", 2, 0.0, lib().rsb_aug_stats, _p(x), x.numel(), _p(ws), _p(out), _stream(), what="aug_stats")
+    return out
+
+
+def aug_affine(x: torch.Tensor, mul: Optional[float] = None, add: Optional[float] = None, noise: Optional[torch.Tensor] = None,
+               noise_std: float = 0.0) -> torch.Tensor:
+    _need(x, torch.float32, "x")
+    if noise is not None:
+        _need(noise, torch.float32, "noise")
+        assert noise.numel() == x.numel()
+    y = torch.empty_like(x)
+    _call("augment", 1, 0.0, lib().rsb_aug_affine, _p(x), _p(y), x.numel(), float(mul if mul is not None else 1.0), int(mul is not None),
+          float(add if add is not None else 0.0), int(add is not None), _p(noise), float(noise_std), _stream(), what="aug_affine")
+    return y
+
+
+def aug_gamma(x: torch.Tensor, gamma: float, retain_stats: bool = True) -> torch.Tensor:
+    _need(x, torch.float32, "x")
+    sx = aug_stats(x)
+    y = torch.empty_like(x)
+    _call("augment", 1, 0.0, lib().rsb_aug_gamma, _p(x), _p(y), x.numel(), _p(sx), float(gamma), _stream(), what="aug_gamma")
+    if retain_stats:
+        sy = aug_stats(y)
+        _call("augment", 1, 0.0, lib().rsb_aug_renorm, _p(y), y.numel(), _p(sy), _p(sx), _stream(), what="aug_renorm")
+    return y
+
+
+def aug_contrast(x: torch.Tensor, factor: float) -> torch.Tensor:
+    _need(x, torch.float32, "x")
+    sx = aug_stats(x)
+    y = torch.empty_like(x)
+    _call("augment", 1, 0.0, lib().rsb_aug_contrast, _p(x), _p(y), x.numel(), _p(sx), float(factor), _stream(), what="aug_contrast")
+    return y
+
+
+def aug_blur(x: torch.Tensor, taps) -> torch.Tensor:
+    """Separable zero-padded blur of every [D, H, W] volume of x with the 1-D kernel `taps` (sequence of floats, odd length)."""
+    _need(x, torch.float32, "x")
+    d, h, w_ = x.shape[-3:]
+    n_vol = x.numel() // (d * h * w_)
+    arr = (C.c_float * len(taps))(*[float(t) for t in taps])
+    a, b = torch.empty_like(x), torch.empty_like(x)
+    src = x
+    for axis, dst in ((0, a), (1, b), (2, a)):
+        _call("augment", 1, 0.0, lib().rsb_aug_blur_axis, _p(src), _p(dst), n_vol, d, h, w_, axis, arr, len(taps), _stream(), what="aug_blur_axis")
+        src = dst
+    return a

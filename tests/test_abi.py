@@ -179,6 +179,14 @@ def test_widened_entry_points_validate_arguments_without_a_gpu():
     assert lib.rsb_cc_label(4096, 4096, 4096, 4096, None, 4, 4, 4, None) != 0 and b"workspace" in lib.rsb_last_error()
     assert lib.rsb_cc_label(4096, 4096, 4096, None, None, 2048, 2048, 2048, None) != 0
     assert lib.rsb_unpack_masks(None, None, 1, 2, 8, 0, None) != 0
+    assert lib.rsb_aug_workspace_bytes() >= 148 * 8 * 32
+    assert lib.rsb_aug_stats(None, 8, None, None, None) != 0 and lib.rsb_aug_stats(4096, 0, 4096, 4096, None) != 0
+    assert lib.rsb_aug_affine(None, None, 8, 1.0, 1, 0.0, 0, None, 0.0, None) != 0
+    assert lib.rsb_aug_gamma(4096, 4096, 8, None, 1.0, None) != 0 and lib.rsb_aug_renorm(None, 8, None, None, None) != 0
+    assert lib.rsb_aug_contrast(4096, 4096, 8, None, 1.0, None) != 0
+    taps = (ctypes.c_float * 4)(0.25, 0.25, 0.25, 0.25)
+    assert lib.rsb_aug_blur_axis(4096, 8192, 1, 4, 4, 4, 0, taps, 4, None) != 0 and b"odd" in lib.rsb_last_error()
+    assert lib.rsb_aug_blur_axis(4096, 4096, 1, 4, 4, 4, 0, taps, 3, None) != 0 and b"distinct" in lib.rsb_last_error()
 
 
 def test_widened_host_wrappers_marshal_their_arguments(monkeypatch):
@@ -201,6 +209,9 @@ def test_widened_host_wrappers_marshal_their_arguments(monkeypatch):
         lambda: ops.cc_label(torch.zeros(4, 5, 6, dtype=torch.uint8), keep_largest=True),
         lambda: ops.cc_label(torch.zeros(4, 5, 6, dtype=torch.uint8)),
         lambda: ops.unpack_masks(torch.zeros(2, 2, 4, 5, 6, dtype=torch.uint8), 11),
+        lambda: ops.aug_stats(torch.zeros(4, 5, 6)),
+        lambda: ops.aug_affine(torch.zeros(4, 5, 6), mul=1.1, add=0.2, noise=torch.zeros(4, 5, 6), noise_std=0.1),
+        lambda: ops.aug_blur(torch.zeros(1, 1, 4, 5, 6), [0.25, 0.5, 0.25]),
     ]
     for i, fn in enumerate(calls):
         with pytest.raises(RuntimeError, match="launch failed"):

@@ -168,3 +168,43 @@ def test_batch_assembly_shapes_and_packed_upload(monkeypatch):
     monkeypatch.undo()                                 # the real device check again: CPU devices are refused
     with pytest.raises(RuntimeError, match="no CPU path"):
         B.assemble_batch([ref["image"][0, 0].numpy()], [synth.pack_masks(ref["label"][0])], len(classes), "cpu")
+
+
+def test_intensity_augmentation_launches_and_rng_stream(monkeypatch):
+    """rsuper_b200.augment consumes np.random / torch's generator exactly like the loader block (same gates, same draws as
+    the oracle's draws_like_reference, which is pinned on the real reference) and issues the expected kernels per op."""
+    import numpy as np
+    from oracle import augment_ref as AR
+    from rsuper_b200 import augment as A
+    x = torch.zeros(1, 1, 8, 10, 12)
+    with recording(monkeypatch) as rec:
+        for seed in range(12):
+            np.random.seed(seed); torch.manual_seed(100 + seed)
+            want = AR.draws_like_reference(x.shape)
+            end_np, end_t = np.random.random(), torch.rand(1).item()
+            del rec.calls[:]
+            np.random.seed(seed); torch.manual_seed(100 + seed)
+            A.online_intensity_augmentation(x)
+            assert (np.random.random(), torch.rand(1).item()) == (end_np, end_t), seed     # both generators advanced identically
+            names = [n for n, _ in rec.calls]
+            expect = []
+            if "multiply" in want: expect += ["rsb_aug_affine"]
+            if "additive" in want: expect += ["rsb_aug_affine"]
+            if "gamma" in want: expect += ["rsb_aug_stats", "rsb_aug_gamma", "rsb_aug_stats", "rsb_aug_renorm"]
+            if "contrast" in want: expect += ["rsb_aug_stats", "rsb_aug_contrast"]
+            if "blur" in want: expect += ["rsb_aug_blur_axis"] * 3
+            if "noise" in want: expect += ["rsb_aug_affine"]
+            assert names == expect, (seed, names, expect)
+            scal = [a for n, a in rec.calls if n == "rsb_aug_affine"]
+            if "multiply" in want:
+                assert scal[0][3] == pytest.approx(want["multiply"], rel=1e-7) and scal[0][4] == 1
+            if "noise" in want:
+                assert scal[-1][7] == "p" and scal[-1][8] == pytest.approx(want["noise"][0])
+            if "blur" in want:
+                blur = [a for n, a in rec.calls if n == "rsb_aug_blur_axis"]
+                assert [a[6] for a in blur] == [0, 1, 2] and blur[0][8] == 2 * int(np.ceil(3 * want["blur"])) + 1
+    taps = A.gaussian_kernel_1d(1.0)
+    assert len(taps) == 7 and abs(sum(taps) - 1) < 1e-12 and taps[3] == max(taps) and taps[0] == pytest.approx(taps[6])
+    with pytest.raises(NotImplementedError):
+        with recording(monkeypatch):
+            A.gamma(torch.zeros(1, 2, 4, 4, 4))

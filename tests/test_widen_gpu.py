@@ -465,3 +465,53 @@ def test_full_size_config_train_step_properties(cuda_dev, name, classes, shape, 
                                  LR.default_args(report_volume_loss_basic=0.0), None, None, None, None, classes)["overall"].item()
     ref = LR.seg_loss(lg, lab.float(), torch.ones_like(lg)).item()
     assert abs(mine - ref) <= 1e-5 * abs(ref), (name, mine, ref)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# N2 (second half): online intensity augmentations
+# ------------------------------------------------------------------------------------------------------------------
+def test_intensity_augmentations_match_reference_golden(cuda_dev):
+    """rsuper_b200.augment with the draws the REAL training/augmentation.py made (tests/golden/reference_augment.npz):
+    multiply / additive / noise / contrast are the same fp32 roundings (1e-6), gamma (powf) and the separable blur 1e-5;
+    then the loader's whole gate block under the same np.random / torch seeds."""
+    import os
+    from oracle import augment_ref as AR
+    from oracle.unet_ref import synthetic_image
+    from rsuper_b200 import augment as A
+    from test_oracle_golden import AUG_SEEDS, AUG_SHAPE, aug_single_draw
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_augment.npz"))
+    x = synthetic_image(1, *AUG_SHAPE, seed=21)
+    xd = x.to(cuda_dev)
+    sub = lambda t: t.cpu().numpy()[0, 0, ::2, ::3, ::2]
+    for name in AUG_SEEDS:
+        d = aug_single_draw(name, AUG_SHAPE)
+        y = {"multiply": lambda: A.brightness_multiply(xd, factor=d), "additive": lambda: A.brightness_additive(xd, 0.1, offset=d),
+             "gamma": lambda: A.gamma(xd, gamma=d), "contrast": lambda: A.contrast(xd, factor=d),
+             "blur": lambda: A.gaussian_blur(xd, sigma=d), "noise": lambda: A.gaussian_noise(xd, 0.13, noise=d.to(cuda_dev))}[name]()
+        assert y.shape == xd.shape and y.is_cuda
+        tol = 1e-5 if name in ("gamma", "blur") else 1e-6
+        np.testing.assert_allclose(sub(y), gold[name], rtol=tol, atol=tol, err_msg=name)
+        assert abs(y.double().sum().item() - float(gold[f"{name}_sum"])) <= 1e-5 * max(1.0, abs(float(gold[f"{name}_sum"]))), name
+    # the statistics kernel itself
+    st = __import__("rsuper_b200.ops", fromlist=["ops"]).aug_stats(xd).cpu()
+    want = torch.stack([x.min(), x.max(), x.mean(), x.std()])
+    torch.testing.assert_close(st, want, rtol=1e-6, atol=1e-6)
+    # the loader's gate block: same seeds as the reference run -> same gates, same draws
+    np.random.seed(5)
+    torch.manual_seed(6)
+    y = A.online_intensity_augmentation(xd)
+    np.testing.assert_allclose(sub(y), gold["seq_gated"], rtol=1e-5, atol=2e-6)
+    np.random.seed(5)
+    torch.manual_seed(6)
+    draws = AR.draws_like_reference(x.shape, gates=[True] * 6)
+    y = xd
+    y = A.brightness_multiply(y, factor=draws["multiply"])
+    y = A.brightness_additive(y, 0.1, offset=draws["additive"])
+    y = A.gamma(y, gamma=draws["gamma"])
+    y = A.contrast(y, factor=draws["contrast"])
+    y = A.gaussian_blur(y, sigma=draws["blur"])
+    y = A.gaussian_noise(y, draws["noise"][0], noise=draws["noise"][1].to(cuda_dev))
+    np.testing.assert_allclose(sub(y), gold["seq_all"], rtol=2e-5, atol=5e-6)
+    # device-side noise: same distribution (mean / std of the increment), different stream
+    z = A.gaussian_noise(xd, 0.2, device_noise=True) - xd
+    assert abs(z.mean().item()) < 5e-3 and abs(z.std().item() - 0.2) < 5e-3
