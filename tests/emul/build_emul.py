@@ -1,0 +1,90 @@
+"""TEST INFRASTRUCTURE: compile csrc/train_glue.cu, csrc/infer.cu and csrc/augment.cu for the HOST against tests/emul/cuda_emul.h
+(see that header) into tests/emul/_build/librsb_emul.so.  The sources are used as they lie in csrc/ — two textual rewrites
+only: the rsb_common.cuh include becomes the shim, and `kernel<<<grid, block, smem, stream>>>(args)` becomes
+EMU_LAUNCH(cooperative?, kernel, grid, block, args)."""
+from __future__ import annotations
+
+import hashlib
+import os
+import re
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "r-super_b200", "csrc")
+OUT = os.path.join(HERE, "_build")
+LIB = os.path.join(OUT, "librsb_emul.so")
+SOURCES = ["train_glue.cu", "infer.cu", "augment.cu"]
+# kernels that use __syncthreads / warp shuffles: their blocks run as real threads
+COOPERATIVE = {"grad_sqnorm_kernel", "clip_adamw_ema_kernel", "aug_stats_partial_kernel", "aug_stats_final_kernel"}
+
+LAUNCH = re.compile(r"(\w+(?:<[\w, ]+>)?)\s*<<<\s*([^;]*?)>>>\s*\(", re.S)
+
+
+def _split_args(s: str):
+    out, depth, cur = [], 0, ""
+    for ch in s:
+        if ch in "(<[":
+            depth += 1
+        elif ch in ")>]":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur.strip()); cur = ""
+        else:
+            cur += ch
+    out.append(cur.strip())
+    return out
+
+
+def rewrite(src: str) -> str:
+    src = src.replace('#include "rsb_common.cuh"', '#include "cuda_emul.h"')
+    pos, out = 0, ""
+    for m in LAUNCH.finditer(src):
+        kernel, cfg = m.group(1), _split_args(m.group(2))
+        base = kernel.split("<")[0]
+        # find the matching ')' of the argument list
+        i, depth = m.end(), 1
+        while depth:
+            depth += {"(": 1, ")": -1}.get(src[i], 0)
+            i += 1
+        args = src[m.end():i - 1]
+        out += src[pos:m.start()] + f"EMU_LAUNCH({'true' if base in COOPERATIVE else 'false'}, {kernel}, {cfg[0]}, {cfg[1]}, {args})"
+        pos = i
+    return out + src[pos:]
+
+
+def build() -> str:
+    os.makedirs(OUT, exist_ok=True)
+    h = hashlib.sha256()
+    texts = []
+    for s in SOURCES + [os.path.join(HERE, "cuda_emul.h"), os.path.abspath(__file__)]:
+        p = s if os.path.isabs(s) else os.path.join(CSRC, s)
+        t = open(p).read()
+        h.update(t.encode())
+        texts.append(t)
+    stamp = os.path.join(OUT, "stamp")
+    if os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == h.hexdigest():
+        return LIB
+    cpps = []
+    for name, text in zip(SOURCES, texts):
+        cpp = os.path.join(OUT, name[:-3] + "_emul.cpp")
+        with open(cpp, "w") as f:
+            f.write(rewrite(text))
+        cpps.append(cpp)
+    with open(os.path.join(OUT, "api_emul.cpp"), "w") as f:
+        f.write('#include "cuda_emul.h"\n#include "../../../include/rsuper_b200.h"\n'
+                'extern "C" const char* rsb_last_error(void) { return rsb::g_last_error; }\n'
+                'extern "C" int rsb_num_sms(void) { return 4; }\n')          # 4 "SMs": small grids keep the emulation quick
+    cpps.append(os.path.join(OUT, "api_emul.cpp"))
+    cmd = ["g++", "-std=c++20", "-O1", "-g", "-pthread", "-shared", "-fPIC", "-ffp-contract=off", "-Wno-attributes", "-I", HERE,
+           "-o", LIB] + cpps
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"emulation build failed:\n{r.stdout}\n{r.stderr[-6000:]}")
+    with open(stamp, "w") as f:
+        f.write(h.hexdigest())
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build())

@@ -1,0 +1,89 @@
+"""CPU: the staged HBM-bound kernels (csrc/train_glue.cu, csrc/infer.cu, csrc/augment.cu) compiled for the HOST against the
+execution-model shim tests/emul/cuda_emul.h and driven through the SAME host code and the SAME parity test bodies as on the GPU
+(tests/test_widen_gpu.py), on CPU tensors.  This checks indexing, reductions, the union-find and the optimizer arithmetic of
+the sources as they lie in csrc/ before their first run on a B200; it is test infrastructure (the product never loads the
+emulated library) and says nothing about the tensor-core kernels, which cannot be emulated this way."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul"))
+
+CPU = torch.device("cpu")
+
+
+@pytest.fixture(scope="module")
+def emu_handle():
+    import build_emul
+    from rsuper_b200 import _lib
+    h = ctypes.CDLL(build_emul.build())
+    names = []
+    for name, (res, args) in _lib.SIGNATURES.items():
+        if hasattr(h, name):
+            fn = getattr(h, name)
+            fn.restype, fn.argtypes = res, args
+            names.append(name)
+    assert len(names) == 19, names
+    return h, set(names)
+
+
+@pytest.fixture
+def emulated(monkeypatch, emu_handle):
+    """rsuper_b200 host code -> emulated kernels on CPU tensors."""
+    from rsuper_b200 import _lib, ops
+    h, names = emu_handle
+    real = _lib.lib()
+
+    class Lib:
+        def __getattr__(self, name):
+            if name in names:
+                return getattr(h, name)
+            raise AttributeError(f"{name} is not emulated (tensor-core / TMA kernels need the GPU)")
+
+    lib = Lib()
+    monkeypatch.setattr(ops, "lib", lambda: lib)
+    monkeypatch.setattr(_lib, "lib", lambda: lib)
+    monkeypatch.setattr(_lib, "check", lambda rc, what: (_ for _ in ()).throw(
+        RuntimeError(f"rsuper_b200: {what} failed (rc={rc}): {h.rsb_last_error().decode()}")) if rc != 0 else None)
+    monkeypatch.setattr(ops, "check", _lib.check)
+    monkeypatch.setattr(ops, "_stream", lambda: None)
+    monkeypatch.setattr(ops, "_on_device", lambda t: True)
+    return lib
+
+
+import test_widen_gpu as W  # noqa: E402  (the GPU test bodies: plain functions of (device, ...))
+
+
+@pytest.mark.parametrize("with_ema,max_norm", [(True, 1.0), (False, 1.0), (True, None)])
+def test_emulated_fused_clip_adamw_ema_matches_torch(emulated, with_ema, max_norm):
+    W.test_fused_clip_adamw_ema_matches_torch(CPU, with_ema, max_norm)
+
+
+def test_emulated_fused_clip_adamw_ema_matches_reference_golden(emulated):
+    W.test_fused_clip_adamw_ema_matches_reference_golden(CPU)
+
+
+@pytest.mark.parametrize("C,shape", [(2, (16, 16, 16)), (3, (8, 12, 20)), (9, (5, 7, 9)), (42, (6, 5, 7))])
+def test_emulated_unpack_masks_bit_exact(emulated, C, shape):
+    W.test_unpack_masks_bit_exact(CPU, C, shape)
+
+
+def test_emulated_sliding_window_blend_matches_reference_golden(emulated, golden):
+    W.test_sliding_window_blend_matches_reference_golden(CPU, golden)
+
+
+@pytest.mark.parametrize("case", ["hand", "random_sparse", "random_dense", "blobs", "empty", "full", "snake"])
+def test_emulated_connected_components_bit_exact(emulated, case):
+    W.test_connected_components_bit_exact(CPU, case)
+
+
+def test_emulated_organ_gating_matches_oracle(emulated):
+    W.test_organ_gating_matches_oracle(CPU)
+
+
+def test_emulated_intensity_augmentations_match_reference_golden(emulated):
+    W.test_intensity_augmentations_match_reference_golden(CPU)
