@@ -51,6 +51,51 @@ def seg_loss(logits, label, known=None, class_weights=None) -> torch.Tensor:
     return _SegLoss.apply(logits, _as_u8(label), _as_u8(known), cw)
 
 
+class _DiceLoss(torch.autograd.Function):
+    """The Dice (adaptive Tversky) term alone: loss_out[2] of the fused kernel, backward with the BCE scale set to 0."""
+
+    @staticmethod
+    def forward(ctx, logits, label_u8, known_u8, class_weights):
+        st = ops.seg_loss_forward(logits.detach().contiguous().float(), label_u8, known_u8, class_weights)
+        ctx.state = st
+        return st.loss_out[2].clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        st = ctx.state
+        dl = torch.empty_like(st.keep[0])
+        scale = torch.cat([torch.zeros(1, dtype=torch.float32, device=dl.device), grad_out.detach().reshape(1).float()]).contiguous()
+        ops.seg_loss_backward(st, scale, dl)
+        ctx.state = None
+        return dl, None, None, None
+
+
+def DiceLossMultiClass(preds, targets, known_voxels, alpha=0.5, beta=0.5, size_average=True, reduce=True, sigmoid=True,
+                       class_weights=None) -> torch.Tensor:
+    """Public copy-out function of the reference (README.md:119-128; losses_foundation.py:541-607), same signature.
+    `alpha` / `beta` are ignored exactly like in the reference (it overwrites them with the batch-adaptive values, :581-586).
+    targets / known_voxels are 0/1 masks; logits fp32.  The variants the reference's own call sites never use
+    (sigmoid=False, reduce=False, size_average=False) raise."""
+    if not (sigmoid and reduce and size_average):
+        raise NotImplementedError("rsuper_b200.DiceLossMultiClass implements sigmoid=True, reduce=True, size_average=True")
+    while preds.dim() < 5:                                   # :543-553: [D,H,W] -> [1,1,D,H,W], [C,D,H,W] -> [1,C,D,H,W]
+        lead = 2 if preds.dim() == 3 else 1
+        for _ in range(lead):
+            preds, targets, known_voxels = preds.unsqueeze(0), targets.unsqueeze(0), known_voxels.unsqueeze(0)
+    assert preds.dim() == 5
+    assert preds.shape == targets.shape and targets.shape == known_voxels.shape, \
+        f"Shapes do not match, pred, target and unk are: {preds.shape}, {targets.shape}, {known_voxels.shape}"
+    cw = None
+    if class_weights is not None:
+        cw = class_weights.float().mean(dim=(-1, -2, -3))    # :593
+        while cw.dim() < 2:
+            cw = cw.unsqueeze(0)
+        assert tuple(cw.shape) == tuple(preds.shape[:2]), \
+            f"Class weights shape {tuple(cw.shape)} does not match the shape of dice loss {tuple(preds.shape[:2])}"
+        cw = cw.contiguous()
+    return _DiceLoss.apply(preds, _as_u8(targets), _as_u8(known_voxels), cw)
+
+
 def get_known_voxels(unk_voxels: torch.Tensor, dilation: int = 5) -> torch.Tensor:
     """1 - dilate(unk, 5) as a uint8 mask (losses_foundation.py:150-199)."""
     unk = _as_u8(unk_voxels)

@@ -1,7 +1,8 @@
 // cuda_emul.h — TEST INFRASTRUCTURE ONLY (never built into, loaded by or shipped with the product).
 //
 // A ~150-line host shim of the CUDA execution model, just wide enough to compile the HBM-bound byte / index kernels of
-// csrc/train_glue.cu, csrc/infer.cu and csrc/augment.cu with g++ and run them in the GPU-less build container:
+// csrc/train_glue.cu, csrc/infer.cu, csrc/augment.cu (staged) and csrc/seg_loss.cu, csrc/morph.cu (GPU-verified: they validate
+// the shim itself) with g++ and run them in the GPU-less build container:
 //   * a launch runs the blocks one after the other; the threads of a block run
 //       - sequentially when the kernel has no barrier / shuffle (any interleaving of independent threads is legal, and
 //         for the lock-free union-find the sequential one is a legal schedule too), or
@@ -21,6 +22,7 @@
 #include <cstdio>
 #include <cstring>
 #include <functional>
+#include <memory>
 #include <thread>
 #include <vector>
 
@@ -33,17 +35,27 @@
 #define __shared__ static
 #define RSB_DEVICE inline
 
-struct dim3_emu { unsigned x = 1, y = 1, z = 1; };
-inline thread_local dim3_emu threadIdx;
-inline dim3_emu blockIdx, gridDim, blockDim;
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+inline thread_local dim3 threadIdx;
+inline dim3 blockIdx, gridDim, blockDim;
 typedef void* cudaStream_t;
+typedef int cudaError_t;
+constexpr cudaError_t cudaSuccess = 0;
+inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
+inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { std::memset(p, v, n); return cudaSuccess; }
 
 struct float4 { float x, y, z, w; };
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+struct uint4 { unsigned x, y, z, w; };
+inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
 
 // ---- cooperative-block machinery -----------------------------------------------------------------------------------
 namespace emu {
 inline std::barrier<>* g_barrier = nullptr;      // non-null while a cooperative block runs
+inline std::vector<std::barrier<>*> g_warp_barrier;   // one per warp: shuffles synchronise a warp, not the block
 inline std::vector<double> g_xchg;               // shuffle exchange slots (one per thread)
 inline bool g_coop = false;
 }  // namespace emu
@@ -57,22 +69,24 @@ inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
   static_assert(sizeof(T) <= sizeof(double), "shuffle payload");
   double slot = 0;
   std::memcpy(&slot, &v, sizeof(T));
+  std::barrier<>* wb = emu::g_warp_barrier[threadIdx.x >> 5];
   emu::g_xchg[threadIdx.x] = slot;
-  emu::g_barrier->arrive_and_wait();
+  wb->arrive_and_wait();
   const unsigned src = (threadIdx.x & ~31u) | ((threadIdx.x & 31u) ^ static_cast<unsigned>(lane_mask));
   slot = emu::g_xchg[src];
-  emu::g_barrier->arrive_and_wait();
+  wb->arrive_and_wait();
   T out;
   std::memcpy(&out, &slot, sizeof(T));
   return out;
 }
 
 template <typename F>
-inline void emu_launch(bool coop, unsigned grid, unsigned block, F&& body) {
-  gridDim.x = grid;
+inline void emu_launch(bool coop, dim3 grid, unsigned block, F&& body) {
+  gridDim = grid;
   blockDim.x = block;
-  for (unsigned b = 0; b < grid; ++b) {
-    blockIdx.x = b;
+  for (unsigned b = 0; b < grid.x * grid.y; ++b) {
+    blockIdx.x = b % grid.x;
+    blockIdx.y = b / grid.x;
     if (!coop) {
       for (unsigned t = 0; t < block; ++t) {
         threadIdx.x = t;
@@ -82,6 +96,12 @@ inline void emu_launch(bool coop, unsigned grid, unsigned block, F&& body) {
     }
     std::barrier<> bar(block);
     emu::g_barrier = &bar;
+    std::vector<std::unique_ptr<std::barrier<>>> warps;
+    emu::g_warp_barrier.clear();
+    for (unsigned w = 0; w * 32 < block; ++w) {
+      warps.emplace_back(new std::barrier<>(std::min(32u, block - w * 32)));
+      emu::g_warp_barrier.push_back(warps.back().get());
+    }
     emu::g_xchg.assign(block, 0.0);
     emu::g_coop = true;
     std::vector<std::thread> th;
@@ -98,7 +118,7 @@ inline void emu_launch(bool coop, unsigned grid, unsigned block, F&& body) {
   threadIdx.x = 0;
 }
 
-#define EMU_LAUNCH(coop, kernel, grid, block, ...) emu_launch(coop, static_cast<unsigned>(grid), static_cast<unsigned>(block), [&]() { kernel(__VA_ARGS__); })
+#define EMU_LAUNCH(coop, kernel, grid, block, ...) emu_launch(coop, dim3(grid), static_cast<unsigned>(block), [&]() { kernel(__VA_ARGS__); })
 
 // ---- intrinsics --------------------------------------------------------------------------------------------------
 template <typename T> inline T __ldg(const T* p) { return *p; }
@@ -114,6 +134,16 @@ inline int atomicMin(int* p, int v) {
   return old;
 }
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline float atomicAdd(float* p, float v) {
+  float old = *p, want;
+  do { want = old + v; } while (!__atomic_compare_exchange(p, &old, &want, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+  return old;
+}
+inline float warp_sum_emu(float v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+namespace rsb { inline float warp_sum(float v) { return warp_sum_emu(v); } }
 inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) {
   unsigned long long old = __atomic_load_n(p, __ATOMIC_RELAXED);
   while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}

@@ -208,3 +208,22 @@ def test_intensity_augmentation_launches_and_rng_stream(monkeypatch):
     with pytest.raises(NotImplementedError):
         with recording(monkeypatch):
             A.gamma(torch.zeros(1, 2, 4, 4, 4))
+
+
+def test_public_dice_loss_wrapper_shapes_and_backward_scale(monkeypatch):
+    """DiceLossMultiClass copy-out wrapper: 3-D / 4-D / 5-D inputs reach the kernel as [B, C, V]; class weights are reduced
+    to [B, C]; backward passes a (0, grad) scale pair (Dice term only)."""
+    from rsuper_b200 import losses
+    with recording(monkeypatch) as rec:
+        lg = torch.zeros(2, 3, 4, 6, 8, requires_grad=True)
+        m = torch.ones(2, 3, 4, 6, 8)
+        cw = torch.ones(2, 3, 4, 6, 8) * 2
+        losses.DiceLossMultiClass(lg, m, m, class_weights=cw).backward()
+        losses.DiceLossMultiClass(lg[0, 0], m[0, 0], m[0, 0])
+        losses.DiceLossMultiClass(lg[0], m[0], m[0])
+    f = [a[0] for n, a in rec.calls if n == "rsb_seg_loss_forward"]
+    assert [(a["B"], a["C"], a["V"]) for a in f] == [(2, 3, 192), (1, 1, 192), (1, 3, 192)]
+    assert f[0]["class_weights"] == "p" and f[1]["class_weights"] is None and f[0]["known"] == "p"
+    assert [n for n, _ in rec.calls].count("rsb_seg_loss_backward") == 1 and lg.grad is not None
+    with pytest.raises(AssertionError):
+        losses.DiceLossMultiClass(torch.zeros(1, 2, 4, 4, 4), torch.zeros(1, 1, 4, 4, 4), torch.zeros(1, 2, 4, 4, 4))

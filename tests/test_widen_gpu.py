@@ -517,3 +517,33 @@ def test_intensity_augmentations_match_reference_golden(cuda_dev):
     # device-side noise: same distribution (mean / std of the increment), different stream
     z = A.gaussian_noise(xd, 0.2, device_noise=True) - xd
     assert abs(z.mean().item()) < 5e-3 and abs(z.std().item() - 0.2) < 5e-3
+
+
+def test_public_dice_loss_multiclass_vs_oracle(cuda_dev):
+    """The reference's public copy-out function DiceLossMultiClass (README.md:119-128) on the seg-loss kernels: value and
+    gradient (alpha carries gradient) against the oracle restatement, with unknown voxels, class weights and the 3-D / 4-D
+    input forms the reference accepts."""
+    from oracle import losses_ref as LR
+    from oracle import synth
+    from rsuper_b200 import losses
+    shape = (24, 20, 28)
+    lab = synth.make_batch(["mask", "report"], ["organ", "a_lesion", "veins"], shape, seed=4, device=cuda_dev)
+    logits = synth.synthetic_logits(2, 3, shape, seed=6, device=cuda_dev)
+    known = 1 - lab["unk_channels"].float()
+    cw = torch.tensor([[1.0, 2.0, 0.5], [1.0, 0.0, 0.5]], device=cuda_dev).view(2, 3, 1, 1, 1).expand(2, 3, *shape)
+    for weights in (None, cw):
+        a = logits.clone().requires_grad_(True)
+        b = logits.clone().requires_grad_(True)
+        ours = losses.DiceLossMultiClass(a, lab["label"], known, class_weights=weights)
+        ref = LR.dice_loss_multiclass(b, lab["label"].float(), known, class_weights=weights)
+        assert abs(ours.item() - ref.item()) <= 1e-5 * abs(ref.item())
+        (3.0 * ours).backward(); (3.0 * ref).backward()
+        assert rel(a.grad, b.grad) <= 1e-4
+    one = losses.DiceLossMultiClass(logits[0, 1], lab["label"][0, 1], known[0, 1])            # [D, H, W]
+    ref1 = LR.dice_loss_multiclass(logits[0:1, 1:2], lab["label"][0:1, 1:2].float(), known[0:1, 1:2])
+    assert abs(one.item() - ref1.item()) <= 1e-5 * abs(ref1.item())
+    four = losses.DiceLossMultiClass(logits[1], lab["label"][1], known[1])                   # [C, D, H, W]
+    ref4 = LR.dice_loss_multiclass(logits[1:2], lab["label"][1:2].float(), known[1:2])
+    assert abs(four.item() - ref4.item()) <= 1e-5 * abs(ref4.item())
+    with pytest.raises(NotImplementedError):
+        losses.DiceLossMultiClass(logits, lab["label"], known, reduce=False)
