@@ -118,6 +118,12 @@ __global__ void __launch_bounds__(OPT_THREADS) clip_adamw_ema_kernel(const RsbOp
     float* m = t.m + begin;
     float* v = t.v + begin;
     float* e = HasEma ? t.ema + begin : nullptr;
+    // the table holds generic pointers; telling the compiler they are global memory turns LD/ST.E into LDG/STG
+    __builtin_assume(__isGlobal(g));
+    __builtin_assume(__isGlobal(p));
+    __builtin_assume(__isGlobal(m));
+    __builtin_assume(__isGlobal(v));
+    if (HasEma) __builtin_assume(__isGlobal(e));
     uintptr_t align = reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(m) |
                       reinterpret_cast<uintptr_t>(v);
     if (HasEma) align |= reinterpret_cast<uintptr_t>(e);

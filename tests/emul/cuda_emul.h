@@ -34,6 +34,8 @@
 #define __launch_bounds__(...)
 #define __shared__ static
 #define RSB_DEVICE inline
+#define __builtin_assume(x) ((void)0)
+#define __isGlobal(p) true
 
 struct dim3 {
   unsigned x, y, z;
