@@ -104,3 +104,7 @@ def test_shim_reproduces_gpu_verified_seg_loss(emulated, golden):
 def test_shim_reproduces_gpu_verified_dilation(emulated, golden):
     import test_kernels_gpu as K
     K.test_dilation_bit_exact(CPU, golden)
+
+
+def test_emulated_widened_edge_cases(emulated):
+    W.test_widened_edge_cases(CPU)

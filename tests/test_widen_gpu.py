@@ -547,3 +547,46 @@ def test_public_dice_loss_multiclass_vs_oracle(cuda_dev):
     assert abs(four.item() - ref4.item()) <= 1e-5 * abs(ref4.item())
     with pytest.raises(NotImplementedError):
         losses.DiceLossMultiClass(logits, lab["label"], known, reduce=False)
+
+
+def test_widened_edge_cases(cuda_dev):
+    """Empty / degenerate / ragged inputs of the widened rows: parameters without gradients and zero-size parameters are left
+    alone by the fused optimizer; batch > 1 and a 1-voxel-thick volume through the sliding-window blend; single-voxel and
+    line-shaped volumes through the connected components; one class (one bit used per packed byte)."""
+    from types import SimpleNamespace
+    from oracle import synth
+    from oracle.inference_ref import connected_components as oracle_cc
+    from oracle.inference_ref import inference_sliding_window as oracle_sw
+    from rsuper_b200 import ops
+    from rsuper_b200.inference import connected_components, inference_sliding_window, keep_largest_component
+    from rsuper_b200.optim import B200AdamW
+    # optimizer: frozen parameter (grad None), empty parameter
+    a, frozen, empty = (torch.nn.Parameter(torch.full((10,), 0.5, device=cuda_dev)), torch.nn.Parameter(torch.ones(7, device=cuda_dev)),
+                        torch.nn.Parameter(torch.zeros(0, device=cuda_dev)))
+    opt = B200AdamW([a, frozen, empty], lr=0.1, weight_decay=0.0, max_norm=None)
+    a.grad = torch.ones_like(a)
+    empty.grad = torch.zeros_like(empty)
+    opt.step()
+    assert torch.equal(frozen.detach().cpu(), torch.ones(7)) and frozen not in opt.state
+    torch.testing.assert_close(a.detach().cpu(), torch.full((10,), 0.4), rtol=1e-5, atol=1e-6)     # first Adam step = -lr * sign(g)
+    B200AdamW([torch.nn.Parameter(torch.ones(3, device=cuda_dev))], max_norm=1.0).step()         # nothing has a gradient: no launch, no error
+    # sliding window: batch of two, window = whole (thin) volume
+    net = _sliding_net(cuda_dev)
+    vol = torch.stack([synth.synthetic_logits(1, 1, (16, 24, 20), seed=s)[0] for s in (1, 2)])
+    got = inference_sliding_window(net, vol.to(cuda_dev), SimpleNamespace(window_size=[16, 16, 16], classes=3))
+    want = oracle_sw(_sliding_net("cpu"), vol, (16, 16, 16), 3)
+    assert got.shape == (2, 3, 16, 24, 20) and (got - want).abs().max().item() <= 2e-6
+    # connected components: single voxel, a line, a 1x1x1 volume
+    for m in (np.ones((1, 1, 1), np.uint8), np.zeros((1, 1, 1), np.uint8), np.array([1, 1, 0, 1, 0, 0, 1, 1, 1], np.uint8).reshape(1, 1, 9),
+              np.array([1, 0, 1, 1], np.uint8).reshape(4, 1, 1)):
+        labels, n = connected_components(torch.from_numpy(m).to(cuda_dev))
+        assert n == oracle_cc(m)[1]
+        big = keep_largest_component(torch.from_numpy(m).to(cuda_dev)).cpu().numpy()
+        assert big.sum() == (np.bincount(oracle_cc(m)[0].reshape(-1))[1:].max() if n else 0)
+    # the raster-first component wins a tie in size (strict '>' in the reference loop)
+    tie = np.array([1, 1, 0, 1, 1], np.uint8).reshape(1, 1, 5)
+    assert keep_largest_component(torch.from_numpy(tie).to(cuda_dev)).cpu().numpy().reshape(-1).tolist() == [1, 1, 0, 0, 0]
+    # one class: bit 7 of every packed byte
+    one = (torch.rand(1, 1, 3, 5, 7) < 0.5).to(torch.uint8)
+    packed = torch.from_numpy(np.stack([synth.pack_masks(one[0])])).to(cuda_dev)
+    assert torch.equal(ops.unpack_masks(packed, 1).cpu(), one)
