@@ -14,10 +14,13 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "r-super_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "librsb_emul.so")
-SOURCES = ["train_glue.cu", "infer.cu", "augment.cu", "seg_loss.cu", "morph.cu"]
+SOURCES = ["train_glue.cu", "infer.cu", "augment.cu", "seg_loss.cu", "morph.cu", "elementwise.cu"]
 # kernels that use __syncthreads / warp shuffles: their blocks run as real threads
 COOPERATIVE = {"grad_sqnorm_kernel", "clip_adamw_ema_kernel", "aug_stats_partial_kernel", "aug_stats_final_kernel",
                "seg_loss_pass1_kernel", "seg_loss_finalize_kernel", "seg_loss_pass2_kernel"}
+
+# files whose every kernel runs as real threads (shared-memory statistics flushes in helper functions)
+ALL_COOPERATIVE = {"elementwise.cu"}
 
 LAUNCH = re.compile(r"(\w+(?:<[\w, ]+>)?)\s*<<<\s*([^;]*?)>>>\s*\(", re.S)
 
@@ -37,8 +40,10 @@ def _split_args(s: str):
     return out
 
 
-def rewrite(src: str) -> str:
-    src = src.replace('#include "rsb_common.cuh"', '#include "cuda_emul.h"')
+def rewrite(src: str, all_coop: bool = False) -> str:
+    src = src.replace('#include "rsb_common.cuh"', '#include "rsb_common_emul.h"')
+    # dynamic shared memory: `extern __shared__ float name[];` -> a pointer into the launch's buffer
+    src = re.sub(r"extern\s+__shared__\s+(\w+)\s+(\w+)\[\];", r"\1* \2 = reinterpret_cast<\1*>(emu::g_dyn_smem.data());", src)
     pos, out = 0, ""
     for m in LAUNCH.finditer(src):
         kernel, cfg = m.group(1), _split_args(m.group(2))
@@ -49,7 +54,9 @@ def rewrite(src: str) -> str:
             depth += {"(": 1, ")": -1}.get(src[i], 0)
             i += 1
         args = src[m.end():i - 1]
-        out += src[pos:m.start()] + f"EMU_LAUNCH({'true' if base in COOPERATIVE else 'false'}, {kernel}, {cfg[0]}, {cfg[1]}, {args})"
+        coop = base in COOPERATIVE or all_coop
+        smem = cfg[2] if len(cfg) > 2 else "0"
+        out += src[pos:m.start()] + f"EMU_LAUNCH({'true' if coop else 'false'}, {kernel}, {cfg[0]}, {cfg[1]}, {smem}, {args})"
         pos = i
     return out + src[pos:]
 
@@ -58,7 +65,7 @@ def build() -> str:
     os.makedirs(OUT, exist_ok=True)
     h = hashlib.sha256()
     texts = []
-    for s in SOURCES + [os.path.join(HERE, "cuda_emul.h"), os.path.abspath(__file__)]:
+    for s in SOURCES + [os.path.join(HERE, "cuda_emul.h"), os.path.abspath(__file__), "rsb_common.cuh"]:
         p = s if os.path.isabs(s) else os.path.join(CSRC, s)
         t = open(p).read()
         h.update(t.encode())
@@ -66,18 +73,23 @@ def build() -> str:
     stamp = os.path.join(OUT, "stamp")
     if os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == h.hexdigest():
         return LIB
+    # the PTX-free tail of rsb_common.cuh (packing / vector access, warp_sum, statistics helpers) is used as it is
+    common = open(os.path.join(CSRC, "rsb_common.cuh")).read()
+    tail = common[common.index("// packing / vector access"):]
+    with open(os.path.join(OUT, "rsb_common_emul.h"), "w") as f:
+        f.write('#pragma once\n#include "cuda_emul.h"\nnamespace rsb {\n// ' + tail)
     cpps = []
     for name, text in zip(SOURCES, texts):
         cpp = os.path.join(OUT, name[:-3] + "_emul.cpp")
         with open(cpp, "w") as f:
-            f.write(rewrite(text))
+            f.write(rewrite(text, all_coop=name in ALL_COOPERATIVE))
         cpps.append(cpp)
     with open(os.path.join(OUT, "api_emul.cpp"), "w") as f:
         f.write('#include "cuda_emul.h"\n#include "../../../include/rsuper_b200.h"\n'
                 'extern "C" const char* rsb_last_error(void) { return rsb::g_last_error; }\n'
                 'extern "C" int rsb_num_sms(void) { return 4; }\n')          # 4 "SMs": small grids keep the emulation quick
     cpps.append(os.path.join(OUT, "api_emul.cpp"))
-    cmd = ["g++", "-std=c++20", "-O1", "-g", "-pthread", "-shared", "-fPIC", "-ffp-contract=off", "-Wno-attributes", "-I", HERE,
+    cmd = ["g++", "-std=c++20", "-O1", "-g", "-pthread", "-shared", "-fPIC", "-ffp-contract=off", "-Wno-attributes", "-I", HERE, "-I", OUT,
            "-o", LIB] + cpps
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

@@ -53,17 +53,59 @@ struct float4 { float x, y, z, w; };
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 struct uint4 { unsigned x, y, z, w; };
 inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
+struct uint2 { unsigned x, y; };
+inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
+struct int4 { int x, y, z, w; };
+inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
+struct float2 { float x, y; };
+inline float2 make_float2(float x, float y) { return float2{x, y}; }
+
+inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
+inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
+using std::min;
+using std::max;
+inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
+
+// bf16 storage type: round-to-nearest-even conversion like cvt.rn.bf16.f32
+struct __nv_bfloat16 { uint16_t bits; };
+inline __nv_bfloat16 __float2bfloat16_rn(float f) {
+  unsigned u = __float_as_uint(f);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return __nv_bfloat16{static_cast<uint16_t>((u >> 16) | 0x40)};   // NaN
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return __nv_bfloat16{static_cast<uint16_t>(u >> 16)};
+}
+inline float __bfloat162float(__nv_bfloat16 b) { return __uint_as_float(static_cast<unsigned>(b.bits) << 16); }
+struct __nv_bfloat162 { __nv_bfloat16 x, y; };
+inline __nv_bfloat162 __floats2bfloat162_rn(float lo, float hi) { return __nv_bfloat162{__float2bfloat16_rn(lo), __float2bfloat16_rn(hi)}; }
 
 // ---- cooperative-block machinery -----------------------------------------------------------------------------------
 namespace emu {
 inline std::barrier<>* g_barrier = nullptr;      // non-null while a cooperative block runs
 inline std::vector<std::barrier<>*> g_warp_barrier;   // one per warp: shuffles synchronise a warp, not the block
 inline std::vector<double> g_xchg;               // shuffle exchange slots (one per thread)
+inline std::vector<double> g_dyn_smem;           // dynamic shared memory of the running block (8-byte aligned)
+inline int g_or_flag[2] = {0, 0};
 inline bool g_coop = false;
 }  // namespace emu
 
 inline void __syncthreads() {
   if (emu::g_coop) emu::g_barrier->arrive_and_wait();   // sequential mode: kernels with barriers are never run that way
+}
+
+inline int __syncthreads_or(int pred) {
+  // two alternating accumulators so that back-to-back calls cannot mix
+  static thread_local int phase = 0;
+  const int p = phase;
+  phase ^= 1;
+  if (pred) __atomic_store_n(&emu::g_or_flag[p], 1, __ATOMIC_RELAXED);
+  emu::g_barrier->arrive_and_wait();
+  const int r = __atomic_load_n(&emu::g_or_flag[p], __ATOMIC_RELAXED);
+  emu::g_barrier->arrive_and_wait();
+  if (threadIdx.x == 0) emu::g_or_flag[p] = 0;
+  emu::g_barrier->arrive_and_wait();
+  return r;
 }
 
 template <typename T>
@@ -82,13 +124,19 @@ inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
   return out;
 }
 
+inline unsigned emu_block(unsigned b) { return b; }
+inline unsigned emu_block(int b) { return static_cast<unsigned>(b); }
+inline unsigned emu_block(dim3 b) { return b.x; }
+
 template <typename F>
-inline void emu_launch(bool coop, dim3 grid, unsigned block, F&& body) {
+inline void emu_launch(bool coop, dim3 grid, unsigned block, size_t smem_bytes, F&& body) {
   gridDim = grid;
   blockDim.x = block;
-  for (unsigned b = 0; b < grid.x * grid.y; ++b) {
+  emu::g_dyn_smem.assign(smem_bytes / 8 + 2, 0.0);
+  for (unsigned b = 0; b < grid.x * grid.y * grid.z; ++b) {
     blockIdx.x = b % grid.x;
-    blockIdx.y = b / grid.x;
+    blockIdx.y = (b / grid.x) % grid.y;
+    blockIdx.z = b / (grid.x * grid.y);
     if (!coop) {
       for (unsigned t = 0; t < block; ++t) {
         threadIdx.x = t;
@@ -120,7 +168,7 @@ inline void emu_launch(bool coop, dim3 grid, unsigned block, F&& body) {
   threadIdx.x = 0;
 }
 
-#define EMU_LAUNCH(coop, kernel, grid, block, ...) emu_launch(coop, dim3(grid), static_cast<unsigned>(block), [&]() { kernel(__VA_ARGS__); })
+#define EMU_LAUNCH(coop, kernel, grid, block, smem, ...) emu_launch(coop, dim3(grid), emu_block(block), static_cast<size_t>(smem), [&]() { kernel(__VA_ARGS__); })
 
 // ---- intrinsics --------------------------------------------------------------------------------------------------
 template <typename T> inline T __ldg(const T* p) { return *p; }
@@ -141,11 +189,15 @@ inline float atomicAdd(float* p, float v) {
   do { want = old + v; } while (!__atomic_compare_exchange(p, &old, &want, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
   return old;
 }
-inline float warp_sum_emu(float v) {
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
+inline int atomicMax(int* p, int v) {
+  int old = __atomic_load_n(p, __ATOMIC_RELAXED);
+  while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+  return old;
 }
-namespace rsb { inline float warp_sum(float v) { return warp_sum_emu(v); } }
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <typename K> inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return cudaSuccess; }
+enum cudaMemcpyKind { cudaMemcpyDeviceToDevice = 3 };
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memcpy(d, s, n); return cudaSuccess; }
 inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) {
   unsigned long long old = __atomic_load_n(p, __ATOMIC_RELAXED);
   while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
@@ -163,6 +215,7 @@ inline void set_last_error(const char* fmt, ...) {
 }
 inline int check_launch(const char*) { return 0; }
 }  // namespace rsb
+extern "C" int rsb_num_sms(void);
 
 #define RSB_REQUIRE(cond, ...)            \
   do {                                    \
