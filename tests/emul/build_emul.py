@@ -14,13 +14,13 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "r-super_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "librsb_emul.so")
-SOURCES = ["train_glue.cu", "infer.cu", "augment.cu", "seg_loss.cu", "morph.cu", "elementwise.cu"]
+SOURCES = ["train_glue.cu", "infer.cu", "augment.cu", "seg_loss.cu", "morph.cu", "elementwise.cu", "stem_head.cu", "report_loss.cu"]
 # kernels that use __syncthreads / warp shuffles: their blocks run as real threads
 COOPERATIVE = {"grad_sqnorm_kernel", "clip_adamw_ema_kernel", "aug_stats_partial_kernel", "aug_stats_final_kernel",
                "seg_loss_pass1_kernel", "seg_loss_finalize_kernel", "seg_loss_pass2_kernel"}
 
 # files whose every kernel runs as real threads (shared-memory statistics flushes in helper functions)
-ALL_COOPERATIVE = {"elementwise.cu"}
+ALL_COOPERATIVE = set()
 
 LAUNCH = re.compile(r"(\w+(?:<[\w, ]+>)?)\s*<<<\s*([^;]*?)>>>\s*\(", re.S)
 
@@ -40,7 +40,37 @@ def _split_args(s: str):
     return out
 
 
+SYNC = re.compile(r"__syncthreads|__shfl_\w+_sync|__syncthreads_or")
+FUNC = re.compile(r"\b(\w+)\s*\([^;{}()]*(?:\([^()]*\)[^;{}()]*)*\)\s*(?:const\s*)?\{")
+
+
+def cooperative_functions(src: str) -> set:
+    """Names of the functions (kernels and device helpers) of a translation unit that reach a barrier or a warp shuffle,
+    directly or through a helper: those kernels must run as real threads.  Fixpoint over a rough brace-matched parse."""
+    bodies = {}
+    for m in FUNC.finditer(src):
+        name = m.group(1)
+        if name in ("if", "for", "while", "switch", "return", "sizeof"):
+            continue
+        i, depth = m.end(), 1
+        while depth and i < len(src):
+            depth += {"{": 1, "}": -1}.get(src[i], 0)
+            i += 1
+        bodies.setdefault(name, "")
+        bodies[name] += src[m.end():i]
+    coop = {n for n, b in bodies.items() if SYNC.search(b)} | {"warp_sum"}
+    changed = True
+    while changed:
+        changed = False
+        for n, b in bodies.items():
+            if n not in coop and any(re.search(r"\b%s\s*(?:<[^;()]*>)?\s*\(" % re.escape(c), b) for c in coop):
+                coop.add(n)
+                changed = True
+    return coop
+
+
 def rewrite(src: str, all_coop: bool = False) -> str:
+    auto = cooperative_functions(src)
     src = src.replace('#include "rsb_common.cuh"', '#include "rsb_common_emul.h"')
     # dynamic shared memory: `extern __shared__ float name[];` -> a pointer into the launch's buffer
     src = re.sub(r"extern\s+__shared__\s+(\w+)\s+(\w+)\[\];", r"\1* \2 = reinterpret_cast<\1*>(emu::g_dyn_smem.data());", src)
@@ -54,9 +84,9 @@ def rewrite(src: str, all_coop: bool = False) -> str:
             depth += {"(": 1, ")": -1}.get(src[i], 0)
             i += 1
         args = src[m.end():i - 1]
-        coop = base in COOPERATIVE or all_coop
+        coop = base in COOPERATIVE or base in auto or all_coop
         smem = cfg[2] if len(cfg) > 2 else "0"
-        out += src[pos:m.start()] + f"EMU_LAUNCH({'true' if coop else 'false'}, {kernel}, {cfg[0]}, {cfg[1]}, {smem}, {args})"
+        out += src[pos:m.start()] + f"EMU_LAUNCH({'true' if coop else 'false'}, ({kernel}), {cfg[0]}, {cfg[1]}, {smem}, {args})"
         pos = i
     return out + src[pos:]
 

@@ -120,3 +120,29 @@ def test_shim_runs_gpu_verified_elementwise_kernels(emulated):
     K.test_maxpool_forward_backward_with_ties(CPU)
     for dims in (((4, 4, 4), (8, 8, 8)), ((2, 2, 2), (4, 4, 4)), ((8, 6, 4), (16, 12, 8))):
         K.test_upsample_trilinear(CPU, dims)
+
+
+def test_shim_runs_gpu_verified_stem_and_head(emulated):
+    import test_kernels_gpu as K
+    K.test_stem_and_head(CPU)
+
+
+full = pytest.mark.skipif(os.environ.get("RSB_EMUL_FULL") != "1",
+                          reason="~2 min of emulated report-loss kernels: developer regression net, run with RSB_EMUL_FULL=1")
+
+
+@full
+def test_shim_runs_gpu_verified_report_losses(emulated, golden):
+    """Volume loss, isolate_tumor (bit-exact pseudo masks), GWRP weights, Ball loss and the calculate_loss dicts — the whole
+    report-supervised loss path (csrc/report_loss.cu + seg_loss.cu + morph.cu) on the CPU."""
+    import test_report_losses_gpu as R
+    R.test_volume_loss(CPU, golden)
+    R.test_isolate_tumor_bit_exact(CPU, golden)
+    R.test_gwrp_weights(CPU, golden)
+    R.test_ball_loss(CPU, golden, dict())
+    R.test_calculate_loss_dicts(CPU, golden)
+
+
+@full
+def test_emulated_assemble_batch_feeds_calculate_loss(emulated):
+    W.test_assemble_batch_feeds_calculate_loss(CPU)

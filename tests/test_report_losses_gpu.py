@@ -136,7 +136,7 @@ def test_calculate_loss_dicts(cuda_dev, golden):
     for tag, lossname, deep in (("ball_dice_last_deep", "ball_dice_last", True), ("dice", "dice", False),
                                 ("ball", "ball", False), ("both", "ball_dice_both", False)):
         a = LR.default_args(loss=lossname)
-        lg = lgb.to(dev).requires_grad_(True)
+        lg = lgb.to(dev).clone().requires_grad_(True)     # clone: on a CPU device (emulated run) .to() would alias lgb
         mo = {"segmentation": [lg, lg * 0.5 + 0.1]} if deep else {"segmentation": lg}
         res = losses.calculate_loss(mo, bb["label"].long().to(dev), bb["unk_channels"].float().to(dev), a, None, bb["mask"].float().to(dev),
                                     bb["volumes"].to(dev), bb["diameters"].to(dev), cls2, input_tensor=bb["image"].to(dev))
