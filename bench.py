@@ -219,6 +219,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fused-optimizer", action="store_true",
                     help="clip + AdamW + EMA through rsuper_b200.optim.B200AdamW (two launches) instead of the stock torch glue")
+    ap.add_argument("--cuda-graph", action="store_true",
+                    help="capture the whole step (forward, loss, backward, fused optimizer) in a CUDA graph and replay it (single GPU)")
     ap.add_argument("--packed-labels", action="store_true",
                     help="e2e leg uploads the label in the reference's bit-packed on-disk format and unpacks it on the device")
     ap.add_argument("--trace", default=None, help="write the per-launch CUDA-event timeline of the timed region to this file")
@@ -265,9 +267,14 @@ def main():
                                                           gradient_as_bucket_view=True, bucket_cap_mb=64)
     ema = [p.detach().clone() for p in net.parameters()]
     params = list(net.parameters())
+    if args.cuda_graph:
+        if world > 1:
+            raise SystemExit("--cuda-graph captures a single-process step; run it with --gpus 1")
+        args.fused_optimizer = True
     if args.fused_optimizer:
         from rsuper_b200.optim import B200AdamW
-        opt = B200AdamW(params, lr=6e-4, betas=(0.9, 0.999), weight_decay=0.05, eps=1e-5, max_norm=1.0, ema_params=ema, ema_alpha=0.99)
+        opt = B200AdamW(params, lr=6e-4, betas=(0.9, 0.999), weight_decay=0.05, eps=1e-5, max_norm=1.0, ema_params=ema, ema_alpha=0.99,
+                        capturable=args.cuda_graph)
     else:
         opt = torch.optim.AdamW(params, lr=6e-4, betas=(0.9, 0.999), weight_decay=0.05, eps=1e-5, fused=True)
     largs = LR.default_args(report_volume_loss_basic=0.0)
@@ -283,6 +290,8 @@ def main():
         loss = losses.calculate_loss(out, lab, None, largs, None, None, None, None, CLASSES)
         loss["overall"].backward()
         if args.fused_optimizer:
+            if args.cuda_graph:
+                opt.prepare_step()          # eager use of the capturable optimizer (warm-up / profiled pass)
             opt.step()                      # gradient norm -> clip -> AdamW -> EMA in two launches (csrc/train_glue.cu)
             state["step"] += 1
             return loss["overall"]
@@ -304,6 +313,17 @@ def main():
     for _ in range(args.warmup):
         train_step(img_d, lab_d)
     barrier()
+    eager_step = train_step
+    gstep = None
+    if args.cuda_graph:
+        from rsuper_b200.graph_step import GraphedTrainStep
+        largs.nan_check = False             # a host sync; the loss value is NaN-checked after .item() instead
+        gstep = GraphedTrainStep(net, lambda out, lb: losses.calculate_loss(out, lb, None, largs, None, None, None, None, CLASSES)["overall"],
+                                 opt, img_d, lab_d, warmup=1)
+        train_step = gstep                  # (img, lab) -> device loss scalar: H2D / D2D into the static inputs + one graph launch
+        for _ in range(2):
+            train_step(img_d, lab_d)
+        barrier()
 
     # ---- timed region 1: device-resident inputs, CUDA events around the K steps (no per-launch instrumentation) ----
     sampler = ClockSampler(local_rank)
@@ -318,7 +338,7 @@ def main():
         train_step(img_d, lab_d)
     e1.record()
     barrier()
-    launches = ops.LAUNCHES
+    launches = ops.LAUNCHES if gstep is None else gstep.launches_per_step * args.steps
     ms_dev = e0.elapsed_time(e1) / args.steps
 
     # ---- timed region 2: end to end through the module API with host buffers ----
@@ -349,13 +369,13 @@ def main():
     from rsuper_b200 import unet as unet_mod
     barrier()
     prev_side = unet_mod.set_side_stream(False)
-    train_step(img_d, lab_d)
+    eager_step(img_d, lab_d)                # the profiled pass is always eager (per-launch events cannot sit inside a graph replay)
     barrier()
     ops.PROFILE = []
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     p0.record()
     for _ in range(args.steps):
-        train_step(img_d, lab_d)
+        eager_step(img_d, lab_d)
     p1.record()
     barrier()
     prof, ops.PROFILE = ops.PROFILE, None
@@ -409,6 +429,7 @@ def main():
                 "dtype": "bf16" if args.precision == "bf16" else "bf16 operands / f32 storage", "data": "synthetic",
                 "config": {"workload": workload_name(args.base, B, S),
                            "global_batch": B * world, "parallelism": f"dp{world}" if world > 1 else "single",
+                           "schedule": "CUDA graph replay of the whole step" if args.cuda_graph else "eager launches",
                            "optimizer": "B200AdamW (fused clip+AdamW+EMA kernel)" if args.fused_optimizer else "torch clip_grad_norm_ + fused AdamW + foreach EMA",
                            "labels_h2d": "bit-packed (np.packbits) + device unpack" if args.packed_labels else "uint8",
                            "l2": "per-step working set (~3 GB of activations) >> 126 MB L2; no flush needed"},

@@ -334,7 +334,16 @@ int rsb_opt_max_blocks(void);
  * clip_grad_norm_.  Scalars are doubles like the python floats torch's AdamW computes with. */
 int rsb_clip_adamw_ema_step(const RsbOptTensor* table_device, int n_tensors, long long total_chunks, int has_ema,
                             float* partials, float* norm_out, double max_norm, double lr, double beta1, double beta2,
-                            double eps, double weight_decay, long long step, double ema_alpha, void* stream);
+                            double eps, double weight_decay, long long step, double ema_alpha, const float* hyper_device,
+                            void* stream);
+/* CUDA-graph mode: hyper_device != NULL points to rsb_opt_hyper_floats() floats in DEVICE memory holding the step-dependent
+ * scalars; the kernel reads them at run time, so a captured launch stays valid while the host rewrites them before every
+ * replay (bias corrections, LR schedule, EMA warm-up).  rsb_opt_fill_hyper computes that block on the HOST from the same
+ * arguments (the by-value scalars of the call above are then ignored, except max_norm <= 0 deciding whether the norm
+ * kernel is launched). */
+int rsb_opt_hyper_floats(void);
+int rsb_opt_fill_hyper(float* hyper_host, double max_norm, double lr, double beta1, double beta2, double eps,
+                       double weight_decay, long long step, double ema_alpha);
 
 /* ---------------------------------------------------------------------------------------------
  * Sliding-window inference post-processing: inference/inference3d.py:28-107 and

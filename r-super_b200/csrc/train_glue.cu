@@ -17,6 +17,9 @@
 // 16-byte aligned (DDP bucket views need not be), scalar otherwise and on the ragged tail.
 #include "rsb_common.cuh"
 
+#include <cmath>
+#include <cstring>
+
 #include "../../include/rsuper_b200.h"
 
 namespace rsb {
@@ -95,8 +98,12 @@ RSB_DEVICE void update_one(float& g, float& p, float& m, float& v, float& e, flo
 template <bool HasEma>
 __global__ void __launch_bounds__(OPT_THREADS) clip_adamw_ema_kernel(const RsbOptTensor* __restrict__ tab, int n_tensors,
                                                                       long long total_chunks, const float* __restrict__ partials,
-                                                                      int n_partials, OptHyper h, float* __restrict__ norm_out) {
+                                                                      int n_partials, OptHyper h_value, const OptHyper* __restrict__ h_device,
+                                                                      float* __restrict__ norm_out) {
   __shared__ float red[OPT_THREADS / 32];
+  // step-dependent scalars either by value (eager launches) or from device memory (CUDA-graph replays: the host rewrites
+  // that struct before every replay, the captured launch itself never changes)
+  const OptHyper h = h_device != nullptr ? *h_device : h_value;
   float clip = 1.f;
   {
     float acc = 0.f;
@@ -159,29 +166,10 @@ __global__ void __launch_bounds__(OPT_THREADS) clip_adamw_ema_kernel(const RsbOp
 
 using namespace rsb;
 
-extern "C" long long rsb_opt_chunk_elems(void) { return OPT_CHUNK; }
-
-extern "C" int rsb_opt_max_blocks(void) {
-  const int sms = rsb_num_sms();
-  return (sms > 0 ? sms : 148) * 8;
-}
-
-extern "C" int rsb_clip_adamw_ema_step(const RsbOptTensor* table_device, int n_tensors, long long total_chunks, int has_ema,
-                                       float* partials, float* norm_out, double max_norm, double lr, double beta1, double beta2,
-                                       double eps, double weight_decay, long long step, double ema_alpha, void* stream) {
-  RSB_REQUIRE(table_device != nullptr && n_tensors > 0 && total_chunks > 0, "clip_adamw_ema_step: empty tensor table");
-  RSB_REQUIRE(step >= 1, "clip_adamw_ema_step: step counts from 1 (got %lld)", step);
-  RSB_REQUIRE(max_norm <= 0.0 || partials != nullptr, "clip_adamw_ema_step: clipping needs the partials workspace");
-  RSB_REQUIRE(beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0, "clip_adamw_ema_step: betas must be in [0, 1)");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int max_blocks = rsb_opt_max_blocks();
-  const int grid = static_cast<int>(total_chunks < max_blocks ? total_chunks : max_blocks);
-  if (partials != nullptr) {
-    grad_sqnorm_kernel<<<grid, OPT_THREADS, 0, st>>>(table_device, n_tensors, total_chunks, partials);
-    if (int rc = check_launch("grad_sqnorm_kernel")) return rc;
-  }
+// python-double scalar arithmetic like torch's single-tensor AdamW (optim/adamw.py), rounded to fp32 once
+static OptHyper make_hyper(double max_norm, double lr, double beta1, double beta2, double eps, double weight_decay, long long step,
+                           double ema_alpha) {
   OptHyper h;
-  // python-double scalar arithmetic like torch's single-tensor AdamW (optim/adamw.py), rounded to fp32 once
   h.clip_max_norm = static_cast<float>(max_norm);
   h.decay = static_cast<float>(1.0 - lr * weight_decay);
   h.one_minus_b1 = static_cast<float>(1.0 - beta1);
@@ -194,9 +182,45 @@ extern "C" int rsb_clip_adamw_ema_step(const RsbOptTensor* table_device, int n_t
   h.eps = static_cast<float>(eps);
   h.ema_alpha = static_cast<float>(ema_alpha);
   h.one_minus_ema_alpha = static_cast<float>(1.0 - ema_alpha);
+  return h;
+}
+
+extern "C" long long rsb_opt_chunk_elems(void) { return OPT_CHUNK; }
+
+extern "C" int rsb_opt_max_blocks(void) {
+  const int sms = rsb_num_sms();
+  return (sms > 0 ? sms : 148) * 8;
+}
+
+extern "C" int rsb_clip_adamw_ema_step(const RsbOptTensor* table_device, int n_tensors, long long total_chunks, int has_ema,
+                                       float* partials, float* norm_out, double max_norm, double lr, double beta1, double beta2,
+                                       double eps, double weight_decay, long long step, double ema_alpha, const float* hyper_device,
+                                       void* stream) {
+  RSB_REQUIRE(table_device != nullptr && n_tensors > 0 && total_chunks > 0, "clip_adamw_ema_step: empty tensor table");
+  RSB_REQUIRE(step >= 1, "clip_adamw_ema_step: step counts from 1 (got %lld)", step);
+  RSB_REQUIRE(max_norm <= 0.0 || partials != nullptr, "clip_adamw_ema_step: clipping needs the partials workspace");
+  RSB_REQUIRE(beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0, "clip_adamw_ema_step: betas must be in [0, 1)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int max_blocks = rsb_opt_max_blocks();
+  const int grid = static_cast<int>(total_chunks < max_blocks ? total_chunks : max_blocks);
+  if (partials != nullptr) {
+    grad_sqnorm_kernel<<<grid, OPT_THREADS, 0, st>>>(table_device, n_tensors, total_chunks, partials);
+    if (int rc = check_launch("grad_sqnorm_kernel")) return rc;
+  }
+  const OptHyper h = make_hyper(max_norm, lr, beta1, beta2, eps, weight_decay, step, ema_alpha);
   if (has_ema)
-    clip_adamw_ema_kernel<true><<<grid, OPT_THREADS, 0, st>>>(table_device, n_tensors, total_chunks, partials, grid, h, norm_out);
+    clip_adamw_ema_kernel<true><<<grid, OPT_THREADS, 0, st>>>(table_device, n_tensors, total_chunks, partials, grid, h, reinterpret_cast<const OptHyper*>(hyper_device), norm_out);
   else
-    clip_adamw_ema_kernel<false><<<grid, OPT_THREADS, 0, st>>>(table_device, n_tensors, total_chunks, partials, grid, h, norm_out);
+    clip_adamw_ema_kernel<false><<<grid, OPT_THREADS, 0, st>>>(table_device, n_tensors, total_chunks, partials, grid, h, reinterpret_cast<const OptHyper*>(hyper_device), norm_out);
   return check_launch("clip_adamw_ema_kernel");
+}
+
+extern "C" int rsb_opt_hyper_floats(void) { return static_cast<int>(sizeof(OptHyper) / sizeof(float)); }
+
+extern "C" int rsb_opt_fill_hyper(float* hyper_host, double max_norm, double lr, double beta1, double beta2, double eps,
+                                  double weight_decay, long long step, double ema_alpha) {
+  RSB_REQUIRE(hyper_host != nullptr && step >= 1, "opt_fill_hyper: null pointer / step < 1");
+  const OptHyper h = make_hyper(max_norm, lr, beta1, beta2, eps, weight_decay, step, ema_alpha);
+  memcpy(hyper_host, &h, sizeof(h));
+  return 0;
 }

@@ -152,7 +152,9 @@ SIGNATURES = {
     "rsb_opt_chunk_elems": (c_ll, []),
     "rsb_opt_max_blocks": (c_int, []),
     "rsb_clip_adamw_ema_step": (c_int, [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_double, c_double, c_double, c_double,
-                                        c_double, c_double, c_ll, c_double, c_void_p]),
+                                        c_double, c_double, c_ll, c_double, c_void_p, c_void_p]),
+    "rsb_opt_hyper_floats": (c_int, []),
+    "rsb_opt_fill_hyper": (c_int, [c_void_p, c_double, c_double, c_double, c_double, c_double, c_double, c_ll, c_double]),
     "rsb_sigmoid_window_accumulate": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                               c_int, c_int, c_int, c_void_p]),
     "rsb_blend_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_ll, c_void_p]),

@@ -33,7 +33,8 @@ from . import ops
 
 class B200AdamW(torch.optim.Optimizer):
     def __init__(self, params: Iterable, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-5, weight_decay: float = 1e-2,
-                 max_norm: Optional[float] = None, ema_params: Optional[Sequence[torch.Tensor]] = None, ema_alpha: float = 0.99):
+                 max_norm: Optional[float] = None, ema_params: Optional[Sequence[torch.Tensor]] = None, ema_alpha: float = 0.99,
+                 capturable: bool = False):
         if lr < 0 or eps < 0 or weight_decay < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1):
             raise ValueError(f"B200AdamW: invalid hyper-parameters lr={lr} betas={betas} eps={eps} weight_decay={weight_decay}")
         super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
@@ -48,6 +49,11 @@ class B200AdamW(torch.optim.Optimizer):
         self.last_grad_norm = None    # device scalar: total gradient norm before clipping
         self._tables = {}             # group index -> (pointer signature, device table, n_tensors, total_chunks)
         self._partials = None
+        # capturable: the step-dependent scalars live in a device block that `prepare_step()` rewrites before every launch
+        # (or CUDA-graph replay); `step()` then only launches — nothing step-dependent is baked into the captured kernels
+        self.capturable = capturable
+        self._hyper_dev = None
+        self._prepared = False
 
     # -- device table of one param group --------------------------------------------------------------------------
     def _table(self, gi: int, group, ema_of):
@@ -55,7 +61,7 @@ class B200AdamW(torch.optim.Optimizer):
         rows, sig = [], []
         begin = 0
         for p in group["params"]:
-            if p.grad is None:
+            if p.grad is None or p.numel() == 0:
                 continue
             if not ops._on_device(p):
                 raise RuntimeError("B200AdamW has no CPU path: parameters must live on a CUDA (sm_100a) device")
@@ -71,8 +77,6 @@ class B200AdamW(torch.optim.Optimizer):
             if e is not None and not (ops._on_device(e) and e.dtype == torch.float32 and e.is_contiguous()):
                 raise RuntimeError("B200AdamW: EMA tensors must be contiguous CUDA fp32")
             n = p.numel()
-            if n == 0:
-                continue
             rows.append((p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
                          e.data_ptr() if e is not None else 0, n, begin))
             sig.append(rows[-1][:5])
@@ -92,6 +96,46 @@ class B200AdamW(torch.optim.Optimizer):
         self._tables[gi] = cached
         return cached
 
+    def _step_scalars(self, group):
+        """(adam step t, EMA alpha) of the NEXT update of a group (t = torch's per-parameter `step` + 1; training/utils.py:156)."""
+        steps = {int(self.state[p]["step"].item()) for p in group["params"] if p in self.state and len(self.state[p])}
+        if len(steps) > 1:
+            raise RuntimeError("B200AdamW: parameters of a group must share their step count")
+        t = (steps.pop() if steps else 0) + 1
+        return t, min(1.0 - 1.0 / (self.global_step + 1), self.ema_alpha)
+
+    @torch.no_grad()
+    def prepare_step(self):
+        """capturable mode: upload the scalars of the next update (bias corrections for step t, the group's current lr,
+        the EMA warm-up alpha) into the device block the kernel reads.  Call once before every `step()` / graph replay;
+        after a replay call `finish_step()` so that the host-side counters follow."""
+        if not self.capturable:
+            raise RuntimeError("prepare_step() is for B200AdamW(capturable=True)")
+        if len(self.param_groups) != 1:
+            raise NotImplementedError("B200AdamW(capturable=True) supports one param group")
+        group = self.param_groups[0]
+        dev = group["params"][0].device
+        n = ops.lib().rsb_opt_hyper_floats()
+        t, alpha = self._step_scalars(group)
+        host = torch.empty(n, dtype=torch.float32)
+        b1, b2 = group["betas"]
+        ops.check(ops.lib().rsb_opt_fill_hyper(C.c_void_p(host.data_ptr()), float(self.max_norm) if self.max_norm is not None else 0.0,
+                                               float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
+                                               t, float(alpha)), "opt_fill_hyper")
+        if self._hyper_dev is None:
+            self._hyper_dev = torch.empty(n, dtype=torch.float32, device=dev)
+        self._hyper_dev.copy_(host)           # pageable source: the staging copy is synchronous for the host, stream-ordered on the device
+        self._prepared = True
+
+    def finish_step(self):
+        """capturable mode, after a CUDA-graph replay of a captured `step()`: advance the host-side counters."""
+        for group in self.param_groups:
+            for p in group["params"]:
+                if p in self.state and len(self.state[p]):
+                    self.state[p]["step"] += 1
+        self.global_step += 1
+        self._prepared = False
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None
@@ -104,17 +148,15 @@ class B200AdamW(torch.optim.Optimizer):
             ema_of = {id(p): e for p, e in zip(flat, self.ema_params)}
         if self.max_norm is not None and len(self.param_groups) != 1:
             raise NotImplementedError("B200AdamW: gradient clipping spans one param group (training/utils.py:29-33 builds one)")
-        alpha = min(1.0 - 1.0 / (self.global_step + 1), self.ema_alpha)   # training/utils.py:156
         for gi, group in enumerate(self.param_groups):
             tab = self._table(gi, group, ema_of)
             if tab is None:
                 continue
             _, table, n_tensors, total_chunks, _ = tab
             dev = table.device
-            steps = {int(self.state[p]["step"].item()) for p in group["params"] if p.grad is not None and p.numel()}
-            if len(steps) != 1:
-                raise RuntimeError("B200AdamW: parameters of a group must share their step count")
-            t = steps.pop() + 1
+            t, alpha = self._step_scalars(group)
+            if self.capturable and not self._prepared:
+                raise RuntimeError("B200AdamW(capturable=True): call prepare_step() before step()")
             if self._partials is None or self._partials.device != dev:
                 self._partials = torch.empty(ops.lib().rsb_opt_max_blocks() + 1, dtype=torch.float32, device=dev)
             norm_out = self._partials[-1:]
@@ -124,10 +166,11 @@ class B200AdamW(torch.optim.Optimizer):
                 ops._call("train_glue", 2 if clip > 0 else 1, 0.0, ops.lib().rsb_clip_adamw_ema_step, C.c_void_p(table.data_ptr()),
                           n_tensors, total_chunks, int(bool(ema_of)), ops._p(self._partials) if clip > 0 else None, ops._p(norm_out),
                           clip, float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]), t,
-                          float(alpha), ops._stream(), what="clip_adamw_ema_step")
+                          float(alpha), ops._p(self._hyper_dev) if self.capturable else None, ops._stream(), what="clip_adamw_ema_step")
             self.last_grad_norm = norm_out if clip > 0 else None
             for p in group["params"]:
                 if p.grad is not None and p.numel():
                     self.state[p]["step"] += 1
         self.global_step += 1
+        self._prepared = False
         return loss

@@ -12,7 +12,7 @@ import torch
 
 HOST_ONLY = {"rsb_version", "rsb_last_error", "rsb_conv3_n_tile", "rsb_conv3_packed_weight_bytes", "rsb_conv3_pack_plan",
              "rsb_conv3_wgrad_workspace_bytes", "rsb_ball_workspace_bytes", "rsb_cc_workspace_bytes", "rsb_opt_chunk_elems",
-             "rsb_opt_max_blocks", "rsb_aug_workspace_bytes"}
+             "rsb_opt_max_blocks", "rsb_aug_workspace_bytes", "rsb_opt_hyper_floats", "rsb_opt_fill_hyper"}
 
 
 class RecordingLib:

@@ -164,12 +164,17 @@ def test_widened_entry_points_validate_arguments_without_a_gpu():
     from rsuper_b200 import _lib
     lib = _lib.lib()
     assert lib.rsb_opt_chunk_elems() == 4096 and lib.rsb_opt_max_blocks() >= 148
-    assert lib.rsb_clip_adamw_ema_step(None, 0, 0, 1, None, None, 1.0, 6e-4, 0.9, 0.999, 1e-5, 0.05, 1, 0.99, None) != 0
+    assert lib.rsb_clip_adamw_ema_step(None, 0, 0, 1, None, None, 1.0, 6e-4, 0.9, 0.999, 1e-5, 0.05, 1, 0.99, None, None) != 0
     assert b"empty tensor table" in lib.rsb_last_error()
-    assert lib.rsb_clip_adamw_ema_step(4096, 1, 1, 1, None, None, 1.0, 6e-4, 0.9, 0.999, 1e-5, 0.05, 0, 0.99, None) != 0
+    assert lib.rsb_clip_adamw_ema_step(4096, 1, 1, 1, None, None, 1.0, 6e-4, 0.9, 0.999, 1e-5, 0.05, 0, 0.99, None, None) != 0
     assert b"step counts from 1" in lib.rsb_last_error()
-    assert lib.rsb_clip_adamw_ema_step(4096, 1, 1, 1, None, None, 1.0, 6e-4, 0.9, 0.999, 1e-5, 0.05, 1, 0.99, None) != 0
+    assert lib.rsb_clip_adamw_ema_step(4096, 1, 1, 1, None, None, 1.0, 6e-4, 0.9, 0.999, 1e-5, 0.05, 1, 0.99, None, None) != 0
     assert b"partials" in lib.rsb_last_error()
+    n = lib.rsb_opt_hyper_floats()
+    buf = (ctypes.c_float * n)()
+    assert n == 10 and lib.rsb_opt_fill_hyper(buf, 1.0, 6e-4, 0.9, 0.999, 1e-5, 0.05, 2, 0.5) == 0      # host-only
+    assert buf[0] == 1.0 and abs(buf[1] - (1 - 6e-4 * 0.05)) < 1e-7 and abs(buf[5] - 6e-4 / (1 - 0.81)) < 1e-9 and buf[8] == 0.5
+    assert lib.rsb_opt_fill_hyper(buf, 1.0, 6e-4, 0.9, 0.999, 1e-5, 0.05, 0, 0.5) != 0
     assert lib.rsb_sigmoid_window_accumulate(None, 4096, 4096, 1, 2, 16, 16, 16, 8, 8, 8, 9, 0, 0, None) != 0
     assert b"leaves the volume" in lib.rsb_last_error()
     assert lib.rsb_blend_finalize(None, None, None, None, 0.5, 1, 1, 8, None) != 0

@@ -146,3 +146,7 @@ def test_shim_runs_gpu_verified_report_losses(emulated, golden):
 @full
 def test_emulated_assemble_batch_feeds_calculate_loss(emulated):
     W.test_assemble_batch_feeds_calculate_loss(CPU)
+
+
+def test_emulated_capturable_optimizer_equals_eager_optimizer(emulated):
+    W.test_capturable_optimizer_equals_eager_optimizer(CPU)

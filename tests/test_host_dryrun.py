@@ -103,10 +103,10 @@ def test_fused_optimizer_launch_and_state(monkeypatch):
             opt.step()
     assert [n for n, _ in rec.calls] == ["rsb_clip_adamw_ema_step"] * 3
     for i, (_, a) in enumerate(rec.calls):
-        # (table, n_tensors, total_chunks, has_ema, partials, norm_out, max_norm, lr, b1, b2, eps, wd, step, ema_alpha, stream)
+        # (table, n_tensors, total_chunks, has_ema, partials, norm_out, max_norm, lr, b1, b2, eps, wd, step, ema_alpha, hyper_device, stream)
         assert a[0] == "p" and a[1] == 2 and a[2] == 2 + 1 and a[3] == 1 and a[4] == "p" and a[5] == "p"
         assert a[6:12] == (1.0, 6e-4, 0.9, 0.999, 1e-5, 0.05) and a[12] == i + 1
-        assert a[13] == pytest.approx(min(1 - 1 / (i + 1), 0.99))
+        assert a[13] == pytest.approx(min(1 - 1 / (i + 1), 0.99)) and a[14] is None and len(a) == 16
     assert float(opt.state[ps[0]]["step"]) == 3 and opt.global_step == 3
     table = opt._tables[0][1]
     assert table.shape == (2, 7) and table[0, 5] == 5000 and table[1, 5] == 21 and table[0, 6] == 0 and table[1, 6] == 2

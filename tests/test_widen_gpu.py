@@ -590,3 +590,80 @@ def test_widened_edge_cases(cuda_dev):
     one = (torch.rand(1, 1, 3, 5, 7) < 0.5).to(torch.uint8)
     packed = torch.from_numpy(np.stack([synth.pack_masks(one[0])])).to(cuda_dev)
     assert torch.equal(ops.unpack_masks(packed, 1).cpu(), one)
+
+
+def test_capturable_optimizer_equals_eager_optimizer(cuda_dev):
+    """B200AdamW(capturable=True) — step-dependent scalars read from device memory, refreshed by prepare_step() — produces
+    bit-identical parameters / state / EMA to the by-value mode over steps with a changing learning rate."""
+    from rsuper_b200.optim import B200AdamW
+    sets = []
+    for capturable in (False, True):
+        ps = [torch.nn.Parameter(t) for t in _param_set(cuda_dev, 0)]
+        ema = [p.detach().clone() for p in ps]
+        opt = B200AdamW(ps, lr=6e-4, weight_decay=0.05, max_norm=1.0, ema_params=ema, capturable=capturable)
+        for step in range(4):
+            opt.param_groups[0]["lr"] = 6e-4 * (0.5 + 0.25 * step)            # an LR schedule writes group['lr']
+            for p, g in zip(ps, _param_set(cuda_dev, 20 + step)):
+                p.grad = g.clone() if p.data_ptr() % 16 == 0 else torch.cat([g.new_zeros(1), g.reshape(-1)])[1:].view(g.shape)
+            if capturable:
+                opt.prepare_step()
+            opt.step()
+        sets.append(([p.detach().clone() for p in ps], ema, [opt.state[p]["exp_avg_sq"] for p in ps], opt.global_step))
+        if capturable:
+            with pytest.raises(RuntimeError, match="prepare_step"):
+                opt.step()
+    (p0, e0, v0, s0), (p1, e1, v1, s1) = sets
+    assert s0 == s1 == 4
+    for a, b in zip(p0 + e0 + v0, p1 + e1 + v1):
+        assert torch.equal(a, b)
+
+
+def test_graphed_train_step_matches_eager(cuda_dev):
+    """The whole step captured in a CUDA graph (GraphedTrainStep) against the same steps issued eagerly from identical
+    initial state: same losses (bf16 / atomics noise), parameters within optimizer rounding."""
+    from oracle import losses_ref as LR
+    from oracle import synth
+    from oracle.unet_ref import synthetic_image, synthetic_state_dict
+    from rsuper_b200 import losses
+    from rsuper_b200.graph_step import GraphedTrainStep
+    from rsuper_b200.optim import B200AdamW
+    from rsuper_b200.unet import B200UNet
+    classes = ["organ", "pancreatic_lesion"]
+    x = synthetic_image(2, 64, 64, 64, seed=5, device=cuda_dev)
+    lab = synth.make_batch(["mask", "mask"], classes, (64, 64, 64), seed=8, device=cuda_dev)["label"]
+    args = LR.default_args(report_volume_loss_basic=0.0)
+    args.nan_check = False                                                    # host sync: moved to GraphedTrainStep.check
+    loss_fn = lambda out, lb: losses.calculate_loss(out, lb, None, args, None, None, None, None, classes)["overall"]
+    runs = []
+    for graphed in (False, True):
+        net = B200UNet(1, 16, num_classes=2, precision="bf16").to(cuda_dev)
+        net.load_state_dict(synthetic_state_dict(16, 2, device=cuda_dev))
+        params = list(net.parameters())
+        ema = [p.detach().clone() for p in params]
+        opt = B200AdamW(params, lr=6e-4, weight_decay=0.05, max_norm=1.0, ema_params=ema, capturable=True)
+        ls = []
+        if graphed:
+            step = GraphedTrainStep(net, loss_fn, opt, x, lab, warmup=1)      # one eager step inside (it is a real update)
+            assert step.warmup_steps == 1 and opt.global_step == 1 and step.launches_per_step > 100
+            ls.append(step.loss.item())
+            for _ in range(3):
+                ls.append(GraphedTrainStep.check(step(x, lab).item()))
+        else:
+            for _ in range(4):
+                opt.zero_grad(set_to_none=True)
+                opt.prepare_step()
+                loss = loss_fn(net(x), lab)
+                loss.backward()
+                opt.step()
+                ls.append(loss.item())
+        runs.append((ls, [p.detach().clone() for p in params], ema, opt.global_step))
+    (l0, p0, e0, s0), (l1, p1, e1, s1) = runs
+    print(f"[graph] eager losses {l0}, graphed losses {l1}")
+    assert s0 == s1 == 4
+    assert all(abs(a - b) <= 2e-2 * abs(a) for a, b in zip(l0, l1)) and abs(l0[0] - l1[0]) <= 1e-4 * abs(l0[0])
+    tot = cnt = 0.0
+    for a, b in zip(p0 + e0, p1 + e1):
+        d = (a - b).abs()
+        assert torch.isfinite(b).all() and d.max().item() <= 2 * 4 * 6e-4 * 1.05
+        tot += d.sum().item(); cnt += d.numel()
+    assert tot / cnt <= 0.25 * 6e-4

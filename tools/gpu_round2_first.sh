@@ -11,13 +11,14 @@ echo "pytest (staged, strict) exit=$?" >> gpurun_out/${tag}_staged_strict.log
 timeout 200 python __graft_entry__.py smoke >> gpurun_out/${tag}_gpu_tests.log 2>&1
 timeout 400 python bench.py --no-cpu-baseline --steps 10 > gpurun_out/${tag}_bench_stock_glue.json 2> gpurun_out/${tag}_bench_stock_glue.err
 timeout 400 python bench.py --no-cpu-baseline --steps 10 --fused-optimizer --packed-labels > gpurun_out/${tag}_bench_fused_glue.json 2> gpurun_out/${tag}_bench_fused_glue.err
+timeout 400 python bench.py --no-cpu-baseline --steps 10 --cuda-graph > gpurun_out/${tag}_bench_cuda_graph.json 2> gpurun_out/${tag}_bench_cuda_graph.err
 timeout 400 python tools/probe_torch_gpu_baseline.py > gpurun_out/${tag}_torch_gpu_baseline.log 2>&1
 timeout 300 python tools/probe_cuda_graph.py > gpurun_out/${tag}_cuda_graph.log 2>&1
 grep -E "passed|failed|FAILED|XPASS|XFAIL|xpassed|xfailed|smoke" gpurun_out/${tag}_gpu_tests.log | tail -60
 tail -5 gpurun_out/${tag}_staged_strict.log
 python - <<PY
 import json
-for f in ("stock_glue", "fused_glue"):
+for f in ("stock_glue", "fused_glue", "cuda_graph"):
     try:
         d = json.loads(open(f"gpurun_out/${tag}_bench_{f}.json").read().strip().splitlines()[-1])
         print(f, "value", round(d["value"], 1), "ms", round(d["ms_per_step"], 2), "e2e ms", round(d["e2e"]["ms_per_step"], 2),
@@ -25,4 +26,4 @@ for f in ("stock_glue", "fused_glue"):
     except Exception as e:
         print(f, "unreadable:", e)
 PY
-tail -8 gpurun_out/${tag}_torch_gpu_baseline.log; tail -8 gpurun_out/${tag}_cuda_graph.log
+tail -3 gpurun_out/${tag}_bench_cuda_graph.err; tail -8 gpurun_out/${tag}_torch_gpu_baseline.log; tail -8 gpurun_out/${tag}_cuda_graph.log
