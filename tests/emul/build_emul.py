@@ -17,7 +17,10 @@ LIB = os.path.join(OUT, "librsb_emul.so")
 SOURCES = ["train_glue.cu", "infer.cu", "augment.cu", "seg_loss.cu", "morph.cu", "elementwise.cu", "stem_head.cu", "report_loss.cu"]
 # kernels that use __syncthreads / warp shuffles: their blocks run as real threads
 COOPERATIVE = {"grad_sqnorm_kernel", "clip_adamw_ema_kernel", "aug_stats_partial_kernel", "aug_stats_final_kernel",
-               "seg_loss_pass1_kernel", "seg_loss_finalize_kernel", "seg_loss_pass2_kernel"}
+               "seg_loss_pass1_kernel", "seg_loss_finalize_kernel", "seg_loss_pass2_kernel",
+               # no barrier inside, but lock-free: run them as 256 truly concurrent threads so that the atomicMin union-find and
+               # the flatten pass are exercised under real interleavings, not only under the sequential schedule
+               "cc_merge_kernel", "cc_flatten_kernel"}
 
 # files whose every kernel runs as real threads (shared-memory statistics flushes in helper functions)
 ALL_COOPERATIVE = set()
