@@ -631,7 +631,7 @@ class B200UNet(nn.Module):
         return st
 
     def forward(self, x):
-        if not x.is_cuda:
+        if not ops._on_device(x):
             raise RuntimeError("B200UNet has no CPU path: inputs must live on a CUDA (sm_100a) device")
         names, params = zip(*self.named_parameters())
         dtype = torch.bfloat16 if self.precision == "bf16" else torch.float32

@@ -98,7 +98,7 @@ def build() -> str:
     os.makedirs(OUT, exist_ok=True)
     h = hashlib.sha256()
     texts = []
-    for s in SOURCES + [os.path.join(HERE, "cuda_emul.h"), os.path.abspath(__file__), "rsb_common.cuh"]:
+    for s in SOURCES + [os.path.join(HERE, "cuda_emul.h"), os.path.join(HERE, "conv3_double.cpp"), os.path.abspath(__file__), "rsb_common.cuh"]:
         p = s if os.path.isabs(s) else os.path.join(CSRC, s)
         t = open(p).read()
         h.update(t.encode())
@@ -122,7 +122,8 @@ def build() -> str:
                 'extern "C" const char* rsb_last_error(void) { return rsb::g_last_error; }\n'
                 'extern "C" int rsb_num_sms(void) { return 4; }\n')          # 4 "SMs": small grids keep the emulation quick
     cpps.append(os.path.join(OUT, "api_emul.cpp"))
-    cmd = ["g++", "-std=c++20", "-O1", "-g", "-pthread", "-shared", "-fPIC", "-ffp-contract=off", "-Wno-attributes", "-I", HERE, "-I", OUT,
+    cpps.append(os.path.join(HERE, "conv3_double.cpp"))       # naive stand-in for the tensor-core kernels (see its header)
+    cmd = ["g++", "-std=c++20", "-O2", "-g", "-pthread", "-shared", "-fPIC", "-ffp-contract=off", "-Wno-attributes", "-I", HERE, "-I", OUT,
            "-o", LIB] + cpps
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
