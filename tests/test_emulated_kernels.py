@@ -201,3 +201,10 @@ def test_emulated_train_step_vs_oracle(emulated):
     opt.step()
     moved = max((a - b).abs().max().item() for a, b in zip(before, [p.detach() for p in net.parameters()]))
     assert 1e-5 < moved <= 6e-4 * 1.1
+
+
+@full
+def test_emulated_singleconv_unet_vs_reference_and_oracle(emulated, golden):
+    """block='SingleConv' engine (post-activation path, act_backward_stats) end to end on the CPU."""
+    import test_unet_gpu as U
+    U.test_singleconv_unet_vs_reference_and_oracle(CPU, golden, "fp32")
