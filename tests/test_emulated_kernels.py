@@ -208,3 +208,48 @@ def test_emulated_singleconv_unet_vs_reference_and_oracle(emulated, golden):
     """block='SingleConv' engine (post-activation path, act_backward_stats) end to end on the CPU."""
     import test_unet_gpu as U
     U.test_singleconv_unet_vs_reference_and_oracle(CPU, golden, "fp32")
+
+
+@full
+def test_emulated_static_gradient_steps_equal_fresh_gradient_steps(emulated):
+    """Precondition of GraphedTrainStep (rsuper_b200/graph_step.py): the captured body starts with
+    zero_grad(set_to_none=False) so that gradients keep their addresses; autograd then ACCUMULATES the engine's gradients into
+    the zeroed buffers.  Gradients obtained that way (buffers pre-filled with garbage) must equal fresh gradients — compared
+    directly, because Adam's update is invariant to a gradient scale — and the optimizer's device table must not be rebuilt
+    between such steps."""
+    from oracle import losses_ref as LR
+    from oracle import synth
+    from oracle.unet_ref import synthetic_image, synthetic_state_dict
+    from rsuper_b200 import losses
+    from rsuper_b200.optim import B200AdamW
+    from rsuper_b200.unet import B200UNet
+    classes = ["organ", "pancreatic_lesion"]
+    x = synthetic_image(1, 32, 32, 32, seed=3)
+    lab = synth.make_batch(["mask"], classes, (32, 32, 32), seed=2)["label"]
+    args = LR.default_args(report_volume_loss_basic=0.0)
+    args.nan_check = False
+    grads = []
+    for static in (False, True):
+        net = B200UNet(1, 8, num_classes=2, precision="bf16")
+        net.load_state_dict(synthetic_state_dict(8, 2))
+        params = list(net.parameters())
+        opt = B200AdamW(params, lr=6e-4, weight_decay=0.05, max_norm=1.0, capturable=True)
+        if static:
+            for p in params:
+                p.grad = torch.full_like(p, 7.0)         # stale content that zero_grad(set_to_none=False) must clear
+        tables = []
+        for step in range(2):
+            opt.zero_grad(set_to_none=not static)
+            opt.prepare_step()
+            loss = losses.calculate_loss(net(x), lab, None, args, None, None, None, None, classes)["overall"]
+            loss.backward()
+            if step == 0:
+                grads.append([p.grad.detach().clone() for p in params])
+            opt.step()
+            tables.append(opt._tables[0][1].data_ptr())
+        if static:
+            assert tables[0] == tables[1]            # same gradient addresses -> the device table was not rebuilt
+        assert opt.global_step == 2
+    for i, (a, b) in enumerate(zip(*grads)):
+        err = ((a - b).norm() / (a.norm() + 1e-20)).item()
+        assert err <= 0.15, (i, err)                 # run-to-run bf16 + atomics-order noise on this 2^3-bottom toy net is ~2 %; a stale or doubled gradient is >= 100 % off
