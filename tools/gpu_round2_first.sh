@@ -14,6 +14,10 @@ timeout 400 python bench.py --no-cpu-baseline --steps 10 --fused-optimizer --pac
 timeout 400 python bench.py --no-cpu-baseline --steps 10 --cuda-graph > gpurun_out/${tag}_bench_cuda_graph.json 2> gpurun_out/${tag}_bench_cuda_graph.err
 timeout 400 python tools/probe_torch_gpu_baseline.py > gpurun_out/${tag}_torch_gpu_baseline.log 2>&1
 timeout 300 python tools/probe_cuda_graph.py > gpurun_out/${tag}_cuda_graph.log 2>&1
+if [ "$2" != "noncu" ]; then
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:clip_adamw_ema -c 2 -o gpurun_out/${tag}_clip_adamw_ema_full \
+   python bench.py --steps 1 --warmup 3 --no-cpu-baseline --fused-optimizer > gpurun_out/${tag}_ncu_optimizer.log 2>&1
+fi
 grep -E "passed|failed|FAILED|XPASS|XFAIL|xpassed|xfailed|smoke" gpurun_out/${tag}_gpu_tests.log | tail -60
 tail -5 gpurun_out/${tag}_staged_strict.log
 python - <<PY
