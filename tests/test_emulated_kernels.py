@@ -61,7 +61,10 @@ def emulated(monkeypatch, emu_handle):
 import test_widen_gpu as W  # noqa: E402  (the GPU test bodies: plain functions of (device, ...))
 
 
-@pytest.mark.parametrize("with_ema,max_norm", [(True, 1.0), (False, 1.0), (True, None)])
+_slow = pytest.mark.skipif(os.environ.get("RSB_EMUL_FULL") != "1", reason="slow under emulation; run with RSB_EMUL_FULL=1")
+
+
+@pytest.mark.parametrize("with_ema,max_norm", [(True, 1.0), pytest.param(False, 1.0, marks=_slow), pytest.param(True, None, marks=_slow)])
 def test_emulated_fused_clip_adamw_ema_matches_torch(emulated, with_ema, max_norm):
     W.test_fused_clip_adamw_ema_matches_torch(CPU, with_ema, max_norm)
 
@@ -89,6 +92,7 @@ def test_emulated_organ_gating_matches_oracle(emulated):
     W.test_organ_gating_matches_oracle(CPU)
 
 
+@_slow
 def test_emulated_intensity_augmentations_match_reference_golden(emulated):
     W.test_intensity_augmentations_match_reference_golden(CPU)
 
