@@ -11,18 +11,6 @@ for p in (ROOT, os.path.join(ROOT, "r-super_b200")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA (sm_100a) device; run with -m gpu on the B200 box")
-    config.addinivalue_line("markers", "staged: GPU test written after the round's GPU budget was spent — never run on "
-                                       "hardware yet; reported as XPASS / XFAIL (non-strict) instead of stopping the suite")
-
-
-def pytest_collection_modifyitems(config, items):
-    """`staged` tests exercise kernels that compile for sm_100a but have not had their first run on a B200 (no GPU in the
-    build container, gpurun budget exhausted).  They run with the suite, last, as non-strict xfail: a pass shows up as
-    XPASS, a failure as XFAIL with its traceback under -rx, and neither masks the verified tests.  Remove the marker from
-    a test once it has been seen green on hardware."""
-    for item in items:
-        if item.get_closest_marker("staged") is not None:
-            item.add_marker(pytest.mark.xfail(strict=False, reason="staged: first run on a B200 pending"))
 
 
 @pytest.fixture(scope="session")

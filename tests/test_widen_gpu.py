@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.staged, pytest.mark.timeout(600)]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
 
 def rel(a, b):
