@@ -319,7 +319,8 @@ int rsb_ball_weight_map(float* wmap, const uint8_t* pseudo, const uint8_t* dilat
  * ------------------------------------------------------------------------------------------ */
 typedef struct RsbOptTensor {
   float* p;     /* parameter (fp32) */
-  float* g;     /* gradient; multiplied by the clip coefficient in place */
+  float* g;     /* gradient; multiplied by the clip coefficient in place.  NULL = no gradient this step: the row is left
+                   out of the norm and of AdamW (m, v unused) and only its EMA copy moves */
   float* m;     /* exp_avg */
   float* v;     /* exp_avg_sq */
   float* ema;   /* EMA copy of the parameter, or NULL when has_ema = 0 */

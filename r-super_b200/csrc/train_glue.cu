@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(OPT_THREADS) grad_sqnorm_kernel(const RsbOptTe
   float acc = 0.f;
   for (long long chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
     const RsbOptTensor t = tab[find_tensor(tab, n_tensors, chunk)];
+    if (t.g == nullptr) continue;  // EMA-only row (parameter without a gradient this step)
     const long long begin = (chunk - t.chunk_begin) * OPT_CHUNK;
     const long long rem = t.n - begin;
     const int cnt = rem < OPT_CHUNK ? static_cast<int>(rem) : OPT_CHUNK;
@@ -120,6 +121,15 @@ __global__ void __launch_bounds__(OPT_THREADS) clip_adamw_ema_kernel(const RsbOp
     const long long begin = (chunk - t.chunk_begin) * OPT_CHUNK;
     const long long rem = t.n - begin;
     const int cnt = rem < OPT_CHUNK ? static_cast<int>(rem) : OPT_CHUNK;
+    if (t.g == nullptr) {
+      // no gradient this step: torch's AdamW skips the parameter, update_ema_variables (training/utils.py:154-158) does not
+      if (HasEma && t.ema != nullptr) {
+        const float* p = t.p + begin;
+        float* e = t.ema + begin;
+        for (int i = threadIdx.x; i < cnt; i += OPT_THREADS) e[i] = h.ema_alpha * e[i] + h.one_minus_ema_alpha * p[i];
+      }
+      continue;
+    }
     float* g = t.g + begin;
     float* p = t.p + begin;
     float* m = t.m + begin;

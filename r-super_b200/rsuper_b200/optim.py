@@ -61,7 +61,19 @@ class B200AdamW(torch.optim.Optimizer):
         rows, sig = [], []
         begin = 0
         for p in group["params"]:
-            if p.grad is None or p.numel() == 0:
+            if p.numel() == 0:
+                continue
+            if p.grad is None:
+                # torch's AdamW skips a parameter without a gradient; update_ema_variables (training/utils.py:154-158) still
+                # moves its EMA copy: an EMA-only row (g = NULL)
+                e = ema_of.get(id(p))
+                if e is not None:
+                    if not (ops._on_device(p) and ops._on_device(e) and e.dtype == torch.float32 and e.is_contiguous()
+                            and p.dtype == torch.float32 and p.is_contiguous()):
+                        raise RuntimeError("B200AdamW: parameters / EMA tensors must be contiguous CUDA fp32")
+                    rows.append((p.data_ptr(), 0, 0, 0, e.data_ptr(), p.numel(), begin))
+                    sig.append(rows[-1][:5])
+                    begin += (p.numel() + chunk - 1) // chunk
                 continue
             if not ops._on_device(p):
                 raise RuntimeError("B200AdamW has no CPU path: parameters must live on a CUDA (sm_100a) device")
@@ -81,7 +93,7 @@ class B200AdamW(torch.optim.Optimizer):
                          e.data_ptr() if e is not None else 0, n, begin))
             sig.append(rows[-1][:5])
             begin += (n + chunk - 1) // chunk
-        if not rows:
+        if not any(r[1] for r in rows):
             return None
         cached = self._tables.get(gi)
         if cached is not None and cached[0] == sig:
@@ -98,19 +110,23 @@ class B200AdamW(torch.optim.Optimizer):
 
     def _step_scalars(self, group):
         """(adam step t, EMA alpha) of the NEXT update of a group (t = torch's per-parameter `step` + 1; training/utils.py:156)."""
-        steps = {int(self.state[p]["step"].item()) for p in group["params"] if p in self.state and len(self.state[p])}
+        steps = {int(self.state[p]["step"].item()) if (p in self.state and len(self.state[p])) else 0
+                 for p in group["params"] if p.grad is not None and p.numel()}
         if len(steps) > 1:
-            raise RuntimeError("B200AdamW: parameters of a group must share their step count")
+            raise RuntimeError("B200AdamW: the parameters that receive a gradient in one step must share their step count "
+                               f"(found {sorted(steps)}): one launch carries one pair of bias corrections")
         t = (steps.pop() if steps else 0) + 1
         return t, min(1.0 - 1.0 / (self.global_step + 1), self.ema_alpha)
 
     @torch.no_grad()
-    def prepare_step(self):
+    def prepare_step(self, global_step: Optional[int] = None):
         """capturable mode: upload the scalars of the next update (bias corrections for step t, the group's current lr,
         the EMA warm-up alpha) into the device block the kernel reads.  Call once before every `step()` / graph replay;
         after a replay call `finish_step()` so that the host-side counters follow."""
         if not self.capturable:
             raise RuntimeError("prepare_step() is for B200AdamW(capturable=True)")
+        if global_step is not None:
+            self.global_step = int(global_step)
         if len(self.param_groups) != 1:
             raise NotImplementedError("B200AdamW(capturable=True) supports one param group")
         group = self.param_groups[0]
@@ -136,8 +152,35 @@ class B200AdamW(torch.optim.Optimizer):
         self.global_step += 1
         self._prepared = False
 
+    # -- checkpoints: update_ema_variables' global_step (train_ddp.py:308: i + epoch * len(loader)) travels with the state ----
+    def state_dict(self):
+        sd = super().state_dict()
+        sd["b200_global_step"] = int(self.global_step)   # extra top-level key: torch.optim.AdamW.load_state_dict ignores it
+        return sd
+
+    def load_state_dict(self, state_dict):
+        sd = dict(state_dict)
+        gs = sd.pop("b200_global_step", None)
+        super().load_state_dict(sd)
+        if gs is None:
+            # a checkpoint written by the reference's torch AdamW: the loop step equals the number of updates taken
+            steps = [int(st["step"]) for st in self.state.values() if "step" in st]
+            gs = max(steps) if steps else 0
+        self.global_step = int(gs)
+        for st in self.state.values():                   # host scalar steps like torch's non-capturable AdamW
+            if "step" in st and isinstance(st["step"], torch.Tensor) and st["step"].device.type != "cpu":
+                st["step"] = st["step"].detach().cpu()
+        self._tables.clear()
+        self._prepared = False
+
     @torch.no_grad()
-    def step(self, closure=None):
+    def step(self, closure=None, global_step: Optional[int] = None):
+        """global_step: the loop step the reference hands to update_ema_variables (train_ddp.py:357); default = the
+        optimizer's own counter (number of step() calls, persisted in state_dict())."""
+        if global_step is not None:
+            if self.capturable and self._prepared and int(global_step) != self.global_step:
+                raise RuntimeError("B200AdamW(capturable=True): pass global_step to prepare_step(), not step()")
+            self.global_step = int(global_step)
         loss = None
         if closure is not None:
             with torch.enable_grad():

@@ -162,6 +162,7 @@ class _Engine:
         # the same SMs, and their persistent CTAs fill the tails of the dgrad launches; the weight packing overlaps the stem.
         self._side = None
         self._side_keep = []
+        self._plan_key = None
         self.plan = None  # ops.PackPlan: persistent packed weight images, refreshed by ONE launch per forward
 
     # ---- zeroed statistics storage: one fill per pass instead of ~50 tiny ones --------------------------
@@ -199,25 +200,28 @@ class _Engine:
         images; conv1 || shortcut merged row-wise without a torch.cat) from the current values."""
         if self.block == "SingleConv":
             pairs = [(P[pre + "conv.conv.weight"], None) for pre in self.SINGLE_CONVS]
-            if self.plan is None or self.plan.ptr_key != ops.PackPlan.pointer_key(pairs):
+            key = ops.PackPlan.pointer_key(pairs)
+            if self.plan is None or self._plan_key != key:
                 jobs = []
                 for pre, (wa, _) in zip(self.SINGLE_CONVS, pairs):
                     jobs.append((pre + "c", wa, None, False))
                     jobs.append((pre + "cT", wa, None, True))
-                self.plan = ops.PackPlan(jobs, split=self.split)
+                self.plan, self._plan_key = ops.PackPlan(jobs, split=self.split), key
             self.plan.refresh()
             return
         pairs = []
         for pre, has_sc in self.BLOCKS:
             pairs.append((P[pre + "conv1.conv.weight"], P[pre + "shortcut.conv.weight"] if has_sc else None))
             pairs.append((P[pre + "conv2.conv.weight"], None))
-        if self.plan is None or self.plan.ptr_key != ops.PackPlan.pointer_key(pairs):
+        # (the key is the parameter storage: one entry per conv — the plan itself holds two jobs per conv, fprop + dgrad image)
+        key = ops.PackPlan.pointer_key(pairs)
+        if self.plan is None or self._plan_key != key:
             jobs = []
             for (pre, _), k in zip(self.BLOCKS, range(0, len(pairs), 2)):
                 for tag, (wa, wb) in (("c1", pairs[k]), ("c2", pairs[k + 1])):
                     jobs.append((pre + tag, wa, wb, False))
                     jobs.append((pre + tag + "T", wa, wb, True))
-            self.plan = ops.PackPlan(jobs, split=self.split)
+            self.plan, self._plan_key = ops.PackPlan(jobs, split=self.split), key
         self.plan.refresh()
 
     # ---- operand / conv / wgrad helpers ------------------------------------------------------------
@@ -568,7 +572,8 @@ class _UNetFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, engine, names, num_classes, *params):
         P = dict(zip(names, [p.detach() for p in params]))
-        need_grad = any(p.requires_grad for p in params)
+        # under torch.no_grad() (sliding-window inference, validation, the EMA net) nothing is kept for a backward pass
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         with torch.no_grad():
             logits, saved = engine.forward(x.detach().contiguous(), P, num_classes, save=need_grad)
         ctx.engine, ctx.names, ctx.saved_acts = engine, names, saved

@@ -69,6 +69,10 @@ def test_emulated_fused_clip_adamw_ema_matches_torch(emulated, with_ema, max_nor
     W.test_fused_clip_adamw_ema_matches_torch(CPU, with_ema, max_norm)
 
 
+def test_emulated_fused_optimizer_resume_and_gradless_parameters(emulated):
+    W.test_fused_optimizer_resume_and_gradless_parameters(CPU)
+
+
 def test_emulated_fused_clip_adamw_ema_matches_reference_golden(emulated):
     W.test_fused_clip_adamw_ema_matches_reference_golden(CPU)
 

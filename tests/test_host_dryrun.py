@@ -69,6 +69,31 @@ def test_basicblock_train_step_launch_sequence(monkeypatch, precision):
     assert flops > 0 and all(p.grad is not None and p.grad.shape == p.shape for p in net.parameters())
 
 
+@pytest.mark.parametrize("block", ["BasicBlock", "SingleConv"])
+def test_pack_plan_is_built_once_across_forwards(monkeypatch, block):
+    """The packed-weight plan (images + device job table, uploaded with a host->device copy) is keyed on the parameter
+    storage: a second forward with the same parameters must reuse it (a rebuild per step is a hidden H2D copy that also
+    breaks CUDA-graph capture), a re-allocated parameter must rebuild it."""
+    from rsuper_b200 import ops
+    from rsuper_b200 import unet as U
+    built = []
+    real_init = ops.PackPlan.__init__
+    monkeypatch.setattr(ops.PackPlan, "__init__", lambda self, *a, **k: (built.append(1), real_init(self, *a, **k))[1])
+    with recording(monkeypatch):
+        net = U.B200UNet(1, 8, num_classes=2, block=block)
+        names, params = zip(*net.named_parameters())
+        eng = U._Engine(8, 0.0, torch.bfloat16, block)
+        x = synthetic_image(1, 32, 32, 32, seed=1)
+        for _ in range(3):
+            U._UNetFunction.apply(x, eng, names, 2, *params)
+        assert len(built) == 1
+        w = dict(net.named_parameters())["down2.conv.1.conv1.conv.weight" if block == "BasicBlock" else "down2.conv.1.conv.conv.weight"]
+        w.data = w.data.clone()                                  # re-allocated storage (e.g. load_state_dict(assign=True))
+        names, params = zip(*net.named_parameters())
+        U._UNetFunction.apply(x, eng, names, 2, *params)
+        assert len(built) == 2
+
+
 def test_singleconv_train_step_launch_sequence(monkeypatch):
     with recording(monkeypatch) as rec:
         net, out, n_fwd = _step(rec, "SingleConv", "bf16")

@@ -106,6 +106,84 @@ def test_fused_clip_adamw_ema_matches_reference_golden(cuda_dev):
         np.testing.assert_allclose(opt.state[p]["exp_avg_sq"].cpu().numpy(), gold[f"exp_avg_sq_{i}"], rtol=1e-5, atol=1e-12)
 
 
+def test_fused_optimizer_resume_and_gradless_parameters(cuda_dev):
+    """(1) state_dict() -> fresh B200AdamW.load_state_dict() resumes bit-identically: the EMA warm-up alpha
+    min(1 - 1/(global_step+1), ema_alpha) follows the persisted loop step (training/utils.py:156) instead of restarting at 0.
+    (2) A checkpoint of torch's AdamW (what the reference writes) loads, global_step derived from the per-parameter steps.
+    (3) A parameter without a gradient is skipped by AdamW like in torch but its EMA copy still moves
+    (update_ema_variables updates every parameter), checked against oracle/train_glue_ref on the other rows."""
+    from oracle.train_glue_ref import clip_adamw_ema_step
+    from rsuper_b200.optim import B200AdamW
+    hyper = dict(lr=6e-4, betas=(0.9, 0.999), eps=1e-5, weight_decay=0.05)
+
+    def make():
+        ps = [torch.nn.Parameter(t) for t in _param_set(cuda_dev, 0)]
+        ema = [p.detach().clone() + 0.25 for p in ps]
+        return ps, ema, B200AdamW(ps, max_norm=1.0, ema_params=ema, ema_alpha=0.99, **hyper)
+
+    def feed(ps, step, skip=()):
+        for i, (p, g) in enumerate(zip(ps, _param_set(cuda_dev, 30 + step))):
+            p.grad = None if i in skip else (g.clone() if p.data_ptr() % 16 == 0 else
+                                             torch.cat([g.new_zeros(1), g.reshape(-1)])[1:].view(g.shape))
+
+    # straight run of 4 steps
+    ps_a, ema_a, opt_a = make()
+    for step in range(4):
+        feed(ps_a, step); opt_a.step()
+    # 2 steps, checkpoint, fresh objects, 2 more steps
+    ps_b, ema_b, opt_b = make()
+    for step in range(2):
+        feed(ps_b, step); opt_b.step()
+    ckpt = opt_b.state_dict()
+    assert ckpt["b200_global_step"] == 2
+    ps_c = [torch.nn.Parameter(p.detach().clone()) for p in ps_b]
+    ema_c = [e.clone() for e in ema_b]
+    opt_c = B200AdamW(ps_c, max_norm=1.0, ema_params=ema_c, ema_alpha=0.99, **hyper)
+    opt_c.load_state_dict(ckpt)
+    assert opt_c.global_step == 2
+    for step in range(2, 4):
+        feed(ps_c, step); opt_c.step()
+    for a, c in zip(ps_a + ema_a, ps_c + ema_c):
+        assert torch.equal(a.detach(), c.detach())
+    # torch AdamW checkpoint (no b200_global_step key): the loop step is recovered from the parameter steps
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ps_b]
+    opt_t = torch.optim.AdamW(ref, foreach=False, fused=False, **hyper)
+    for step in range(3):
+        feed(ref, step); opt_t.step()
+    opt_d = B200AdamW([torch.nn.Parameter(p.detach().clone()) for p in ref], max_norm=1.0, **hyper)
+    opt_d.load_state_dict(opt_t.state_dict())
+    assert opt_d.global_step == 3
+    # explicit loop step like the reference's update_ema_variables(net, ema_net, alpha, step)
+    ps_e, ema_e, opt_e = make()
+    feed(ps_e, 0); opt_e.step(global_step=500)
+    assert opt_e.global_step == 501
+
+    # gradient-less parameter: rows 1 and 4 have grad None at step 1
+    ps_g, ema_g, opt_g = make()
+    feed(ps_g, 0); opt_g.step()
+    before_p = [p.detach().clone() for p in ps_g]
+    before_e = [e.clone() for e in ema_g]
+    feed(ps_g, 1, skip=(1, 4)); opt_g.step()
+    alpha = min(1 - 1 / 2, 0.99)
+    for i in (1, 4):
+        assert torch.equal(ps_g[i].detach(), before_p[i])                       # AdamW left it alone
+        torch.testing.assert_close(ema_g[i], alpha * before_e[i] + (1 - alpha) * before_p[i], rtol=1e-6, atol=1e-7)
+        assert float(opt_g.state[ps_g[i]]["step"]) == 1
+    # the rows that did get a gradient follow the oracle (norm over those rows only, like clip_grad_norm_)
+    ps_o, ema_o, opt_o = make()
+    feed(ps_o, 0); opt_o.step()
+    keep = [0, 2, 3, 5]
+    P = [ps_o[i].detach().clone().contiguous() for i in keep]
+    G = [g.clone() for i, g in enumerate(_param_set(cuda_dev, 31)) if i in keep]
+    M = [opt_o.state[ps_o[i]]["exp_avg"].clone() for i in keep]
+    V = [opt_o.state[ps_o[i]]["exp_avg_sq"].clone() for i in keep]
+    E = [ema_o[i].clone().contiguous() for i in keep]
+    clip_adamw_ema_step(P, G, M, V, E, step=2, global_step=1, max_norm=1.0, ema_alpha=0.99, **hyper)
+    for j, i in enumerate(keep):
+        torch.testing.assert_close(ps_g[i].detach(), P[j], rtol=2e-6, atol=2e-7)
+        torch.testing.assert_close(ema_g[i], E[j], rtol=2e-6, atol=2e-7)
+
+
 def test_fused_optimizer_rejects_cpu_parameters():
     from rsuper_b200.optim import B200AdamW
     p = torch.nn.Parameter(torch.zeros(8))
