@@ -61,6 +61,7 @@ struct FpropDev {
   int b_stages;
   int issuers;  // 1 or 2 MMA issuer warps
   int acc_stages;  // TMEM accumulator stages: 2..4 (as many as fit 512 columns)
+  int groups;      // parity mode (parts > 1): accumulator GROUPS of one item instead of stages (see the generic issuer); else 1
   int tps;      // filter taps per B stage: 3 (one kh row) for narrow N tiles, else 1
   uint32_t b_tap_bytes, b_stage_bytes, a_unit_bytes;
   long long* dbg;
@@ -380,10 +381,29 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_const
               const int kh = t / 3, kw = t - kh * 3;
               const uint32_t b_lo = b_stage_lo + tt * tap16;
               const uint32_t a_tap_lo = a_unit_lo + static_cast<uint32_t>(kh * 10 + kw) * 4u;  // 64-byte rows
+              // Parity mode (a.groups = G > 1).  The tensor pipe adds every MMA into the fp32 accumulator with TRUNCATION
+              // toward zero (~0.3 ulp of the running sum per MMA, all of one sign: tools/probe_accum_error.py measures a
+              // relative error of 4.6e-9 * K, i.e. 7e-5 for a 576-channel layer, and six split products are worse than
+              // three).  So one item's K loop is spread over G accumulator groups that the epilogue adds in fp32 registers
+              // with round-to-nearest: the hi*hi taps go round-robin to groups 0..G-2 (each chain is G-1 times shorter and
+              // the chains' errors no longer share a sign), every low-order product (hi*lo, lo*hi, ...: 2^-9 of the result,
+              // their truncation is irrelevant there) goes to group G-1 instead of truncating the big sums.
+              uint32_t d_g = d_base;
+              bool first_g = (c == 0) && (t == 0);
+              if (a.groups > 1) {
+                if (c < a.nchunks) {
+                  const int idx = cb * 9 + t;
+                  d_g = tmem_base + static_cast<uint32_t>(idx % (a.groups - 1)) * acc_cols;
+                  first_g = idx < a.groups - 1;
+                } else {
+                  d_g = tmem_base + static_cast<uint32_t>(a.groups - 1) * acc_cols;
+                  first_g = (c == a.nchunks) && (t == 0);
+                }
+              }
               for (int ks = 0; ks < ksteps; ++ks) {
                 const uint32_t a_ks = a_tap_lo + ks * 2u;   // 16 channels = 32 bytes inside the row
                 const uint32_t b_ks = b_lo + ks * 16u;      // two 8-wide k groups = 256 bytes
-                if (c == 0 && t == 0 && ks == 0) {
+                if (first_g && ks == 0) {
                   // first touch of every accumulator: plane p initialises output plane q = p (kd = 0)
 #pragma unroll
                   for (int p = 0; p < NP; ++p) {
@@ -391,17 +411,17 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_const
                     if (p < PZ) {
                       if (p > 0) {
                         const int qlo = p - 2 > 0 ? p - 2 : 0;
-                        umma_bf16_ss(d_base + pl_d[p], ad, desc_join(b_hi, b_ks + pl_b[p]), make_idesc_bf16(128, (p - qlo) * a.NT, 0, 0), 1u);
+                        umma_bf16_ss(d_g + pl_d[p], ad, desc_join(b_hi, b_ks + pl_b[p]), make_idesc_bf16(128, (p - qlo) * a.NT, 0, 0), 1u);
                       }
-                      umma_bf16_ss(d_base + p * a.NT, ad, desc_join(b_hi, b_ks + 2 * slot16), idesc1, 0u);
+                      umma_bf16_ss(d_g + p * a.NT, ad, desc_join(b_hi, b_ks + 2 * slot16), idesc1, 0u);
                     } else {
-                      umma_bf16_ss(d_base + pl_d[p], ad, desc_join(b_hi, b_ks + pl_b[p]), pl_idesc[p], 1u);
+                      umma_bf16_ss(d_g + pl_d[p], ad, desc_join(b_hi, b_ks + pl_b[p]), pl_idesc[p], 1u);
                     }
                   }
                 } else {
 #pragma unroll
                   for (int p = 0; p < NP; ++p)
-                    umma_bf16_ss(d_base + pl_d[p], desc_join(a_hi, a_ks + pl_a[p]), desc_join(b_hi, b_ks + pl_b[p]), pl_idesc[p], 1u);
+                    umma_bf16_ss(d_g + pl_d[p], desc_join(a_hi, a_ks + pl_a[p]), desc_join(b_hi, b_ks + pl_b[p]), pl_idesc[p], 1u);
                 }
               }
             }
@@ -638,11 +658,17 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_const
           __syncwarp();
           tmem_ld16(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * acc_cols + p * a.NT + cc, r);
           tmem_ld_wait();
-          if (nvalid <= 0 || !row_ok) continue;
-          const size_t vox = vox0 + p * vox_plane;
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          for (int g = 1; g < a.groups; ++g) {   // parity mode: the item's accumulator groups, added with round-to-nearest
+            tmem_ld16(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + g * acc_cols + p * a.NT + cc, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(r[j]);
+          }
+          if (nvalid <= 0 || !row_ok) continue;
+          const size_t vox = vox0 + p * vox_plane;
           if (has_aux) {
             float xh[16];
             cur.to_float(xh);
@@ -955,6 +981,10 @@ extern "C" int rsb_conv3_forward(const RsbConv3Args* p, void* stream) {
   RSB_REQUIRE(sms > 0, "conv3: could not query the SM count");
 
   int PZ = p->planes_per_item;
+  if (PZ == 0 && d.parts > 1) {
+    // parity mode: accumulator GROUPS instead of stages (kernel comment) — few planes per item leave more groups
+    PZ = (d.NT <= 32 && p->D >= 2) ? 2 : 1;
+  }
   if (PZ == 0) {
     // as many planes per item as the double-buffered accumulators allow (more planes = wider merged MMAs and
     // more reuse of every weight slice: an item streams the whole packed weight tensor of its N tile from L2, so the
@@ -972,17 +1002,24 @@ extern "C" int rsb_conv3_forward(const RsbConv3Args* p, void* stream) {
   RSB_REQUIRE(2 * PZ * d.NT <= 512, "conv3: 2*PZ*n_tile = %d exceeds the 512 TMEM columns", 2 * PZ * d.NT);
   d.acc_stages = 512 / (PZ * d.NT);
   if (d.acc_stages > 4) d.acc_stages = 4;
+  d.groups = 1;
+  if (d.parts > 1 && getenv("RSB_FPROP_NO_GROUPS") == nullptr) {
+    d.groups = 512 / (PZ * d.NT);
+    if (d.groups > 8) d.groups = 8;   // groups - 1 <= 9 taps of the first chunk: every group gets its first touch
+    if (d.groups < 2) d.groups = 1;
+  }
   {
     const char* e = getenv("RSB_FPROP_ACC_STAGES");
     if (e && e[0] >= '2' && e[0] <= '4' && (e[0] - '0') <= d.acc_stages) d.acc_stages = e[0] - '0';
   }
+  if (d.groups > 1) d.acc_stages = 1;   // the groups occupy the stages: one item in flight
   RSB_REQUIRE(3 * d.NT <= 256 || PZ <= 2, "conv3: merged N exceeds 256");
   {
     // One issuer warp by default.  The two-issuer schedule (alternate taps, see the kernel) is 15-30 % faster on the
     // layers where it runs, but it hit timing-dependent launch failures on B200 (first seen with N = 256 merged MMAs,
     // then inside the full network) that are not understood yet; it stays available for experiments only.
     const char* e = getenv("RSB_FPROP_ISSUERS");
-    d.issuers = (e && e[0] == '2') ? 2 : 1;
+    d.issuers = (e && e[0] == '2' && d.groups == 1) ? 2 : 1;
   }
   d.zblocks = (p->D + PZ - 1) / PZ;
   const long long items = static_cast<long long>(p->N) * d.zblocks * d.tiles_y * d.tiles_x * d.ntiles;
@@ -1021,7 +1058,7 @@ extern "C" int rsb_conv3_forward(const RsbConv3Args* p, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
   // compile-time N tile instantiations (bf16 storage, single issuer, no profiling hooks); everything else is generic
-  if (p->dtype == RSB_BF16 && d.issuers == 1 && d.dbg == nullptr && getenv("RSB_FPROP_GENERIC") == nullptr) {
+  if (p->dtype == RSB_BF16 && d.issuers == 1 && d.groups == 1 && d.dbg == nullptr && getenv("RSB_FPROP_GENERIC") == nullptr) {
 #define RSB_SPEC(PZ_, NT_) if (PZ == PZ_ && d.NT == NT_) return launch_fprop<__nv_bfloat16, PZ_, NT_>(tm_hi, tm_lo, tm_lo2, d, grid, smem, st);
     RSB_SPEC(4, 32) RSB_SPEC(2, 32) RSB_SPEC(1, 32)
     RSB_SPEC(4, 64) RSB_SPEC(2, 64) RSB_SPEC(1, 64)

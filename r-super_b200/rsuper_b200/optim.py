@@ -110,11 +110,20 @@ class B200AdamW(torch.optim.Optimizer):
 
     def _step_scalars(self, group):
         """(adam step t, EMA alpha) of the NEXT update of a group (t = torch's per-parameter `step` + 1; training/utils.py:156)."""
-        steps = {int(self.state[p]["step"].item()) if (p in self.state and len(self.state[p])) else 0
-                 for p in group["params"] if p.grad is not None and p.numel()}
-        if len(steps) > 1:
-            raise RuntimeError("B200AdamW: the parameters that receive a gradient in one step must share their step count "
-                               f"(found {sorted(steps)}): one launch carries one pair of bias corrections")
+        def count(p):
+            return int(self.state[p]["step"].item()) if (p in self.state and len(self.state[p])) else 0
+        with_grad = [p for p in group["params"] if p.grad is not None and p.numel()]
+        if with_grad:
+            # the parameters this launch updates share one pair of bias corrections (a parameter that sat out some steps
+            # and returns with a smaller count would need its own: rejected instead of silently mis-corrected)
+            steps = {count(p) for p in with_grad}
+            if len(steps) > 1:
+                raise RuntimeError("B200AdamW: the parameters that receive a gradient in one step must share their step count "
+                                   f"(found {sorted(steps)}): one launch carries one pair of bias corrections")
+        else:
+            # prepare_step() before backward (zero_grad(set_to_none=True) left no gradients yet): the count of the parameters
+            # that have been stepping, i.e. the largest one
+            steps = {max([count(p) for p in group["params"] if p.numel()] or [0])}
         t = (steps.pop() if steps else 0) + 1
         return t, min(1.0 - 1.0 / (self.global_step + 1), self.ema_alpha)
 

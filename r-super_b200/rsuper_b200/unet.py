@@ -570,10 +570,11 @@ class _Engine:
 
 class _UNetFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, engine, names, num_classes, *params):
+    def forward(ctx, x, engine, names, num_classes, grad_mode, *params):
         P = dict(zip(names, [p.detach() for p in params]))
-        # under torch.no_grad() (sliding-window inference, validation, the EMA net) nothing is kept for a backward pass
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        # grad_mode = torch.is_grad_enabled() of the CALLER (it is always off inside Function.forward): under torch.no_grad()
+        # (sliding-window inference, validation, the EMA net) nothing is kept for a backward pass
+        need_grad = grad_mode and any(p.requires_grad for p in params)
         with torch.no_grad():
             logits, saved = engine.forward(x.detach().contiguous(), P, num_classes, save=need_grad)
         ctx.engine, ctx.names, ctx.saved_acts = engine, names, saved
@@ -590,7 +591,7 @@ class _UNetFunction(torch.autograd.Function):
             G = ctx.engine.backward(ctx.saved_acts, P, dlogits.contiguous().float())
         ctx.saved_acts = None
         grads = tuple(G[nm] if p.requires_grad else None for nm, p in zip(ctx.names, params))
-        return (None, None, None, None) + grads
+        return (None, None, None, None, None) + grads
 
 
 class B200UNet(nn.Module):
@@ -644,6 +645,6 @@ class B200UNet(nn.Module):
         if engine is None or engine.dtype != dtype or engine.slope != float(self.negative_slope):
             engine = _Engine(self.base_ch, self.negative_slope, dtype, self.block)
             self.__dict__["_engine"] = engine  # persistent packed-weight buffers; never pickled / deep-copied
-        out = _UNetFunction.apply(x.float(), engine, names, self.num_classes, *params)
+        out = _UNetFunction.apply(x.float(), engine, names, self.num_classes, torch.is_grad_enabled(), *params)
         # calculate_loss indexes model_output['segmentation'] (losses_foundation.py:859)
         return {"segmentation": out} if self.return_dict else out

@@ -23,7 +23,7 @@ def _step(rec, block, precision, base=8, side=32, batch=1):
     names, params = zip(*net.named_parameters())
     eng = U._Engine(base, 0.0, torch.bfloat16 if precision == "bf16" else torch.float32, block)
     x = synthetic_image(batch, side, side, side, seed=1)
-    out = U._UNetFunction.apply(x, eng, names, 2, *params)       # B200UNet.forward minus its CUDA check
+    out = U._UNetFunction.apply(x, eng, names, 2, True, *params)       # B200UNet.forward minus its CUDA check
     n_fwd = len(rec.calls)
     lab = synth.make_batch(["mask"] * batch, CLASSES, (side,) * 3, seed=2)["label"]
     losses.seg_loss(out, lab).backward()
@@ -85,12 +85,12 @@ def test_pack_plan_is_built_once_across_forwards(monkeypatch, block):
         eng = U._Engine(8, 0.0, torch.bfloat16, block)
         x = synthetic_image(1, 32, 32, 32, seed=1)
         for _ in range(3):
-            U._UNetFunction.apply(x, eng, names, 2, *params)
+            U._UNetFunction.apply(x, eng, names, 2, True, *params)
         assert len(built) == 1
         w = dict(net.named_parameters())["down2.conv.1.conv1.conv.weight" if block == "BasicBlock" else "down2.conv.1.conv.conv.weight"]
         w.data = w.data.clone()                                  # re-allocated storage (e.g. load_state_dict(assign=True))
         names, params = zip(*net.named_parameters())
-        U._UNetFunction.apply(x, eng, names, 2, *params)
+        U._UNetFunction.apply(x, eng, names, 2, True, *params)
         assert len(built) == 2
 
 

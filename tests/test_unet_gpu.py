@@ -40,17 +40,27 @@ def test_logits_vs_reference_golden(cuda_dev, golden):
     The bf16 perf mode is bounded by the bf16-operand noise of this net (2^3 voxels at the bottom level, where one
     operand rounding is a visible perturbation); the fp64-yardstick tests below show it equals the oracle's own
     noise when the oracle rounds at the same points."""
-    from oracle.unet_ref import synthetic_image
-    for precision, bound, min_agree in (("fp32", 1e-3, 1.0), ("bf16", 6e-1, 0.93)):
-        net, _ = _make(cuda_dev, precision)
-        x = synthetic_image(1, S, S, S, seed=3, device=cuda_dev)
+    from oracle.unet_ref import synthetic_image, unet_forward
+    x = synthetic_image(1, S, S, S, seed=3, device=cuda_dev)
+    ref = torch.from_numpy(golden["unet_logits"]).to(cuda_dev)
+    for precision in ("fp32", "bf16"):
+        net, sd = _make(cuda_dev, precision)
         with torch.no_grad():
             out = net(x)["segmentation"]
-        ref = torch.from_numpy(golden["unet_logits"]).to(cuda_dev)
         e = rel(out, ref)
         agree = (out.argmax(1) == ref.argmax(1)).float().mean().item()
         print(f"[golden] {precision}: rel_to_max={e:.3e} argmax agreement={agree:.5f}")
-        assert e <= bound and agree >= min_agree
+        if precision == "fp32":
+            assert e <= 1e-3 and agree == 1.0
+        else:
+            # the perf mode is held to the error the ORACLE itself makes against the real reference's logits when it rounds
+            # at the same points (bf16 conv operands, bf16 activation storage): at most twice that, argmax no worse
+            with torch.no_grad():
+                emul = unet_forward(x, sd, emulate=True, storage="bf16")
+            e_emul = rel(emul, ref)
+            agree_emul = (emul.argmax(1) == ref.argmax(1)).float().mean().item()
+            print(f"[golden] bf16-emulating oracle: rel_to_max={e_emul:.3e} argmax agreement={agree_emul:.5f}")
+            assert e <= 2.0 * e_emul + 1e-3 and agree >= agree_emul - 5e-3
 
 
 @pytest.mark.parametrize("precision,slope,side", [("fp32", 0.0, 64), ("bf16", 0.0, 64), ("fp32", 0.01, 32), ("bf16", 0.0, 32)])

@@ -406,6 +406,10 @@ def test_full_size_logits_mask_and_component_count_vs_oracle(cuda_dev):
     from oracle.inference_ref import connected_components
     from oracle.unet_ref import synthetic_image, unet_forward
     net, sd = _full_net(cuda_dev, "fp32")
+    for side in (32, 64):                      # growth of the error with the depth of reduction, on record
+        xs = synthetic_image(1, side, side, side, seed=6, device=cuda_dev)
+        with torch.no_grad():
+            print(f"[full-size] parity mode at {side}^3: logits rel-to-max {rel(net(xs)['segmentation'], unet_forward(xs, sd)):.3e}")
     x = synthetic_image(1, 128, 128, 128, seed=6, device=cuda_dev)
     with torch.no_grad():
         got = net(x)["segmentation"]
@@ -422,6 +426,30 @@ def test_full_size_logits_mask_and_component_count_vs_oracle(cuda_dev):
         a = connected_components(got.argmax(1)[0].cpu().numpy())[1]
         b = connected_components(want.argmax(1)[0].cpu().numpy())[1]
         assert a == b
+
+
+def test_bf16_mode_error_growth_vs_emulating_oracle(cuda_dev):
+    """The benchmarked mode (bf16 operands + bf16 activation storage) at 32^3 / 64^3 / 128^3 and at the benchmark shape
+    2 x 128^3, base 32: its logits error against the fp32 oracle (cuDNN, TF32 off) may not exceed twice the error of the
+    oracle evaluated with bf16 rounding at the same points (`emulate=True, storage='bf16'`) — the kernels add no error
+    of their own at any depth of reduction — and the argmax mask agrees with the fp32 oracle's at least as often."""
+    from oracle.unet_ref import synthetic_image, unet_forward
+    net, sd = _full_net(cuda_dev, "bf16")
+    for n, side in ((1, 32), (1, 64), (1, 128), (2, 128)):
+        x = synthetic_image(n, side, side, side, seed=6, device=cuda_dev)
+        with torch.no_grad():
+            got = net(x)["segmentation"]
+            want = unet_forward(x, sd)
+            emul = unet_forward(x, sd, emulate=True, storage="bf16")
+        e, e_emul = rel(got, want), rel(emul, want)
+        agree = (got.argmax(1) == want.argmax(1)).float().mean().item()
+        agree_emul = (emul.argmax(1) == want.argmax(1)).float().mean().item()
+        print(f"[bf16 growth] {n} x {side}^3: kernels vs fp32 oracle {e:.3e} (argmax {agree:.6f}) | bf16-emulating oracle vs fp32 oracle "
+              f"{e_emul:.3e} (argmax {agree_emul:.6f}) | kernels vs emulating oracle {rel(got, emul):.3e}")
+        assert torch.isfinite(got).all()
+        assert e <= 2.0 * e_emul + 1e-3
+        assert agree >= agree_emul - 2e-3
+        del got, want, emul
 
 
 def test_full_size_seg_loss_vs_oracle_at_identical_logits(cuda_dev):

@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 tag=${1:-r02b}
-timeout 600 python -m pytest tests/test_widen_gpu.py -m gpu -q -rfEs --no-header -p no:cacheprovider -x -k "graphed or resume or capturable" > gpurun_out/${tag}_graph_tests.log 2>&1
+timeout 600 python -m pytest tests/test_widen_gpu.py -m gpu -q -rfEs --no-header -p no:cacheprovider -x -k "graphed or resume or capturable or sliding" > gpurun_out/${tag}_graph_tests.log 2>&1
 tail -30 gpurun_out/${tag}_graph_tests.log
 timeout 600 python tools/probe_parity_depth.py 32 64 128 > gpurun_out/${tag}_parity_depth.log 2>&1
 cat gpurun_out/${tag}_parity_depth.log | tail -40

@@ -52,12 +52,18 @@ for S in sizes:
     ours = {"inc": Sv["enc_out"][0]}
     for l in range(1, 5):
         ours[f"down{l}.2"] = Sv["enc_out"][l]
+    for j, l in enumerate((3, 2, 1, 0), start=1):
+        ours[f"up{j}.cat"] = Sv["cat"][l]
+        ours[f"up{j}.0"] = Sv["saved"][8 + 2 * j][0]          # input of block up{j}.1 = output of block up{j}.0
     ours["up4.1"] = Sv["final"]
     print(f"==== S={S} precision={precision}: logits ours-vs-fp64 {rel(logits, want64):.3e}  oracle32-vs-fp64 {rel(want32, want64):.3e}  "
           f"ours-vs-oracle32 {rel(logits, want32):.3e}" + (f"  emul-oracle-vs-fp64 {rel(wante, want64):.3e}" if precision == "bf16" else ""))
     for k, a in ours.items():
         t = ncdhw(a.t).float()
         line = f"  {k:9s} ours-vs-fp64 {rel(t, tr64[k]):.3e}   oracle32-vs-fp64 {rel(tr32[k], tr64[k]):.3e}"
+        if k.endswith(".cat"):
+            nsk = {"up1.cat": 8, "up2.cat": 4, "up3.cat": 2, "up4.cat": 1}[k] * base
+            line += f" (skip half {rel(t[:, :nsk], tr64[k][:, :nsk]):.2e}, upsampled half {rel(t[:, nsk:], tr64[k][:, nsk:]):.2e})"
         if a.st is not None:
             n = t[0, 0].numel()
             t64 = t.double()
