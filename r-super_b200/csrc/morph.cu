@@ -50,21 +50,84 @@ static int make_ball(int diameter, BallOffsets& b) {
 }
 
 // conv3d (cross-correlation) with a symmetric ball == OR over offsets; zero padding.
-__global__ void dilate_pass_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
-                                   const BallOffsets b, int D, int H, int W) {
+//
+// Bit-sliced tile kernel.  A block owns an 8 (z) x 8 (y) x 32 (x) output tile.  Every haloed input row (38 voxels: reach
+// <= 3 on both sides) is packed into one 64-bit word with two warp ballots, then spread along x for the four possible half
+// widths (S_w[row] = OR_{|dx| <= w} row << dx).  A ball is, for every (dz, dy), the x range [-w(dz,dy), w(dz,dy)], so an
+// output row is the OR of <= 49 pre-spread words — ~1.5 instructions per voxel instead of up to 123 byte loads.  A tile
+// whose haloed input is empty (most of a lesion channel, all of an unused one) writes zeros without touching the table.
+constexpr int kDilReach = 3;                 // k <= 7  =>  |offset| <= 3
+constexpr int kDilTZ = 8, kDilTY = 8, kDilTX = 32;
+constexpr int kDilRows = (kDilTZ + 2 * kDilReach) * (kDilTY + 2 * kDilReach);   // 196 haloed rows
+struct BallRows {
+  signed char w[2 * kDilReach + 1][2 * kDilReach + 1];   // half width of the x range at (dz, dy), -1 = empty
+};
+
+__global__ void __launch_bounds__(256) dilate_tile_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, const BallRows b,
+                                                          int D, int H, int W, int tiles_x, int tiles_y) {
+  __shared__ unsigned long long S[kDilReach + 1][kDilRows];
+  __shared__ unsigned int out_bits[kDilTZ * kDilTY];
   const long long V = static_cast<long long>(D) * H * W;
-  const long long vol = blockIdx.y;
-  const uint8_t* s = src + vol * V;
-  for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < V;
-       v += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int x = static_cast<int>(v % W), y = static_cast<int>((v / W) % H), z = static_cast<int>(v / (static_cast<long long>(W) * H));
-    uint8_t out = 0;
-    for (int i = 0; i < b.count && !out; ++i) {
-      const int zz = z + b.off[i][0], yy = y + b.off[i][1], xx = x + b.off[i][2];
-      if (zz >= 0 && zz < D && yy >= 0 && yy < H && xx >= 0 && xx < W)
-        out = s[(static_cast<long long>(zz) * H + yy) * W + xx] ? 1 : 0;
+  const uint8_t* s = src + blockIdx.y * V;
+  uint8_t* d = dst + blockIdx.y * V;
+  int t = blockIdx.x;
+  const int tx = t % tiles_x; t /= tiles_x;
+  const int ty = t % tiles_y; t /= tiles_y;
+  const int z0 = t * kDilTZ, y0 = ty * kDilTY, x0 = tx * kDilTX;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int HY = kDilTY + 2 * kDilReach;
+  int any = 0;
+  for (int r = warp; r < kDilRows; r += 8) {
+    const int z = z0 - kDilReach + r / HY, y = y0 - kDilReach + r % HY;
+    unsigned lo = 0u, hi = 0u;
+    if (z >= 0 && z < D && y >= 0 && y < H) {          // warp-uniform
+      const uint8_t* row = s + (static_cast<long long>(z) * H + y) * W;
+      const int xa = x0 - kDilReach + lane, xb = xa + 32;
+      lo = __ballot_sync(0xffffffffu, xa >= 0 && xa < W && row[xa] != 0);
+      hi = __ballot_sync(0xffffffffu, lane < 2 * kDilReach && xb < W && row[xb] != 0);
     }
-    dst[vol * V + v] = out;
+    if (lane == 0) {
+      const unsigned long long w0 = static_cast<unsigned long long>(lo) | (static_cast<unsigned long long>(hi) << 32);
+      unsigned long long acc = w0;
+      S[0][r] = acc;
+#pragma unroll
+      for (int w = 1; w <= kDilReach; ++w) {
+        acc |= (w0 << w) | (w0 >> w);
+        S[w][r] = acc;
+      }
+    }
+    any |= (lo | hi) != 0u;
+  }
+  any = __syncthreads_or(any);
+  if (threadIdx.x < kDilTZ * kDilTY) {
+    unsigned long long acc = 0ull;
+    if (any) {
+      const int oz = threadIdx.x / kDilTY, oy = threadIdx.x % kDilTY;
+#pragma unroll
+      for (int dz = 0; dz <= 2 * kDilReach; ++dz)
+#pragma unroll
+        for (int dy = 0; dy <= 2 * kDilReach; ++dy) {
+          const int w = b.w[dz][dy];
+          if (w >= 0) acc |= S[w][(oz + dz) * HY + oy + dy];
+        }
+    }
+    out_bits[threadIdx.x] = static_cast<unsigned int>(acc >> kDilReach);   // bit i = output voxel x0 + i
+  }
+  __syncthreads();
+  // 256 threads x 8 voxels: thread -> (row, 8-voxel group)
+  const int r = threadIdx.x >> 2, g = threadIdx.x & 3;
+  const int z = z0 + r / kDilTY, y = y0 + r % kDilTY, x = x0 + g * 8;
+  if (z < D && y < H && x < W) {
+    const unsigned bits = (out_bits[r] >> (g * 8)) & 0xFFu;
+    uint8_t* o = d + (static_cast<long long>(z) * H + y) * W + x;
+    if (x + 8 <= W && (reinterpret_cast<uintptr_t>(o) & 7) == 0) {
+      // bit j -> byte j (0/1): multiply spreads the 8 bits, the mask keeps bit j of byte j, the second step normalises to 1
+      unsigned long long v = (static_cast<unsigned long long>(bits) * 0x0101010101010101ull) & 0x8040201008040201ull;
+      v = ((v + 0x7F7F7F7F7F7F7F7Full) >> 7) & 0x0101010101010101ull;
+      *reinterpret_cast<unsigned long long*>(o) = v;
+    } else {
+      for (int j = 0; j < 8 && x + j < W; ++j) o[j] = (bits >> j) & 1u;
+    }
   }
 }
 
@@ -90,21 +153,34 @@ extern "C" int rsb_dilate_ball(const uint8_t* src, uint8_t* dst, uint8_t* tmp, i
     for (int i = 0; i < num_full; ++i) passes[np++] = 7;
     if (rem > 0) passes[np++] = 2 * rem + 1;
   }
-  const int sms = rsb_num_sms();
-  RSB_REQUIRE(sms > 0, "no CUDA device");
-  const long long V = static_cast<long long>(D) * H * W;
-  long long bx = (V + 255) / 256;
-  if (bx > sms * 8LL) bx = sms * 8LL;
-  dim3 grid(static_cast<unsigned>(bx), n_vol);
+  const int tiles_x = (W + kDilTX - 1) / kDilTX, tiles_y = (H + kDilTY - 1) / kDilTY, tiles_z = (D + kDilTZ - 1) / kDilTZ;
+  const long long tiles = static_cast<long long>(tiles_x) * tiles_y * tiles_z;
+  RSB_REQUIRE(tiles < (1LL << 31), "dilate_ball: volume too large");
+  dim3 grid(static_cast<unsigned>(tiles), n_vol);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // ping-pong so that the last pass lands in dst
   const uint8_t* cur = src;
   for (int i = 0; i < np; ++i) {
     BallOffsets b;
     RSB_REQUIRE(make_ball(passes[i], b) == 0, "dilate_ball: structuring element too large");
+    // the ball as x ranges: for every (dz, dy) the offsets form the symmetric run [-w, w] (checked)
+    BallRows rows;
+    int cnt[2 * kDilReach + 1][2 * kDilReach + 1] = {};
+    for (int z = 0; z <= 2 * kDilReach; ++z)
+      for (int y = 0; y <= 2 * kDilReach; ++y) rows.w[z][y] = -1;
+    for (int k = 0; k < b.count; ++k) {
+      const int dz = b.off[k][0], dy = b.off[k][1], dx = b.off[k][2];
+      RSB_REQUIRE(abs(dz) <= kDilReach && abs(dy) <= kDilReach && abs(dx) <= kDilReach, "dilate_ball: pass reach exceeds %d", kDilReach);
+      signed char& w = rows.w[dz + kDilReach][dy + kDilReach];
+      if (abs(dx) > w) w = static_cast<signed char>(abs(dx));
+      ++cnt[dz + kDilReach][dy + kDilReach];
+    }
+    for (int z = 0; z <= 2 * kDilReach; ++z)
+      for (int y = 0; y <= 2 * kDilReach; ++y)
+        RSB_REQUIRE(rows.w[z][y] < 0 || cnt[z][y] == 2 * rows.w[z][y] + 1, "dilate_ball: structuring element is not a union of x runs");
     uint8_t* out = ((np - 1 - i) % 2 == 0) ? dst : tmp;
-    dilate_pass_kernel<<<grid, 256, 0, st>>>(cur, out, b, D, H, W);
-    int rc = check_launch("dilate_pass_kernel");
+    dilate_tile_kernel<<<grid, 256, 0, st>>>(cur, out, rows, D, H, W, tiles_x, tiles_y);
+    int rc = check_launch("dilate_tile_kernel");
     if (rc) return rc;
     cur = out;
   }

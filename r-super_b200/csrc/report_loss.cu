@@ -188,6 +188,112 @@ __global__ void __launch_bounds__(512) ball_correlate_kernel(const float* __rest
   if ((threadIdx.x & 31) == 0 && key != 0ull) atomicMax(best, key);
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same correlation in three separable stages (rsb_ball_correlate_argmax_sep).  The reference's kernel is a Gaussian
+// truncated to a ball, k(d) = exp(-|d|^2 / 2 sigma^2) [|d|^2 <= r^2] / Z (create_ball_kernel, :1161-1232).  The Gaussian
+// factorises, the ball does not — but the ball is, for every (dz, dy), the x range |dx| <= w(dz, dy), so
+//   rows    R_w(z, y, x) = sum_{|dx| <= w} g(dx) x(z, y, x + dx)                       w = 0 .. R   (cumulative in w)
+//   discs   D_a(z, y, x) = sum_{dy : a^2 + dy^2 <= r^2} g(dy) R_{w(a, |dy|)}(z, y + dy, x)   a = |dz| = 0 .. R
+//   score   S(z, y, x)   = sum_{|dz| <= R} g(dz) D_{|dz|}(z + dz, y, x)
+// is the identical sum with (R+1) + ~1.6 R^2 + (2R+1) multiply-adds per voxel instead of ~4.2 R^3 (R = 15: ~400 vs 15.6 k).
+// 1 / Z is dropped: only the argmax is used.  Rows of x that are empty are skipped by all stages (row occupancy).
+// ---------------------------------------------------------------------------------------------
+constexpr int kSepMaxR = 64;
+
+// rowocc[z * H + y] = any(x[z, y, :] > 0)
+__global__ void ball_row_occupancy_kernel(const float* __restrict__ x, uint8_t* __restrict__ rowocc, int W, long long rows) {
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + row * W;
+  bool any = false;
+  for (int i = threadIdx.x & 31; i < W; i += 32) any |= xr[i] > 0.f;
+  any = __any_sync(0xffffffffu, any);
+  if ((threadIdx.x & 31) == 0) rowocc[row] = any ? 1 : 0;
+}
+
+// one block per occupied row: Rw[w][row][x] for w = 0..R
+__global__ void __launch_bounds__(128) ball_rows_kernel(const float* __restrict__ x, const uint8_t* __restrict__ rowocc, const float* __restrict__ g,
+                                                        float* __restrict__ Rw, int R, int W, long long V) {
+  extern __shared__ float srow[];   // W + 2R, zero padded
+  const long long row = blockIdx.x;
+  if (!rowocc[row]) return;
+  for (int i = threadIdx.x; i < W + 2 * R; i += blockDim.x) {
+    const int xx = i - R;
+    srow[i] = (xx >= 0 && xx < W) ? x[row * W + xx] : 0.f;
+  }
+  __syncthreads();
+  for (int xq = threadIdx.x; xq < W; xq += blockDim.x) {
+    float acc = g[0] * srow[xq + R];
+    float* out = Rw + row * W + xq;
+    out[0] = acc;
+    for (int w = 1; w <= R; ++w) {
+      acc = fmaf(g[w], srow[xq + R + w] + srow[xq + R - w], acc);
+      out[static_cast<long long>(w) * V] = acc;
+    }
+  }
+}
+
+// one block per (z, y): Da[a][z][y][x] for a = 0..R; docc[z*H+y] = any contributing row occupied
+__global__ void __launch_bounds__(128) ball_discs_kernel(const float* __restrict__ Rw, const uint8_t* __restrict__ rowocc, const float* __restrict__ g,
+                                                         const int* __restrict__ wtab, float* __restrict__ Da, uint8_t* __restrict__ docc, int R,
+                                                         int H, int W, long long V) {
+  __shared__ int s_any;
+  const long long row = blockIdx.x;
+  const int y = static_cast<int>(row % H);
+  const long long zrow0 = row - y;   // z * H
+  if (threadIdx.x == 0) {
+    int any = 0;
+    for (int dy = -R; dy <= R && !any; ++dy) {
+      const int yy = y + dy;
+      if (yy >= 0 && yy < H && rowocc[zrow0 + yy]) any = 1;
+    }
+    s_any = any;
+    docc[row] = static_cast<uint8_t>(any);
+  }
+  __syncthreads();
+  if (!s_any) return;
+  for (int xq = threadIdx.x; xq < W; xq += blockDim.x) {
+    for (int a = 0; a <= R; ++a) {
+      float acc = 0.f;
+      for (int dy = -R; dy <= R; ++dy) {
+        const int ady = dy < 0 ? -dy : dy;
+        const int w = wtab[a * (R + 1) + ady];
+        const int yy = y + dy;
+        if (w < 0 || yy < 0 || yy >= H || !rowocc[zrow0 + yy]) continue;
+        acc = fmaf(g[ady], Rw[static_cast<long long>(w) * V + (zrow0 + yy) * W + xq], acc);
+      }
+      Da[static_cast<long long>(a) * V + row * W + xq] = acc;
+    }
+  }
+}
+
+// one block per (z, y): score = sum_dz g(dz) D_|dz|(z + dz, y, x), fused first-maximum argmax (same packed key as above)
+__global__ void __launch_bounds__(128) ball_planes_argmax_kernel(const float* __restrict__ Da, const uint8_t* __restrict__ docc,
+                                                                 const float* __restrict__ g, unsigned long long* __restrict__ best, int R, int D,
+                                                                 int H, int W, long long V) {
+  const long long row = blockIdx.x;
+  const int z = static_cast<int>(row / H), y = static_cast<int>(row % H);
+  unsigned long long key = 0ull;
+  for (int xq = threadIdx.x; xq < W; xq += blockDim.x) {
+    float acc = 0.f;
+    for (int dz = -R; dz <= R; ++dz) {
+      const int zz = z + dz, a = dz < 0 ? -dz : dz;
+      if (zz < 0 || zz >= D) continue;
+      const long long r2 = static_cast<long long>(zz) * H + y;
+      if (!docc[r2]) continue;
+      acc = fmaf(g[a], Da[static_cast<long long>(a) * V + r2 * W + xq], acc);
+    }
+    const unsigned long long idx = static_cast<unsigned long long>(row) * W + xq;
+    const unsigned long long k = (static_cast<unsigned long long>(__float_as_uint(acc)) << 32) | (0xFFFFFFFFull - idx);
+    key = k > key ? k : key;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+    key = other > key ? other : key;
+  }
+  if ((threadIdx.x & 31) == 0 && key != 0ull) atomicMax(best, key);
+}
+
 // candidates inside the clipped ball: cand[i] = {value bits, voxel index}; ball = centre + odd(ceil(d)) rule of
 // create_ball_kernel / insert_ball (d2 <= radius^2 inside a grid of half-width `half`).
 //   mode 0: value = x_iter (only > 0 kept)            mode 1: candidates = voxels with mask != 0, value = sigmoid(x)
@@ -367,6 +473,43 @@ extern "C" int rsb_ball_correlate_argmax(const float* x_iter, const void* taps, 
   // unpack on device into the caller's int64: index = 0xFFFFFFFF - low word
   e = cudaMemcpyAsync(argmax_out, best, 8, cudaMemcpyDeviceToDevice, RSB_ST);
   RSB_REQUIRE(e == cudaSuccess, "ball_correlate: copy failed");
+  return 0;
+}
+
+extern "C" size_t rsb_ball_sep_workspace_bytes(int D, int H, int W, int R) {
+  const size_t V = static_cast<size_t>(D) * H * W, rows = static_cast<size_t>(D) * H;
+  const size_t occ = (rows + 255) / 256 * 256;
+  return 2 * static_cast<size_t>(R + 1) * V * sizeof(float) + 2 * occ + 256;
+}
+
+extern "C" int rsb_ball_correlate_argmax_sep(const float* x_iter, const float* gauss, const int* wtab, int R, void* workspace,
+                                             long long* argmax_out, int D, int H, int W, void* stream) {
+  RSB_REQUIRE(x_iter && gauss && wtab && workspace && argmax_out && D > 0 && H > 0 && W > 0, "ball_correlate_sep: bad arguments");
+  RSB_REQUIRE(R >= 0 && R <= kSepMaxR, "ball_correlate_sep: reach %d outside [0, %d]", R, kSepMaxR);
+  const long long V = static_cast<long long>(D) * H * W, rows = static_cast<long long>(D) * H;
+  RSB_REQUIRE(V < (1LL << 32) && rows < (1LL << 31), "ball_correlate_sep: volume too large");
+  const size_t occ_bytes = (static_cast<size_t>(rows) + 255) / 256 * 256;
+  float* Rw = reinterpret_cast<float*>(workspace);
+  float* Da = Rw + static_cast<size_t>(R + 1) * V;
+  uint8_t* rowocc = reinterpret_cast<uint8_t*>(Da + static_cast<size_t>(R + 1) * V);
+  uint8_t* docc = rowocc + occ_bytes;
+  unsigned long long* best = reinterpret_cast<unsigned long long*>(docc + occ_bytes);
+  cudaError_t e = cudaMemsetAsync(best, 0, 8, RSB_ST);
+  RSB_REQUIRE(e == cudaSuccess, "ball_correlate_sep: memset failed");
+  ball_row_occupancy_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, RSB_ST>>>(x_iter, rowocc, W, rows);
+  int rc = check_launch("ball_row_occupancy_kernel");
+  if (rc) return rc;
+  ball_rows_kernel<<<static_cast<unsigned>(rows), 128, (W + 2 * R) * sizeof(float), RSB_ST>>>(x_iter, rowocc, gauss, Rw, R, W, V);
+  rc = check_launch("ball_rows_kernel");
+  if (rc) return rc;
+  ball_discs_kernel<<<static_cast<unsigned>(rows), 128, 0, RSB_ST>>>(Rw, rowocc, gauss, wtab, Da, docc, R, H, W, V);
+  rc = check_launch("ball_discs_kernel");
+  if (rc) return rc;
+  ball_planes_argmax_kernel<<<static_cast<unsigned>(rows), 128, 0, RSB_ST>>>(Da, docc, gauss, best, R, D, H, W, V);
+  rc = check_launch("ball_planes_argmax_kernel");
+  if (rc) return rc;
+  e = cudaMemcpyAsync(argmax_out, best, 8, cudaMemcpyDeviceToDevice, RSB_ST);
+  RSB_REQUIRE(e == cudaSuccess, "ball_correlate_sep: copy failed");
   return 0;
 }
 

@@ -1,6 +1,6 @@
 """calculate_loss — host-side mirror of rsuper_train/training/losses_foundation.py:685-1076 for the
-hot path, computing on the librsuper_b200.so kernels (no torch math on [B,C,V] tensors, no host
-syncs in the segmentation path).
+hot path, computing on the librsuper_b200.so kernels (no torch math on [B,C,V] tensors; the segmentation
+path has no host sync once `args.nan_check = False` moves the reference's NaN check to the caller).
 
 Same call signature, same returned dict keys ('segmentation', 'report' | 'ball_loss_bce' /
 'ball_loss_dice' / 'dice_volume_loss', 'overall'), same error behaviour (ValueError / AssertionError
@@ -104,9 +104,51 @@ def get_known_voxels(unk_voxels: torch.Tensor, dilation: int = 5) -> torch.Tenso
     return unk.logical_not().to(torch.uint8)
 
 
+_ALL_ONES: Dict[tuple, bool] = {}
+
+
+def _drop_unit_class_weights(class_weights: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """`if torch.equal(class_weights, ones): class_weights = None` (losses_foundation.py:871-873) without a host sync per
+    step: the comparison runs once per (storage, version) of the weight tensor and is cached."""
+    if class_weights is None:
+        return None
+    key = (class_weights.data_ptr(), class_weights._version, tuple(class_weights.shape), str(class_weights.device))
+    hit = _ALL_ONES.get(key)
+    if hit is None:
+        if class_weights.is_cuda and torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("rsuper_b200.calculate_loss: class_weights must have been seen by one eager step before CUDA-graph "
+                               "capture (their all-ones test is a host sync)")
+        if len(_ALL_ONES) > 64:
+            _ALL_ONES.clear()
+        hit = _ALL_ONES[key] = bool(torch.equal(class_weights, torch.ones_like(class_weights)))
+    return None if hit else class_weights
+
+
+def capturable(args, report_batches: bool) -> bool:
+    """True when calculate_loss can sit inside a CUDA-graph capture for this configuration: no host-side control flow on
+    device values.  The mask-only path qualifies once the NaN check (`args.nan_check`, a host sync mirroring
+    losses_foundation.py:1070) is moved to the caller; the report path qualifies when report_losses runs device-side."""
+    if getattr(args, "nan_check", True):
+        return False
+    if report_batches and float(args.report_volume_loss_basic) > 0:
+        from . import report_losses
+        return bool(getattr(report_losses, "DEVICE_SIDE", False))
+    return True
+
+
 def calculate_loss(model_output, label, unk_voxels, args, matcher, chosen_segment_mask, tumor_volumes_report,
                    tumor_diameters, classes, input_tensor=None, class_weights=None, model_genesis=False,
                    clip_only=False, report_embeddings=None, dist=None) -> Dict[str, torch.Tensor]:
+    """Host syncs: none on the mask-only path when `args.nan_check` is False (the reference's NaN check, default on, reads
+    the loss back) — that is the configuration `B200TrainStep(schedule='graph')` captures; `class_weights` cost one
+    comparison the first time a tensor is seen."""
+    dev = model_output["segmentation"][0].device if isinstance(model_output["segmentation"], (tuple, list)) \
+        else model_output["segmentation"].device
+    if dev.type == "cuda" and dev.index is not None and dev.index != torch.cuda.current_device():
+        with torch.cuda.device(dev):          # kernels launch on the current device's stream: follow the tensors
+            return calculate_loss(model_output, label, unk_voxels, args, matcher, chosen_segment_mask, tumor_volumes_report,
+                                  tumor_diameters, classes, input_tensor, class_weights, model_genesis, clip_only,
+                                  report_embeddings, dist)
     if model_genesis or clip_only or getattr(args, "classification_branch", False) or getattr(args, "multi_ch_tumor", False):
         raise NotImplementedError("rsuper_b200.calculate_loss implements the R-Super segmentation/report path only")
     result = model_output["segmentation"]
@@ -120,8 +162,7 @@ def calculate_loss(model_output, label, unk_voxels, args, matcher, chosen_segmen
         from . import report_losses  # Volume / Ball loss kernels
         return report_losses.calculate_loss_with_reports(heads, deep, label, unk_voxels, args, chosen_segment_mask,
                                                          tumor_volumes_report, tumor_diameters, classes, class_weights)
-    if class_weights is not None and torch.equal(class_weights, torch.ones_like(class_weights)):
-        class_weights = None
+    class_weights = _drop_unit_class_weights(class_weights)
     label_u8 = _as_u8(label)
     known = get_known_voxels(unk_voxels) if unk_voxels is not None else None
     loss_seg = 0

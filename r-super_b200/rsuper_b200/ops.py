@@ -518,6 +518,26 @@ def ball_correlate_argmax(x_iter, taps, kernel_half):
     return out
 
 
+_SEP_WS = {}
+
+
+def ball_correlate_argmax_sep(x_iter, gauss, wtab, reach):
+    """Same packed argmax as ball_correlate_argmax through the rows -> discs -> planes decomposition of the truncated
+    Gaussian ball (gauss: device fp32 [reach + 1], wtab: device int32 [(reach + 1)^2])."""
+    d, h, w_ = x_iter.shape
+    assert x_iter.dtype == torch.float32 and x_iter.is_contiguous() and gauss.dtype == torch.float32 and wtab.dtype == torch.int32
+    key = (d, h, w_, reach, str(x_iter.device))
+    ws = _SEP_WS.get(key)
+    if ws is None:
+        if len(_SEP_WS) > 8:
+            _SEP_WS.clear()
+        ws = _SEP_WS[key] = torch.empty(lib().rsb_ball_sep_workspace_bytes(d, h, w_, reach), dtype=torch.uint8, device=x_iter.device)
+    out = torch.empty(1, dtype=torch.int64, device=x_iter.device)
+    _call("report", 4, 0.0, lib().rsb_ball_correlate_argmax_sep, _p(x_iter), _p(gauss), _p(wtab), reach, _p(ws), _p(out), d, h, w_,
+          _stream(), what="ball_correlate_argmax_sep")
+    return out
+
+
 def ball_candidates(x, mask, mode, center, half, radius2, cand, n_cand, ball_out):
     d, h, w_ = x.shape
     cz, cy, cx = center

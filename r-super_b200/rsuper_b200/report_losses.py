@@ -21,6 +21,9 @@ import torch
 from . import ops
 
 _SUFFIXES = ("lesion", "cyst", "pdac", "pnet")
+# isolate_tumor's ball correlation through the rows -> discs -> planes decomposition (csrc/report_loss.cu); False = the direct
+# tap-list kernel (kept: it is the definition the decomposition is tested against)
+SEPARABLE_CORRELATION = True
 
 
 def lesion_channels(classes: Sequence[str]) -> List[int]:
@@ -86,6 +89,30 @@ def _gauss_ball_taps(diameter: int, gaussian: bool, std: float, device):
     taps[:, 3] = k[zz, yy, xx].view(np.int32)
     hit = (torch.from_numpy(taps).to(device), int(len(zz)), half)
     _TAPS[key] = hit
+    return hit
+
+
+_SEP: Dict[tuple, tuple] = {}
+
+
+def _gauss_ball_sep(diameter: int, std: float, device):
+    """The Gaussian ball of create_ball_kernel(d, gaussian=True, std) in separable form: g(d) for d = 0..R (fp32), the table
+    w(a, b) = largest dx with a^2 + b^2 + dx^2 <= r^2 (or -1), and R = floor(radius)."""
+    key = (diameter, float(std), str(device))
+    hit = _SEP.get(key)
+    if hit is not None:
+        return hit
+    _, r2 = _ball_geometry(diameter)
+    radius = np.float32(_odd_ceil(diameter) / 2.0)
+    reach = int(math.floor(float(radius)))
+    c = np.arange(0, reach + 1, dtype=np.float32)
+    sigma = np.float32(std) * radius
+    g = np.exp(-(c * c) / (np.float32(2.0) * sigma ** 2)).astype(np.float32)
+    d2 = c[:, None, None] ** 2 + c[None, :, None] ** 2 + c[None, None, :] ** 2       # same fp32 test as the tap list: d2 <= r2
+    inside = d2 <= r2
+    wtab = np.where(inside.any(-1), inside.sum(-1) - 1, -1).astype(np.int32)         # runs are contiguous from dx = 0
+    hit = (torch.from_numpy(g).to(device), torch.from_numpy(wtab.reshape(-1).copy()).to(device), reach)
+    _SEP[key] = hit
     return hit
 
 
@@ -178,7 +205,11 @@ def isolate_tumor(x_iter: torch.Tensor, diameter, gaussian: bool, gaussian_std: 
         assert tumor_volume <= support * 1.2
     if support > tumor_volume:
         tumor_volume = support - 1
-    key = int(ops.ball_correlate_argmax(x_iter, taps, khalf).item())
+    if gaussian and SEPARABLE_CORRELATION:
+        g1d, wtab, reach = _gauss_ball_sep(diameter, gaussian_std, x_iter.device)
+        key = int(ops.ball_correlate_argmax_sep(x_iter, g1d, wtab, reach).item())
+    else:
+        key = int(ops.ball_correlate_argmax(x_iter, taps, khalf).item())
     flat_idx = 0xFFFFFFFF - (key & 0xFFFFFFFF)
     center = tuple(int(c) for c in np.unravel_index(flat_idx, shape))
     half, r2 = _ball_geometry(diameter * (1 + diameter_margin))
@@ -365,8 +396,8 @@ def calculate_loss_with_reports(heads, deep, label, unk_voxels, args, chosen_seg
         for b in range(label.shape[0]):   # sanity checks of :864-869
             if csm_any[b] > 0 and (unk_any[b] == 0 or vol_any[b] == 0):
                 raise ValueError("report sample without unk_voxels / tumor volumes")
-    if class_weights is not None and torch.equal(class_weights, torch.ones_like(class_weights)):
-        class_weights = None
+    from .losses import _drop_unit_class_weights
+    class_weights = _drop_unit_class_weights(class_weights)
     cw_seg = None if class_weights is None else class_weights.to(label.device)
     label_u8 = _u8(label)
     known = get_known_voxels(unk_voxels) if unk_voxels is not None else None

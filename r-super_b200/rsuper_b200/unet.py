@@ -645,6 +645,10 @@ class B200UNet(nn.Module):
         if engine is None or engine.dtype != dtype or engine.slope != float(self.negative_slope):
             engine = _Engine(self.base_ch, self.negative_slope, dtype, self.block)
             self.__dict__["_engine"] = engine  # persistent packed-weight buffers; never pickled / deep-copied
-        out = _UNetFunction.apply(x.float(), engine, names, self.num_classes, torch.is_grad_enabled(), *params)
+        if x.device.index is not None and x.device.index != torch.cuda.current_device():
+            with torch.cuda.device(x.device):     # kernels launch on the current device's stream: follow the tensors
+                out = _UNetFunction.apply(x.float(), engine, names, self.num_classes, torch.is_grad_enabled(), *params)
+        else:
+            out = _UNetFunction.apply(x.float(), engine, names, self.num_classes, torch.is_grad_enabled(), *params)
         # calculate_loss indexes model_output['segmentation'] (losses_foundation.py:859)
         return {"segmentation": out} if self.return_dict else out

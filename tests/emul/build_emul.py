@@ -43,7 +43,7 @@ def _split_args(s: str):
     return out
 
 
-SYNC = re.compile(r"__syncthreads|__shfl_\w+_sync|__syncthreads_or")
+SYNC = re.compile(r"__syncthreads|__shfl_\w+_sync|__syncthreads_or|__ballot_sync|__any_sync")
 FUNC = re.compile(r"\b(\w+)\s*\([^;{}()]*(?:\([^()]*\)[^;{}()]*)*\)\s*(?:const\s*)?\{")
 
 

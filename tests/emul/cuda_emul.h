@@ -124,6 +124,19 @@ inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
   return out;
 }
 
+inline unsigned __ballot_sync(unsigned, int pred) {
+  std::barrier<>* wb = emu::g_warp_barrier[threadIdx.x >> 5];
+  emu::g_xchg[threadIdx.x] = pred ? 1.0 : 0.0;
+  wb->arrive_and_wait();
+  unsigned mask = 0u;
+  const unsigned base = threadIdx.x & ~31u;
+  for (unsigned l = 0; l < 32 && base + l < blockDim.x; ++l)
+    if (emu::g_xchg[base + l] != 0.0) mask |= 1u << l;
+  wb->arrive_and_wait();
+  return mask;
+}
+inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0u; }
+
 inline unsigned emu_block(unsigned b) { return b; }
 inline unsigned emu_block(int b) { return static_cast<unsigned>(b); }
 inline unsigned emu_block(dim3 b) { return b.x; }

@@ -151,3 +151,49 @@ def test_calculate_loss_dicts(cuda_dev, golden):
                               torch.zeros_like(bb["unk_channels"]).float().to(dev), LR.default_args(loss="ball"), None,
                               bb["mask"].float().to(dev), bb["volumes"].to(dev), bb["diameters"].to(dev), cls2)
 
+
+
+@pytest.mark.parametrize("shape,diameter", [((32, 32, 32), 9), ((24, 40, 56), 15), ((64, 64, 64), 31), ((17, 23, 37), 5), ((8, 8, 8), 3)])
+def test_separable_ball_correlation_matches_tap_list(cuda_dev, shape, diameter):
+    """The rows -> discs -> planes decomposition of the truncated Gaussian ball (rsb_ball_correlate_argmax_sep) against the
+    direct tap-list kernel (the definition): same first maximum, scores equal up to the dropped normalisation 1 / Z and fp32
+    re-association; ragged shapes, ball larger than the volume, empty rows, all-zero volume."""
+    from rsuper_b200 import ops
+    from rsuper_b200 import report_losses as RL
+    g = torch.Generator().manual_seed(diameter)
+    x = torch.rand(shape, generator=g)
+    blob = torch.zeros(shape)
+    blob[shape[0] // 4:shape[0] // 4 * 3, shape[1] // 3:shape[1] // 3 * 2, 2:shape[2] - 3] = 1      # empty rows around a block
+    for vol in (x * blob, x, torch.zeros(shape)):
+        xi = vol.to(cuda_dev).contiguous()
+        taps, support, khalf = RL._gauss_ball_taps(diameter, True, 1.5, cuda_dev)
+        g1d, wtab, reach = RL._gauss_ball_sep(diameter, 1.5, cuda_dev)
+        k_tap = int(ops.ball_correlate_argmax(xi, taps, khalf).item())
+        k_sep = int(ops.ball_correlate_argmax_sep(xi, g1d, wtab, reach).item())
+        assert (k_tap & 0xFFFFFFFF) == (k_sep & 0xFFFFFFFF), (shape, diameter)
+        s_tap = np.array([k_tap >> 32], dtype=np.uint32).view(np.float32)[0]
+        s_sep = np.array([k_sep >> 32], dtype=np.uint32).view(np.float32)[0]
+        # tap weights are normalised to sum 1; the separable factors are not: Z = sum of g(dz) g(dy) g(dx) over the ball
+        w = taps.cpu().numpy()[:, 3].copy().view(np.float32)
+        gz = g1d.cpu().numpy()
+        off = np.abs(taps.cpu().numpy()[:, :3])
+        Z = float((gz[off[:, 0]] * gz[off[:, 1]] * gz[off[:, 2]]).sum(dtype=np.float64))
+        assert abs(s_sep / Z - s_tap) <= 2e-5 * max(s_tap, 1e-12) + 1e-12
+        np.testing.assert_allclose(gz[off[:, 0]] * gz[off[:, 1]] * gz[off[:, 2]] / Z, w, rtol=2e-5)
+
+
+@pytest.mark.parametrize("shape", [(16, 24, 32), (9, 13, 70), (8, 8, 31), (40, 33, 64)])
+@pytest.mark.parametrize("k", [1, 3, 5, 7, 11, 31])
+def test_dilation_tile_kernel_edge_shapes(cuda_dev, shape, k):
+    """The bit-sliced tile kernel against the oracle's conv-based dilation on ragged volumes (W not a multiple of 8 / 32,
+    tiles cut by every border), several volumes per launch incl. an empty one."""
+    from oracle import losses_ref as LR
+    from rsuper_b200 import ops
+    g = torch.Generator().manual_seed(k)
+    vols = (torch.rand((3,) + shape, generator=g) < 0.01).to(torch.uint8)
+    vols[1] = 0
+    vols[2, 0, 0, 0] = 1
+    vols[2, -1, -1, -1] = 1
+    got = ops.dilate_ball(vols.to(cuda_dev), k).cpu()
+    ref = torch.stack([LR.dilate_volume(v.float(), k) for v in vols]).to(torch.uint8)
+    assert torch.equal(got, ref)
