@@ -543,9 +543,20 @@ def main():
                 "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4},
                 "gpu_launches": launches, "clocks": clocks}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if dist is not None:
-        dist.destroy_process_group()
+        # Teardown with NCCL collectives captured in a live CUDA graph: release the graph first, then leave without
+        # ProcessGroupNCCL's destructor (it can wait forever on communicators the captured kernels still reference; the JSON
+        # line is already flushed and every rank has passed the barrier below).
+        try:
+            step.graph = None
+        except NameError:
+            pass
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

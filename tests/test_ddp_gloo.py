@@ -99,6 +99,77 @@ def test_ddp_world2_gradients_are_rank_means(tmp_path):
         assert torch.equal(r0["params"][k], r1["params"][k]), k        # ranks stay in lock-step after the step
 
 
+def _step_worker(rank, world, port, out_dir):
+    """B200TrainStep(schedule='eager', process_group=gloo): the product's own train-step object — flat gradient buffer,
+    one all-reduce, fused optimizer — with the engine running on the emulated kernels (tests/emul)."""
+    for p in (ROOT, os.path.join(ROOT, "r-super_b200"), os.path.join(ROOT, "tests", "emul")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    torch.set_num_threads(2)
+    import install
+    install.install()
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        from oracle import losses_ref as LR
+        from oracle.unet_ref import synthetic_state_dict
+        from rsuper_b200 import losses
+        from rsuper_b200.optim import B200AdamW
+        from rsuper_b200.train_step import B200TrainStep
+        from rsuper_b200.unet import B200UNet
+        net = B200UNet(1, 8, num_classes=len(CLASSES), precision="fp32")
+        net.load_state_dict(synthetic_state_dict(8, len(CLASSES)))
+        params = list(net.parameters())
+        ema = [p.detach().clone() for p in params]
+        opt = B200AdamW(params, lr=6e-4, weight_decay=0.05, max_norm=1.0, ema_params=ema, capturable=True)
+        args = LR.default_args(report_volume_loss_basic=0.0)
+        args.nan_check = False
+        x, lab = _rank_batch(rank)
+        loss_fn = lambda out, lb: losses.calculate_loss(out, lb, None, args, None, None, None, None, CLASSES)["overall"]
+        loss_fn(net(x), lab.to(torch.uint8)).backward()           # this rank's LOCAL gradient through the same engine
+        local = [p.grad.clone() for p in params]
+        for p in params:
+            p.grad = None
+        step = B200TrainStep(net, loss_fn, opt, (x, lab.to(torch.uint8)), schedule="eager", process_group=dist.group.WORLD)
+        assert all(p.grad.data_ptr() >= step.flat_grad.data_ptr() for p in params)       # every grad is a view of the flat buffer
+        before = [p.detach().clone() for p in params]
+        loss = step(x, lab.to(torch.uint8))
+        torch.save({"local": local, "loss": loss.item(), "grad_norm": float(opt.last_grad_norm), "flat": step.flat_grad.clone(),
+                    "params": [p.detach().clone() for p in params], "before": before, "ema": ema, "step": opt.global_step},
+                   os.path.join(out_dir, f"step{rank}.pt"))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_train_step_world2_allreduces_the_flat_gradient(tmp_path):
+    """N > 1 path of B200TrainStep on CPU (gloo, world 2): after one step both ranks hold the same averaged (then clipped)
+    flat gradient, the same parameters and EMA; the average equals the mean of the two ranks' local gradients (oracle)."""
+    world = 2
+    mp.spawn(_step_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r0 = torch.load(tmp_path / "step0.pt")
+    r1 = torch.load(tmp_path / "step1.pt")
+    assert r0["step"] == r1["step"] == 1 and r0["loss"] != r1["loss"]                    # different shards, same update
+    assert torch.equal(r0["flat"], r1["flat"])
+    for a, b in zip(r0["params"] + r0["ema"], r1["params"] + r1["ema"]):
+        assert torch.equal(a, b)
+    assert any(not torch.equal(a, b) for a, b in zip(r0["params"], r0["before"]))       # the step really updated the weights
+    mean = [(a + b) / world for a, b in zip(r0["local"], r1["local"])]   # DDP averages, like the reference (train_ddp.py:661-671)
+    norm = torch.sqrt(sum((g.double() ** 2).sum() for g in mean)).item()
+    # (tolerances: two passes of the engine differ by the order of their fp32 atomics, amplified by this 2^3-bottom toy net;
+    #  a missing average or a dropped rank is off by O(1))
+    assert abs(r0["grad_norm"] - norm) <= 2e-2 * norm                                    # norm of the AVERAGED gradient, before clipping
+    clip = min(1.0, 1.0 / (norm + 1e-6))
+    # whole-vector comparison: single tensors of this toy net move by several per cent between two passes of the engine
+    off, num, den = 0, 0.0, 0.0
+    for g in mean:
+        n = g.numel()
+        got = r0["flat"][off:off + n].view_as(g)
+        num += (got.double() - g.double() * clip).pow(2).sum().item()
+        den += (g.double() * clip).pow(2).sum().item()
+        off += (n + 3) // 4 * 4
+    assert (num / den) ** 0.5 <= 5e-2
+
+
 def test_bench_job_accounting():
     """bench.py: per-rank seeds differ, the whole-job metric counts every rank's voxels (weak scaling)."""
     sys.path.insert(0, ROOT)
