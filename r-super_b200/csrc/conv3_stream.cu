@@ -460,11 +460,12 @@ using namespace rsb;
 
 // Called by rsb_conv3_forward (conv3_fprop.cu) for eligible layers; returns 1 when the layer is not eligible.
 int rsb_conv3_stream_try(const RsbConv3Args* p, void* stream) {
-  // Opt-in (RSB_FPROP_STREAM=1): standalone it beats the item-based kernel by 8-13 % on the 32-channel layers
-  // (0.212-0.234 ms vs 0.244-0.262 ms at 2 x 128^3), but inside the train step — where the weight gradients share the
-  // SMs from a second stream — the end-to-end time did not improve, so the item-based kernel stays the default.
+  // Default for the eligible layers (RSB_FPROP_STREAM=0 disables it).  Standalone it beats the item-based kernel by 8-13 % on
+  // the 32-channel layers (0.212-0.234 ms vs 0.244-0.262 ms at 2 x 128^3); inside the graph-captured train step with the
+  // weight gradients on the second stream: 19.97 vs 20.41 ms per step (profiles/r02_*).  (Round 1 measured no gain with
+  // eagerly enqueued streams, where the kernel order depended on host timing.)
   const char* on = getenv("RSB_FPROP_STREAM");
-  if (on == nullptr || on[0] != '1') return 1;
+  if (on != nullptr && on[0] == '0') return 1;
   if (p->Cin > 32 || p->Cout > 32 || p->Cout <= 16 || p->a_lo != nullptr || p->planes_per_item != 0) return 1;
   if (p->dtype != RSB_BF16 && p->dtype != RSB_F32) return 1;
   int sms = p->max_ctas > 0 ? p->max_ctas : rsb_num_sms();

@@ -32,6 +32,106 @@ import torch
 from .optim import B200AdamW
 
 
+def _production_order(names):
+    """Parameter names in the order B200UNet's backward produces their gradients (block='BasicBlock': head, up4 .. up1,
+    down4 .. down1, inc, stem) and the four buckets the engine reports (unet._Engine._stage_done); conv1 / shortcut of a block
+    are adjacent (their gradients come out of ONE merged weight-gradient GEMM).  Any other parameter set: given order, no
+    buckets."""
+    have = set(names)
+
+    def block(pre, shortcut):
+        out = [pre + "conv2.conv.weight", pre + "conv1.conv.weight"]
+        if shortcut:
+            out.append(pre + "shortcut.conv.weight")
+        return out
+
+    stages = [["outc.weight", "outc.bias"] + block("up4.conv.1.", False) + block("up4.conv.0.", True)]
+    s1 = []
+    for j in (3, 2, 1):
+        s1 += block(f"up{j}.conv.1.", False) + block(f"up{j}.conv.0.", True)
+    stages.append(s1)
+    s2 = []
+    for l in (4, 3, 2, 1):
+        s2 += block(f"down{l}.conv.2.", False) + block(f"down{l}.conv.1.", True)
+    stages.append(s2)
+    stages.append(block("inc.conv2.", False) + ["inc.conv1.weight"])
+    order = [n for st in stages for n in st]
+    if set(order) != have or len(order) != len(names):
+        return list(names), None
+    return order, stages
+
+
+class _FlatGradSink:
+    """What unet._Engine writes weight gradients into when B200TrainStep owns the gradients (see _Engine._dw / _stage_done)."""
+
+    def __init__(self, step, by_name, offs, bounds):
+        self.step, self.by_name, self.offs, self.bounds = step, by_name, offs, bounds
+        self.works = []
+        self.done = set()
+        self.comm = None
+
+    def _view(self, name):
+        p = self.by_name.get(name)
+        if p is None or p.grad is None:
+            return None
+        o = self.offs[name]
+        v = self.step.flat_grad[o:o + p.numel()]
+        return v if p.grad.data_ptr() == v.data_ptr() else None     # the caller may have replaced / dropped p.grad
+
+    def owns(self, name) -> bool:
+        return self._view(name) is not None
+
+    def covers_all(self) -> bool:
+        return all(self.owns(n) for n in self.by_name)
+
+    def buffer(self, name):
+        if isinstance(name, tuple):                                   # (conv1, shortcut): one [2c, cin, 3, 3, 3] tensor
+            a, b = self._view(name[0]), self._view(name[1])
+            if a is None or b is None or a.data_ptr() + a.numel() * 4 != b.data_ptr():
+                return None
+            pa = self.by_name[name[0]]
+            o = self.offs[name[0]]
+            return self.step.flat_grad[o:o + a.numel() + b.numel()].view(2 * pa.shape[0], *pa.shape[1:])
+        v = self._view(name)
+        return None if v is None else v.view_as(self.by_name[name])
+
+    def begin(self):
+        self.works, self.done = [], set()
+
+    def stage_done(self, k, side_stream):
+        """Bucket k of the flat buffer is fully enqueued (main stream + the weight-gradient side stream): start its all-reduce
+        on the communication stream while backward goes on."""
+        st = self.step
+        if st.world == 1 or not self.covers_all():
+            return
+        lo, hi = self.bounds[k]
+        bucket = st.flat_grad[lo:hi]
+        if bucket.is_cuda:
+            if self.comm is None:
+                self.comm = torch.cuda.Stream(device=bucket.device)
+            cur = torch.cuda.current_stream()
+            self.comm.wait_stream(cur)
+            if side_stream is not None:
+                self.comm.wait_stream(side_stream)
+            with torch.cuda.stream(self.comm):
+                w = st._allreduce_range(bucket, async_op=True)
+            self.works.append((w, bucket))
+        else:
+            st._allreduce_range(bucket)
+        self.done.add(k)
+
+    def flush(self) -> bool:
+        """Join the in-flight buckets into the current stream; True when they covered the whole buffer."""
+        for w, bucket in self.works:
+            if w is not None:
+                w.wait()
+            if bucket.is_cuda:
+                torch.cuda.current_stream().wait_stream(self.comm)
+        ok = len(self.done) == len(self.bounds)
+        self.works = []
+        return ok
+
+
 class B200TrainStep:
     def __init__(self, net: torch.nn.Module, loss_fn: Callable, optimizer: B200AdamW, example_inputs: Sequence[Optional[torch.Tensor]],
                  *, schedule: str = "graph", process_group=None, side_stream: Optional[bool] = None, warmup: int = 3):
@@ -63,33 +163,56 @@ class B200TrainStep:
 
     # -- one flat gradient buffer; every p.grad is a 16-byte-aligned view of it ---------------------------------------------
     def _make_flat_grads(self):
-        params = [p for p in self.net.parameters() if p.requires_grad]
-        offs, total = [], 0
-        for p in params:
-            offs.append(total)
-            total += (p.numel() + 3) // 4 * 4
-        dev = params[0].device
+        named = [(n, p) for n, p in self.net.named_parameters() if p.requires_grad]
+        order, stages = _production_order([n for n, _ in named])
+        by_name = dict(named)
+        offs, total = {}, 0
+        for n in order:
+            offs[n] = total
+            total += (by_name[n].numel() + 3) // 4 * 4
+        dev = named[0][1].device
         self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
-        for p, o in zip(params, offs):
-            p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
-        self.params = params
+        for n in order:
+            p = by_name[n]
+            p.grad = self.flat_grad[offs[n]:offs[n] + p.numel()].view_as(p)
+        self.params = [by_name[n] for n in order]
+        self.sink = None
+        if stages is not None:
+            # stage k = [lo, hi) of the flat buffer, complete when the engine reports stage_done(k)
+            bounds = []
+            for names in stages:
+                lo = offs[names[0]]
+                hi = offs[names[-1]] + (by_name[names[-1]].numel() + 3) // 4 * 4
+                bounds.append((lo, hi))
+            self.sink = _FlatGradSink(self, by_name, offs, bounds)
+            self.net.__dict__["_grad_sink"] = self.sink
 
     def _allreduce(self):
-        """DDP's gradient averaging (train_ddp.py:661-671) as one NCCL all-reduce of the flat buffer."""
+        """DDP's gradient averaging (train_ddp.py:661-671) on the flat buffer: the buckets the engine reported during backward
+        are already in flight on the communication stream (the main stream joins them here); whatever is not covered by
+        buckets goes in one all-reduce of the whole buffer."""
         if self.world == 1:
             return
+        if self.sink is not None and self.sink.flush():
+            return
+        self._allreduce_range(self.flat_grad)
+
+    def _allreduce_range(self, t, async_op=False):
         import torch.distributed as dist
         if dist.get_backend(self.pg) == "nccl":
-            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG, group=self.pg)
-        else:                                   # gloo (CPU tests of the host logic): no AVG
-            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.pg)
-            self.flat_grad.mul_(1.0 / self.world)
+            return dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.pg, async_op=async_op)
+        w = dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg, async_op=False)   # gloo (CPU tests of the host logic): no AVG
+        t.mul_(1.0 / self.world)
+        return w if async_op else None
 
     def _body(self):
         from . import unet as unet_mod
         prev = unet_mod.set_side_stream(self.side_stream)
         try:
-            self.flat_grad.zero_()                 # p.grad are views: autograd accumulates in place
+            if self.sink is None or not self.sink.covers_all():
+                self.flat_grad.zero_()             # p.grad are views: autograd accumulates in place
+            if self.sink is not None:
+                self.sink.begin()
             out = self.net(self.static[0])
             loss = self.loss_fn(out, *self.static[1:])
             loss.backward()

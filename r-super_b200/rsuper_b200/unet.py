@@ -163,6 +163,9 @@ class _Engine:
         self._side = None
         self._side_keep = []
         self._plan_key = None
+        # Optional gradient sink (train_step.B200TrainStep): name -> preallocated fp32 tensor the weight gradient is written
+        # INTO (views of one flat buffer); `stage_done(k)` is called when a bucket of them has been enqueued
+        self.sink = None
         self.plan = None  # ops.PackPlan: persistent packed weight images, refreshed by ONE launch per forward
 
     # ---- zeroed statistics storage: one fill per pass instead of ~50 tiny ones --------------------------
@@ -462,8 +465,19 @@ class _Engine:
         n, d, h, w_, _ = like.shape
         return torch.empty((n, d, h, w_, c), dtype=self.dtype, device=like.device)
 
-    def _dw(self, like: torch.Tensor, cout: int, cin: int) -> torch.Tensor:
+    def _dw(self, like: torch.Tensor, cout: int, cin: int, name=None) -> torch.Tensor:
+        """Destination of a weight gradient: the sink's tensor for `name` (a parameter name, or a (conv1, shortcut) pair whose
+        gradients are adjacent in the sink's flat buffer) when a sink is attached, else a fresh tensor."""
+        if self.sink is not None and name is not None:
+            t = self.sink.buffer(name)
+            if t is not None:
+                assert tuple(t.shape) == (cout, cin, 3, 3, 3) and t.dtype == torch.float32 and t.is_contiguous()
+                return t
         return torch.empty((cout, cin, 3, 3, 3), dtype=torch.float32, device=like.device)
+
+    def _stage_done(self, k: int):
+        if self.sink is not None:
+            self.sink.stage_done(k, self._side)
 
     def _block_bwd_identity(self, x: Act, hh: Act, a_x, a_h, pre: str, d_out: torch.Tensor, dx_dest: torch.Tensor):
         c = hh.C
@@ -471,13 +485,13 @@ class _Engine:
         g_h = self._new(d_out, c)
         sums_h = self._sums_like(hh)
         self._conv(d_op, pre + "c2", g_h, flip=True, mask_x=hh.t, mask_stats=hh.st, bwd_sums=sums_h)
-        dw2 = self._wgrad(a_h, d_op, self._dw(d_out, c, c))
+        dw2 = self._wgrad(a_h, d_op, self._dw(d_out, c, c, pre + "conv2.conv.weight"))
         ops.instnorm_backward_apply(g_h, hh.t, hh.st, sums_h, g_h)  # in place: g_h becomes d(h)
         gh_op = self._operand(g_h)
         g_x = self._new(d_out, x.C)
         sums_x = self._sums_like(x)
         self._conv(gh_op, pre + "c1", g_x, flip=True, mask_x=x.t, mask_stats=x.st, bwd_sums=sums_x)
-        dw1 = self._wgrad(a_x, gh_op, self._dw(d_out, c, x.C))
+        dw1 = self._wgrad(a_x, gh_op, self._dw(d_out, c, x.C, pre + "conv1.conv.weight"))
         ops.instnorm_backward_apply(g_x, x.t, x.st, sums_x, dx_dest, add=d_out)
         return dw1, dw2
 
@@ -489,13 +503,13 @@ class _Engine:
         d_op = self._operand(d_out)
         sums_h = self._sums_like(hh)
         self._conv(d_op, pre + "c2", dh, flip=True, mask_x=hh.t, mask_stats=hh.st, bwd_sums=sums_h)
-        dw2 = self._wgrad(a_h, d_op, self._dw(dcat2, c, c))
+        dw2 = self._wgrad(a_h, d_op, self._dw(dcat2, c, c, pre + "conv2.conv.weight"))
         ops.instnorm_backward_apply(dh, hh.t, hh.st, sums_h, dh)
         dcat_op = self._operand(dcat2)
         g_x = self._new(dcat2, x.C)
         sums_x = self._sums_like(x)
         self._conv(dcat_op, pre + "c1", g_x, flip=True, mask_x=x.t, mask_stats=x.st, bwd_sums=sums_x)
-        dwcat = self._wgrad(a_x, dcat_op, self._dw(dcat2, 2 * c, x.C))
+        dwcat = self._wgrad(a_x, dcat_op, self._dw(dcat2, 2 * c, x.C, (pre + "conv1.conv.weight", pre + "shortcut.conv.weight")))
         ops.instnorm_backward_apply(g_x, x.t, x.st, sums_x, dx_dest)
         return dwcat[:c], dw2, dwcat[c:]
 
@@ -513,8 +527,11 @@ class _Engine:
         #                                  9,10 up1 | 11,12 up2 | 13,14 up3 | 15,16 up4
         w_out = P["outc.weight"].reshape(num_classes, b).contiguous()
         d_cur = self._new(final.t, b)
-        dw_out = torch.empty_like(w_out)
-        db_out = torch.empty_like(P["outc.bias"])
+        dw_out = db_out = None
+        if self.sink is not None:
+            dw_out, db_out = self.sink.buffer("outc.weight"), self.sink.buffer("outc.bias")
+        dw_out = torch.empty_like(w_out) if dw_out is None else dw_out.view(num_classes, b)
+        db_out = torch.empty_like(P["outc.bias"]) if db_out is None else db_out
         ops.head_backward(final.t, w_out, dlogits, d_cur, dw_out, db_out)
         G["outc.weight"] = dw_out.reshape(P["outc.weight"].shape)
         G["outc.bias"] = db_out
@@ -538,6 +555,9 @@ class _Engine:
             n, d, h, w_, _ = d_cat.shape
             d_cur = torch.empty((n, d // 2, h // 2, w_ // 2, up_in[l]), dtype=self.dtype, device=d_cat.device)
             ops.upsample_backward(d_cat[..., ch[l]:], d_cur)
+            if j == 4:
+                self._stage_done(0)           # head + up4 (the full-resolution layers: the longest weight gradients)
+        self._stage_done(1)                   # up3 .. up1
         # encoder
         for l in (4, 3, 2, 1):
             pre = f"down{l}.conv."
@@ -554,17 +574,21 @@ class _Engine:
             x_prev = S["enc_out"][l - 1]
             d_cur = self._new(x_prev.t, ch[l - 1])
             ops.maxpool2_backward(x_prev.t, d_p, d_cur, dskip=dskip[l - 1])
+        self._stage_done(2)                   # down4 .. down1 (two thirds of the parameters)
         # inc block + stem
         x0, h0, ax0, ah0 = saved[0]
         d_t0 = self._new(x0.t, b)
         dw1, dw2 = self._block_bwd_identity(x0, h0, ax0, ah0, "inc.conv2.", d_cur, d_t0)
         G["inc.conv2.conv1.conv.weight"], G["inc.conv2.conv2.conv.weight"] = dw1, dw2
-        dws = torch.empty_like(P["inc.conv1.weight"])
+        dws = self.sink.buffer("inc.conv1.weight") if self.sink is not None else None
+        if dws is None:
+            dws = torch.empty_like(P["inc.conv1.weight"])
         ops.stem_conv_wgrad(S["x"], d_t0, dws)
         G["inc.conv1.weight"] = dws
         if self._side is not None:
             torch.cuda.current_stream().wait_stream(self._side)   # all weight gradients done before autograd hands them on
         self._side_keep.clear()
+        self._stage_done(3)                   # inc + stem
         return G
 
 
@@ -590,7 +614,10 @@ class _UNetFunction(torch.autograd.Function):
         with torch.no_grad():
             G = ctx.engine.backward(ctx.saved_acts, P, dlogits.contiguous().float())
         ctx.saved_acts = None
-        grads = tuple(G[nm] if p.requires_grad else None for nm, p in zip(ctx.names, params))
+        sink = ctx.engine.sink
+        # gradients the kernels wrote straight into the sink's buffers (= p.grad) are not handed to autograd again
+        grads = tuple(G[nm] if (p.requires_grad and not (sink is not None and sink.owns(nm))) else None
+                      for nm, p in zip(ctx.names, params))
         return (None, None, None, None, None) + grads
 
 
@@ -634,6 +661,7 @@ class B200UNet(nn.Module):
     def __getstate__(self):
         st = dict(self.__dict__)
         st.pop("_engine", None)  # raw device pointers: rebuilt on the next forward
+        st.pop("_grad_sink", None)
         return st
 
     def forward(self, x):
@@ -645,6 +673,7 @@ class B200UNet(nn.Module):
         if engine is None or engine.dtype != dtype or engine.slope != float(self.negative_slope):
             engine = _Engine(self.base_ch, self.negative_slope, dtype, self.block)
             self.__dict__["_engine"] = engine  # persistent packed-weight buffers; never pickled / deep-copied
+        engine.sink = self.__dict__.get("_grad_sink") if self.block == "BasicBlock" else None
         if x.device.index is not None and x.device.index != torch.cuda.current_device():
             with torch.cuda.device(x.device):     # kernels launch on the current device's stream: follow the tensors
                 out = _UNetFunction.apply(x.float(), engine, names, self.num_classes, torch.is_grad_enabled(), *params)

@@ -397,7 +397,7 @@ def test_conv3_plane_streaming_kernel(cuda_dev, case, monkeypatch):
     """The plane-streaming kernel of the 32-channel layers (conv3_stream.cu) against F.conv3d on identical bf16
     operands; max_ctas forces it at test sizes (it needs >= 3 units per CTA)."""
     from rsuper_b200 import ops
-    monkeypatch.setenv("RSB_FPROP_STREAM", "1")   # opt-in kernel (see conv3_stream.cu)
+    monkeypatch.delenv("RSB_FPROP_STREAM", raising=False)   # the default for eligible layers (RSB_FPROP_STREAM=0 disables it)
     N, D, H, W, Cin, Cout, dt, mode, ctas = case
     g = torch.Generator().manual_seed(31)
     w = (torch.randn(Cout, Cin, 3, 3, 3, generator=g) / (27 * Cin) ** 0.5).to(cuda_dev)
