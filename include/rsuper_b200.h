@@ -277,6 +277,14 @@ int rsb_dilate_ball(const uint8_t* src, uint8_t* dst, uint8_t* tmp, int n_vol, i
 /* get_lesion_channels (:204-248) for single-channel groups: dst[r] = src[row_map[r]]; and its adjoint */
 int rsb_rows_gather(const void* src, const int* row_map, void* dst, int n_rows, long long V, int elem_bytes, void* stream);
 int rsb_rows_scatter_add(const float* src, const int* row_map, float* dst, int n_rows, long long V, void* stream);
+/* get_lesion_channels with groups that merge several channels of one organ (:215-220, torch.stack(...).max(dim=0)):
+ * group_map[r * group_size + k] = source row of member k of output row r, -1 = none (member 0 always exists);
+ * dst[r] = max over the members (uint8 masks: OR).  rows_scatter_add_max is its backward for the logits: the gradient of
+ * row r is added to the member row that attained the maximum (the first one on ties), x = the tensor that was gathered. */
+int rsb_rows_gather_max(const void* src, const int* group_map, int group_size, void* dst, int n_rows, long long V, int elem_bytes,
+                        void* stream);
+int rsb_rows_scatter_add_max(const float* grad_rows, const float* x, const int* group_map, int group_size, float* dst, int n_rows,
+                             long long V, void* stream);
 /* mask algebra on uint8 0/1 volumes; op: 0 a|b, 1 a&b, 2 a&~b, 3 ~(a|b), 4 ~a   (to_penalize :1605, borders :1721-1737) */
 int rsb_u8_binary(const uint8_t* a, const uint8_t* b, uint8_t* out, int op, long long n, void* stream);
 /* counts[r] = number of non-zero voxels of row r (the `.sum() > 0` / `.sum() < t` tests) */

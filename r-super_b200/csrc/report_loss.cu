@@ -51,6 +51,41 @@ __global__ void rows_scatter_add_kernel(const float* __restrict__ src, const int
     d[v] += s[v];
 }
 
+// Lesion groups that merge several channels of one organ (get_lesion_channels, :215-220: torch.stack(...).max(dim=0)):
+// gmap[r * G + k] = source row of member k of output row r (-1 = no such member).  uint8 masks: max == OR.
+template <typename T>
+__global__ void rows_gather_max_kernel(const T* __restrict__ src, const int* __restrict__ gmap, int G, T* __restrict__ dst, long long V) {
+  const long long r = blockIdx.y;
+  const int* g = gmap + r * G;
+  T* d = dst + r * V;
+  for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < V; v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    T best = src[static_cast<long long>(g[0]) * V + v];
+    for (int k = 1; k < G; ++k)
+      if (g[k] >= 0) {
+        const T o = src[static_cast<long long>(g[k]) * V + v];
+        best = o > best ? o : best;
+      }
+    d[v] = best;
+  }
+}
+// backward of the max-merge: the gradient of output row r goes to the member that attained the maximum (first one on ties)
+__global__ void rows_scatter_add_max_kernel(const float* __restrict__ grad, const float* __restrict__ x, const int* __restrict__ gmap, int G,
+                                            float* __restrict__ dst, long long V) {
+  const long long r = blockIdx.y;
+  const int* g = gmap + r * G;
+  const float* s = grad + r * V;
+  for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < V; v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    int arg = g[0];
+    float best = x[static_cast<long long>(arg) * V + v];
+    for (int k = 1; k < G; ++k)
+      if (g[k] >= 0) {
+        const float o = x[static_cast<long long>(g[k]) * V + v];
+        if (o > best) { best = o; arg = g[k]; }
+      }
+    dst[static_cast<long long>(arg) * V + v] += s[v];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // mask algebra on uint8 0/1 volumes; op: 0 OR, 1 AND, 2 a AND NOT b, 3 NOR, 4 NOT a
 // ---------------------------------------------------------------------------------------------
@@ -402,6 +437,25 @@ extern "C" int rsb_rows_scatter_add(const float* src, const int* row_map, float*
   dim3 grid(grid_for(V, 256), n_rows);
   rows_scatter_add_kernel<<<grid, 256, 0, RSB_ST>>>(src, row_map, dst, V);
   return check_launch("rows_scatter_add_kernel");
+}
+
+extern "C" int rsb_rows_gather_max(const void* src, const int* group_map, int group_size, void* dst, int n_rows, long long V, int elem_bytes,
+                                   void* stream) {
+  RSB_REQUIRE(src && group_map && dst && n_rows > 0 && n_rows <= 65535 && V > 0 && group_size >= 1, "rows_gather_max: bad arguments");
+  dim3 grid(grid_for(V, 256), n_rows);
+  if (elem_bytes == 4) rows_gather_max_kernel<float><<<grid, 256, 0, RSB_ST>>>((const float*)src, group_map, group_size, (float*)dst, V);
+  else if (elem_bytes == 1) rows_gather_max_kernel<uint8_t><<<grid, 256, 0, RSB_ST>>>((const uint8_t*)src, group_map, group_size, (uint8_t*)dst, V);
+  else { set_last_error("rows_gather_max: element size must be 1 or 4"); return -1; }
+  return check_launch("rows_gather_max_kernel");
+}
+
+extern "C" int rsb_rows_scatter_add_max(const float* grad_rows, const float* x, const int* group_map, int group_size, float* dst, int n_rows,
+                                        long long V, void* stream) {
+  RSB_REQUIRE(grad_rows && x && group_map && dst && n_rows > 0 && n_rows <= 65535 && V > 0 && group_size >= 1,
+              "rows_scatter_add_max: bad arguments");
+  dim3 grid(grid_for(V, 256), n_rows);
+  rows_scatter_add_max_kernel<<<grid, 256, 0, RSB_ST>>>(grad_rows, x, group_map, group_size, dst, V);
+  return check_launch("rows_scatter_add_max_kernel");
 }
 
 extern "C" int rsb_u8_binary(const uint8_t* a, const uint8_t* b, uint8_t* out, int op, long long n, void* stream) {

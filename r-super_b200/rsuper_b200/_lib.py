@@ -136,6 +136,8 @@ SIGNATURES = {
                                 c_void_p]),
     "rsb_rows_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p]),
     "rsb_rows_scatter_add": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_ll, c_void_p]),
+    "rsb_rows_gather_max": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_void_p]),
+    "rsb_rows_scatter_add_max": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_ll, c_void_p]),
     "rsb_u8_binary": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_ll, c_void_p]),
     "rsb_u8_row_count": (c_int, [c_void_p, c_void_p, c_int, c_ll, c_void_p]),
     "rsb_masked_sigmoid_sum": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_void_p]),

@@ -452,15 +452,28 @@ def _rows(t: torch.Tensor, v: int) -> int:
 
 
 def rows_gather(src, row_map, n_rows, v):
-    """dst[r] = src.view(-1, V)[row_map[r]] — lesion-channel selection (get_lesion_channels)."""
+    """dst[r] = src.view(-1, V)[row_map[r]] — lesion-channel selection (get_lesion_channels); row_map int32 [n_rows], or
+    int32 [n_rows, G] for groups that max-merge several channels (-1 = no such member)."""
     assert src.is_contiguous() and row_map.dtype == torch.int32 and src.element_size() in (1, 4)
     dst = torch.empty((n_rows, v), dtype=src.dtype, device=src.device)
+    if row_map.dim() == 2 and row_map.shape[1] > 1:
+        assert row_map.is_contiguous() and row_map.shape[0] == n_rows
+        _call("report", 1, 0.0, lib().rsb_rows_gather_max, _p(src), _p(row_map), row_map.shape[1], _p(dst), n_rows, v, src.element_size(),
+              _stream(), what="rows_gather_max")
+        return dst
     _call("report", 1, 0.0, lib().rsb_rows_gather, _p(src), _p(row_map), _p(dst), n_rows, v, src.element_size(), _stream(), what="rows_gather")
     return dst
 
 
-def rows_scatter_add(src, row_map, dst, v):
+def rows_scatter_add(src, row_map, dst, v, x=None):
+    """Backward of rows_gather for the logits; with a group table the gradient goes to the member that attained the maximum
+    (x = the gathered tensor)."""
     assert src.dtype == torch.float32 and dst.dtype == torch.float32 and src.is_contiguous() and dst.is_contiguous()
+    if row_map.dim() == 2 and row_map.shape[1] > 1:
+        assert x is not None and x.dtype == torch.float32 and x.is_contiguous() and x.numel() == dst.numel()
+        _call("report", 1, 0.0, lib().rsb_rows_scatter_add_max, _p(src), _p(x), _p(row_map), row_map.shape[1], _p(dst), _rows(src, v), v,
+              _stream(), what="rows_scatter_add_max")
+        return dst
     _call("report", 1, 0.0, lib().rsb_rows_scatter_add, _p(src), _p(row_map), _p(dst), _rows(src, v), v, _stream(), what="rows_scatter_add")
     return dst
 

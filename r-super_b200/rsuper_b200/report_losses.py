@@ -26,9 +26,11 @@ _SUFFIXES = ("lesion", "cyst", "pdac", "pnet")
 SEPARABLE_CORRELATION = True
 
 
-def lesion_channels(classes: Sequence[str]) -> List[int]:
-    """Channel index of every lesion group (get_lesion_channels, :204-248).  Groups that max-merge several channels
-    of one organ (e.g. pancreatic_pdac + pancreatic_cyst) are not implemented yet and raise."""
+def lesion_channels(classes: Sequence[str]) -> List[List[int]]:
+    """Channel indices of every lesion group (get_lesion_channels, :204-248): channels whose name contains
+    lesion | cyst | pdac | pnet, grouped by the name up to and including the suffix ('pancreatic' -> 'pancreas'); a group
+    with several members (e.g. 'liver_lesion_1', 'liver_lesion_2') is max-merged.  Mirrors the reference loop, including
+    that a name matching several suffixes joins one group per matching suffix."""
     names: List[str] = []
     groups: Dict[str, List[int]] = {}
     for i, cl in enumerate(classes):
@@ -41,9 +43,7 @@ def lesion_channels(classes: Sequence[str]) -> List[int]:
                 groups[key].append(i)
     if not names:
         raise ValueError("no lesion channel in `classes`")
-    if any(len(groups[k]) != 1 for k in names):
-        raise NotImplementedError("rsuper_b200: lesion groups that merge several channels of one organ are not implemented")
-    return [groups[k][0] for k in names]
+    return [groups[k] for k in names]
 
 
 def _u8(t: torch.Tensor) -> torch.Tensor:
@@ -138,16 +138,17 @@ class _MaskedSigmoidSum(torch.autograd.Function):
         v = lg[0, 0].numel()
         x_rows = ops.rows_gather(lg, row_map, n_b * n_l, v)
         sums = ops.masked_sigmoid_sum(x_rows, mask_rows, scale, v)
-        ctx.keep = (x_rows, row_map, mask_rows, scale, lg.shape, v)
+        ctx.keep = (x_rows, row_map, mask_rows, scale, lg, v)
         return sums.view(n_b, n_l)
 
     @staticmethod
     def backward(ctx, g):
-        x_rows, row_map, mask_rows, scale, shape, v = ctx.keep
+        x_rows, row_map, mask_rows, scale, lg, v = ctx.keep
+        shape = lg.shape
         dx_rows = torch.empty_like(x_rows)
         ops.masked_sigmoid_grad(x_rows, mask_rows, scale, g.detach().reshape(-1).float().contiguous(), dx_rows, v)
         dl = torch.zeros(shape, dtype=torch.float32, device=x_rows.device)
-        ops.rows_scatter_add(dx_rows, row_map, dl, v)
+        ops.rows_scatter_add(dx_rows, row_map, dl, v, x=lg)
         ctx.keep = None
         return dl, None, None, None, None, None
 
@@ -160,8 +161,26 @@ def dice_based_volume_loss(x, y, tolerance: float = 0.1, E: float = 500.0):
     return loss.clamp(0, 1)
 
 
-def _row_map(n_b: int, n_c: int, chans: Sequence[int], device) -> torch.Tensor:
-    return torch.tensor([b * n_c + c for b in range(n_b) for c in chans], dtype=torch.int32, device=device)
+_ROW_MAPS: Dict[tuple, torch.Tensor] = {}
+
+
+def _row_map(n_b: int, n_c: int, groups: Sequence[Sequence[int]], device) -> torch.Tensor:
+    """Source rows of the [B * L] lesion rows in a [B * C, V] view: int32 [B * L] when every group has one channel, else
+    int32 [B * L, G] padded with -1 (ops.rows_gather max-merges).  Cached: the table is a host -> device copy."""
+    key = (n_b, n_c, tuple(tuple(g) for g in groups), str(device))
+    hit = _ROW_MAPS.get(key)
+    if hit is None:
+        width = max(len(g) for g in groups)
+        rows = [[b * n_c + c for c in g] + [-1] * (width - len(g)) for b in range(n_b) for g in groups]
+        t = torch.tensor(rows, dtype=torch.int32)
+        hit = _ROW_MAPS[key] = (t[:, 0].contiguous() if width == 1 else t.contiguous()).to(device)
+    return hit
+
+
+def _group_weights(class_weights, n_c: int, groups, n_b: int, n_l: int):
+    """class weights of the merged lesion channels ([B, L]): get_lesion_channels(class_weights) = max over the group."""
+    cw = class_weights.reshape(class_weights.shape[0], n_c).float()
+    return torch.stack([cw[:, g].max(dim=1).values for g in groups], dim=1).expand(n_b, n_l).contiguous()
 
 
 def volume_loss_basic(out, chosen_segment_mask, tumor_volumes, labels, unk_voxels, classes, dilation_segment: int = 31,
@@ -183,7 +202,7 @@ def volume_loss_basic(out, chosen_segment_mask, tumor_volumes, labels, unk_voxel
     report_volume = tumor_volumes.float().sum(-1, keepdim=True).expand(n_b, n_l)
     loss = dice_based_volume_loss(sums, report_volume * gate, tolerance=tolerance, E=500.0)
     if class_weights is not None:
-        loss = loss * class_weights.reshape(class_weights.shape[0], n_c)[:, chans].float().expand(n_b, n_l)
+        loss = loss * _group_weights(class_weights, n_c, chans, n_b, n_l)
     return {"dice_volume_loss": loss.mean()}
 
 
@@ -286,7 +305,7 @@ class _BallLoss(torch.autograd.Function):
         seg_cnt = ops.u8_row_count(csm, v).view(n_b, n_l).cpu().numpy()  # `seg.sum(...) > 0` tests of the reference
         cw = None
         if class_weights is not None:
-            cw = class_weights.reshape(class_weights.shape[0], n_c)[:, chans].float().expand(n_b, n_l).contiguous()
+            cw = _group_weights(class_weights, n_c, chans, n_b, n_l)
         states, bce_terms, dice_terms = [], [], []
         for b in range(n_b):
             vols, dias = volumes_h[b], diameters_h[b]
@@ -345,14 +364,15 @@ class _BallLoss(torch.autograd.Function):
             states.append((st, slice(r, r + 1)))
             bce_terms.append(st.loss_out[1])
             dice_terms.append(st.loss_out[2])
-        ctx.states, ctx.meta = states, (x_rows.shape, rm, lg.shape, v, n_b, apply_dice)
+        ctx.states, ctx.meta = states, (x_rows.shape, rm, lg, v, n_b, apply_dice)
         bce = torch.stack(bce_terms).mean()
         dice = torch.stack(dice_terms).mean() if apply_dice else torch.zeros_like(bce)
         return bce, dice
 
     @staticmethod
     def backward(ctx, g_bce, g_dice):
-        rows_shape, rm, shape, v, n_b, apply_dice = ctx.meta
+        rows_shape, rm, lg, v, n_b, apply_dice = ctx.meta
+        shape = lg.shape
         dev = g_bce.device
         dx_rows = torch.zeros(rows_shape, dtype=torch.float32, device=dev)
         scales = torch.stack([g_bce.detach().float().reshape(()), (g_dice.detach().float().reshape(()) if apply_dice
@@ -361,7 +381,7 @@ class _BallLoss(torch.autograd.Function):
         for st, rows in ctx.states:
             ops.seg_loss_backward(st, scales, dx_rows[rows])
         dl = torch.zeros(shape, dtype=torch.float32, device=dev)
-        ops.rows_scatter_add(dx_rows, rm, dl, v)
+        ops.rows_scatter_add(dx_rows, rm, dl, v, x=lg)
         ctx.states = None
         return (dl,) + (None,) * 17
 

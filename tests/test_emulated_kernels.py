@@ -156,6 +156,12 @@ def test_shim_runs_gpu_verified_report_losses(emulated, golden):
     R.test_calculate_loss_dicts(CPU, golden)
 
 
+@pytest.mark.parametrize("tag", ["merged", pytest.param("single", marks=_slow)])
+def test_emulated_lesion_group_max_merge(emulated, tag):
+    import test_report_losses_gpu as R
+    R.test_lesion_group_max_merge(CPU, tag)
+
+
 @full
 def test_emulated_assemble_batch_feeds_calculate_loss(emulated):
     W.test_assemble_batch_feeds_calculate_loss(CPU)

@@ -197,3 +197,61 @@ def test_dilation_tile_kernel_edge_shapes(cuda_dev, shape, k):
     got = ops.dilate_ball(vols.to(cuda_dev), k).cpu()
     ref = torch.stack([LR.dilate_volume(v.float(), k) for v in vols]).to(torch.uint8)
     assert torch.equal(got, ref)
+
+
+MERGE_CLASSES = ["liver", "liver_lesion_1", "liver_lesion_2", "pancreatic_cyst", "kidney_cyst_lesion"]
+
+
+def _merge_inputs(tag):
+    from oracle import synth
+    lg = synth.synthetic_logits(2, len(MERGE_CLASSES), (16, 24, 32), seed=4)
+    bt = synth.make_batch(["report", "mask"], MERGE_CLASSES, (16, 24, 32), seed={"merged": 20, "single": 23}[tag])
+    return lg, bt
+
+
+def _golden_merge():
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_merge.npz"))
+
+
+@pytest.mark.parametrize("tag", ["merged", "single"])
+def test_lesion_group_max_merge(cuda_dev, tag):
+    """Lesion groups that merge several channels of one organ (get_lesion_channels, losses_foundation.py:204-248): a
+    two-channel group ('liver_lesion_1' + 'liver_lesion_2') and a channel that joins two groups ('kidney_cyst_lesion') —
+    Volume and Ball loss values and the per-channel gradient mass against values recorded from the REAL reference
+    (tests/golden/make_golden_merge.py) and against the oracle element by element (the gradient of a merged row goes to the
+    member that attained the maximum)."""
+    from oracle import losses_ref as LR
+    from rsuper_b200 import report_losses as RL
+    gold = _golden_merge()
+    lg, bt = _merge_inputs(tag)
+    assert RL.lesion_channels(MERGE_CLASSES) == [[1, 2], [3], [4], [4]] and list(gold["names"]) == ["liver_lesion", "pancreas_cyst",
+                                                                                                    "kidney_cyst_lesion", "kidney_cyst"]
+    dev = {k: v.to(cuda_dev) for k, v in bt.items()}
+    # volume loss
+    xr = lg.detach().clone().requires_grad_(True)
+    ref = LR.volume_loss_basic(xr, bt["mask"].float(), bt["volumes"], bt["label"].float(), bt["unk_channels"].float(), MERGE_CLASSES,
+                               tolerance=0.2)["dice_volume_loss"]
+    ref.backward()
+    x = lg.detach().clone().to(cuda_dev).requires_grad_(True)
+    out = RL.volume_loss_basic(x, dev["mask"], dev["volumes"], dev["label"], dev["unk_channels"], MERGE_CLASSES, tolerance=0.2)["dice_volume_loss"]
+    out.backward()
+    assert abs(out.item() - float(gold[f"{tag}_volume_loss"])) <= 1e-6 and abs(out.item() - ref.item()) <= 1e-6
+    assert rel(x.grad.cpu(), xr.grad) <= 1e-4
+    np.testing.assert_allclose(x.grad.double().abs().sum(dim=(0, 2, 3, 4)).cpu().numpy(), gold[f"{tag}_volume_grad_per_channel"], rtol=1e-4, atol=1e-9)
+    if tag == "merged":
+        assert x.grad[:, 1].abs().sum() > 0 and x.grad[:, 2].abs().sum() > 0          # both members of the group receive gradient
+    # ball loss
+    x2r = lg.detach().clone().requires_grad_(True)
+    rb = LR.ball_loss(x2r, bt["label"].float(), bt["unk_channels"].float(), bt["mask"].float(), bt["volumes"], bt["diameters"], MERGE_CLASSES,
+                      apply_dice_loss=True, diameter_margin=0.2, volume_margin=0.2)
+    (rb["ball_loss_bce"] + rb["ball_loss_dice"]).backward()
+    x2 = lg.detach().clone().to(cuda_dev).requires_grad_(True)
+    gb = RL.ball_loss(x2, dev["label"], dev["unk_channels"], dev["mask"], dev["volumes"], dev["diameters"], MERGE_CLASSES,
+                      apply_dice_loss=True, diameter_margin=0.2, volume_margin=0.2)
+    (gb["ball_loss_bce"] + gb["ball_loss_dice"]).backward()
+    for k in ("ball_loss_bce", "ball_loss_dice"):
+        assert abs(gb[k].item() - float(gold[f"{tag}_{k}"])) <= 1e-5 * max(1.0, abs(float(gold[f"{tag}_{k}"]))), k
+        assert abs(gb[k].item() - rb[k].item()) <= 1e-5 * max(1.0, abs(rb[k].item())), k
+    assert rel(x2.grad.cpu(), x2r.grad) <= 1e-4
+    np.testing.assert_allclose(x2.grad.double().abs().sum(dim=(0, 2, 3, 4)).cpu().numpy(), gold[f"{tag}_ball_grad_per_channel"], rtol=1e-4, atol=1e-9)
