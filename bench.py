@@ -84,27 +84,21 @@ def mvox_per_s(voxels: int, ms: float) -> float:
     return voxels / (ms * 1e-3) / 1e6
 
 
-def profiled_traffic(prefix: str = "r02"):
-    """dram read+write bytes of ONE launch of the dominant kernel at the benchmark's dominant shape (32->32 @ 2x128^3) from
-    the committed ncu --set full capture (profiles/<round>_conv3_fprop_ncu_full_summary.txt: first captured launch), or None."""
-    import glob
-    import re
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*conv3_fprop_ncu_full_summary.txt")))
-    if not files:
+def profiled_traffic():
+    """dram read + write bytes of ONE launch of the dominant kernel at the benchmark's dominant shape (32 -> 32 channels at
+    2 x 128^3, plane-streaming kernel) from the committed ncu --set full capture (profiles/r02_kernels_ncu_summary.txt,
+    written by tools/summarize_ncu.py roofline), or None."""
+    path = os.path.join(ROOT, "profiles", "r02_kernels_ncu_summary.txt")
+    if not os.path.exists(path):
         return None, None
-    rd = wr = None
-    for ln in open(files[-1]):
-        m = re.search(r"dram__bytes_(read|write)\.sum\s+([0-9.]+)\s+(\w+)", ln)
-        if not m:
-            continue
-        v = float(m.group(2)) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(m.group(3), 1.0)
-        if m.group(1) == "read" and rd is None:
-            rd = v
-        elif m.group(1) == "write" and wr is None:
-            wr = v
-        if rd is not None and wr is not None:
-            return rd + wr, os.path.basename(files[-1])
-    return None, os.path.basename(files[-1])
+    for ln in open(path):
+        if "conv3_stream32_kernel" in ln:
+            f = ln.split()
+            # ... kernel name tokens | grid regs us dram_MB GB/s %HBM tensor% warps% | stalls
+            for i, tok in enumerate(f):
+                if tok == "148":
+                    return float(f[i + 3]) * 1e6, os.path.basename(path)
+    return None, os.path.basename(path)
 
 
 def load_peaks():

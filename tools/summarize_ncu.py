@@ -66,5 +66,52 @@ def full(src, dst, note=""):
     print(open(dst).read())
 
 
+def _num(v):
+    try:
+        return float(v.replace(",", ""))
+    except (ValueError, AttributeError):
+        return None
+
+
+def roofline(src, dst, hbm_gbs="6545", tensor_tf="1399.3"):
+    """One line per captured launch: duration, DRAM bytes read + written (ncu), achieved DRAM GB/s against the measured copy
+    bandwidth (MEASURED_PEAKS.json), tensor-pipe activity, occupancy and the two leading stall reasons."""
+    hbm = float(hbm_gbs)
+    tables = []                    # (header, units, rows) per report: ncu picks the unit of a column per report
+    if src.endswith(".csv"):      # `ncu -i x.ncu-rep --page raw --csv` exported on the GPU box (several files: comma-separated)
+        for part in src.split(","):
+            rows = list(csv.reader(open(part)))
+            tables.append((rows[0], rows[1], rows[2:]))
+    else:
+        out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(out)))
+        tables.append((rows[0], rows[1], rows[2:]))
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "nsecond": 1e-9, "usecond": 1e-6,
+             "msecond": 1e-3, "second": 1.0}
+    with open(dst, "w") as f:
+        f.write(f"# ncu --set full --clock-control none --import-source on; source {src}\n")
+        f.write(f"# achieved GB/s = (dram__bytes_read.sum + dram__bytes_write.sum) / gpu__time_duration.sum; peak = {hbm:.0f} GB/s (measured copy bandwidth)\n")
+        f.write(f"# {'kernel':46s} {'grid':>7s} {'regs':>4s} {'us':>8s} {'dram MB':>8s} {'GB/s':>6s} {'%HBM':>5s} {'tensor%':>7s} {'warps%':>6s}  top stalls\n")
+        for hdr, units, row in [(h, u_, r) for h, u_, rows_ in tables for r in rows_]:
+            d = dict(zip(hdr, row))
+            u = dict(zip(hdr, units))
+
+            def val(m):
+                v = _num(d.get(m))
+                return None if v is None else v * scale.get(u.get(m, ""), 1.0)
+            t = val("gpu__time_duration.sum")
+            rdb, wrb = val("dram__bytes_read.sum") or 0.0, val("dram__bytes_write.sum") or 0.0
+            name = re.sub(r"\(.*", "", d.get("Kernel Name", "")).replace("rsb::", "")[:46]
+            gbs = (rdb + wrb) / t / 1e9 if t else 0.0
+            tens = _num(d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")) or 0.0
+            warps = _num(d.get("sm__warps_active.avg.pct_of_peak_sustained_active")) or 0.0
+            stalls = sorted(((_num(v) or 0.0, k.replace("smsp__pcsamp_warps_issue_stalled_", "")) for k, v in d.items()
+                             if k.startswith("smsp__pcsamp_warps_issue_stalled_") and "not_issued" not in k), reverse=True)[:2]
+            f.write(f"  {name:46s} {d.get('launch__grid_size', ''):>7s} {d.get('launch__registers_per_thread', ''):>4s} {t * 1e6:8.1f} "
+                    f"{(rdb + wrb) / 1e6:8.1f} {gbs:6.0f} {100 * gbs / hbm:5.1f} {tens:7.1f} {warps:6.1f}  "
+                    + ", ".join(f"{k} {int(v)}" for v, k in stalls) + "\n")
+    print(open(dst).read())
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](*sys.argv[2:])
+    {"launches": launches, "full": full, "roofline": roofline}[sys.argv[1]](*sys.argv[2:])
