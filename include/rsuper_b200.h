@@ -83,6 +83,9 @@ typedef struct RsbPackJob {
   int co_eff, ci_eff, NT, ntiles, nchunks;
   unsigned int block_begin;
   unsigned long long total;
+  /* 1 => w_a / w_b are 1x1x1 kernels [rows][Cin]: embedded at the centre tap of the packed 3x3x3 image, other taps zero
+   * (consumed with RsbConv3Args.pointwise = 1, or as an ordinary 3x3x3 image) */
+  int pointwise;
 } RsbPackJob;
 int rsb_conv3_pack_plan(RsbPackJob* jobs_host, int n_jobs, unsigned int* total_blocks);
 int rsb_conv3_pack_weights_batched(const RsbPackJob* jobs_device, int n_jobs, unsigned int total_blocks, void* stream);
@@ -119,6 +122,10 @@ typedef struct RsbConv3Args {
   /* tuning (0 = auto) */
   int planes_per_item; /* PZ in {1,2,4} */
   int max_ctas;        /* 0 => number of SMs */
+  /* 1 => w_packed is a 1x1x1 convolution ([Cout][Cin][1][1][1]: Bottleneck conv1 / conv3, conv_layers.py:104-108) embedded at the
+   * centre tap of a 3x3x3 image whose other 26 taps are zero: only the centre tap is streamed and multiplied (same result,
+   * 1/27 of the tensor work) */
+  int pointwise;
 } RsbConv3Args;
 
 int rsb_conv3_forward(const RsbConv3Args* args, void* stream);

@@ -75,6 +75,28 @@ def _basic_block(xs, xf, sd, prefix, cfg):
     return cfg.store(out), out
 
 
+def _cna_k(xs, xf, w, cfg):
+    """ConvNormAct(preact=True) with the kernel size read off the weight (1x1x1: padding 0; 3x3x3: padding 1)."""
+    a = cfg.operand(_norm_act(xs, xf, cfg))
+    return F.conv3d(a, cfg.operand(w), padding=w.shape[-1] // 2)
+
+
+def _bottleneck(xs, xf, sd, prefix, cfg):
+    """Bottleneck.forward (conv_layers.py:97-123): 1x1x1 (C -> C/2) -> 3x3x3 -> 1x1x1 (C/2 -> C), all pre-activation, plus
+    the 3x3x3 ConvNormAct shortcut when the channel count changes; returns (stored, full) of the block output."""
+    h1_full = _cna_k(xs, xf, sd[prefix + "conv1.conv.weight"], cfg)
+    h1_st = cfg.store(h1_full)
+    h2_full = _cna_k(h1_st, h1_full, sd[prefix + "conv2.conv.weight"], cfg)
+    h2_st = cfg.store(h2_full)
+    out = _cna_k(h2_st, h2_full, sd[prefix + "conv3.conv.weight"], cfg)
+    key = prefix + "shortcut.conv.weight"
+    if key in sd:
+        out = out + cfg.store(_cna_k(xs, xf, sd[key], cfg))
+    else:
+        out = out + xs
+    return cfg.store(out), out
+
+
 def _single_conv(xs, sd, prefix, cfg):
     """SingleConv = ConvNormAct(preact=False): act(norm(conv(x))) (conv_layers.py:50-68); returns the stored output.
     With emulation the raw conv output is what gets stored / re-read (statistics from the fp32 accumulators)."""
@@ -109,16 +131,17 @@ def unet_forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], slope: float = 0.
     tr = trace if trace is not None else {}
     if "inc.conv2.conv.conv.weight" in sd:
         return _unet_forward_single(x, sd, cfg, tr)
+    block = _bottleneck if "inc.conv2.conv3.conv.weight" in sd else _basic_block
     # inconv: raw conv then BasicBlock (unet_utils.py:17-21)
     t_full = F.conv3d(x, sd["inc.conv1.weight"], padding=1)
     t_st = cfg.store(t_full)
-    xs, xf = _basic_block(t_st, t_full, sd, "inc.conv2.", cfg)
+    xs, xf = block(t_st, t_full, sd, "inc.conv2.", cfg)
     tr["t0"], tr["inc"] = t_st, xs
     skips = [(xs, xf)]
     for l in range(1, 5):  # down_block: MaxPool3d then two blocks (unet_utils.py:33-41)
         ps = F.max_pool3d(xs, 2)
-        ys, yf = _basic_block(ps, ps, sd, f"down{l}.conv.1.", cfg)
-        xs, xf = _basic_block(ys, yf, sd, f"down{l}.conv.2.", cfg)
+        ys, yf = block(ps, ps, sd, f"down{l}.conv.1.", cfg)
+        xs, xf = block(ys, yf, sd, f"down{l}.conv.2.", cfg)
         tr[f"pool{l}"], tr[f"down{l}.1"], tr[f"down{l}.2"] = ps, ys, xs
         skips.append((xs, xf))
     cur = skips[4][0]
@@ -128,8 +151,8 @@ def unet_forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], slope: float = 0.
         up_st = cfg.store(up_full)
         cat_s = torch.cat([sk_s, up_st], dim=1)
         cat_f = torch.cat([sk_f, up_full], dim=1)
-        ys, yf = _basic_block(cat_s, cat_f, sd, f"up{j}.conv.0.", cfg)
-        cur, _ = _basic_block(ys, yf, sd, f"up{j}.conv.1.", cfg)
+        ys, yf = block(cat_s, cat_f, sd, f"up{j}.conv.0.", cfg)
+        cur, _ = block(ys, yf, sd, f"up{j}.conv.1.", cfg)
         tr[f"up{j}.cat"], tr[f"up{j}.0"], tr[f"up{j}.1"] = cat_s, ys, cur
     w = sd["outc.weight"]
     return F.conv3d(cur, w, sd["outc.bias"])  # unet.py:62
@@ -153,6 +176,20 @@ def synthetic_state_dict(base_ch: int, num_classes: int, in_ch: int = 1, device=
         for j, l in enumerate((3, 2, 1, 0), start=1):
             shapes += [(f"up{j}.conv.0.conv.conv.weight", (ch[l], ch[l] + ch[l + 1], 3, 3, 3)),
                        (f"up{j}.conv.1.conv.conv.weight", (ch[l], ch[l], 3, 3, 3))]
+        shapes += [("outc.weight", (num_classes, b, 1, 1, 1)), ("outc.bias", (num_classes,))]
+        return _fill_state_dict(shapes, gain, device)
+    if block == "Bottleneck":
+        def bneck(p, ci, co):
+            out = [(p + "conv1.conv.weight", (co // 2, ci, 1, 1, 1)), (p + "conv2.conv.weight", (co // 2, co // 2, 3, 3, 3)),
+                   (p + "conv3.conv.weight", (co, co // 2, 1, 1, 1))]
+            if ci != co:
+                out.append((p + "shortcut.conv.weight", (co, ci, 3, 3, 3)))
+            return out
+        shapes = [("inc.conv1.weight", (b, in_ch, 3, 3, 3))] + bneck("inc.conv2.", b, b)
+        for l in range(1, 5):
+            shapes += bneck(f"down{l}.conv.1.", ch[l - 1], ch[l]) + bneck(f"down{l}.conv.2.", ch[l], ch[l])
+        for j, l in enumerate((3, 2, 1, 0), start=1):
+            shapes += bneck(f"up{j}.conv.0.", ch[l] + ch[l + 1], ch[l]) + bneck(f"up{j}.conv.1.", ch[l], ch[l])
         shapes += [("outc.weight", (num_classes, b, 1, 1, 1)), ("outc.bias", (num_classes,))]
         return _fill_state_dict(shapes, gain, device)
     assert block == "BasicBlock", block

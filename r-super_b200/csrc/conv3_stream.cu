@@ -466,7 +466,7 @@ int rsb_conv3_stream_try(const RsbConv3Args* p, void* stream) {
   // eagerly enqueued streams, where the kernel order depended on host timing.)
   const char* on = getenv("RSB_FPROP_STREAM");
   if (on != nullptr && on[0] == '0') return 1;
-  if (p->Cin > 32 || p->Cout > 32 || p->Cout <= 16 || p->a_lo != nullptr || p->planes_per_item != 0) return 1;
+  if (p->Cin > 32 || p->Cout > 32 || p->Cout <= 16 || p->a_lo != nullptr || p->planes_per_item != 0 || p->pointwise) return 1;
   if (p->dtype != RSB_BF16 && p->dtype != RSB_F32) return 1;
   int sms = p->max_ctas > 0 ? p->max_ctas : rsb_num_sms();
   if (sms <= 0) return 1;

@@ -133,7 +133,7 @@ template <typename T>
 __global__ void __launch_bounds__(kStemThreads) stem_fwd_tiled_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                       T* __restrict__ y, long long yp, float* __restrict__ stats,
                                                                       int D, int H, int W, int Cout) {
-  extern __shared__ __align__(16) float sm[];
+  extern __shared__ float sm[];   // dynamic shared memory is 16-byte aligned (float4 weight loads below)
   float* sw = sm;                    // [27][CoutPad16]
   const int cpad = (Cout + 15) / 16 * 16;
   float* sacc = sm + 27 * cpad;      // [Cout][2]

@@ -37,6 +37,7 @@ class RsbConv3Args(C.Structure):
         ("bwd_sums", c_void_p),
         ("eps", c_float), ("slope", c_float),
         ("planes_per_item", c_int), ("max_ctas", c_int),
+        ("pointwise", c_int),
     ]
 
 
@@ -48,6 +49,7 @@ class RsbPackJob(C.Structure):
         ("co_eff", c_int), ("ci_eff", c_int), ("NT", c_int), ("ntiles", c_int), ("nchunks", c_int),
         ("block_begin", C.c_uint),
         ("total", C.c_ulonglong),
+        ("pointwise", c_int),
     ]
 
 

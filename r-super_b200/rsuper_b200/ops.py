@@ -139,7 +139,8 @@ class PackPlan:
         self._keep = []
         dev = jobs[0][1].device
         for j, (key, w_a, w_b, flip) in enumerate(jobs):
-            assert w_a.dtype == torch.float32 and _on_device(w_a) and w_a.is_contiguous() and w_a.shape[2:] == (3, 3, 3)
+            pointwise = tuple(w_a.shape[2:]) == (1, 1, 1)          # 1x1x1 kernel: embedded at the centre tap of a 3x3x3 image
+            assert w_a.dtype == torch.float32 and _on_device(w_a) and w_a.is_contiguous() and (pointwise or w_a.shape[2:] == (3, 3, 3))
             cin = w_a.shape[1]
             cout = w_a.shape[0]
             if w_b is not None:
@@ -152,6 +153,7 @@ class PackPlan:
             jb = arr[j]
             jb.w_a, jb.w_b, jb.packed = w_a.data_ptr(), (w_b.data_ptr() if w_b is not None else None), img.data_ptr()
             jb.rows_a, jb.Cout, jb.Cin, jb.transpose_flip, jb.parts = w_a.shape[0], cout, cin, int(flip), parts
+            jb.pointwise = int(pointwise)
         nblk = C.c_uint(0)
         check(lib().rsb_conv3_pack_plan(arr, n, C.byref(nblk)), "conv3_pack_plan")
         self.n_jobs, self.n_blocks = n, nblk.value
@@ -169,7 +171,7 @@ class PackPlan:
 
 
 def conv3_forward(a_op, w_packed, y, *, a_lo=None, a_lo2=None, slope=0.0, res=None, out_stats=None,
-                  mask_x=None, mask_stats=None, bwd_sums=None, planes_per_item=0, max_ctas=0, eps=EPS_IN):
+                  mask_x=None, mask_stats=None, bwd_sums=None, planes_per_item=0, max_ctas=0, eps=EPS_IN, pointwise=False):
     """y = conv3x3x3(a_op) [+ res]; a_op is the bf16 operand from norm_act (a_lo: its split-precision low part,
     with weights packed split=True); optional fused output statistics / dgrad masking epilogue."""
     a = _lib.RsbConv3Args()
@@ -197,8 +199,10 @@ def conv3_forward(a_op, w_packed, y, *, a_lo=None, a_lo2=None, slope=0.0, res=No
         a.mask_x, a.mask_x_pitch = _p(mask_x), _check_cl(mask_x, "mask_x")
         a.mask_stats, a.bwd_sums = _st(mask_stats, mask_x, "mask_stats"), _st(bwd_sums, mask_x, "bwd_sums")
     a.planes_per_item, a.max_ctas = planes_per_item, max_ctas
-    _call("conv3_igemm", 1, 2.0 * 27 * cin * cout * n * d * h * w_, lib().rsb_conv3_forward, C.byref(a), _stream(), what="conv3_forward",
-          desc=f"{cin}->{cout} {n}x{d}x{h}x{w_}{' dgrad' if mask_x is not None else ''}{' res' if res is not None else ''}")
+    a.pointwise = int(bool(pointwise))
+    _call("conv3_igemm", 1, 2.0 * (1 if pointwise else 27) * cin * cout * n * d * h * w_, lib().rsb_conv3_forward, C.byref(a), _stream(),
+          what="conv3_forward", desc=f"{cin}->{cout} {n}x{d}x{h}x{w_}{' 1x1x1' if pointwise else ''}{' dgrad' if mask_x is not None else ''}"
+                                     f"{' res' if res is not None else ''}")
     return y
 
 

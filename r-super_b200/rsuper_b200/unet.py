@@ -41,9 +41,22 @@ from . import ops
 class _CNA(nn.Module):
     """ConvNormAct(preact=True, norm=InstanceNorm3d) — only the conv carries parameters."""
 
+    def __init__(self, cin, cout, k=3):
+        super().__init__()
+        self.conv = nn.Conv3d(cin, cout, kernel_size=k, padding=k // 2, bias=False)
+
+
+class _Bottleneck(nn.Module):
+    """Bottleneck (conv_layers.py:97-123): 1x1x1 (C -> C/2), 3x3x3, 1x1x1 (C/2 -> C), 3x3x3 shortcut when cin != cout."""
+
     def __init__(self, cin, cout):
         super().__init__()
-        self.conv = nn.Conv3d(cin, cout, kernel_size=3, padding=1, bias=False)
+        self.conv1 = _CNA(cin, cout // 2, 1)
+        self.conv2 = _CNA(cout // 2, cout // 2)
+        self.conv3 = _CNA(cout // 2, cout, 1)
+        self.shortcut = nn.Sequential()
+        if cin != cout:
+            self.shortcut = _CNA(cin, cout)
 
 
 class _BasicBlock(nn.Module):
@@ -212,6 +225,20 @@ class _Engine:
                 self.plan, self._plan_key = ops.PackPlan(jobs, split=self.split), key
             self.plan.refresh()
             return
+        if self.block == "Bottleneck":
+            names = [pre + t for pre, has_sc in self.BLOCKS for t in ("conv1", "conv2", "conv3") + (("shortcut",) if has_sc else ())]
+            pairs = [(P[n + ".conv.weight"], None) for n in names]
+            key = ops.PackPlan.pointer_key(pairs)
+            if self.plan is None or self._plan_key != key:
+                short = {"conv1": "c1", "conv2": "c2", "conv3": "c3", "shortcut": "sc"}
+                jobs = []
+                for n, (w, _) in zip(names, pairs):
+                    pre, t = n.rsplit(".", 1)[0] + ".", n.rsplit(".", 1)[1]
+                    jobs.append((pre + short[t], w, None, False))
+                    jobs.append((pre + short[t] + "T", w, None, True))
+                self.plan, self._plan_key = ops.PackPlan(jobs, split=self.split), key
+            self.plan.refresh()
+            return
         pairs = []
         for pre, has_sc in self.BLOCKS:
             pairs.append((P[pre + "conv1.conv.weight"], P[pre + "shortcut.conv.weight"] if has_sc else None))
@@ -266,6 +293,110 @@ class _Engine:
         if self.split:
             ops.conv3_wgrad(a_op[1], dy_op[0], dw, accumulate=True)
             ops.conv3_wgrad(a_op[0], dy_op[1], dw, accumulate=True)
+
+    def _wgrad_pointwise(self, a_op, dy_op, cout: int, cin: int, like: torch.Tensor) -> torch.Tensor:
+        """Weight gradient of a 1x1x1 conv: the centre tap of the 27-tap weight-gradient kernel's output (the other 26 taps are
+        computed and dropped — a dedicated single-tap kernel is future work), returned as [cout, cin, 1, 1, 1]."""
+        dw27 = self._wgrad(a_op, dy_op, self._dw(like, cout, cin))
+        return dw27[:, :, 1:2, 1:2, 1:2]
+
+    # ---- block='Bottleneck' (conv_layers.py:97-123) ------------------------------------------------
+    def _bneck_fwd(self, x: Act, pre: str, has_sc: bool, cout: int, out: Act, saved: list):
+        n, d, h, w_, _ = x.t.shape
+        dev = x.t.device
+        mid = cout // 2
+        a_x = self._operand(x.t, x.st)
+        h1 = self._new_act(n, d, h, w_, mid, self.dtype, dev)
+        self._conv(a_x, pre + "c1", h1.t, out_stats=h1.st, pointwise=True)
+        a_1 = self._operand(h1.t, h1.st)
+        h2 = self._new_act(n, d, h, w_, mid, self.dtype, dev)
+        self._conv(a_1, pre + "c2", h2.t, out_stats=h2.st)
+        a_2 = self._operand(h2.t, h2.st)
+        if has_sc:
+            sc = torch.empty((n, d, h, w_, cout), dtype=self.dtype, device=dev)
+            self._conv(a_x, pre + "sc", sc)
+            res = sc
+        else:
+            res = x.t
+        self._conv(a_2, pre + "c3", out.t, res=res, out_stats=out.st, pointwise=True)
+        saved.append((x, h1, h2, a_x, a_1, a_2, has_sc))
+
+    def _bneck_bwd(self, blk, pre: str, d_out: torch.Tensor, dx_dest: torch.Tensor, G: dict):
+        """d_out = dL/d(block output) -> weight gradients into G, dL/d(block input) into dx_dest."""
+        x, h1, h2, a_x, a_1, a_2, has_sc = blk
+        cin, mid, cout = x.C, h1.C, d_out.shape[4]
+        d_op = self._operand(d_out)
+        # conv3 (1x1x1): data gradient with the act'(IN(h2)) mask and the InstanceNorm-backward sums in the epilogue
+        g2 = self._new(d_out, mid)
+        sums2 = self._sums_like(h2)
+        self._conv(d_op, pre + "c3", g2, flip=True, mask_x=h2.t, mask_stats=h2.st, bwd_sums=sums2, pointwise=True)
+        G[pre + "conv3.conv.weight"] = self._wgrad_pointwise(a_2, d_op, cout, mid, d_out)
+        ops.instnorm_backward_apply(g2, h2.t, h2.st, sums2, g2)
+        g2op = self._operand(g2)
+        # conv2 (3x3x3)
+        g1 = self._new(d_out, mid)
+        sums1 = self._sums_like(h1)
+        self._conv(g2op, pre + "c2", g1, flip=True, mask_x=h1.t, mask_stats=h1.st, bwd_sums=sums1)
+        G[pre + "conv2.conv.weight"] = self._wgrad(a_1, g2op, self._dw(d_out, mid, mid))
+        ops.instnorm_backward_apply(g1, h1.t, h1.st, sums1, g1)
+        g1op = self._operand(g1)
+        # conv1 (1x1x1) and the shortcut both consume a_x = act(IN(x))
+        G[pre + "conv1.conv.weight"] = self._wgrad_pointwise(a_x, g1op, mid, cin, d_out)
+        sums_x = self._sums_like(x)
+        if has_sc:
+            G[pre + "shortcut.conv.weight"] = self._wgrad(a_x, d_op, self._dw(d_out, cout, cin))
+            t = self._new(d_out, cin)                 # d(a_x): the two data gradients summed BEFORE the activation mask
+            self._conv(g1op, pre + "c1", t, flip=True, pointwise=True)
+            self._conv(d_op, pre + "sc", t, flip=True, res=t)
+            g = self._new(d_out, cin)
+            ops.act_backward_stats(t, x.t, x.st, sums_x, g, slope=self.slope)
+            ops.instnorm_backward_apply(g, x.t, x.st, sums_x, dx_dest)
+        else:
+            g = self._new(d_out, cin)
+            self._conv(g1op, pre + "c1", g, flip=True, mask_x=x.t, mask_stats=x.st, bwd_sums=sums_x, pointwise=True)
+            ops.instnorm_backward_apply(g, x.t, x.st, sums_x, dx_dest, add=d_out)
+
+    def _backward_bottleneck(self, S: dict, P: dict, dlogits: torch.Tensor) -> dict:
+        ch, up_in, saved = S["ch"], S["up_in"], S["saved"]
+        self._zp = None
+        b = self.b
+        G = {}
+        num_classes = dlogits.shape[1]
+        final = S["final"]
+        w_out = P["outc.weight"].reshape(num_classes, b).contiguous()
+        d_cur = self._new(final.t, b)
+        dw_out, db_out = torch.empty_like(w_out), torch.empty_like(P["outc.bias"])
+        ops.head_backward(final.t, w_out, dlogits, d_cur, dw_out, db_out)
+        G["outc.weight"], G["outc.bias"] = dw_out.reshape(P["outc.weight"].shape), db_out
+        dskip = [None] * 4
+        for j, l in zip((4, 3, 2, 1), (0, 1, 2, 3)):          # up4 .. up1 (block index map: see backward())
+            pre = f"up{j}.conv."
+            d_y = self._new(d_cur, ch[l])
+            self._bneck_bwd(saved[8 + 2 * j], pre + "1.", d_cur, d_y, G)
+            d_cat = self._new(d_cur, ch[l] + up_in[l])
+            self._bneck_bwd(saved[7 + 2 * j], pre + "0.", d_y, d_cat, G)
+            dskip[l] = d_cat[..., :ch[l]]
+            n, d, h, w_, _ = d_cat.shape
+            d_cur = torch.empty((n, d // 2, h // 2, w_ // 2, up_in[l]), dtype=self.dtype, device=d_cat.device)
+            ops.upsample_backward(d_cat[..., ch[l]:], d_cur)
+        for l in (4, 3, 2, 1):
+            pre = f"down{l}.conv."
+            d_y = self._new(d_cur, ch[l])
+            self._bneck_bwd(saved[2 * l], pre + "2.", d_cur, d_y, G)
+            d_p = self._new(d_cur, ch[l - 1])
+            self._bneck_bwd(saved[2 * l - 1], pre + "1.", d_y, d_p, G)
+            x_prev = S["enc_out"][l - 1]
+            d_cur = self._new(x_prev.t, ch[l - 1])
+            ops.maxpool2_backward(x_prev.t, d_p, d_cur, dskip=dskip[l - 1])
+        d_t0 = self._new(d_cur, b)
+        self._bneck_bwd(saved[0], "inc.conv2.", d_cur, d_t0, G)
+        dws = torch.empty_like(P["inc.conv1.weight"])
+        ops.stem_conv_wgrad(S["x"], d_t0, dws)
+        G["inc.conv1.weight"] = dws
+        if self._side is not None:
+            torch.cuda.current_stream().wait_stream(self._side)
+        self._side_keep.clear()
+        return G
 
     # ---- forward -------------------------------------------------------------------------------
     def _block_fwd(self, x: Act, pre: str, has_sc: bool, cout: int, out: Act, saved: list):
@@ -430,7 +561,8 @@ class _Engine:
         ops.stem_conv_forward(x, P["inc.conv1.weight"], t0.t, t0.st)
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)   # packed weights ready before the first tensor-core conv
-        self._block_fwd(t0, "inc.conv2.", False, b, cat[0].view(0, ch[0]), saved)
+        blk = self._bneck_fwd if self.block == "Bottleneck" else self._block_fwd
+        blk(t0, "inc.conv2.", False, b, cat[0].view(0, ch[0]), saved)
         enc_out = [cat[0].view(0, ch[0])]
         pooled = []
         for l in range(1, 5):
@@ -439,9 +571,9 @@ class _Engine:
             pooled.append(p)
             y = self._new_act(n, *dims[l], ch[l], dt, dev)
             pre = f"down{l}.conv."
-            self._block_fwd(p, pre + "1.", True, ch[l], y, saved)
+            blk(p, pre + "1.", True, ch[l], y, saved)
             out = cat[l].view(0, ch[l]) if l < 4 else self._new_act(n, *dims[4], ch[4], dt, dev)
-            self._block_fwd(y, pre + "2.", False, ch[l], out, saved)
+            blk(y, pre + "2.", False, ch[l], out, saved)
             enc_out.append(out)
         cur = enc_out[4]
         for j, l in enumerate((3, 2, 1, 0), start=1):
@@ -449,9 +581,9 @@ class _Engine:
             ops.upsample_forward(cur.t, upv.t, upv.st)
             y = self._new_act(n, *dims[l], ch[l], dt, dev)
             pre = f"up{j}.conv."
-            self._block_fwd(cat[l], pre + "0.", True, ch[l], y, saved)
+            blk(cat[l], pre + "0.", True, ch[l], y, saved)
             out = self._new_act(n, *dims[l], ch[l], dt, dev, stats=(l != 0))
-            self._block_fwd(y, pre + "1.", False, ch[l], out, saved)
+            blk(y, pre + "1.", False, ch[l], out, saved)
             cur = out
         logits = torch.empty((n, num_classes, D, H, W), dtype=torch.float32, device=dev)
         w_out = P["outc.weight"].reshape(num_classes, b).contiguous()
@@ -516,6 +648,8 @@ class _Engine:
     def backward(self, S: dict, P: dict, dlogits: torch.Tensor) -> dict:
         if self.block == "SingleConv":
             return self._backward_single(S, P, dlogits)
+        if self.block == "Bottleneck":
+            return self._backward_bottleneck(S, P, dlogits)
         ch, up_in, cat = S["ch"], S["up_in"], S["cat"]
         saved = S["saved"]
         self._zp = None
@@ -631,11 +765,12 @@ class B200UNet(nn.Module):
         super().__init__()
         if in_ch != 1:
             raise NotImplementedError("B200UNet: in_ch must be 1")
-        if block not in ("BasicBlock", "SingleConv") or norm != "in" or not pool:
-            raise NotImplementedError("B200UNet implements block='BasicBlock' | 'SingleConv', norm='in', pool=True "
+        if block not in ("BasicBlock", "SingleConv", "Bottleneck") or norm != "in" or not pool:
+            raise NotImplementedError("B200UNet implements block='BasicBlock' | 'SingleConv' | 'Bottleneck', norm='in', pool=True "
                                       "(config/abdomenatlas/resunet_3d.yaml:9-14; model/dim3/utils.py:7-13)")
-        if base_ch % 8:
-            raise ValueError("base_ch must be a multiple of 8 (16-byte channel groups)")
+        if base_ch % 8 or (block == "Bottleneck" and base_ch % 16):
+            raise ValueError("base_ch must be a multiple of 8 (16-byte channel groups; 16 for block='Bottleneck': its inner "
+                             "convolutions run at half the channels)")
         sc = [list(s) if isinstance(s, (list, tuple)) else [s] * 3 for s in scale]
         ks = [list(k) if isinstance(k, (list, tuple)) else [k] * 3 for k in kernel_size]
         if any(s != [2, 2, 2] for s in sc) or len(sc) != 4 or any(k != [3, 3, 3] for k in ks):
@@ -646,7 +781,7 @@ class B200UNet(nn.Module):
         self.base_ch, self.num_classes = b, num_classes
         self.negative_slope, self.precision, self.return_dict = negative_slope, precision, return_dict
         self.block = block
-        blk = _SingleConv if block == "SingleConv" else _BasicBlock
+        blk = {"SingleConv": _SingleConv, "Bottleneck": _Bottleneck}.get(block, _BasicBlock)
         self.inc = _InConv(in_ch, b, blk)
         self.down1 = _Stage(b, 2 * b, True, blk)
         self.down2 = _Stage(2 * b, 4 * b, True, blk)

@@ -13,14 +13,15 @@ namespace {
 
 inline float bf(const __nv_bfloat16* p, long long i) { return __bfloat162float(p[i]); }
 
-void pack_one(const float* w_a, const float* w_b, int rows_a, int Cout, int Cin, int flip, int parts, __nv_bfloat16* out) {
+void pack_one(const float* w_a, const float* w_b, int rows_a, int Cout, int Cin, int flip, int parts, __nv_bfloat16* out, int pointwise = 0) {
   const int co_eff = flip ? Cin : Cout, ci_eff = flip ? Cout : Cin;
   const long long plane = 27LL * co_eff * ci_eff;
+  const int taps = pointwise ? 1 : 27;   // 1x1x1 sources are embedded at the centre tap (13), the other taps are zero
   for (int co = 0; co < Cout; ++co) {
-    const float* row = co < rows_a ? w_a + static_cast<long long>(co) * Cin * 27 : w_b + static_cast<long long>(co - rows_a) * Cin * 27;
+    const float* row = co < rows_a ? w_a + static_cast<long long>(co) * Cin * taps : w_b + static_cast<long long>(co - rows_a) * Cin * taps;
     for (int ci = 0; ci < Cin; ++ci)
       for (int t = 0; t < 27; ++t) {
-        const float w = row[ci * 27 + t];
+        const float w = pointwise ? (t == 13 ? row[ci] : 0.f) : row[ci * 27 + t];
         // dgrad image: conv with Cin' = Cout, Cout' = Cin and the taps flipped in all three axes
         const long long dst = flip ? (static_cast<long long>(ci) * ci_eff + co) * 27 + (26 - t) : (static_cast<long long>(co) * ci_eff + ci) * 27 + t;
         const __nv_bfloat16 hi = __float2bfloat16_rn(w);
@@ -118,7 +119,7 @@ extern "C" int rsb_conv3_pack_weights_batched(const RsbPackJob* jobs, int n_jobs
   for (int j = 0; j < n_jobs; ++j) {
     const RsbPackJob& b = jobs[j];
     RSB_REQUIRE(b.parts == 1 || b.parts == 3, "conv3 double: pack supports parts 1 and 3 (got %d)", b.parts);
-    pack_one(b.w_a, b.w_b, b.rows_a, b.Cout, b.Cin, b.transpose_flip, b.parts, static_cast<__nv_bfloat16*>(b.packed));
+    pack_one(b.w_a, b.w_b, b.rows_a, b.Cout, b.Cin, b.transpose_flip, b.parts, static_cast<__nv_bfloat16*>(b.packed), b.pointwise);
   }
   return 0;
 }

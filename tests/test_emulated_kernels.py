@@ -226,6 +226,14 @@ def test_emulated_singleconv_unet_vs_reference_and_oracle(emulated, golden):
     U.test_singleconv_unet_vs_reference_and_oracle(CPU, golden, "fp32")
 
 
+def test_emulated_bottleneck_unet_vs_reference_and_oracle(emulated, monkeypatch):
+    """block='Bottleneck' engine (centre-tap 1x1x1 convolutions, summed data gradients ahead of the activation mask) end to end
+    on the CPU against the real reference's recorded run and the fp64 oracle."""
+    import test_unet_gpu as U
+    monkeypatch.setenv("RSB_TEST_SINGLE_S", "32")
+    U.test_bottleneck_unet_vs_reference_and_oracle(CPU, "fp32")
+
+
 @full
 def test_emulated_static_gradient_steps_equal_fresh_gradient_steps(emulated):
     """Precondition of GraphedTrainStep (rsuper_b200/graph_step.py): the captured body starts with

@@ -287,3 +287,71 @@ def test_singleconv_unet_vs_reference_and_oracle(cuda_dev, golden, precision):
     else:
         assert e_mine <= 2.0 * e_emul + 1e-3
         assert abs(loss["overall"].item() - l64["overall"].item()) <= 2e-2 * abs(l64["overall"].item())
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_bottleneck_unet_vs_reference_and_oracle(cuda_dev, precision):
+    """block='Bottleneck' (1x1x1 -> 3x3x3 -> 1x1x1 pre-activation residual block, conv_layers.py:97-123): same
+    state-dict names as the reference, logits / loss / gradient norms against values recorded from the REAL reference module
+    (tests/golden/make_golden_bneck.py, base 16, 32^3), and logits + every weight gradient against the fp64 oracle on a patch
+    whose bottom level is not 2^3 voxels.  The 1x1x1 convolutions run through the tensor-core kernel's centre-tap mode."""
+    import os
+    from oracle import losses_ref as LR
+    from oracle import synth
+    from oracle.unet_ref import synthetic_image, synthetic_state_dict, unet_forward
+    from rsuper_b200 import losses
+    from rsuper_b200.unet import B200UNet
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_bottleneck.npz"))
+    base, classes = 16, ["organ", "pancreatic_lesion"]
+    net = B200UNet(1, base, num_classes=2, scale=[[2, 2, 2]] * 4, norm="in", kernel_size=[[3, 3, 3]] * 5, block="Bottleneck",
+                   precision=precision).to(cuda_dev)
+    sd = synthetic_state_dict(base, 2, device=cuda_dev, block="Bottleneck")
+    assert list(sd.keys()) == [k for k, _ in net.named_parameters()] == list(gold["names"]) and len(sd) == 62
+    net.load_state_dict(sd, strict=True)
+    args = LR.default_args(report_volume_loss_basic=0.0)
+    # the real reference's recorded run (1 x 32^3)
+    x32 = synthetic_image(1, 32, 32, 32, seed=3, device=cuda_dev)
+    b32 = synth.make_batch(["mask"], classes, (32, 32, 32), seed=5, device=cuda_dev)
+    out32 = net(x32)
+    loss32 = losses.calculate_loss(out32, b32["label"], None, args, None, None, None, None, classes)["overall"]
+    loss32.backward()
+    ref32 = torch.from_numpy(gold["logits"]).to(cuda_dev)
+    e32 = rel(out32["segmentation"][:, :, ::2, ::2, ::2], ref32)
+    gn = np.array([p.grad.double().norm().item() for p in net.parameters()])
+    gn_err = np.abs(gn - gold["grad_norms"]) / (gold["grad_norms"] + 1e-12)
+    print(f"[bottleneck] {precision}: 32^3 logits vs real reference rel {e32:.3e}; loss {loss32.item():.6f} vs {float(gold['loss']):.6f}; "
+          f"gradient-norm rel err median {np.median(gn_err):.2e} max {gn_err.max():.2e}")
+    # fp64 oracle on a better conditioned patch
+    S = int(os.environ.get("RSB_TEST_SINGLE_S", "64"))
+    for p in net.parameters():
+        p.grad = None
+    x = synthetic_image(1, S, S, S, seed=6, device=cuda_dev)
+    batch = synth.make_batch(["mask"], classes, (S, S, S), seed=8, device=cuda_dev)
+    out = net(x)
+    loss = losses.calculate_loss(out, batch["label"], None, args, None, None, None, None, classes)["overall"]
+    loss.backward()
+    sd64 = {k: v.double().clone().requires_grad_(True) for k, v in sd.items()}
+    truth = unet_forward(x.double(), sd64)
+    l64 = LR.calculate_loss({"segmentation": truth}, batch["label"].long(), None, args, None, None, None, None, classes)["overall"]
+    l64.backward()
+    with torch.no_grad():
+        emul = unet_forward(x, sd, emulate=True, storage="bf16")
+    e_mine, e_emul = rel(out["segmentation"].double(), truth), rel(emul.double(), truth)
+    agree = (out["segmentation"].argmax(1) == truth.argmax(1)).float().mean().item()
+    errs = {k: rel(p.grad.double(), sd64[k].grad) for k, p in net.named_parameters()}
+    worst = max(errs, key=errs.get)
+    print(f"[bottleneck] {precision}: {S}^3 vs fp64 oracle {e_mine:.3e} (bf16-emulating oracle {e_emul:.3e}) argmax {agree:.5f} | loss "
+          f"{loss.item():.6f} vs {l64.item():.6f} | worst grad err {errs[worst]:.3e} at {worst}, median {np.median(list(errs.values())):.2e}")
+    for k, p in net.named_parameters():
+        assert p.grad is not None and p.grad.shape == p.shape and torch.isfinite(p.grad).all(), k
+    if precision == "fp32":
+        assert e32 <= 3e-3 and abs(loss32.item() - float(gold["loss"])) <= 1e-4 * float(gold["loss"])
+        assert np.median(gn_err) <= 2e-3 and gn_err.max() <= 5e-2
+        if S >= 64:     # (a 32^3 patch normalises over 2^3 voxels at the bottom level: see test_logits_vs_reference_golden)
+            assert e_mine <= 1e-3 and agree == 1.0 and abs(loss.item() - l64.item()) <= 1e-5 * abs(l64.item())
+            assert errs[worst] <= 5e-2 and np.median(list(errs.values())) <= 2e-3
+        else:
+            assert e_mine <= 1e-2 and agree >= 0.9999 and abs(loss.item() - l64.item()) <= 1e-4 * abs(l64.item())
+    else:
+        assert e_mine <= 2.0 * e_emul + 1e-3
+        assert abs(loss.item() - l64.item()) <= 2e-2 * abs(l64.item())
