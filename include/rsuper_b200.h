@@ -208,6 +208,16 @@ int rsb_maxpool2_backward(const void* x, int x_pitch, const void* dy, int dy_pit
                           const void* dskip, int dskip_pitch, void* dx, int dx_pitch, int dtype,
                           int N, int D, int H, int W, int C, void* stream);
 
+/* ConvTranspose3d(C_in, C, kernel_size = 2, stride = 2) up-sampling (the transposed-conv variant of up_block; semantics of
+ * model/dim3/vnet.py:108) = a 1x1x1 conv to 8 * C channels at the INPUT resolution (rsb_conv3_forward, pointwise = 1, weight
+ * rows (4a + 2b + c) * C + co = w[ci][co][a][b][c]) followed by this rearrangement:
+ *   up[n, 2z+a, 2y+b, 2x+c, co] = q[n, z, y, x, (4a+2b+c) * C + co] + bias[co]   (+ InstanceNorm statistics of up)
+ * D, H, W = the INPUT (low) resolution; rsb_space_to_depth2 is the inverse copy (the adjoint, used on the gradient). */
+int rsb_depth_to_space2(const void* q, int q_pitch, const float* bias, void* up, int up_pitch, int dtype, float* out_stats,
+                        int N, int D, int H, int W, int C, void* stream);
+int rsb_space_to_depth2(const void* up, int up_pitch, void* q, int q_pitch, int dtype, int N, int D, int H, int W, int C,
+                        void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * F.interpolate(mode='trilinear', align_corners=True) (unet_utils.py:69), NDHWC, output
  * statistics fused, and its adjoint (deterministic gather).

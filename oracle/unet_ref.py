@@ -147,7 +147,11 @@ def unet_forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], slope: float = 0.
     cur = skips[4][0]
     for j, l in enumerate((3, 2, 1, 0), start=1):  # up_block (unet_utils.py:68-75)
         sk_s, sk_f = skips[l]
-        up_full = F.interpolate(cur, size=sk_s.shape[2:], mode="trilinear", align_corners=True)
+        if f"up{j}.up.weight" in sd:
+            # up_mode='transposed': ConvTranspose3d(C, C, kernel_size=2, stride=2) in place of F.interpolate (vnet.py:108 semantics)
+            up_full = F.conv_transpose3d(cfg.operand(cur), cfg.operand(sd[f"up{j}.up.weight"]), sd[f"up{j}.up.bias"], stride=2)
+        else:
+            up_full = F.interpolate(cur, size=sk_s.shape[2:], mode="trilinear", align_corners=True)
         up_st = cfg.store(up_full)
         cat_s = torch.cat([sk_s, up_st], dim=1)
         cat_f = torch.cat([sk_f, up_full], dim=1)
@@ -159,7 +163,7 @@ def unet_forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], slope: float = 0.
 
 
 def synthetic_state_dict(base_ch: int, num_classes: int, in_ch: int = 1, device="cpu",
-                         gain: float = 1.0, block: str = "BasicBlock") -> Dict[str, torch.Tensor]:
+                         gain: float = 1.0, block: str = "BasicBlock", up_mode: str = "trilinear") -> Dict[str, torch.Tensor]:
     """Deterministic, version-independent weights with the reference UNet's names and shapes
     (SURVEY.md §8b state-dict contract).  Values mimic nn.Conv3d's default init
     (kaiming_uniform(a=sqrt(5)) => U(-1/sqrt(fan_in), 1/sqrt(fan_in))) through a hash
@@ -189,6 +193,8 @@ def synthetic_state_dict(base_ch: int, num_classes: int, in_ch: int = 1, device=
         for l in range(1, 5):
             shapes += bneck(f"down{l}.conv.1.", ch[l - 1], ch[l]) + bneck(f"down{l}.conv.2.", ch[l], ch[l])
         for j, l in enumerate((3, 2, 1, 0), start=1):
+            if up_mode == "transposed":
+                shapes += [(f"up{j}.up.weight", (ch[l + 1], ch[l + 1], 2, 2, 2)), (f"up{j}.up.bias", (ch[l + 1],))]
             shapes += bneck(f"up{j}.conv.0.", ch[l] + ch[l + 1], ch[l]) + bneck(f"up{j}.conv.1.", ch[l], ch[l])
         shapes += [("outc.weight", (num_classes, b, 1, 1, 1)), ("outc.bias", (num_classes,))]
         return _fill_state_dict(shapes, gain, device)
@@ -205,6 +211,8 @@ def synthetic_state_dict(base_ch: int, num_classes: int, in_ch: int = 1, device=
     for j, l in enumerate((3, 2, 1, 0), start=1):
         ci, co = ch[l] + ch[l + 1], ch[l]
         p = f"up{j}.conv."
+        if up_mode == "transposed":
+            shapes += [(f"up{j}.up.weight", (ch[l + 1], ch[l + 1], 2, 2, 2)), (f"up{j}.up.bias", (ch[l + 1],))]
         shapes += [(p + "0.conv1.conv.weight", (co, ci, 3, 3, 3)), (p + "0.conv2.conv.weight", (co, co, 3, 3, 3)),
                    (p + "0.shortcut.conv.weight", (co, ci, 3, 3, 3)),
                    (p + "1.conv1.conv.weight", (co, co, 3, 3, 3)), (p + "1.conv2.conv.weight", (co, co, 3, 3, 3))]

@@ -162,6 +162,74 @@ __global__ void maxpool2_fwd_kernel(const T* __restrict__ x, long long xp, T* __
   if (stats != nullptr) block_stats_flush(sm_acc, s1, s2, m.cg, C, stats + static_cast<long long>(n) * yp * 2);
 }
 
+// ------------------------------------------------------------------------------------------
+// ConvTranspose3d(kernel = stride = 2) epilogues: the transposed conv is a 1x1x1 conv to 8 * C channels at the input
+// resolution (column block k = 4a + 2b + c holds the output voxel (2z + a, 2y + b, 2x + c)); these two kernels move between
+// that layout and the up-sampled NDHWC tensor (8 channels = one 128-bit access).
+//   depth_to_space2:  up[n, 2z+a, 2y+b, 2x+c, co] = q[n, z, y, x, k * C + co] + bias[co]   (+ InstanceNorm statistics of up)
+//   space_to_depth2:  q[n, z, y, x, k * C + co]   = up[n, 2z+a, 2y+b, 2x+c, co]           (its adjoint, for the backward pass)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void depth_to_space2_kernel(const T* __restrict__ q, long long qp, const float* __restrict__ bias, T* __restrict__ up,
+                                       long long upp, float* __restrict__ stats, int D, int H, int W, int C) {
+  extern __shared__ float sm_acc[];
+  const int CG = C / 8;
+  const int n = blockIdx.y;
+  const long long Vi = static_cast<long long>(D) * H * W;
+  ClMap m = cl_map(CG);
+  float b8[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) b8[j] = bias != nullptr ? bias[m.cg * 8 + j] : 0.f;
+  float s1[8] = {0}, s2[8] = {0};
+  for (long long v = m.v0; v < Vi; v += m.vstride) {
+    const unsigned vu = static_cast<unsigned>(v);
+    const unsigned row = vu / static_cast<unsigned>(W);
+    const int xi = static_cast<int>(vu - row * W);
+    const int zi = static_cast<int>(row / static_cast<unsigned>(H));
+    const int yi = static_cast<int>(row - static_cast<unsigned>(zi) * H);
+    const T* src = q + (static_cast<long long>(n) * Vi + v) * qp + m.cg * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float f[8];
+      Vec8<T>::load(src + k * C, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += b8[j];
+      const int z = 2 * zi + (k >> 2), yy = 2 * yi + ((k >> 1) & 1), xx = 2 * xi + (k & 1);
+      const long long vo = ((static_cast<long long>(n) * (2 * D) + z) * (2 * H) + yy) * (2 * W) + xx;
+      Vec8<T>::store(up + vo * upp + m.cg * 8, f);
+      // statistics of the STORED values' fp32 originals, like every other producer
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s1[j] += f[j]; s2[j] = fmaf(f[j], f[j], s2[j]); }
+    }
+  }
+  if (stats != nullptr) block_stats_flush(sm_acc, s1, s2, m.cg, C, stats + static_cast<long long>(n) * upp * 2);
+}
+
+template <typename T>
+__global__ void space_to_depth2_kernel(const T* __restrict__ up, long long upp, T* __restrict__ q, long long qp, int D, int H, int W,
+                                       int C) {
+  const int CG = C / 8;
+  const int n = blockIdx.y;
+  const long long Vi = static_cast<long long>(D) * H * W;
+  ClMap m = cl_map(CG);
+  for (long long v = m.v0; v < Vi; v += m.vstride) {
+    const unsigned vu = static_cast<unsigned>(v);
+    const unsigned row = vu / static_cast<unsigned>(W);
+    const int xi = static_cast<int>(vu - row * W);
+    const int zi = static_cast<int>(row / static_cast<unsigned>(H));
+    const int yi = static_cast<int>(row - static_cast<unsigned>(zi) * H);
+    T* dst = q + (static_cast<long long>(n) * Vi + v) * qp + m.cg * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int z = 2 * zi + (k >> 2), yy = 2 * yi + ((k >> 1) & 1), xx = 2 * xi + (k & 1);
+      const long long vo = ((static_cast<long long>(n) * (2 * D) + z) * (2 * H) + yy) * (2 * W) + xx;
+      float f[8];
+      Vec8<T>::load(up + vo * upp + m.cg * 8, f);
+      Vec8<T>::store(dst + k * C, f);
+    }
+  }
+}
+
 // dx[window voxel k] = (k is the first maximum in (d,h,w) scan order ? dy : 0) + dskip
 // (ATen max_pool3d_with_indices keeps the first maximum: it updates only on `val > max`).
 template <typename T>
@@ -687,6 +755,35 @@ extern "C" int rsb_maxpool2_backward(const void* x, int x_pitch, const void* dy,
                (maxpool2_bwd_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)x, x_pitch, (const __nv_bfloat16*)dy, dy_pitch, (const __nv_bfloat16*)dskip, dskip_pitch, (__nv_bfloat16*)dx, dx_pitch, D, H, W, C)),
                (maxpool2_bwd_kernel<float><<<grid, block, 0, st>>>((const float*)x, x_pitch, (const float*)dy, dy_pitch, (const float*)dskip, dskip_pitch, (float*)dx, dx_pitch, D, H, W, C)))
   return check_launch("maxpool2_backward");
+}
+
+extern "C" int rsb_depth_to_space2(const void* q, int q_pitch, const float* bias, void* up, int up_pitch, int dtype, float* out_stats,
+                                   int N, int D, int H, int W, int C, void* stream) {
+  RSB_REQUIRE(q && up, "depth_to_space2: null pointer");
+  RSB_REQUIRE(D > 0 && H > 0 && W > 0 && q_pitch >= 8 * C, "depth_to_space2: bad geometry (q needs 8 * C channels)");
+  RSB_CL_COMMON(C, N)
+  const long long Vi = static_cast<long long>(D) * H * W;
+  RSB_REQUIRE(Vi < (1LL << 31), "depth_to_space2: volume too large");
+  dim3 grid(cl_grid(Vi * CG, block, sms, 8), N);
+  const size_t sm = sizeof(float) * 2 * C;
+  RSB_BY_DTYPE(dtype,
+               (depth_to_space2_kernel<__nv_bfloat16><<<grid, block, sm, st>>>((const __nv_bfloat16*)q, q_pitch, bias, (__nv_bfloat16*)up, up_pitch, out_stats, D, H, W, C)),
+               (depth_to_space2_kernel<float><<<grid, block, sm, st>>>((const float*)q, q_pitch, bias, (float*)up, up_pitch, out_stats, D, H, W, C)))
+  return check_launch("depth_to_space2");
+}
+
+extern "C" int rsb_space_to_depth2(const void* up, int up_pitch, void* q, int q_pitch, int dtype, int N, int D, int H, int W, int C,
+                                   void* stream) {
+  RSB_REQUIRE(q && up, "space_to_depth2: null pointer");
+  RSB_REQUIRE(D > 0 && H > 0 && W > 0 && q_pitch >= 8 * C, "space_to_depth2: bad geometry (q needs 8 * C channels)");
+  RSB_CL_COMMON(C, N)
+  const long long Vi = static_cast<long long>(D) * H * W;
+  RSB_REQUIRE(Vi < (1LL << 31), "space_to_depth2: volume too large");
+  dim3 grid(cl_grid(Vi * CG, block, sms), N);
+  RSB_BY_DTYPE(dtype,
+               (space_to_depth2_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)up, up_pitch, (__nv_bfloat16*)q, q_pitch, D, H, W, C)),
+               (space_to_depth2_kernel<float><<<grid, block, 0, st>>>((const float*)up, up_pitch, (float*)q, q_pitch, D, H, W, C)))
+  return check_launch("space_to_depth2");
 }
 
 extern "C" int rsb_upsample_trilinear_forward(const void* x, int x_pitch, void* y, int y_pitch, int dtype,

@@ -116,6 +116,8 @@ SIGNATURES = {
     "rsb_maxpool2_backward": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
                                       c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                       c_void_p]),
+    "rsb_depth_to_space2": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "rsb_space_to_depth2": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "rsb_upsample_trilinear_forward": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p,
                                                c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                                c_int, c_void_p]),

@@ -342,6 +342,28 @@ def upsample_forward(x, y, out_stats=None):
     return y
 
 
+def depth_to_space2(q, bias, up, out_stats=None):
+    """up[n, 2z+a, 2y+b, 2x+c, co] = q[n, z, y, x, (4a+2b+c) * C + co] + bias[co] (+ statistics of up): the rearrangement that
+    turns a 1x1x1 conv to 8 * C channels into ConvTranspose3d(kernel = stride = 2)."""
+    n, d, h, w_, c8 = q.shape
+    c = up.shape[4]
+    assert c8 == 8 * c and tuple(up.shape[:4]) == (n, 2 * d, 2 * h, 2 * w_) and q.dtype == up.dtype
+    assert bias is None or (bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == c)
+    _call("upsample", 1, 0.0, lib().rsb_depth_to_space2, _p(q), _check_cl(q, "q"), _p(bias), _p(up), _check_cl(up, "up"), dtype_code(q),
+          _st(out_stats, up, "out_stats"), n, d, h, w_, c, _stream(), what="depth_to_space2", desc=f"{c} {n}x{2 * d}x{2 * h}x{2 * w_}")
+    return up
+
+
+def space_to_depth2(up, q):
+    """q[n, z, y, x, (4a+2b+c) * C + co] = up[n, 2z+a, 2y+b, 2x+c, co] — the adjoint copy of depth_to_space2."""
+    n, d, h, w_, c8 = q.shape
+    c = up.shape[4]
+    assert c8 == 8 * c and tuple(up.shape[:4]) == (n, 2 * d, 2 * h, 2 * w_) and q.dtype == up.dtype
+    _call("upsample", 1, 0.0, lib().rsb_space_to_depth2, _p(up), _check_cl(up, "up"), _p(q), _check_cl(q, "q"), dtype_code(q),
+          n, d, h, w_, c, _stream(), what="space_to_depth2", desc=f"{c} {n}x{2 * d}x{2 * h}x{2 * w_}")
+    return q
+
+
 def upsample_backward(dy, dx, two_pass=True):
     """Adjoint of upsample_forward.  two_pass (default): separable z / y / x adjoint passes through a scratch buffer;
     False: the single-pass 3-D gather."""

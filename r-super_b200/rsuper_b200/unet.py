@@ -91,9 +91,12 @@ class _InConv(nn.Module):
 class _Stage(nn.Module):
     """down_block (index 0 is the parameter-free MaxPool3d) / up_block."""
 
-    def __init__(self, cin, cout, down: bool, block=None):
+    def __init__(self, cin, cout, down: bool, block=None, up_channels: int = 0):
         super().__init__()
         block = block or _BasicBlock
+        if up_channels:
+            # up_mode='transposed': ConvTranspose3d(kernel = stride = 2) replaces F.interpolate (semantics of vnet.py:108)
+            self.up = nn.ConvTranspose3d(up_channels, up_channels, kernel_size=2, stride=2)
         blocks: List[nn.Module] = []
         if down:
             blocks.append(nn.Identity())  # placeholder for nn.MaxPool3d: keeps the index -> name map
@@ -163,8 +166,10 @@ class _Engine:
                       products, but the tensor pipe's truncating fp32 accumulation already bounds a conv at ~1e-5 of
                       its output range, so the third piece buys nothing — tests/test_kernels_gpu.py.)"""
 
-    def __init__(self, base_ch: int, slope: float, dtype: torch.dtype, block: str = "BasicBlock"):
+    def __init__(self, base_ch: int, slope: float, dtype: torch.dtype, block: str = "BasicBlock", up_mode: str = "trilinear"):
         self.block = block
+        self.up_mode = up_mode
+        self._upw = {}      # up_mode='transposed': persistent [8C, C, 1, 1, 1] images of the ConvTranspose3d weights
         self.b = base_ch
         self.slope = float(slope)
         self.dtype = dtype
@@ -211,6 +216,23 @@ class _Engine:
     SINGLE_CONVS = (["inc.conv2."] + [f"down{l}.conv.{i}." for l in range(1, 5) for i in (1, 2)]
                     + [f"up{j}.conv.{i}." for j in range(1, 5) for i in (0, 1)])
 
+    def _up_weight_images(self, P: dict):
+        """up_mode='transposed': W'[(4a + 2b + c) * C + co][ci] = w[ci][co][a][b][c] — the ConvTranspose3d(k = s = 2) weight as
+        the [8C, C, 1, 1, 1] kernel of the equivalent 1x1x1 conv, kept in persistent buffers (the pack plan holds their
+        pointers) and refreshed from the parameters every forward."""
+        out = []
+        if self.up_mode != "transposed":
+            return out
+        for j in range(1, 5):
+            w = P[f"up{j}.up.weight"]
+            c = w.shape[0]
+            buf = self._upw.get(j)
+            if buf is None or buf.device != w.device or buf.shape[1] != c:
+                buf = self._upw[j] = torch.empty((8 * c, c, 1, 1, 1), dtype=torch.float32, device=w.device)
+            buf.view(2, 2, 2, c, c).copy_(w.permute(2, 3, 4, 1, 0))
+            out.append((f"up{j}.upw", buf))
+        return out
+
     def prepare(self, P: dict):
         """(Re)build the pack plan when the parameter storage changed, then re-pack every conv (forward and dgrad
         images; conv1 || shortcut merged row-wise without a torch.cat) from the current values."""
@@ -228,7 +250,8 @@ class _Engine:
         if self.block == "Bottleneck":
             names = [pre + t for pre, has_sc in self.BLOCKS for t in ("conv1", "conv2", "conv3") + (("shortcut",) if has_sc else ())]
             pairs = [(P[n + ".conv.weight"], None) for n in names]
-            key = ops.PackPlan.pointer_key(pairs)
+            ups = self._up_weight_images(P)
+            key = ops.PackPlan.pointer_key(pairs + [(t, None) for _, t in ups])
             if self.plan is None or self._plan_key != key:
                 short = {"conv1": "c1", "conv2": "c2", "conv3": "c3", "shortcut": "sc"}
                 jobs = []
@@ -236,6 +259,8 @@ class _Engine:
                     pre, t = n.rsplit(".", 1)[0] + ".", n.rsplit(".", 1)[1]
                     jobs.append((pre + short[t], w, None, False))
                     jobs.append((pre + short[t] + "T", w, None, True))
+                for k, t in ups:
+                    jobs += [(k, t, None, False), (k + "T", t, None, True)]
                 self.plan, self._plan_key = ops.PackPlan(jobs, split=self.split), key
             self.plan.refresh()
             return
@@ -244,13 +269,16 @@ class _Engine:
             pairs.append((P[pre + "conv1.conv.weight"], P[pre + "shortcut.conv.weight"] if has_sc else None))
             pairs.append((P[pre + "conv2.conv.weight"], None))
         # (the key is the parameter storage: one entry per conv — the plan itself holds two jobs per conv, fprop + dgrad image)
-        key = ops.PackPlan.pointer_key(pairs)
+        ups = self._up_weight_images(P)
+        key = ops.PackPlan.pointer_key(pairs + [(t, None) for _, t in ups])
         if self.plan is None or self._plan_key != key:
             jobs = []
             for (pre, _), k in zip(self.BLOCKS, range(0, len(pairs), 2)):
                 for tag, (wa, wb) in (("c1", pairs[k]), ("c2", pairs[k + 1])):
                     jobs.append((pre + tag, wa, wb, False))
                     jobs.append((pre + tag + "T", wa, wb, True))
+            for kk, t in ups:
+                jobs += [(kk, t, None, False), (kk + "T", t, None, True)]
             self.plan, self._plan_key = ops.PackPlan(jobs, split=self.split), key
         self.plan.refresh()
 
@@ -293,6 +321,35 @@ class _Engine:
         if self.split:
             ops.conv3_wgrad(a_op[1], dy_op[0], dw, accumulate=True)
             ops.conv3_wgrad(a_op[0], dy_op[1], dw, accumulate=True)
+
+    # ---- up-sampling: trilinear (the reference, unet_utils.py:69) or ConvTranspose3d(k = s = 2) (up_mode='transposed') ----
+    def _up_fwd(self, cur: Act, upv: Act, j: int, P: dict, up_ops: dict):
+        if self.up_mode != "transposed":
+            ops.upsample_forward(cur.t, upv.t, upv.st)
+            return
+        n, d, h, w_, c = cur.t.shape
+        a_cur = self._operand(cur.t)          # the raw block output is the operand: no normalisation ahead of the transposed conv
+        q = torch.empty((n, d, h, w_, 8 * c), dtype=self.dtype, device=cur.t.device)
+        self._conv(a_cur, f"up{j}.upw", q, pointwise=True)
+        ops.depth_to_space2(q, P[f"up{j}.up.bias"], upv.t, upv.st)
+        up_ops[j] = a_cur
+
+    def _up_bwd(self, d_up: torch.Tensor, j: int, S: dict, G: dict) -> torch.Tensor:
+        """d_up = dL/d(up-sampled tensor) (a channel slice of d_cat) -> dL/d(low-resolution input); parameter gradients into G."""
+        n, d2, h2, w2, c = d_up.shape
+        d, h, w_ = d2 // 2, h2 // 2, w2 // 2
+        d_cur = torch.empty((n, d, h, w_, c), dtype=self.dtype, device=d_up.device)
+        if self.up_mode != "transposed":
+            ops.upsample_backward(d_up, d_cur)
+            return d_cur
+        dq = torch.empty((n, d, h, w_, 8 * c), dtype=self.dtype, device=d_up.device)
+        ops.space_to_depth2(d_up, dq)
+        G[f"up{j}.up.bias"] = ops.channel_stats(d_up)[..., 0].sum(0)
+        dq_op = self._operand(dq)
+        self._conv(dq_op, f"up{j}.upw", d_cur, flip=True, pointwise=True)
+        dwp = self._wgrad_pointwise(S["up_ops"][j], dq_op, 8 * c, c, dq)                  # [8C, C, 1, 1, 1]
+        G[f"up{j}.up.weight"] = dwp.reshape(2, 2, 2, c, c).permute(4, 3, 0, 1, 2)        # -> [ci, co, a, b, c]
+        return d_cur
 
     def _wgrad_pointwise(self, a_op, dy_op, cout: int, cin: int, like: torch.Tensor) -> torch.Tensor:
         """Weight gradient of a 1x1x1 conv: the centre tap of the 27-tap weight-gradient kernel's output (the other 26 taps are
@@ -376,9 +433,7 @@ class _Engine:
             d_cat = self._new(d_cur, ch[l] + up_in[l])
             self._bneck_bwd(saved[7 + 2 * j], pre + "0.", d_y, d_cat, G)
             dskip[l] = d_cat[..., :ch[l]]
-            n, d, h, w_, _ = d_cat.shape
-            d_cur = torch.empty((n, d // 2, h // 2, w_ // 2, up_in[l]), dtype=self.dtype, device=d_cat.device)
-            ops.upsample_backward(d_cat[..., ch[l]:], d_cur)
+            d_cur = self._up_bwd(d_cat[..., ch[l]:], j, S, G)
         for l in (4, 3, 2, 1):
             pre = f"down{l}.conv."
             d_y = self._new(d_cur, ch[l])
@@ -576,9 +631,10 @@ class _Engine:
             blk(y, pre + "2.", False, ch[l], out, saved)
             enc_out.append(out)
         cur = enc_out[4]
+        up_ops: dict = {}
         for j, l in enumerate((3, 2, 1, 0), start=1):
             upv = cat[l].view(ch[l], ch[l] + up_in[l])
-            ops.upsample_forward(cur.t, upv.t, upv.st)
+            self._up_fwd(cur, upv, j, P, up_ops)
             y = self._new_act(n, *dims[l], ch[l], dt, dev)
             pre = f"up{j}.conv."
             blk(cat[l], pre + "0.", True, ch[l], y, saved)
@@ -590,7 +646,7 @@ class _Engine:
         ops.head_forward(cur.t, w_out, P["outc.bias"], logits)
         if not save:
             return logits, None
-        return logits, dict(saved=saved, cat=cat, enc_out=enc_out, final=cur, x=x, dims=dims, ch=ch, up_in=up_in)
+        return logits, dict(saved=saved, cat=cat, enc_out=enc_out, final=cur, x=x, dims=dims, ch=ch, up_in=up_in, up_ops=up_ops)
 
     # ---- backward ------------------------------------------------------------------------------
     def _new(self, like: torch.Tensor, c: int) -> torch.Tensor:
@@ -686,9 +742,7 @@ class _Engine:
             G[pre + "0.conv1.conv.weight"], G[pre + "0.conv2.conv.weight"] = dw1, dw2
             G[pre + "0.shortcut.conv.weight"] = dwsc
             dskip[l] = d_cat[..., :ch[l]]
-            n, d, h, w_, _ = d_cat.shape
-            d_cur = torch.empty((n, d // 2, h // 2, w_ // 2, up_in[l]), dtype=self.dtype, device=d_cat.device)
-            ops.upsample_backward(d_cat[..., ch[l]:], d_cur)
+            d_cur = self._up_bwd(d_cat[..., ch[l]:], j, S, G)
             if j == 4:
                 self._stage_done(0)           # head + up4 (the full-resolution layers: the longest weight gradients)
         self._stage_done(1)                   # up3 .. up1
@@ -761,7 +815,7 @@ class B200UNet(nn.Module):
 
     def __init__(self, in_ch, base_ch, scale=((2, 2, 2),) * 4, kernel_size=((3, 3, 3),) * 5, num_classes=1,
                  block="BasicBlock", pool=True, norm="in", negative_slope: float = 0.0,
-                 precision: str = "bf16", return_dict: bool = True):
+                 precision: str = "bf16", return_dict: bool = True, up_mode: str = "trilinear"):
         super().__init__()
         if in_ch != 1:
             raise NotImplementedError("B200UNet: in_ch must be 1")
@@ -775,22 +829,28 @@ class B200UNet(nn.Module):
         ks = [list(k) if isinstance(k, (list, tuple)) else [k] * 3 for k in kernel_size]
         if any(s != [2, 2, 2] for s in sc) or len(sc) != 4 or any(k != [3, 3, 3] for k in ks):
             raise NotImplementedError("B200UNet implements scale=[[2,2,2]]*4 and kernel_size=[[3,3,3]]*5")
+        if up_mode not in ("trilinear", "transposed"):
+            raise ValueError("up_mode must be 'trilinear' (the reference up_block: F.interpolate, unet_utils.py:69) or 'transposed' "
+                             "(ConvTranspose3d(kernel_size=2, stride=2) instead — the transposed-conv variant; vnet.py:108)")
+        if up_mode == "transposed" and block == "SingleConv":
+            raise NotImplementedError("up_mode='transposed' is implemented for block='BasicBlock' | 'Bottleneck'")
         if precision not in ("bf16", "fp32"):
             raise ValueError("precision must be 'bf16' (bf16 storage / operands) or 'fp32' (fp32 storage, split 3xbf16 products)")
         b = base_ch
         self.base_ch, self.num_classes = b, num_classes
         self.negative_slope, self.precision, self.return_dict = negative_slope, precision, return_dict
-        self.block = block
+        self.block, self.up_mode = block, up_mode
         blk = {"SingleConv": _SingleConv, "Bottleneck": _Bottleneck}.get(block, _BasicBlock)
         self.inc = _InConv(in_ch, b, blk)
         self.down1 = _Stage(b, 2 * b, True, blk)
         self.down2 = _Stage(2 * b, 4 * b, True, blk)
         self.down3 = _Stage(4 * b, 8 * b, True, blk)
         self.down4 = _Stage(8 * b, 10 * b, True, blk)
-        self.up1 = _Stage(10 * b + 8 * b, 8 * b, False, blk)
-        self.up2 = _Stage(8 * b + 4 * b, 4 * b, False, blk)
-        self.up3 = _Stage(4 * b + 2 * b, 2 * b, False, blk)
-        self.up4 = _Stage(2 * b + b, b, False, blk)
+        tr = up_mode == "transposed"
+        self.up1 = _Stage(10 * b + 8 * b, 8 * b, False, blk, up_channels=10 * b if tr else 0)
+        self.up2 = _Stage(8 * b + 4 * b, 4 * b, False, blk, up_channels=8 * b if tr else 0)
+        self.up3 = _Stage(4 * b + 2 * b, 2 * b, False, blk, up_channels=4 * b if tr else 0)
+        self.up4 = _Stage(2 * b + b, b, False, blk, up_channels=2 * b if tr else 0)
         self.outc = nn.Conv3d(b, num_classes, kernel_size=1)
 
     def __getstate__(self):
@@ -806,9 +866,9 @@ class B200UNet(nn.Module):
         dtype = torch.bfloat16 if self.precision == "bf16" else torch.float32
         engine = self.__dict__.get("_engine")
         if engine is None or engine.dtype != dtype or engine.slope != float(self.negative_slope):
-            engine = _Engine(self.base_ch, self.negative_slope, dtype, self.block)
+            engine = _Engine(self.base_ch, self.negative_slope, dtype, self.block, getattr(self, "up_mode", "trilinear"))
             self.__dict__["_engine"] = engine  # persistent packed-weight buffers; never pickled / deep-copied
-        engine.sink = self.__dict__.get("_grad_sink") if self.block == "BasicBlock" else None
+        engine.sink = self.__dict__.get("_grad_sink") if (self.block == "BasicBlock" and engine.up_mode == "trilinear") else None
         if x.device.index is not None and x.device.index != torch.cuda.current_device():
             with torch.cuda.device(x.device):     # kernels launch on the current device's stream: follow the tensors
                 out = _UNetFunction.apply(x.float(), engine, names, self.num_classes, torch.is_grad_enabled(), *params)

@@ -234,6 +234,14 @@ def test_emulated_bottleneck_unet_vs_reference_and_oracle(emulated, monkeypatch)
     U.test_bottleneck_unet_vs_reference_and_oracle(CPU, "fp32")
 
 
+@pytest.mark.parametrize("block", ["BasicBlock", pytest.param("Bottleneck", marks=_slow)])
+def test_emulated_transposed_conv_upsampling_variant(emulated, monkeypatch, block):
+    """up_mode='transposed' (1x1x1 conv to 8 C channels + depth-to-space, space-to-depth + summed-bias backward) on the CPU."""
+    import test_unet_gpu as U
+    monkeypatch.setenv("RSB_TEST_SINGLE_S", "32")
+    U.test_transposed_conv_upsampling_variant(CPU, block, "fp32")
+
+
 @full
 def test_emulated_static_gradient_steps_equal_fresh_gradient_steps(emulated):
     """Precondition of GraphedTrainStep (rsuper_b200/graph_step.py): the captured body starts with

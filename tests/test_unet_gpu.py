@@ -355,3 +355,61 @@ def test_bottleneck_unet_vs_reference_and_oracle(cuda_dev, precision):
     else:
         assert e_mine <= 2.0 * e_emul + 1e-3
         assert abs(loss.item() - l64.item()) <= 2e-2 * abs(l64.item())
+
+
+@pytest.mark.parametrize("block,precision", [("BasicBlock", "fp32"), ("BasicBlock", "bf16"), ("Bottleneck", "fp32")])
+def test_transposed_conv_upsampling_variant(cuda_dev, block, precision):
+    """up_mode='transposed': ConvTranspose3d(C, C, kernel_size=2, stride=2) + bias in place of the trilinear interpolation of
+    up_block (the north star's transposed-conv variant; vnet.py:108 semantics) — run as a 1x1x1 tensor-core conv to 8 C
+    channels + a depth-to-space pass.  Checked against the torch composition of the same primitives (the oracle with
+    F.conv_transpose3d) in fp64: logits, loss and every gradient incl. the transposed-conv weights and biases."""
+    import os
+    from oracle import losses_ref as LR
+    from oracle import synth
+    from oracle.unet_ref import synthetic_image, synthetic_state_dict, unet_forward
+    from rsuper_b200 import losses
+    from rsuper_b200.unet import B200UNet
+    base, classes = 16, ["organ", "pancreatic_lesion"]
+    S = int(os.environ.get("RSB_TEST_SINGLE_S", "64"))
+    net = B200UNet(1, base, num_classes=2, block=block, precision=precision, up_mode="transposed").to(cuda_dev)
+    sd = synthetic_state_dict(base, 2, device=cuda_dev, block=block, up_mode="transposed")
+    assert list(sd.keys()) == [k for k, _ in net.named_parameters()]
+    assert tuple(sd["up1.up.weight"].shape) == (10 * base, 10 * base, 2, 2, 2) and tuple(sd["up4.up.bias"].shape) == (2 * base,)
+    net.load_state_dict(sd, strict=True)
+    args = LR.default_args(report_volume_loss_basic=0.0)
+    x = synthetic_image(1, S, S, S, seed=6, device=cuda_dev)
+    batch = synth.make_batch(["mask"], classes, (S, S, S), seed=8, device=cuda_dev)
+    out = net(x)
+    loss = losses.calculate_loss(out, batch["label"], None, args, None, None, None, None, classes)["overall"]
+    loss.backward()
+    sd64 = {k: v.double().clone().requires_grad_(True) for k, v in sd.items()}
+    truth = unet_forward(x.double(), sd64)
+    l64 = LR.calculate_loss({"segmentation": truth}, batch["label"].long(), None, args, None, None, None, None, classes)["overall"]
+    l64.backward()
+    with torch.no_grad():
+        emul = unet_forward(x, sd, emulate=True, storage="bf16")
+    e_mine, e_emul = rel(out["segmentation"].double(), truth), rel(emul.double(), truth)
+    agree = (out["segmentation"].argmax(1) == truth.argmax(1)).float().mean().item()
+    errs = {k: rel(p.grad.double(), sd64[k].grad) for k, p in net.named_parameters()}
+    # the transposed-conv bias feeds an InstanceNorm: its true gradient is zero (fp64: ~1e-15), so it is compared on the scale
+    # of the matching weight gradient instead of relative to itself
+    for j in range(1, 5):
+        wmax = sd64[f"up{j}.up.weight"].grad.abs().max().item()
+        bp = dict(net.named_parameters())[f"up{j}.up.bias"]
+        errs[f"up{j}.up.bias"] = (bp.grad.double() - sd64[f"up{j}.up.bias"].grad).abs().max().item() / wmax
+    worst = max(errs, key=errs.get)
+    up_errs = {k: v for k, v in errs.items() if ".up." in k}
+    print(f"[transposed] {block} {precision} {S}^3: logits vs fp64 oracle {e_mine:.3e} (bf16-emulating oracle {e_emul:.3e}) argmax {agree:.5f} | "
+          f"loss {loss.item():.6f} vs {l64.item():.6f} | worst grad err {errs[worst]:.3e} at {worst}; transposed-conv params "
+          + " ".join(f"{k}={v:.1e}" for k, v in up_errs.items()))
+    for k, p in net.named_parameters():
+        assert p.grad is not None and p.grad.shape == p.shape and torch.isfinite(p.grad).all(), k
+    if precision == "fp32":
+        if S >= 64:
+            assert e_mine <= 1e-3 and agree == 1.0 and abs(loss.item() - l64.item()) <= 1e-5 * abs(l64.item())
+            assert errs[worst] <= 5e-2 and max(up_errs.values()) <= 1e-2
+        else:
+            assert e_mine <= 1e-2 and agree >= 0.9999 and abs(loss.item() - l64.item()) <= 1e-4 * abs(l64.item())
+            assert max(up_errs.values()) <= 5e-2
+    else:
+        assert e_mine <= 2.0 * e_emul + 1e-3 and abs(loss.item() - l64.item()) <= 2e-2 * abs(l64.item())
