@@ -47,8 +47,10 @@ __global__ void rows_scatter_add_kernel(const float* __restrict__ src, const int
   const long long r = blockIdx.y;
   const float* s = src + r * V;
   float* d = dst + static_cast<long long>(row_map[r]) * V;
+  // atomic: a channel that belongs to two lesion groups ('kidney_cyst_lesion' matches both suffixes) is the destination of two
+  // rows, and rows run concurrently
   for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < V; v += static_cast<long long>(gridDim.x) * blockDim.x)
-    d[v] += s[v];
+    atomicAdd(&d[v], s[v]);
 }
 
 // Lesion groups that merge several channels of one organ (get_lesion_channels, :215-220: torch.stack(...).max(dim=0)):
@@ -82,7 +84,7 @@ __global__ void rows_scatter_add_max_kernel(const float* __restrict__ grad, cons
         const float o = x[static_cast<long long>(g[k]) * V + v];
         if (o > best) { best = o; arg = g[k]; }
       }
-    dst[static_cast<long long>(arg) * V + v] += s[v];
+    atomicAdd(&dst[static_cast<long long>(arg) * V + v], s[v]);
   }
 }
 
