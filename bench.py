@@ -322,13 +322,17 @@ def main():
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--base", type=int, default=32)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--schedule", default="auto", choices=["auto", "graph", "eager"],
-                    help="auto: CUDA-graph replay of the whole step when the loss path is capturable, launch by launch otherwise")
+    ap.add_argument("--schedule", default="auto", choices=["auto", "graph", "split", "eager"],
+                    help="auto: CUDA-graph replay of the whole step when the loss path is capturable, else 'split' (network forward and "
+                         "backward + all-reduce + optimizer as two graphs, the host-controlled report losses launch by launch in between)")
     ap.add_argument("--no-side-stream", action="store_true", help="weight gradients on the main stream (default: second stream inside the graph)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-torch-gpu-baseline", action="store_true")
     ap.add_argument("--packed-labels", action="store_true",
                     help="e2e leg uploads the masks in the reference's bit-packed on-disk format and unpacks them on the device")
+    ap.add_argument("--no-allreduce", action="store_true",
+                    help="diagnostic for N > 1: every rank steps on its own (no gradient all-reduce) — separates chip-to-chip / host "
+                         "variation from communication cost in the max-over-ranks time; NOT a training configuration")
     ap.add_argument("--trace", default=None, help="write the per-launch CUDA-event timeline of the profiled pass to this file")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -401,8 +405,8 @@ def main():
 
     schedule = args.schedule
     if schedule == "auto":
-        schedule = "graph" if losses.capturable(largs, report) else "eager"
-    step = B200TrainStep(net, loss_fn, opt, [devb[k] for k in keys], schedule=schedule, process_group=pg,
+        schedule = "graph" if losses.capturable(largs, report) else "split"
+    step = B200TrainStep(net, loss_fn, opt, [devb[k] for k in keys], schedule=schedule, process_group=None if args.no_allreduce else pg,
                          side_stream=(False if args.no_side_stream else None), warmup=args.warmup)
 
     def barrier():
@@ -459,13 +463,14 @@ def main():
     # CUDA events, so that a kernel's events measure that kernel alone ----
     barrier()
     prev_side, step.side_stream = step.side_stream, False
-    step._eager()
+    eager_body = step._eager_split if schedule == "split" else step._eager
+    eager_body()
     barrier()
     ops.PROFILE = []
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     p0.record()
     for _ in range(args.steps):
-        step._eager()
+        eager_body()
     p1.record()
     barrier()
     prof, ops.PROFILE = ops.PROFILE, None
@@ -473,7 +478,11 @@ def main():
     step.side_stream = prev_side
 
     t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
+    per_rank = None
     if dist is not None:
+        gathered = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(gathered, t)
+        per_rank = [round(g[0].item(), 3) for g in gathered]      # every rank's own device time per step (the value uses the max)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_dev, ms_e2e = t.tolist()
     vox = job_voxels(world, B, shape)
@@ -527,10 +536,15 @@ def main():
                 "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16" if args.precision == "bf16" else "bf16 operands / f32 storage", "data": "synthetic",
                 "config": config,
-                "impl_detail": {"schedule": "CUDA graph replay of the whole step" if schedule == "graph" else "eager launches",
+                "impl_detail": {"schedule": {"graph": "CUDA graph replay of the whole step", "eager": "eager launches",
+                                             "split": "two CUDA graphs (UNet forward | UNet backward + all-reduce + optimizer), "
+                                                      "calculate_loss with its host-controlled report losses eager in between"}[schedule],
                                 "side_stream": bool(prev_side), "precision": args.precision,
                                 "optimizer": "B200AdamW (fused clip+AdamW+EMA kernel)",
-                                "gradient_allreduce": "one NCCL all-reduce (AVG) of the flat fp32 gradient buffer inside the step" if world > 1 else None,
+                                "gradient_allreduce": (None if world == 1 else "DISABLED (--no-allreduce diagnostic)" if args.no_allreduce else
+                                                       "NCCL all-reduce (AVG) of the flat fp32 gradient buffer in four buckets on a communication "
+                                                       "stream while backward runs, inside the captured step"),
+                                "ms_per_step_per_rank": per_rank,
                                 "masks_h2d": "bit-packed (np.packbits) + device unpack" if args.packed_labels else "uint8"},
                 "conv3d_flop_roofline_frac": value / flop_roof_mvox,
                 "roofline": roof, "kernels": kern, "cpu_baseline": cb, "torch_gpu_baseline": tgb,

@@ -323,10 +323,13 @@ int rsb_ball_correlate_argmax(const float* x_iter, const void* taps, int n_taps,
 /* The same argmax in three separable stages (rows -> discs -> planes; csrc/report_loss.cu): gauss = device float[R + 1],
  * g(d) = exp(-d^2 / 2 sigma^2); wtab = device int[(R + 1)^2], wtab[a * (R + 1) + b] = largest dx with a^2 + b^2 + dx^2 <= r^2
  * or -1 (the ball of create_ball_kernel as x ranges); R = floor(radius).  The normalisation of the reference's kernel is a
- * positive factor and is dropped.  workspace: rsb_ball_sep_workspace_bytes(D, H, W, R) bytes. */
+ * positive factor and is dropped.  gauss_host / wtab_host: the same two tables in HOST memory (optional; with them and
+ * R <= 16 the disc stage runs from shared-memory tiles with the tables passed by value).
+ * workspace: rsb_ball_sep_workspace_bytes(D, H, W, R) bytes. */
 size_t rsb_ball_sep_workspace_bytes(int D, int H, int W, int R);
-int rsb_ball_correlate_argmax_sep(const float* x_iter, const float* gauss, const int* wtab, int R, void* workspace,
-                                  long long* argmax_out, int D, int H, int W, void* stream);
+int rsb_ball_correlate_argmax_sep(const float* x_iter, const float* gauss, const int* wtab, const float* gauss_host,
+                                  const int* wtab_host, int R, void* workspace, long long* argmax_out, int D, int H, int W,
+                                  void* stream);
 /* candidates {value bits, voxel index}: mode 0 = voxels of the ball (centre, grid half-width, radius^2 — insert_ball
  * :1336-1385) with x > 0 (also writes the 0/1 ball volume); mode 1 = voxels with mask != 0, value sigmoid(x) */
 int rsb_ball_candidates(const float* x, const uint8_t* mask, int mode, int cz, int cy, int cx, int half, float radius2,

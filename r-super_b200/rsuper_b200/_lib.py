@@ -151,7 +151,8 @@ SIGNATURES = {
     "rsb_ball_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "rsb_ball_correlate_argmax": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "rsb_ball_sep_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
-    "rsb_ball_correlate_argmax_sep": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "rsb_ball_correlate_argmax_sep": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
+                                              c_void_p]),
     "rsb_ball_candidates": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_int,
                                     c_void_p, c_int, c_int, c_int, c_void_p]),
     "rsb_ball_rank_select": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -560,7 +560,7 @@ def ball_correlate_argmax(x_iter, taps, kernel_half):
 _SEP_WS = {}
 
 
-def ball_correlate_argmax_sep(x_iter, gauss, wtab, reach):
+def ball_correlate_argmax_sep(x_iter, gauss, wtab, reach, gauss_host=None, wtab_host=None):
     """Same packed argmax as ball_correlate_argmax through the rows -> discs -> planes decomposition of the truncated
     Gaussian ball (gauss: device fp32 [reach + 1], wtab: device int32 [(reach + 1)^2])."""
     d, h, w_ = x_iter.shape
@@ -572,7 +572,11 @@ def ball_correlate_argmax_sep(x_iter, gauss, wtab, reach):
             _SEP_WS.clear()
         ws = _SEP_WS[key] = torch.empty(lib().rsb_ball_sep_workspace_bytes(d, h, w_, reach), dtype=torch.uint8, device=x_iter.device)
     out = torch.empty(1, dtype=torch.int64, device=x_iter.device)
-    _call("report", 4, 0.0, lib().rsb_ball_correlate_argmax_sep, _p(x_iter), _p(gauss), _p(wtab), reach, _p(ws), _p(out), d, h, w_,
+    if gauss_host is not None:     # host copies of the two tables (numpy float32 / int32): the tiled disc stage takes them by value
+        assert gauss_host.dtype.name == "float32" and wtab_host.dtype.name == "int32" and gauss_host.size == reach + 1
+    gh = C.c_void_p(gauss_host.ctypes.data) if gauss_host is not None else None
+    wh = C.c_void_p(wtab_host.ctypes.data) if wtab_host is not None else None
+    _call("report", 4, 0.0, lib().rsb_ball_correlate_argmax_sep, _p(x_iter), _p(gauss), _p(wtab), gh, wh, reach, _p(ws), _p(out), d, h, w_,
           _stream(), what="ball_correlate_argmax_sep")
     return out
 

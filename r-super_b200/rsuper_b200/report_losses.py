@@ -111,7 +111,8 @@ def _gauss_ball_sep(diameter: int, std: float, device):
     d2 = c[:, None, None] ** 2 + c[None, :, None] ** 2 + c[None, None, :] ** 2       # same fp32 test as the tap list: d2 <= r2
     inside = d2 <= r2
     wtab = np.where(inside.any(-1), inside.sum(-1) - 1, -1).astype(np.int32)         # runs are contiguous from dx = 0
-    hit = (torch.from_numpy(g).to(device), torch.from_numpy(wtab.reshape(-1).copy()).to(device), reach)
+    wflat = np.ascontiguousarray(wtab.reshape(-1))
+    hit = (torch.from_numpy(g).to(device), torch.from_numpy(wflat.copy()).to(device), reach, np.ascontiguousarray(g), wflat)
     _SEP[key] = hit
     return hit
 
@@ -225,8 +226,8 @@ def isolate_tumor(x_iter: torch.Tensor, diameter, gaussian: bool, gaussian_std: 
     if support > tumor_volume:
         tumor_volume = support - 1
     if gaussian and SEPARABLE_CORRELATION:
-        g1d, wtab, reach = _gauss_ball_sep(diameter, gaussian_std, x_iter.device)
-        key = int(ops.ball_correlate_argmax_sep(x_iter, g1d, wtab, reach).item())
+        g1d, wtab, reach, g_host, w_host = _gauss_ball_sep(diameter, gaussian_std, x_iter.device)
+        key = int(ops.ball_correlate_argmax_sep(x_iter, g1d, wtab, reach, g_host, w_host).item())
     else:
         key = int(ops.ball_correlate_argmax(x_iter, taps, khalf).item())
     flat_idx = 0xFFFFFFFF - (key & 0xFFFFFFFF)

@@ -34,9 +34,11 @@ from .optim import B200AdamW
 
 def _production_order(names):
     """Parameter names in the order B200UNet's backward produces their gradients (block='BasicBlock': head, up4 .. up1,
-    down4 .. down1, inc, stem) and the four buckets the engine reports (unet._Engine._stage_done); conv1 / shortcut of a block
-    are adjacent (their gradients come out of ONE merged weight-gradient GEMM).  Any other parameter set: given order, no
-    buckets."""
+    down4 .. down1, inc, stem) and the four buckets the engine reports (unet._Engine._stage_done): {head, up4} 0.3 M parameters,
+    {up3 .. up1} 17 M, {down4, down3} 20 M, {down2, down1, inc, stem} 2.3 M — the two large buckets leave while the encoder /
+    the full-resolution layers are still in backward, only the last 9 MB are exposed (measured at N = 8: profiles/r02_scale_*).
+    conv1 / shortcut of a block are adjacent (their gradients come out of ONE merged weight-gradient GEMM).  Any other
+    parameter set: given order, no buckets."""
     have = set(names)
 
     def block(pre, shortcut):
@@ -50,11 +52,13 @@ def _production_order(names):
     for j in (3, 2, 1):
         s1 += block(f"up{j}.conv.1.", False) + block(f"up{j}.conv.0.", True)
     stages.append(s1)
-    s2 = []
-    for l in (4, 3, 2, 1):
+    s2, s3 = [], []
+    for l in (4, 3):
         s2 += block(f"down{l}.conv.2.", False) + block(f"down{l}.conv.1.", True)
+    for l in (2, 1):
+        s3 += block(f"down{l}.conv.2.", False) + block(f"down{l}.conv.1.", True)
     stages.append(s2)
-    stages.append(block("inc.conv2.", False) + ["inc.conv1.weight"])
+    stages.append(s3 + block("inc.conv2.", False) + ["inc.conv1.weight"])
     order = [n for st in stages for n in st]
     if set(order) != have or len(order) != len(names):
         return list(names), None
@@ -137,8 +141,8 @@ class B200TrainStep:
                  *, schedule: str = "graph", process_group=None, side_stream: Optional[bool] = None, warmup: int = 3):
         if not isinstance(optimizer, B200AdamW) or not optimizer.capturable:
             raise ValueError("B200TrainStep needs a B200AdamW(capturable=True) optimizer")
-        if schedule not in ("graph", "eager"):
-            raise ValueError("schedule must be 'graph' or 'eager'")
+        if schedule not in ("graph", "split", "eager"):
+            raise ValueError("schedule must be 'graph', 'split' or 'eager'")
         if isinstance(net, torch.nn.parallel.DistributedDataParallel):
             raise NotImplementedError("B200TrainStep does its own gradient all-reduce: pass the bare module and process_group=")
         from . import ops
@@ -151,15 +155,18 @@ class B200TrainStep:
         if process_group is not None:
             import torch.distributed as dist
             self.world = dist.get_world_size(process_group)
-        self.side_stream = (schedule == "graph") if side_stream is None else bool(side_stream)
+        self.side_stream = (schedule in ("graph", "split")) if side_stream is None else bool(side_stream)
         self.static = [None if t is None else t.clone() for t in example_inputs]
         self.loss = torch.zeros((), dtype=torch.float32, device=img.device)
         self._make_flat_grads()
         self.graph = None
         self.launches_per_step = None
         self.warmup_steps = 0
+        self.graph_fwd = self.graph_bwd = None
         if schedule == "graph":
             self._capture(max(1, warmup))
+        elif schedule == "split":
+            self._capture_split(max(1, warmup))
 
     # -- one flat gradient buffer; every p.grad is a 16-byte-aligned view of it ---------------------------------------------
     def _make_flat_grads(self):
@@ -226,6 +233,100 @@ class B200TrainStep:
         self.opt.prepare_step()
         self._body()
 
+    # -- schedule='split': the network in two graphs, the loss launch by launch in between ------------------------------------
+    # For losses with host control flow (the report-supervised Volume / Ball losses read a few scalars back per tumour, like
+    # the reference): graph A = UNet forward, graph B = UNet backward + gradient all-reduce + optimizer; only
+    # calculate_loss and its backward to d(logits) run eagerly.  The engine is driven directly (same kernels, same order as
+    # through autograd); the saved activations live in graph A's memory pool, which graph B shares.
+    def _engine(self):
+        from .unet import _Engine
+        net = self.net
+        dtype = torch.bfloat16 if net.precision == "bf16" else torch.float32
+        eng = net.__dict__.get("_engine")
+        if eng is None or eng.dtype != dtype or eng.slope != float(net.negative_slope):
+            eng = _Engine(net.base_ch, net.negative_slope, dtype, net.block, getattr(net, "up_mode", "trilinear"))
+            net.__dict__["_engine"] = eng
+        eng.sink = net.__dict__.get("_grad_sink") if (net.block == "BasicBlock" and eng.up_mode == "trilinear") else None
+        return eng
+
+    def _split_fwd(self):
+        from . import unet as unet_mod
+        prev = unet_mod.set_side_stream(self.side_stream)
+        try:
+            eng = self._engine()
+            self._P = {k: v.detach() for k, v in self.net.named_parameters()}
+            with torch.no_grad():
+                self._logits, self._saved = eng.forward(self.static[0].float().contiguous(), self._P, self.net.num_classes, save=True)
+        finally:
+            unet_mod.set_side_stream(prev)
+
+    def _split_loss(self):
+        lg = self._logits.detach().requires_grad_(True)          # a leaf that shares the logits' storage
+        out = {"segmentation": lg} if self.net.return_dict else lg
+        loss = self.loss_fn(out, *self.static[1:])
+        loss.backward()
+        self._dlogits.copy_(lg.grad)
+        self.loss.copy_(loss.detach())
+
+    def _split_bwd(self):
+        from . import unet as unet_mod
+        prev = unet_mod.set_side_stream(self.side_stream)
+        try:
+            eng = self._engine()
+            if self.sink is None or not self.sink.covers_all():
+                self.flat_grad.zero_()
+            if self.sink is not None:
+                self.sink.begin()
+            with torch.no_grad():
+                G = eng.backward(self._saved, self._P, self._dlogits)
+                for name, p in self.net.named_parameters():
+                    if p.requires_grad and not (eng.sink is not None and eng.sink.owns(name)):
+                        p.grad.add_(G[name])
+            self._allreduce()
+            self.opt.step()
+        finally:
+            unet_mod.set_side_stream(prev)
+
+    def _eager_split(self):
+        self.opt.prepare_step()
+        self._split_fwd()
+        self._split_loss()
+        self._split_bwd()
+
+    def _capture_split(self, warmup: int):
+        from . import ops
+        dev = self.loss.device
+        img = self.static[0]
+        self._dlogits = torch.zeros((img.shape[0], self.net.num_classes) + tuple(img.shape[2:]), dtype=torch.float32, device=dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._eager_split()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.warmup_steps = warmup
+        before = ops.LAUNCHES
+        self.graph_fwd = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_fwd, capture_error_mode="thread_local"):
+            self._split_fwd()
+        n_fwd = ops.LAUNCHES - before
+        self.graph_fwd.replay()                  # real logits / activations for the loss that seeds the second capture
+        before = ops.LAUNCHES
+        self._split_loss()
+        self._loss_launches = ops.LAUNCHES - before
+        self.opt.prepare_step()
+        before = ops.LAUNCHES
+        self.graph_bwd = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_bwd, pool=self.graph_fwd.pool(), capture_error_mode="thread_local"):
+            self._split_bwd()
+        self.launches_per_step = n_fwd + self._loss_launches + (ops.LAUNCHES - before)
+        self.opt._prepared = False
+        self.opt.global_step -= 1
+        for p in self.params:
+            if p in self.opt.state and len(self.opt.state[p]):
+                self.opt.state[p]["step"] -= 1
+
     def _capture(self, warmup: int):
         from . import ops
         dev = self.loss.device
@@ -259,6 +360,13 @@ class B200TrainStep:
         for dst, src in zip(self.static, inputs):
             if dst is not None:
                 dst.copy_(src, non_blocking=True)
+        if self.graph_fwd is not None:
+            self.opt.prepare_step()
+            self.graph_fwd.replay()
+            self._split_loss()
+            self.graph_bwd.replay()
+            self.opt.finish_step()
+            return self.loss
         if self.graph is None:
             from . import ops
             before = ops.LAUNCHES

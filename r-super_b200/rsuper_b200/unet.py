@@ -762,7 +762,8 @@ class _Engine:
             x_prev = S["enc_out"][l - 1]
             d_cur = self._new(x_prev.t, ch[l - 1])
             ops.maxpool2_backward(x_prev.t, d_p, d_cur, dskip=dskip[l - 1])
-        self._stage_done(2)                   # down4 .. down1 (two thirds of the parameters)
+            if l == 3:
+                self._stage_done(2)           # down4 + down3: half of the parameters, with down2 / down1 / inc still to run
         # inc block + stem
         x0, h0, ax0, ah0 = saved[0]
         d_t0 = self._new(x0.t, b)
@@ -776,7 +777,7 @@ class _Engine:
         if self._side is not None:
             torch.cuda.current_stream().wait_stream(self._side)   # all weight gradients done before autograd hands them on
         self._side_keep.clear()
-        self._stage_done(3)                   # inc + stem
+        self._stage_done(3)                   # down2, down1, inc, stem (9 MB: the only all-reduce that is not hidden)
         return G
 
 

@@ -167,9 +167,10 @@ def test_separable_ball_correlation_matches_tap_list(cuda_dev, shape, diameter):
     for vol in (x * blob, x, torch.zeros(shape)):
         xi = vol.to(cuda_dev).contiguous()
         taps, support, khalf = RL._gauss_ball_taps(diameter, True, 1.5, cuda_dev)
-        g1d, wtab, reach = RL._gauss_ball_sep(diameter, 1.5, cuda_dev)
+        g1d, wtab, reach, g_host, w_host = RL._gauss_ball_sep(diameter, 1.5, cuda_dev)
         k_tap = int(ops.ball_correlate_argmax(xi, taps, khalf).item())
-        k_sep = int(ops.ball_correlate_argmax_sep(xi, g1d, wtab, reach).item())
+        k_sep = int(ops.ball_correlate_argmax_sep(xi, g1d, wtab, reach, g_host, w_host).item())
+        assert k_sep == int(ops.ball_correlate_argmax_sep(xi, g1d, wtab, reach).item())      # tiled and per-row disc stages agree bit for bit
         assert (k_tap & 0xFFFFFFFF) == (k_sep & 0xFFFFFFFF), (shape, diameter)
         s_tap = np.array([k_tap >> 32], dtype=np.uint32).view(np.float32)[0]
         s_sep = np.array([k_sep >> 32], dtype=np.uint32).view(np.float32)[0]

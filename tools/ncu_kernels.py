@@ -62,8 +62,8 @@ if want("sat"):
     ops.dilate_ball(lab[:, 1].contiguous(), 7)
     prob = torch.rand(S, S, S, generator=g).to(dev) * (torch.rand(S, S, S, generator=g) < 0.3).to(dev)
     from rsuper_b200 import report_losses as RL
-    g1d, wtab, reach = RL._gauss_ball_sep(31, 1.5, torch.device(dev))
-    ops.ball_correlate_argmax_sep(prob.contiguous(), g1d, wtab, reach)
+    g1d, wtab, reach, g_host, w_host = RL._gauss_ball_sep(31, 1.5, torch.device(dev))
+    ops.ball_correlate_argmax_sep(prob.contiguous(), g1d, wtab, reach, g_host, w_host)
 if want("opt"):
     # ---- optimizer end: clip + AdamW + EMA over the 40.56 M parameters of the base-32 UNet; weight packing ----
     from rsuper_b200.optim import B200AdamW
