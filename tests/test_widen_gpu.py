@@ -776,3 +776,51 @@ def test_graphed_train_step_matches_eager(cuda_dev):
         assert torch.isfinite(b).all() and d.max().item() <= 2 * 4 * 6e-4 * 1.05
         tot += d.sum().item(); cnt += d.numel()
     assert tot / cnt <= 0.25 * 6e-4
+
+
+def test_split_schedule_matches_eager_on_report_batches(cuda_dev):
+    """B200TrainStep(schedule='split') — UNet forward and backward + optimizer as two CUDA graphs, calculate_loss with the
+    Volume / Ball report losses (host-controlled tumour loop) launched eagerly in between — against schedule='eager' from
+    identical initial state on a mixed mask / report batch: same loss dictionaries' total at every step, parameters and EMA
+    within optimizer rounding."""
+    from oracle import losses_ref as LR
+    from oracle import synth
+    from oracle.unet_ref import synthetic_state_dict
+    from rsuper_b200 import losses
+    from rsuper_b200.optim import B200AdamW
+    from rsuper_b200.train_step import B200TrainStep
+    from rsuper_b200.unet import B200UNet
+    classes = ["organ", "pancreatic_lesion"]
+    shape = (48, 64, 48)
+    bt = synth.make_batch(["report", "mask"], classes, shape, seed=17, device=cuda_dev)
+    args = LR.default_args()
+    args.nan_check = False
+    assert not losses.capturable(args, True) and losses.capturable(args, False)
+
+    def loss_fn(out, lab, unk, msk, vol, dia):
+        return losses.calculate_loss(out, lab, unk, args, None, msk, vol, dia, classes)["overall"]
+
+    keys = ["image", "label", "unk_channels", "mask", "volumes", "diameters"]
+    runs = []
+    for schedule in ("eager", "split"):
+        net = B200UNet(1, 16, num_classes=2, precision="bf16").to(cuda_dev)
+        net.load_state_dict(synthetic_state_dict(16, 2, device=cuda_dev))
+        params = list(net.parameters())
+        ema = [p.detach().clone() for p in params]
+        opt = B200AdamW(params, lr=6e-4, weight_decay=0.05, max_norm=1.0, ema_params=ema, capturable=True)
+        step = B200TrainStep(net, loss_fn, opt, [bt[k] for k in keys], schedule=schedule, warmup=1)
+        ls = [step.loss.item()] if schedule == "split" else []
+        for _ in range(3 if schedule == "split" else 4):
+            ls.append(B200TrainStep.check(step(*[bt[k] for k in keys]).item()))
+        assert step.launches_per_step > 150
+        runs.append((ls, [p.detach().clone() for p in params], ema, opt.global_step))
+    (l0, p0, e0, s0), (l1, p1, e1, s1) = runs
+    print(f"[split] eager losses {l0}, split-graph losses {l1}")
+    assert s0 == s1 == 4
+    assert all(abs(a - b) <= 2e-2 * abs(a) for a, b in zip(l0, l1)) and abs(l0[0] - l1[0]) <= 2e-3 * abs(l0[0])
+    tot = cnt = 0.0
+    for a, b in zip(p0 + e0, p1 + e1):
+        d = (a - b).abs()
+        assert torch.isfinite(b).all() and d.max().item() <= 2 * 4 * 6e-4 * 1.05
+        tot += d.sum().item(); cnt += d.numel()
+    assert tot / cnt <= 0.25 * 6e-4
