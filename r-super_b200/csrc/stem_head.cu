@@ -166,26 +166,34 @@ __global__ void __launch_bounds__(kStemThreads) stem_fwd_tiled_kernel(const floa
   }
   const long long v0 = (static_cast<long long>(zq) * H + yq) * W + x0;
   for (int c0 = 0; c0 < Cout; c0 += 16) {
-    float acc[kStemVX][16];
+    // packed FP32 FMA (FFMA2, sm_100): the three-register scalar FFMA issues every second cycle per scheduler, the packed form
+    // carries two FMAs per issue slot — this loop is FMA-issue bound (864 FMA per voxel).  Same rounding as fmaf.
+    float2 acc2[kStemVX][8];
 #pragma unroll
     for (int q = 0; q < kStemVX; ++q)
 #pragma unroll
-      for (int j = 0; j < 16; ++j) acc[q][j] = 0.f;
+      for (int j = 0; j < 8; ++j) acc2[q][j] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int r = 0; r < 9; ++r) {
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
         const float4* wr = reinterpret_cast<const float4*>(sw + (r * 3 + kw) * cpad + c0);
         const float4 w0 = wr[0], w1 = wr[1], w2 = wr[2], w3 = wr[3];
-        const float wv[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+        const float2 wv[8] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y), make_float2(w1.z, w1.w),
+                              make_float2(w2.x, w2.y), make_float2(w2.z, w2.w), make_float2(w3.x, w3.y), make_float2(w3.z, w3.w)};
 #pragma unroll
         for (int q = 0; q < kStemVX; ++q) {
-          const float xv = xin[r][q + kw];
+          const float2 xv = make_float2(xin[r][q + kw], xin[r][q + kw]);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) acc[q][j] = fmaf(xv, wv[j], acc[q][j]);
+          for (int j = 0; j < 8; ++j) acc2[q][j] = __ffma2_rn(xv, wv[j], acc2[q][j]);
         }
       }
     }
+    float acc[kStemVX][16];
+#pragma unroll
+    for (int q = 0; q < kStemVX; ++q)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { acc[q][2 * j] = acc2[q][j].x; acc[q][2 * j + 1] = acc2[q][j].y; }
     const int nvalid = Cout - c0;
     if (ok) {
 #pragma unroll
@@ -279,11 +287,11 @@ __global__ void __launch_bounds__(576) stem_wgrad_tiled_kernel(const float* __re
   const int khd = r / CG, cg = r % CG;
   const int dz = khd / 3, dyy = khd % 3;
   for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) sacc[i] = 0.f;
-  float acc[3][8];
+  float2 acc2[3][4];                       // packed FP32 FMA (FFMA2): two channels per instruction, same rounding as fmaf
 #pragma unroll
   for (int k = 0; k < 3; ++k)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc2[k][j] = make_float2(0.f, 0.f);
   for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     long long t = tile;
     const int xt = static_cast<int>(t % tiles_x); t /= tiles_x;
@@ -321,17 +329,23 @@ __global__ void __launch_bounds__(576) stem_wgrad_tiled_kernel(const float* __re
       const float xc = xr[vx + 2];
       const float4* d4 = reinterpret_cast<const float4*>(dr + vx * Cout);
       const float4 a = d4[0], b = d4[1];
-      const float d[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      const float2 d[4] = {make_float2(a.x, a.y), make_float2(a.z, a.w), make_float2(b.x, b.y), make_float2(b.z, b.w)};
+      const float2 xa2 = make_float2(xa, xa), xb2 = make_float2(xb, xb), xc2 = make_float2(xc, xc);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        acc[0][j] = fmaf(xa, d[j], acc[0][j]);
-        acc[1][j] = fmaf(xb, d[j], acc[1][j]);
-        acc[2][j] = fmaf(xc, d[j], acc[2][j]);
+      for (int j = 0; j < 4; ++j) {
+        acc2[0][j] = __ffma2_rn(xa2, d[j], acc2[0][j]);
+        acc2[1][j] = __ffma2_rn(xb2, d[j], acc2[1][j]);
+        acc2[2][j] = __ffma2_rn(xc2, d[j], acc2[2][j]);
       }
       xa = xb;
       xb = xc;
     }
   }
+  float acc[3][8];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[k][2 * j] = acc2[k][j].x; acc[k][2 * j + 1] = acc2[k][j].y; }
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < 3; ++k)
