@@ -313,10 +313,14 @@ static inline float ac_scale(int in_size, int out_size) {
 template <typename T>
 __global__ void upsample_fwd_kernel(const T* __restrict__ x, long long xp, T* __restrict__ y, long long yp,
                                     float* __restrict__ stats, int Di, int Hi, int Wi, int Do, int Ho,
-                                    int Wo, int C, float sd, float sh, float sw) {
+                                    int Wo, int C, float sd, float sh, float sw, int zchunks) {
   extern __shared__ float sm_acc[];  // [2*C] statistics scratch
   const int CG = C / 8;
-  const int n = blockIdx.z, yo = blockIdx.y;
+  // z is walked in `zchunks` independent pieces: the walk is a chain of dependent loads (ncu, one piece: 36.7 % of HBM with
+  // every warp waiting on long_scoreboard at 32 % occupancy); more, shorter walks put more loads in flight
+  const int n = blockIdx.z / zchunks, zc = blockIdx.z % zchunks, yo = blockIdx.y;
+  const int zlen = (Do + zchunks - 1) / zchunks;
+  const int zo_begin = zc * zlen, zo_end = min(Do, zo_begin + zlen);
   const int cg = threadIdx.x % CG;  // blockDim.x is a multiple of CG
   const int xo = blockIdx.x * (blockDim.x / CG) + threadIdx.x / CG;
   float s1[8] = {0}, s2[8] = {0};
@@ -341,7 +345,7 @@ __global__ void upsample_fwd_kernel(const T* __restrict__ x, long long xp, T* __
     int z0 = -1, z1 = -1;  // input planes held in P0 / P1
     T* yc = y + ((static_cast<long long>(n) * Do * Ho + yo) * Wo + xo) * yp + cg * 8;
     const long long ystep = static_cast<long long>(Ho) * Wo * yp;
-    for (int zo = 0; zo < Do; ++zo) {
+    for (int zo = zo_begin; zo < zo_end; ++zo) {
       const Lerp lz = lerp_src(zo, sd, Di);
       if (lz.i0 != z0) {
         if (lz.i0 == z1) {
@@ -795,12 +799,20 @@ extern "C" int rsb_upsample_trilinear_forward(const void* x, int x_pitch, void* 
   RSB_REQUIRE(Ho <= 65535, "upsample: output height too large");
   (void)sms;
   const int xt = block / CG;
-  dim3 grid(static_cast<unsigned>((Wo + xt - 1) / xt), Ho, N);
+  int zchunks = 1;
+  {
+    // enough blocks for ~8 per SM, pieces of at least 8 output planes (a piece re-computes two bilinear input planes)
+    const long long blocks = static_cast<long long>((Wo + xt - 1) / xt) * Ho * N;
+    const int sms_now = rsb_num_sms() > 0 ? rsb_num_sms() : 148;
+    while (zchunks < 8 && blocks * zchunks < 8LL * sms_now && Do / (zchunks * 2) >= 8) zchunks *= 2;
+    if (static_cast<long long>(N) * zchunks > 65535) zchunks = 1;
+  }
+  dim3 grid(static_cast<unsigned>((Wo + xt - 1) / xt), Ho, N * zchunks);
   const size_t sm = sizeof(float) * 2 * C;
   const float sd = ac_scale(Di, Do), sh = ac_scale(Hi, Ho), sw = ac_scale(Wi, Wo);
   RSB_BY_DTYPE(dtype,
-               (upsample_fwd_kernel<__nv_bfloat16><<<grid, block, sm, st>>>((const __nv_bfloat16*)x, x_pitch, (__nv_bfloat16*)y, y_pitch, out_stats, Di, Hi, Wi, Do, Ho, Wo, C, sd, sh, sw)),
-               (upsample_fwd_kernel<float><<<grid, block, sm, st>>>((const float*)x, x_pitch, (float*)y, y_pitch, out_stats, Di, Hi, Wi, Do, Ho, Wo, C, sd, sh, sw)))
+               (upsample_fwd_kernel<__nv_bfloat16><<<grid, block, sm, st>>>((const __nv_bfloat16*)x, x_pitch, (__nv_bfloat16*)y, y_pitch, out_stats, Di, Hi, Wi, Do, Ho, Wo, C, sd, sh, sw, zchunks)),
+               (upsample_fwd_kernel<float><<<grid, block, sm, st>>>((const float*)x, x_pitch, (float*)y, y_pitch, out_stats, Di, Hi, Wi, Do, Ho, Wo, C, sd, sh, sw, zchunks)))
   return check_launch("upsample_trilinear_forward");
 }
 
