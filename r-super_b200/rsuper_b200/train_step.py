@@ -229,6 +229,13 @@ class B200TrainStep:
         finally:
             unet_mod.set_side_stream(prev)
 
+    def _capture_stream(self):
+        import os
+        if getattr(self, "_cap_stream", None) is None:
+            prio = -1 if os.environ.get("RSB_CAPTURE_PRIORITY", "0") == "1" else 0
+            self._cap_stream = torch.cuda.Stream(device=self.loss.device, priority=prio)
+        return self._cap_stream
+
     def _eager(self):
         self.opt.prepare_step()
         self._body()
@@ -308,7 +315,7 @@ class B200TrainStep:
         self.warmup_steps = warmup
         before = ops.LAUNCHES
         self.graph_fwd = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph_fwd, capture_error_mode="thread_local"):
+        with torch.cuda.graph(self.graph_fwd, stream=self._capture_stream(), capture_error_mode="thread_local"):
             self._split_fwd()
         n_fwd = ops.LAUNCHES - before
         self.graph_fwd.replay()                  # real logits / activations for the loss that seeds the second capture
@@ -318,7 +325,7 @@ class B200TrainStep:
         self.opt.prepare_step()
         before = ops.LAUNCHES
         self.graph_bwd = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph_bwd, pool=self.graph_fwd.pool(), capture_error_mode="thread_local"):
+        with torch.cuda.graph(self.graph_bwd, pool=self.graph_fwd.pool(), stream=self._capture_stream(), capture_error_mode="thread_local"):
             self._split_bwd()
         self.launches_per_step = n_fwd + self._loss_launches + (ops.LAUNCHES - before)
         self.opt._prepared = False
@@ -344,8 +351,11 @@ class B200TrainStep:
         self.graph = torch.cuda.CUDAGraph()
         self.opt.prepare_step()
         before = ops.LAUNCHES
-        # thread_local: other threads (NCCL watchdog, data loader pinning) may call CUDA while this thread captures
-        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+        # thread_local: other threads (NCCL watchdog, data loader pinning) may call CUDA while this thread captures.
+        # The capture stream has a HIGHER priority than the engine's second stream (default priority): when a data gradient
+        # (main chain) and a weight gradient (second stream) become ready together, the data gradient goes first and the
+        # weight gradient then runs beside the HBM-bound InstanceNorm-backward pass that follows it.
+        with torch.cuda.graph(self.graph, stream=self._capture_stream(), capture_error_mode="thread_local"):
             self._body()
         self.launches_per_step = ops.LAUNCHES - before   # kernels of ours inside one replay (bench.py's gpu_launches)
         # the capture itself executed nothing, but step() advanced the host counters: they describe the NEXT replay already

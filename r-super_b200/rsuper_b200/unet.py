@@ -299,7 +299,7 @@ class _Engine:
         if not SIDE_STREAM:
             return None
         if self._side is None or self._side.device != device:
-            self._side = torch.cuda.Stream(device=device)
+            self._side = torch.cuda.Stream(device=device, priority=-1 if os.environ.get("RSB_SIDE_PRIORITY", "0") == "1" else 0)
         return self._side
 
     def _wgrad(self, a_op, dy_op, dw):
