@@ -26,5 +26,5 @@ def get_model(args, pretrain: bool = False, classes=None):
     net = B200UNet(args.in_chan, args.base_chan, num_classes=num_classes, scale=args.down_scale,
                    norm=args.norm, kernel_size=args.kernel_size, block=args.block,
                    negative_slope=getattr(args, "negative_slope", 0.0),
-                   precision=getattr(args, "precision", "bf16"))
+                   precision=getattr(args, "precision", "bf16"), up_mode=getattr(args, "up_mode", "trilinear"))
     return net
