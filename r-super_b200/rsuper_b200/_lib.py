@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librsuper_b200.so")
+# RSB_LIB: an alternative build of the same library (A/B measurements of a kernel change on one box); default = the in-tree .so
+LIB_PATH = os.environ.get("RSB_LIB") or os.path.join(_HERE, "librsuper_b200.so")
 
 RSB_BF16 = 0
 RSB_F32 = 1
