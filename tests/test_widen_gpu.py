@@ -769,7 +769,8 @@ def test_graphed_train_step_matches_eager(cuda_dev):
     (l0, p0, e0, s0), (l1, p1, e1, s1) = runs
     print(f"[graph] eager losses {l0}, graphed losses {l1}")
     assert s0 == s1 == 4
-    assert all(abs(a - b) <= 2e-2 * abs(a) for a, b in zip(l0, l1)) and abs(l0[0] - l1[0]) <= 2e-3 * abs(l0[0])
+    assert len(l0) == 4 and len(l1) == 3
+    assert all(abs(a - b) <= 2e-2 * abs(a) for a, b in zip(l0[1:], l1)) and abs(l0[1] - l1[0]) <= 2e-3 * abs(l0[1])
     tot = cnt = 0.0
     for a, b in zip(p0 + e0, p1 + e1):
         d = (a - b).abs()
@@ -809,7 +810,9 @@ def test_split_schedule_matches_eager_on_report_batches(cuda_dev):
         ema = [p.detach().clone() for p in params]
         opt = B200AdamW(params, lr=6e-4, weight_decay=0.05, max_norm=1.0, ema_params=ema, capturable=True)
         step = B200TrainStep(net, loss_fn, opt, [bt[k] for k in keys], schedule=schedule, warmup=1)
-        ls = [step.loss.item()] if schedule == "split" else []
+        # the split constructor already took its one warm-up step on this batch (and left the loss of the NEXT forward,
+        # evaluated while seeding the second capture, in step.loss): its three calls are steps 2-4 of the eager run
+        ls = []
         for _ in range(3 if schedule == "split" else 4):
             ls.append(B200TrainStep.check(step(*[bt[k] for k in keys]).item()))
         assert step.launches_per_step > 150
@@ -817,7 +820,8 @@ def test_split_schedule_matches_eager_on_report_batches(cuda_dev):
     (l0, p0, e0, s0), (l1, p1, e1, s1) = runs
     print(f"[split] eager losses {l0}, split-graph losses {l1}")
     assert s0 == s1 == 4
-    assert all(abs(a - b) <= 2e-2 * abs(a) for a, b in zip(l0, l1)) and abs(l0[0] - l1[0]) <= 2e-3 * abs(l0[0])
+    assert len(l0) == 4 and len(l1) == 3
+    assert all(abs(a - b) <= 2e-2 * abs(a) for a, b in zip(l0[1:], l1)) and abs(l0[1] - l1[0]) <= 2e-3 * abs(l0[1])
     tot = cnt = 0.0
     for a, b in zip(p0 + e0, p1 + e1):
         d = (a - b).abs()
