@@ -440,6 +440,43 @@ int rsb_aug_contrast(const float* x, float* y, long long n, const float* stats4,
 int rsb_aug_blur_axis(const float* x, float* y, int n_vol, int D, int H, int W, int axis, const float* taps_host,
                       int ntaps, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * MedFormer voxel-side kernels (rsuper_train/model/dim3/medformer_utils.py, conv_layers.py).
+ * NDHWC tensors with a channel pitch, dtype RSB_BF16 / RSB_F32; small map-side tensors are fp32.
+ * ------------------------------------------------------------------------------------------ */
+/* nn.Conv3d(C, C, 3, padding=1, groups=C, bias=False) (conv_layers.py:125-157, 192-230): w fp32 [C,1,3,3,3];
+ * flip = 1 mirrors the taps (the data gradient).  rsb_dwconv3_wgrad overwrites dw [C,1,3,3,3]. */
+int rsb_dwconv3_forward(const void* a, int a_pitch, const float* w, void* y, int y_pitch, int dtype, int flip, int N, int D,
+                        int H, int W, int C, void* stream);
+int rsb_dwconv3_wgrad(const void* a, int a_pitch, const void* dy, int dy_pitch, int dtype, float* dw, int N, int D, int H,
+                      int W, int C, void* stream);
+/* SEBlock (conv_layers.py:159-173): y[n,v,c] = x[n,v,c] * s[n,c]; out[n,c] = sum_v a[n,v,c] * b[n,v,c] (overwritten) */
+int rsb_scale_channels(const void* x, int x_pitch, const float* s, void* y, int y_pitch, int dtype, int N, long long V, int C,
+                       void* stream);
+int rsb_channel_dot(const void* a, int a_pitch, const void* b, int b_pitch, int dtype, float* out, int N, long long V, int C,
+                    void* stream);
+/* scratch (floats) for the column statistics of `rows` independent (sample[, head]) problems */
+size_t rsb_colstats_workspace_floats(int rows);
+/* SemanticMapGeneration (medformer_utils.py:222-235): smap[n,c,k] = sum_v feat[n,v,c] * softmax_v(logit[n,:,k])[v], K <= 27;
+ * ms [N,64] receives the column (max, sum of exp) pairs the backward pass reuses.
+ * backward: dS [N,C,K], tk[n,k] = sum_c dS[n,c,k] * smap[n,c,k]  ->  dfeat, dlogit (columns K..Kp-1 zeroed). */
+int rsb_softmax_pool_forward(const void* feat, int feat_pitch, const void* logit, int logit_pitch, int dtype, float* ms,
+                             float* workspace, float* smap, int N, long long V, int C, int K, void* stream);
+int rsb_softmax_pool_backward(const void* feat, int feat_pitch, const void* logit, int logit_pitch, int dtype, const float* ms,
+                              const float* dS, const float* tk, void* dfeat, int dfeat_pitch, void* dlogit, int dlogit_pitch,
+                              int N, long long V, int C, int K, int Kp, void* stream);
+/* BidirectionAttention (medformer_utils.py:67-103): q / fv = voxel-side query / value (channel c = dim * heads + head),
+ * mq / mv = map-side query / value fp32 [N, heads, J, dim_head]; A = scale * q . mq; feat_out = softmax_j(A) mv (voxel side),
+ * map_out = softmax_i(A)^T fv (fp32 [N, heads, J, dim_head]); ms [N*heads, 64] keeps the column statistics.
+ * backward: tj[n,h,j] = dmap_out[n,h,j,:] . map_out[n,h,j,:]. */
+int rsb_biattention_forward(const void* q, const void* fv, int qv_pitch, int dtype, const float* mq, const float* mv, float* ms,
+                            float* workspace, void* feat_out, int feat_out_pitch, float* map_out, int N, long long V,
+                            int heads, int dim_head, int J, float scale, void* stream);
+int rsb_biattention_backward(const void* q, const void* fv, int qv_pitch, int dtype, const float* mq, const float* mv,
+                             const float* ms, const void* dfeat_out, int dfeat_out_pitch, const float* dmap_out,
+                             const float* tj, void* dq, void* dfv, int dqv_pitch, float* dmq, float* dmv, int N, long long V,
+                             int heads, int dim_head, int J, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

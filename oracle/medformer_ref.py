@@ -233,3 +233,21 @@ def fill_like(named_shapes: Sequence[Tuple[str, Tuple[int, ...]]], gain: float =
             v = 0.1 * u
         sd[name] = v.to(torch.float32).reshape(shp)
     return sd
+
+
+SEMANTIC_PROJ_SCALE = 0.02
+
+
+def conditioned_state(named_shapes: Sequence[Tuple[str, Tuple[int, ...]]]) -> Dict[str, torch.Tensor]:
+    """fill_like with the `map_gen.semantic_proj` weights scaled by SEMANTIC_PROJ_SCALE.  With the plain hash init the code
+    logits of SemanticMapGeneration span +-1000, the softmax over the voxels is one-hot on ONE voxel for all 27 codes, every
+    channel of the semantic map is constant and the InstanceNorm that follows (medformer_utils.py:134-136) returns rounding
+    noise: the reference's own fp32 and fp64 evaluations then differ by 2.8e-2 on the logits.  Scaled, they agree to 3e-6 —
+    a state on which an independent implementation CAN be compared (tests/golden/make_golden_medformer.py records the real
+    reference on it)."""
+    sd = fill_like(named_shapes)
+    for k in sd:
+        if k.endswith("semantic_proj.weight"):
+            sd[k] = sd[k] * SEMANTIC_PROJ_SCALE
+    return sd
+

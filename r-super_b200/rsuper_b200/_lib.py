@@ -180,6 +180,19 @@ SIGNATURES = {
     "rsb_aug_renorm": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p]),
     "rsb_aug_contrast": (c_int, [c_void_p, c_void_p, c_ll, c_void_p, c_float, c_void_p]),
     "rsb_aug_blur_axis": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, C.POINTER(c_float), c_int, c_void_p]),
+    "rsb_dwconv3_forward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "rsb_dwconv3_wgrad": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "rsb_scale_channels": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_ll, c_int, c_void_p]),
+    "rsb_channel_dot": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_ll, c_int, c_void_p]),
+    "rsb_colstats_workspace_floats": (c_size_t, [c_int]),
+    "rsb_softmax_pool_forward": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_int,
+                                         c_void_p]),
+    "rsb_softmax_pool_backward": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                          c_int, c_int, c_ll, c_int, c_int, c_int, c_void_p]),
+    "rsb_biattention_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                        c_int, c_ll, c_int, c_int, c_int, c_float, c_void_p]),
+    "rsb_biattention_backward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_int, c_float, c_void_p]),
 }
 
 _lib = None

@@ -736,3 +736,113 @@ def aug_blur(x: torch.Tensor, taps) -> torch.Tensor:
         _call("augment", 1, 0.0, lib().rsb_aug_blur_axis, _p(src), _p(dst), n_vol, d, h, w_, axis, arr, len(taps), _stream(), what="aug_blur_axis")
         src = dst
     return a
+
+
+# --------------------------------------------------------------------------------------------
+# MedFormer voxel-side kernels (csrc/medformer.cu)
+# --------------------------------------------------------------------------------------------
+def dwconv3(a, w, y=None, flip=False):
+    """Depthwise 3x3x3 conv (padding 1, groups = C, no bias): a NDHWC, w fp32 [C,1,3,3,3]; flip=True = its data gradient."""
+    n, d, h, w_, c = a.shape
+    assert w.dtype == torch.float32 and w.is_contiguous() and w.numel() == c * 27
+    if y is None:
+        y = torch.empty_like(a)
+    assert y.shape == a.shape and y.dtype == a.dtype
+    _call("medformer", 1, 2.0 * 27 * c * n * d * h * w_, lib().rsb_dwconv3_forward, _p(a), _check_cl(a, "a"), _p(w), _p(y), _check_cl(y, "y"),
+          dtype_code(a), int(flip), n, d, h, w_, c, _stream(), what="dwconv3_forward", desc=f"{c} {n}x{d}x{h}x{w_}")
+    return y
+
+
+def dwconv3_wgrad(a, dy, dw=None):
+    n, d, h, w_, c = a.shape
+    assert dy.shape == a.shape and dy.dtype == a.dtype
+    if dw is None:
+        dw = torch.empty((c, 1, 3, 3, 3), dtype=torch.float32, device=a.device)
+    assert dw.dtype == torch.float32 and dw.is_contiguous() and dw.numel() == c * 27
+    _call("medformer", 1, 2.0 * 27 * c * n * d * h * w_, lib().rsb_dwconv3_wgrad, _p(a), _check_cl(a, "a"), _p(dy), _check_cl(dy, "dy"),
+          dtype_code(a), _p(dw), n, d, h, w_, c, _stream(), what="dwconv3_wgrad", desc=f"{c} {n}x{d}x{h}x{w_}")
+    return dw
+
+
+def scale_channels(x, s, y=None):
+    """y[n,...,c] = x[n,...,c] * s[n,c] (SEBlock)."""
+    n, c = x.shape[0], x.shape[4]
+    v = x.shape[1] * x.shape[2] * x.shape[3]
+    assert s.dtype == torch.float32 and s.is_contiguous() and tuple(s.shape) == (n, c)
+    if y is None:
+        y = torch.empty_like(x)
+    _call("medformer", 1, 0.0, lib().rsb_scale_channels, _p(x), _check_cl(x, "x"), _p(s), _p(y), _check_cl(y, "y"), dtype_code(x), n, v, c,
+          _stream(), what="scale_channels")
+    return y
+
+
+def channel_dot(a, b):
+    """out[n,c] = sum over the voxels of a * b (fp32)."""
+    n, c = a.shape[0], a.shape[4]
+    v = a.shape[1] * a.shape[2] * a.shape[3]
+    assert b.shape == a.shape and b.dtype == a.dtype
+    out = torch.empty((n, c), dtype=torch.float32, device=a.device)
+    _call("medformer", 1, 0.0, lib().rsb_channel_dot, _p(a), _check_cl(a, "a"), _p(b), _check_cl(b, "b"), dtype_code(a), _p(out), n, v, c,
+          _stream(), what="channel_dot")
+    return out
+
+
+def _colstats_ws(rows, device):
+    return torch.empty(lib().rsb_colstats_workspace_floats(rows), dtype=torch.float32, device=device)
+
+
+def softmax_pool_forward(feat, logit, k):
+    """SemanticMapGeneration's softmax over the voxels + pooling: -> (smap [N,C,k] fp32, ms [N,64] column statistics)."""
+    n, c = feat.shape[0], feat.shape[4]
+    v = feat.shape[1] * feat.shape[2] * feat.shape[3]
+    assert logit.shape[:4] == feat.shape[:4] and logit.dtype == feat.dtype and logit.shape[4] >= k
+    ms = torch.empty((n, 64), dtype=torch.float32, device=feat.device)
+    smap = torch.empty((n, c, k), dtype=torch.float32, device=feat.device)
+    ws = _colstats_ws(n, feat.device)
+    _call("medformer", 4, 2.0 * n * v * c * k, lib().rsb_softmax_pool_forward, _p(feat), _check_cl(feat, "feat"), _p(logit), _check_cl(logit, "logit"),
+          dtype_code(feat), _p(ms), _p(ws), _p(smap), n, v, c, k, _stream(), what="softmax_pool_forward")
+    return smap, ms
+
+
+def softmax_pool_backward(feat, logit, ms, d_smap, tk):
+    n, c = feat.shape[0], feat.shape[4]
+    v = feat.shape[1] * feat.shape[2] * feat.shape[3]
+    k, kp = d_smap.shape[2], logit.shape[4]
+    assert d_smap.dtype == torch.float32 and d_smap.is_contiguous() and tk.dtype == torch.float32 and tk.is_contiguous()
+    dfeat, dlogit = torch.empty_like(feat), torch.empty_like(logit)
+    _call("medformer", 1, 4.0 * n * v * c * k, lib().rsb_softmax_pool_backward, _p(feat), _check_cl(feat, "feat"), _p(logit), _check_cl(logit, "logit"),
+          dtype_code(feat), _p(ms), _p(d_smap), _p(tk), _p(dfeat), _check_cl(dfeat, "dfeat"), _p(dlogit), _check_cl(dlogit, "dlogit"),
+          n, v, c, k, kp, _stream(), what="softmax_pool_backward")
+    return dfeat, dlogit
+
+
+def biattention_forward(qv, mq, mv, heads):
+    """qv NDHWC [N,D,H,W,2C] (query channels then value channels); mq / mv fp32 [N,heads,J,dh] -> (feat_out NDHWC [.., C],
+    map_out fp32 [N,heads,J,dh], ms)."""
+    n, d, h, w_, c2 = qv.shape
+    c = c2 // 2
+    dh, j = c // heads, mq.shape[2]
+    v = d * h * w_
+    assert tuple(mq.shape) == (n, heads, j, dh) and mq.dtype == torch.float32 and mq.is_contiguous() and mv.shape == mq.shape and mv.is_contiguous()
+    fo = torch.empty((n, d, h, w_, c), dtype=qv.dtype, device=qv.device)
+    mo = torch.empty_like(mq)
+    ms = torch.empty((n * heads, 64), dtype=torch.float32, device=qv.device)
+    ws = _colstats_ws(n * heads, qv.device)
+    _call("medformer", 4, 6.0 * n * v * c * j, lib().rsb_biattention_forward, _p(qv), _p(qv[..., c:]), _check_cl(qv, "qv"), dtype_code(qv), _p(mq), _p(mv),
+          _p(ms), _p(ws), _p(fo), _check_cl(fo, "fo"), _p(mo), n, v, heads, dh, j, float(dh) ** -0.5, _stream(),
+          what="biattention_forward")
+    return fo, mo, ms
+
+
+def biattention_backward(qv, mq, mv, ms, dfo, dmo, tj, heads):
+    n, d, h, w_, c2 = qv.shape
+    c = c2 // 2
+    dh, j = c // heads, mq.shape[2]
+    v = d * h * w_
+    assert dfo.dtype == qv.dtype and dmo.dtype == torch.float32 and dmo.is_contiguous() and tj.is_contiguous()
+    dqv = torch.empty_like(qv)
+    dmq, dmv = torch.empty_like(mq), torch.empty_like(mv)
+    _call("medformer", 1, 12.0 * n * v * c * j, lib().rsb_biattention_backward, _p(qv), _p(qv[..., c:]), _check_cl(qv, "qv"), dtype_code(qv), _p(mq), _p(mv),
+          _p(ms), _p(dfo), _check_cl(dfo, "dfo"), _p(dmo), _p(tj), _p(dqv), _p(dqv[..., c:]), _check_cl(dqv, "dqv"), _p(dmq), _p(dmv), n, v, heads, dh, j,
+          float(dh) ** -0.5, _stream(), what="biattention_backward")
+    return dqv, dmq, dmv

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "r-super_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "librsb_emul.so")
-SOURCES = ["train_glue.cu", "infer.cu", "augment.cu", "seg_loss.cu", "morph.cu", "elementwise.cu", "stem_head.cu", "report_loss.cu"]
+SOURCES = ["train_glue.cu", "infer.cu", "augment.cu", "seg_loss.cu", "morph.cu", "elementwise.cu", "stem_head.cu", "report_loss.cu", "medformer.cu"]
 # kernels that use __syncthreads / warp shuffles: their blocks run as real threads
 COOPERATIVE = {"grad_sqnorm_kernel", "clip_adamw_ema_kernel", "aug_stats_partial_kernel", "aug_stats_final_kernel",
                "seg_loss_pass1_kernel", "seg_loss_finalize_kernel", "seg_loss_pass2_kernel",

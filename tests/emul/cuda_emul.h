@@ -68,6 +68,7 @@ inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
 using std::min;
 using std::max;
 inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
+inline float __expf(float x) { return std::exp(x); }
 
 // bf16 storage type: round-to-nearest-even conversion like cvt.rn.bf16.f32
 struct __nv_bfloat16 { uint16_t bits; };
@@ -119,6 +120,21 @@ inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
   wb->arrive_and_wait();
   const unsigned src = (threadIdx.x & ~31u) | ((threadIdx.x & 31u) ^ static_cast<unsigned>(lane_mask));
   slot = emu::g_xchg[src];
+  wb->arrive_and_wait();
+  T out;
+  std::memcpy(&out, &slot, sizeof(T));
+  return out;
+}
+
+template <typename T>
+inline T __shfl_sync(unsigned, T v, int src_lane) {
+  static_assert(sizeof(T) <= sizeof(double), "shuffle payload");
+  double slot = 0;
+  std::memcpy(&slot, &v, sizeof(T));
+  std::barrier<>* wb = emu::g_warp_barrier[threadIdx.x >> 5];
+  emu::g_xchg[threadIdx.x] = slot;
+  wb->arrive_and_wait();
+  slot = emu::g_xchg[(threadIdx.x & ~31u) | (static_cast<unsigned>(src_lane) & 31u)];
   wb->arrive_and_wait();
   T out;
   std::memcpy(&out, &slot, sizeof(T));

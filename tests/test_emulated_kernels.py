@@ -285,3 +285,29 @@ def test_emulated_static_gradient_steps_equal_fresh_gradient_steps(emulated):
     for i, (a, b) in enumerate(zip(*grads)):
         err = ((a - b).norm() / (a.norm() + 1e-20)).item()
         assert err <= 0.15, (i, err)                 # run-to-run bf16 + atomics-order noise on this 2^3-bottom toy net is ~2 %; a stale or doubled gradient is >= 100 % off
+
+
+# ---- MedFormer voxel-side kernels (csrc/medformer.cu) and the module built on them -----------------------------------------
+def test_emulated_medformer_dwconv_se_and_softmax_pool(emulated):
+    """Depthwise 3x3x3 conv (forward, data gradient, weight gradient; channel counts spanning several chunks), SEBlock scale /
+    dot, SemanticMapGeneration's softmax-over-voxels pooling forward and backward — against torch in fp64."""
+    import test_medformer_gpu as MF
+    MF.test_medformer_dwconv_kernels_vs_torch(CPU)
+    MF.test_medformer_se_scale_and_dot_vs_torch(CPU)
+    MF.test_medformer_softmax_pool_vs_torch(CPU)
+
+
+def test_emulated_medformer_biattention(emulated):
+    """BidirectionAttention core: both softmaxes of one logit matrix, both einsums and all four gradients (warp-per-voxel
+    kernels run as real threads: shuffles, shared-memory staging, block and global atomics)."""
+    import test_medformer_gpu as MF
+    MF.test_medformer_biattention_vs_torch(CPU)
+
+
+@_slow
+def test_emulated_medformer_blocks_and_whole_model(emulated):
+    """Every composite block forward + backward against the fp64 oracle, then the whole B200MedFormer against the real
+    reference's recorded logits / deep-supervision head / loss and the fp64 oracle's gradients (~5 min under emulation)."""
+    import test_medformer_gpu as MF
+    MF.test_medformer_blocks_forward_backward_vs_oracle(CPU)
+    MF.test_medformer_vs_reference_golden_and_oracle(CPU, "fp32")
