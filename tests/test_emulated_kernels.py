@@ -309,5 +309,5 @@ def test_emulated_medformer_blocks_and_whole_model(emulated):
     """Every composite block forward + backward against the fp64 oracle, then the whole B200MedFormer against the real
     reference's recorded logits / deep-supervision head / loss and the fp64 oracle's gradients (~5 min under emulation)."""
     import test_medformer_gpu as MF
-    MF.test_medformer_blocks_forward_backward_vs_oracle(CPU)
+    MF.test_medformer_blocks_forward_backward_vs_oracle(CPU, "fp32")
     MF.test_medformer_vs_reference_golden_and_oracle(CPU, "fp32")
