@@ -882,6 +882,9 @@ pack_conv3_weights_batched_kernel(const RsbPackJob* __restrict__ jobs, int n_job
     const int piece = jb.parts == 3 ? (part == 2 ? 1 : 0) : (jb.parts == 6 ? ((0x102010 >> (4 * part)) & 0xF) : 0);
 #pragma unroll 3
     for (int tap = 0; tap < 27; ++tap) {
+      // 1x1x1 sources: only the centre tap carries values; the other 26 slices of the image were zeroed once when the plan
+      // allocated it (rsuper_b200.ops.PackPlan) and are never written again
+      if (jb.pointwise && tap != 13) continue;
       const int slot = 2 - tap / 9, khw = tap % 9;
       float v = mine[flip ? 26 - tap : tap];
       __nv_bfloat16 q = __float2bfloat16_rn(v);

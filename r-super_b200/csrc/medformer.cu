@@ -43,13 +43,15 @@ RSB_DEVICE void mf_st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); 
 struct MfGrid {
   int cgb, chunks, gx;
 };
-static inline MfGrid mf_grid(int C, long long V, int sms, int zmul = 1) {
+// voxels_per_thread > 1: reduction kernels (every block ends with one round of global atomics per channel and tap — with
+// few voxels and many channels one voxel per thread would spend the launch on contended atomics)
+static inline MfGrid mf_grid(int C, long long V, int sms, int zmul = 1, int voxels_per_thread = 1) {
   MfGrid g;
   const int CG = C / 8;
   g.cgb = CG < 32 ? CG : 32;
   g.chunks = (CG + g.cgb - 1) / g.cgb;
   const int vpb = kMfBlock / g.cgb;
-  long long want = (V + vpb - 1) / vpb;
+  long long want = (V + static_cast<long long>(vpb) * voxels_per_thread - 1) / (static_cast<long long>(vpb) * voxels_per_thread);
   long long cap = static_cast<long long>(sms) * 8 / (static_cast<long long>(g.chunks) * zmul);
   if (cap < 1) cap = 1;
   if (want > cap) want = cap;
@@ -570,7 +572,7 @@ extern "C" int rsb_dwconv3_wgrad(const void* a, int a_pitch, const void* dy, int
   RSB_REQUIRE(V < (1LL << 31), "dwconv3_wgrad: volume too large");
   cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * 27 * C, st);
   RSB_REQUIRE(e == cudaSuccess, "dwconv3_wgrad: memset failed: %s", cudaGetErrorString(e));
-  const MfGrid g = mf_grid(C, V, sms, 3);
+  const MfGrid g = mf_grid(C, V, sms, 3, 8);
   dim3 grid(g.gx, N, g.chunks * 3);
   const size_t sm = sizeof(float) * 9 * g.cgb * 8;
   MF_BY_DTYPE(dtype,
@@ -597,7 +599,7 @@ extern "C" int rsb_channel_dot(const void* a, int a_pitch, const void* b, int b_
   MF_COMMON(C, N)
   cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * static_cast<size_t>(N) * C, st);
   RSB_REQUIRE(e == cudaSuccess, "channel_dot: memset failed: %s", cudaGetErrorString(e));
-  const MfGrid g = mf_grid(C, V, sms);
+  const MfGrid g = mf_grid(C, V, sms, 1, 8);
   dim3 grid(g.gx, N, g.chunks);
   const size_t sm = sizeof(float) * g.cgb * 8;
   MF_BY_DTYPE(dtype,

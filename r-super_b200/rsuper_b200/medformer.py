@@ -41,8 +41,9 @@ class _NormAct(torch.autograd.Function):
     """a = act(instance_norm(x)); slope = 0 -> ReLU, slope = 1 -> no activation."""
 
     @staticmethod
-    def forward(ctx, x, eps, slope):
-        st = ops.channel_stats(x)
+    def forward(ctx, x, st, eps, slope):
+        if st is None:
+            st = ops.channel_stats(x)
         a = torch.empty_like(x)
         ops.norm_act(x, st, slope=slope, eps=eps, full=a)
         ctx.save_for_backward(x, st)
@@ -58,7 +59,15 @@ class _NormAct(torch.autograd.Function):
         ops.act_backward_stats(da, x, st, sums, g, slope=ctx.slope, eps=ctx.eps)
         dx = torch.empty_like(x)
         ops.instnorm_backward_apply(g, x, st, sums, dx, eps=ctx.eps)
-        return dx, None, None
+        return dx, None, None, None
+
+
+def _gemm_tn_f32(dy2d: torch.Tensor, a2d: torch.Tensor) -> torch.Tensor:
+    """dy2d [V, Cout]^T @ a2d [V, Cin] -> fp32 [Cout, Cin]: the weight gradient of a 1x1x1 convolution is a plain GEMM over the
+    voxels with nothing to fuse — the one place this model calls cuBLAS (bf16 operands, fp32 accumulation and output)."""
+    if dy2d.is_cuda:
+        return torch.mm(dy2d.t(), a2d, out_dtype=torch.float32)
+    return torch.mm(dy2d.t().float(), a2d.float())          # CPU emulation of the test suite
 
 
 def _operand(t: torch.Tensor, st, slope, eps):
@@ -75,18 +84,23 @@ class _ConvNA(torch.autograd.Function):
     the tensor cores; norm=False feeds x itself.  img / img_t: the packed forward / data-gradient weight images (PackPlan)."""
 
     @staticmethod
-    def forward(ctx, x, w, res, img, img_t, norm, slope, eps, pointwise, cout):
-        st = ops.channel_stats(x) if norm else None
+    def forward(ctx, x, x_st, w, res, img, img_t, norm, slope, eps, pointwise, cout, want_stats):
+        st = (x_st if x_st is not None else ops.channel_stats(x)) if norm else None
         op = _operand(x, st, slope, eps)
         n, d, h, w_, _ = x.shape
         y = torch.empty((n, d, h, w_, cout), dtype=x.dtype, device=x.device)
-        ops.conv3_forward(op[0], img, y, a_lo=op[1] if len(op) > 1 else None, slope=slope, res=res, eps=eps, pointwise=pointwise)
+        y_st = torch.zeros((n, cout, 2), dtype=torch.float32, device=x.device) if want_stats else None   # epilogue: (sum, sumsq) of y
+        ops.conv3_forward(op[0], img, y, a_lo=op[1] if len(op) > 1 else None, slope=slope, res=res, out_stats=y_st, eps=eps,
+                          pointwise=pointwise)
         ctx.save_for_backward(x, st, img_t, *op)
         ctx.cfg = (norm, slope, eps, pointwise, cout, tuple(w.shape), res is not None)
-        return y
+        if y_st is None:
+            y_st = torch.empty(0, device=x.device)
+        ctx.mark_non_differentiable(y_st)
+        return y, y_st
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _unused):
         x, st, img_t, *op = ctx.saved_tensors
         norm, slope, eps, pointwise, cout, wshape, has_res = ctx.cfg
         dy = dy.contiguous()
@@ -94,13 +108,19 @@ class _ConvNA(torch.autograd.Function):
         split = len(op) > 1
         cin = x.shape[4]
         dw = dx = None
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[2] and pointwise:
+            a2, g2 = [t.reshape(-1, cin) for t in op], [t.reshape(-1, cout) for t in d_op]
+            dw = _gemm_tn_f32(g2[0], a2[0])
+            if split:
+                dw = dw + _gemm_tn_f32(g2[0], a2[1]) + _gemm_tn_f32(g2[1], a2[0])
+            dw = dw[:wshape[0]].reshape(wshape)
+        elif ctx.needs_input_grad[2]:
             dw27 = torch.empty((cout, cin, 3, 3, 3), dtype=torch.float32, device=x.device)
             ops.conv3_wgrad(op[0], d_op[0], dw27)
             if split:
                 ops.conv3_wgrad(op[1], d_op[0], dw27, accumulate=True)
                 ops.conv3_wgrad(op[0], d_op[1], dw27, accumulate=True)
-            dw = dw27[:wshape[0], :, 1:2, 1:2, 1:2] if pointwise else dw27[:wshape[0]]
+            dw = dw27[:wshape[0]]
         if ctx.needs_input_grad[0]:
             lo = d_op[1] if split else None
             dx = torch.empty_like(x)
@@ -111,7 +131,7 @@ class _ConvNA(torch.autograd.Function):
                 ops.instnorm_backward_apply(g, x, st, sums, dx, eps=eps)
             else:
                 ops.conv3_forward(d_op[0], img_t, dx, a_lo=lo, pointwise=pointwise)
-        return dx, dw, (dy if has_res else None), None, None, None, None, None, None, None
+        return dx, None, dw, (dy if has_res else None), None, None, None, None, None, None, None, None
 
 
 class _DwConv(torch.autograd.Function):
@@ -455,25 +475,35 @@ class B200MedFormer(nn.Module):
         self._plan.refresh()
 
     # ---- blocks (oracle/medformer_ref.py is the line-by-line statement of the same graph) ------------------------------------
-    def _cna(self, x, key, *, norm=True, act=True, res=None, eps=EPS_CNA):
+    def _cna(self, x, key, *, norm=True, act=True, res=None, eps=EPS_CNA, stats=True):
+        """ConvNormAct on the tensor cores.  The conv epilogue also leaves the (sum, sumsq) InstanceNorm statistics of its output
+        (attribute `rsb_stats` of the returned tensor), which the next normalisation of that tensor picks up instead of
+        running a statistics pass."""
         w = self._P[key]
         cout = (w.shape[0] + 7) // 8 * 8
-        return _ConvNA.apply(x, w, res, self._plan.images[key], self._plan.images[key + "T"], norm, 0.0 if act else 1.0, eps,
-                             w.shape[-1] == 1, cout)
+        y, y_st = _ConvNA.apply(x, getattr(x, "rsb_stats", None) if norm else None, w, res, self._plan.images[key],
+                                self._plan.images[key + "T"], norm, 0.0 if act else 1.0, eps, w.shape[-1] == 1, cout, stats)
+        if stats:
+            y.rsb_stats = y_st
+        return y
+
+    @staticmethod
+    def _norm_act(x, eps, slope):
+        return _NormAct.apply(x, getattr(x, "rsb_stats", None), eps, slope)
 
     def _basic_block(self, x, pre):
         key = pre + "shortcut.conv.weight"
         sc = self._cna(x, key) if key in self._P else x
         return self._cna(self._cna(x, pre + "conv1.conv.weight"), pre + "conv2.conv.weight", res=sc)
 
-    def _dsconv(self, x, pre, res=None):
+    def _dsconv(self, x, pre, res=None, stats=True):
         h = _DwConv.apply(x, self._P[pre + "depthwise.weight"])
-        return self._cna(h, pre + "pointwise.weight", norm=False, act=False, res=res)
+        return self._cna(h, pre + "pointwise.weight", norm=False, act=False, res=res, stats=stats)
 
     def _mbconv(self, x, pre):
         P = self._P
         h = self._cna(x, pre + "expand_proj.conv.weight")
-        h = _DwConv.apply(_NormAct.apply(h, EPS_CNA, 0.0), P[pre + "depthwise.conv.weight"])
+        h = _DwConv.apply(self._norm_act(h, EPS_CNA, 0.0), P[pre + "depthwise.conv.weight"])
         s = _ChannelMean.apply(h)                                                      # SEBlock (conv_layers.py:159-173)
         w0, w2 = P[pre + "se.excitation.0.weight"], P[pre + "se.excitation.2.weight"]
         s = F.relu(F.linear(s, w0.flatten(1), P[pre + "se.excitation.0.bias"]))
@@ -484,9 +514,9 @@ class B200MedFormer(nn.Module):
     def _attention_block(self, x, smap, pre, heads):
         P = self._P
         n, d, h, w_, _ = x.shape
-        xn = _NormAct.apply(x, EPS_DEF, 1.0)
+        xn = self._norm_act(x, EPS_DEF, 1.0)
         mn = F.instance_norm(smap, eps=EPS_DEF)
-        qv = self._dsconv(xn, pre + "attn.feat_qv.")
+        qv = self._dsconv(xn, pre + "attn.feat_qv.", stats=False)
         c = qv.shape[4] // 2
         dh = c // heads
         mqv = F.conv3d(mn, P[pre + "attn.map_qv.weight"])                             # [N, 2C, 3, 3, 3]
@@ -507,15 +537,15 @@ class B200MedFormer(nn.Module):
         return x, smap
 
     def _map_generation(self, x, pre):
-        feat = self._cna(x, pre + "base_proj.weight", norm=False, act=False)
-        logit = self._cna(x, pre + "semantic_proj.weight", norm=False, act=False)      # 27 codes in a 32-channel tensor
+        feat = self._cna(x, pre + "base_proj.weight", norm=False, act=False, stats=False)
+        logit = self._cna(x, pre + "semantic_proj.weight", norm=False, act=False, stats=False)   # 27 codes in a 32-channel tensor
         smap = _SoftmaxPool.apply(feat, logit, 27)
         return smap.reshape(x.shape[0], feat.shape[4], 3, 3, 3)
 
     def _down(self, x, i, map_generate):
         pre = f"down{i}."
         c = self.cfg
-        x = self._dsconv(_NormAct.apply(_SpaceToDepth.apply(x), EPS_DEF, 1.0), pre + "patch_merging.reduction.")
+        x = self._dsconv(self._norm_act(_SpaceToDepth.apply(x), EPS_DEF, 1.0), pre + "patch_merging.reduction.")
         for j in range(c["conv_num"][i - 1]):
             x = self._basic_block(x, f"{pre}conv_blocks.{j}.")
         smap = self._map_generation(x, pre + "map_gen.") if map_generate else None

@@ -147,7 +147,8 @@ class PackPlan:
                 assert w_b.dtype == torch.float32 and w_b.is_contiguous() and w_b.shape[1:] == w_a.shape[1:]
                 cout += w_b.shape[0]
             co_eff, ci_eff = (cin, cout) if flip else (cout, cin)
-            img = torch.empty(lib().rsb_conv3_packed_weight_bytes(co_eff, ci_eff, parts), dtype=torch.uint8, device=dev)
+            # 1x1x1 sources live at the centre tap of a 3x3x3 image whose other taps stay zero: zeroed here, once
+            img = (torch.zeros if pointwise else torch.empty)(lib().rsb_conv3_packed_weight_bytes(co_eff, ci_eff, parts), dtype=torch.uint8, device=dev)
             self.images[key] = img
             self._keep.append((w_a, w_b))
             jb = arr[j]

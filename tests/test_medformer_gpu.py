@@ -138,7 +138,7 @@ def test_medformer_biattention_vs_torch(cuda_dev):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_medformer_blocks_forward_backward_vs_oracle(cuda_dev, precision="fp32"):
+def test_medformer_blocks_forward_backward_vs_oracle(cuda_dev, precision):
     """Every composite block of the model on its own, on well-conditioned random inputs: output, input gradient and every
     parameter gradient of the block against the oracle's block evaluated in fp64 (precision='fp32': split-precision tensor-core
     products, everything else fp32)."""
@@ -203,7 +203,7 @@ def test_medformer_blocks_forward_backward_vs_oracle(cuda_dev, precision="fp32")
     run("BasicBlock+shortcut", lambda x: net._basic_block(x, "up3.conv_blocks.0."), lambda x: R._basic_block(x, sd64, "up3.conv_blocks.0."), 48, 8)
     run("BasicBlock", lambda x: net._basic_block(x, "down1.conv_blocks.0."), lambda x: R._basic_block(x, sd64, "down1.conv_blocks.0."), 16, 8)
     from rsuper_b200.medformer import EPS_DEF, _NormAct, _SpaceToDepth
-    run("PatchMerging", lambda x: net._dsconv(_NormAct.apply(_SpaceToDepth.apply(x), EPS_DEF, 1.0), "down2.patch_merging.reduction."),
+    run("PatchMerging", lambda x: net._dsconv(_NormAct.apply(_SpaceToDepth.apply(x), None, EPS_DEF, 1.0), "down2.patch_merging.reduction."),
         lambda x: R._patch_merging(x, sd64, "down2.patch_merging."), 16, 8)
     run("SemanticMapGeneration", lambda x: net._map_generation(x, "down2.map_gen."), lambda x: R._map_generation(x, sd64, "down2.map_gen.", [3, 3, 3]), 32, 6)
     run("MBConv", lambda x: net._mbconv(x, "down2.trans_blocks.blocks.0.feedforward."),

@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m pytest tests/test_medformer_gpu.py tests/test_widen_gpu.py::test_split_schedule_matches_eager_on_report_batches -m gpu -x -q -s 2>&1 | grep -v "Saved to" | tail -40 > gpurun_out/r02_medformer_tests.log
-tail -30 gpurun_out/r02_medformer_tests.log
-timeout 600 python tools/bench_medformer.py --batch 1 --side 128 > gpurun_out/r02_medformer_bench_b1.json 2> gpurun_out/r02_medformer_bench_b1.err
-tail -3 gpurun_out/r02_medformer_bench_b1.err; cat gpurun_out/r02_medformer_bench_b1.json
+python -m pytest tests/test_medformer_gpu.py tests/test_widen_gpu.py::test_split_schedule_matches_eager_on_report_batches -m gpu -q -s 2>&1 | grep -v "Saved to" > gpurun_out/r02_medformer_tests.log
+grep "^\[\|passed\|failed\|Error" gpurun_out/r02_medformer_tests.log | tail -40
+timeout 900 python tools/bench_medformer.py --batch 1 --side 128 --schedule both --trace gpurun_out/r02_medformer_trace.txt > gpurun_out/r02_medformer_bench_b1.json 2> gpurun_out/r02_medformer_bench_b1.err
+tail -5 gpurun_out/r02_medformer_bench_b1.err; cat gpurun_out/r02_medformer_bench_b1.json; head -30 gpurun_out/r02_medformer_trace.txt
