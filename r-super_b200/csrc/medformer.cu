@@ -64,6 +64,8 @@ static inline MfGrid mf_grid(int C, long long V, int sms, int zmul = 1, int voxe
 // depthwise 3x3x3 convolution (padding 1, no bias): y[n,v,c] = sum_t w[c][t] * a[n, v + t - 1, c]
 // flip = 1 computes the data gradient (the same sum with the taps mirrored).
 // ------------------------------------------------------------------------------------------
+constexpr int kDwRun = 4;
+
 template <typename T>
 __global__ void dwconv3_kernel(const T* __restrict__ a, long long ap, const float* __restrict__ w, T* __restrict__ y, long long yp,
                                int D, int H, int W, int C, int cgb, int flip) {
@@ -72,43 +74,66 @@ __global__ void dwconv3_kernel(const T* __restrict__ a, long long ap, const floa
   const int n = blockIdx.y;
   const int cg0 = static_cast<int>(blockIdx.z) * cgb;
   const int ncg = (CG - cg0) < cgb ? (CG - cg0) : cgb;
-  const int row = cgb * 8;
+  const int row_w = cgb * 8;
   for (int i = threadIdx.x; i < 27 * ncg * 8; i += blockDim.x) {
     const int t = i / (ncg * 8), cl = i - t * (ncg * 8);
-    sm_w[t * row + cl] = w[static_cast<long long>(cg0 * 8 + cl) * 27 + (flip ? 26 - t : t)];
+    sm_w[t * row_w + cl] = w[static_cast<long long>(cg0 * 8 + cl) * 27 + (flip ? 26 - t : t)];
   }
   __syncthreads();
   MfMap m = mf_map(CG, cgb);
   if (!m.active) return;
   const int cl0 = (m.cg - cg0) * 8;
   const long long V = static_cast<long long>(D) * H * W;
-  for (long long v = m.v0; v < V; v += m.vstride) {
-    const unsigned vu = static_cast<unsigned>(v);
-    const unsigned r = vu / static_cast<unsigned>(W);
-    const int x = static_cast<int>(vu - r * W);
-    const int z = static_cast<int>(r / static_cast<unsigned>(H));
-    const int yy = static_cast<int>(r - static_cast<unsigned>(z) * H);
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  // A thread produces a run of kDwRun consecutive x positions of one row: the 3 x 3 x (kDwRun + 2) input columns it needs are
+  // loaded once (13.5 loads per output voxel instead of 27) and every weight slice is read from shared memory once per run.
+  const int rpr = (W + kDwRun - 1) / kDwRun;
+  const long long runs = static_cast<long long>(D) * H * rpr;
+  for (long long r = m.v0; r < runs; r += m.vstride) {
+    const unsigned ru = static_cast<unsigned>(r);
+    const unsigned row = ru / static_cast<unsigned>(rpr);
+    const int x0 = static_cast<int>(ru - row * rpr) * kDwRun;
+    const int z = static_cast<int>(row / static_cast<unsigned>(H));
+    const int yy = static_cast<int>(row - static_cast<unsigned>(z) * H);
+    float acc[kDwRun][8];
+#pragma unroll
+    for (int i = 0; i < kDwRun; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
     for (int dz = 0; dz < 3; ++dz) {
       const int zz = z + dz - 1;
       if (zz < 0 || zz >= D) continue;
       for (int dy = 0; dy < 3; ++dy) {
         const int y2 = yy + dy - 1;
         if (y2 < 0 || y2 >= H) continue;
+        const long long rowbase = ((static_cast<long long>(n) * D + zz) * H + y2) * W;
+        float col[kDwRun + 2][8];
+#pragma unroll
+        for (int i = 0; i < kDwRun + 2; ++i) {
+          const int x2 = x0 + i - 1;
+          if (x2 >= 0 && x2 < W) {
+            Vec8<T>::load(a + (rowbase + x2) * ap + m.cg * 8, col[i]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) col[i][j] = 0.f;
+          }
+        }
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
-          const int x2 = x + dx - 1;
-          if (x2 < 0 || x2 >= W) continue;
-          const long long vin = ((static_cast<long long>(n) * D + zz) * H + y2) * W + x2;
-          float f[8];
-          Vec8<T>::load(a + vin * ap + m.cg * 8, f);
-          const float* wt = sm_w + ((dz * 3 + dy) * 3 + dx) * row + cl0;
+          const float* wt = sm_w + ((dz * 3 + dy) * 3 + dx) * row_w + cl0;
+          float w8[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = fmaf(f[j], wt[j], acc[j]);
+          for (int j = 0; j < 8; ++j) w8[j] = wt[j];
+#pragma unroll
+          for (int i = 0; i < kDwRun; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(col[i + dx][j], w8[j], acc[i][j]);
         }
       }
     }
-    Vec8<T>::store(y + (static_cast<long long>(n) * V + v) * yp + m.cg * 8, acc);
+    const long long obase = ((static_cast<long long>(n) * D + z) * H + yy) * W;
+#pragma unroll
+    for (int i = 0; i < kDwRun; ++i)
+      if (x0 + i < W) Vec8<T>::store(y + (obase + x0 + i) * yp + m.cg * 8, acc[i]);
   }
 }
 
@@ -129,12 +154,12 @@ __global__ void dwconv3_wgrad_kernel(const T* __restrict__ a, long long ap, cons
   const int cg = cg0 + cgl;
   const bool active = static_cast<int>(threadIdx.x) < vpb * cgb && cg < CG;
   const long long V = static_cast<long long>(D) * H * W;
+  float acc[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
   if (active) {
-    float acc[9][8];
-#pragma unroll
-    for (int t = 0; t < 9; ++t)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
     for (long long v = static_cast<long long>(blockIdx.x) * vpb + threadIdx.x / cgb; v < V; v += static_cast<long long>(gridDim.x) * vpb) {
       const unsigned vu = static_cast<unsigned>(v);
       const unsigned r = vu / static_cast<unsigned>(W);
@@ -156,12 +181,28 @@ __global__ void dwconv3_wgrad_kernel(const T* __restrict__ a, long long ap, cons
         for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(g[j], f[j], acc[t][j]);
       }
     }
-#pragma unroll
-    for (int t = 0; t < 9; ++t)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(&sm_acc[t * row + cgl * 8 + j], acc[t][j]);
   }
-  __syncthreads();
+  // block reduction into sm_acc.  Few voxel slots per block: the threads that share a channel group take turns (conflict
+  // free, no atomics; every thread of the block passes the same barriers); many slots (small C): shared-memory atomics.
+  if (vpb <= 16) {
+    for (int k = 0; k < vpb; ++k) {
+      if (active && static_cast<int>(threadIdx.x) / cgb == k) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sm_acc[t * row + cgl * 8 + j] += acc[t][j];
+      }
+      __syncthreads();
+    }
+  } else {
+    if (active) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(&sm_acc[t * row + cgl * 8 + j], acc[t][j]);
+    }
+    __syncthreads();
+  }
   const int ncg = (CG - cg0) < cgb ? (CG - cg0) : cgb;
   for (int i = threadIdx.x; i < 9 * ncg * 8; i += blockDim.x) {
     const int t = i / (ncg * 8), cl = i - t * (ncg * 8);
@@ -554,7 +595,7 @@ extern "C" int rsb_dwconv3_forward(const void* a, int a_pitch, const float* w, v
   MF_COMMON(C, N)
   const long long V = static_cast<long long>(D) * H * W;
   RSB_REQUIRE(V < (1LL << 31), "dwconv3: volume too large");
-  const MfGrid g = mf_grid(C, V, sms);
+  const MfGrid g = mf_grid(C, static_cast<long long>(D) * H * ((W + kDwRun - 1) / kDwRun), sms);
   dim3 grid(g.gx, N, g.chunks);
   const size_t sm = sizeof(float) * 27 * g.cgb * 8;
   MF_BY_DTYPE(dtype,
@@ -572,7 +613,7 @@ extern "C" int rsb_dwconv3_wgrad(const void* a, int a_pitch, const void* dy, int
   RSB_REQUIRE(V < (1LL << 31), "dwconv3_wgrad: volume too large");
   cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * 27 * C, st);
   RSB_REQUIRE(e == cudaSuccess, "dwconv3_wgrad: memset failed: %s", cudaGetErrorString(e));
-  const MfGrid g = mf_grid(C, V, sms, 3, 8);
+  const MfGrid g = mf_grid(C, V, sms, 3, 16);
   dim3 grid(g.gx, N, g.chunks * 3);
   const size_t sm = sizeof(float) * 9 * g.cgb * 8;
   MF_BY_DTYPE(dtype,
