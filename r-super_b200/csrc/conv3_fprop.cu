@@ -852,7 +852,21 @@ pack_conv3_weights_batched_kernel(const RsbPackJob* __restrict__ jobs, int n_job
   const int L = Cc * 27, pitch = L + 1;
   const int ncols = min(Cc, jb.Cin - col0);          // valid columns (may be <= 0 for padded groups)
   const int nvalid = ncols > 0 ? ncols * 27 : 0;
-  for (int e = threadIdx.x; e < R * L; e += kPackThreads) {
+  if (jb.pointwise) {
+    // [Cout][Cin][1][1][1] source: R x Cc values, placed at the centre tap (13) of the tile — the only tap the store loop reads
+    for (int e = threadIdx.x; e < R * Cc; e += kPackThreads) {
+      const int r = e / Cc, c = e - r * Cc;
+      const int row = row0 + r;
+      float v = 0.f;
+      if (row < jb.Cout && c < ncols) {
+        const float* src = row < jb.rows_a ? jb.w_a + static_cast<size_t>(row) * jb.Cin
+                                           : jb.w_b + static_cast<size_t>(row - jb.rows_a) * jb.Cin;
+        v = src[col0 + c];
+      }
+      sm_w[r * pitch + c * 27 + 13] = v;
+    }
+  }
+  for (int e = threadIdx.x; e < (jb.pointwise ? 0 : R * L); e += kPackThreads) {
     const int r = e / L, c = e - r * L;
     const int row = row0 + r;
     float v = 0.f;

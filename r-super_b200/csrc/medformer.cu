@@ -86,9 +86,16 @@ __global__ void dwconv3_kernel(const T* __restrict__ a, long long ap, const floa
   const long long V = static_cast<long long>(D) * H * W;
   // A thread produces a run of kDwRun consecutive x positions of one row: the 3 x 3 x (kDwRun + 2) input columns it needs are
   // loaded once (13.5 loads per output voxel instead of 27) and every weight slice is read from shared memory once per run.
+  // A block walks a CONTIGUOUS range of runs (not a grid stride): the rows y - 1, y of the three input planes it needs for row
+  // y were loaded for the previous rows and are still in L1 — with a grid stride every neighbour row came from L2
+  // (256 channels at 64^3: 273 us -> see profiles/r02_medformer_trace.txt).
   const int rpr = (W + kDwRun - 1) / kDwRun;
   const long long runs = static_cast<long long>(D) * H * rpr;
-  for (long long r = m.v0; r < runs; r += m.vstride) {
+  const int vpb = blockDim.x / cgb;
+  const long long per = ((runs + gridDim.x - 1) / gridDim.x + vpb - 1) / vpb * vpb;
+  const long long r_lo = static_cast<long long>(blockIdx.x) * per;
+  const long long r_hi = r_lo + per < runs ? r_lo + per : runs;
+  for (long long r = r_lo + threadIdx.x / cgb; r < r_hi; r += vpb) {
     const unsigned ru = static_cast<unsigned>(r);
     const unsigned row = ru / static_cast<unsigned>(rpr);
     const int x0 = static_cast<int>(ru - row * rpr) * kDwRun;
@@ -160,7 +167,11 @@ __global__ void dwconv3_wgrad_kernel(const T* __restrict__ a, long long ap, cons
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
   if (active) {
-    for (long long v = static_cast<long long>(blockIdx.x) * vpb + threadIdx.x / cgb; v < V; v += static_cast<long long>(gridDim.x) * vpb) {
+    // contiguous voxel range per block (see dwconv3_kernel): the three input rows of plane z + dz - 1 stay in L1 from row to row
+    const long long per = ((V + gridDim.x - 1) / gridDim.x + vpb - 1) / vpb * vpb;
+    const long long v_lo = static_cast<long long>(blockIdx.x) * per;
+    const long long v_hi = v_lo + per < V ? v_lo + per : V;
+    for (long long v = v_lo + threadIdx.x / cgb; v < v_hi; v += vpb) {
       const unsigned vu = static_cast<unsigned>(v);
       const unsigned r = vu / static_cast<unsigned>(W);
       const int x = static_cast<int>(vu - r * W);
@@ -649,9 +660,9 @@ extern "C" int rsb_channel_dot(const void* a, int a_pitch, const void* b, int b_
   return check_launch("channel_dot");
 }
 
-static inline int mf_voxel_blocks(long long V, int sms, int rows) {
-  long long want = (V + 7) / 8;                    // 8 warps = 8 voxels per block round
-  long long cap = static_cast<long long>(sms) * 4 / (rows > 0 ? rows : 1);
+static inline int mf_voxel_blocks(long long V, int sms, int rows, int per_sm = 4) {
+  long long want = (V + 7) / 8;                    // one warp per voxel: a few voxels per block round
+  long long cap = static_cast<long long>(sms) * per_sm / (rows > 0 ? rows : 1);
   if (cap < 1) cap = 1;
   if (cap > 256) cap = 256;
   if (want > cap) want = cap;
@@ -711,17 +722,17 @@ extern "C" int rsb_biattention_forward(const void* q, const void* fv, int qv_pit
   RSB_REQUIRE(sms > 0, "no CUDA device");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int rows = N * heads;
-  const int nblk = mf_voxel_blocks(V, sms, rows);
+  const int nblk = mf_voxel_blocks(V, sms, rows, 10);
   dim3 grid(nblk, rows);
   MF_BY_DTYPE(dtype,
-              (attn_colstats_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)q, qv_pitch, mq, workspace, heads, dim_head, J, V, scale)),
-              (attn_colstats_kernel<float><<<grid, 256, 0, st>>>((const float*)q, qv_pitch, mq, workspace, heads, dim_head, J, V, scale)))
+              (attn_colstats_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>((const __nv_bfloat16*)q, qv_pitch, mq, workspace, heads, dim_head, J, V, scale)),
+              (attn_colstats_kernel<float><<<grid, 128, 0, st>>>((const float*)q, qv_pitch, mq, workspace, heads, dim_head, J, V, scale)))
   colstats_merge_kernel<<<rows, 32, 0, st>>>(workspace, nblk, ms);
   cudaError_t e = cudaMemsetAsync(map_out, 0, sizeof(float) * static_cast<size_t>(rows) * J * dim_head, st);
   RSB_REQUIRE(e == cudaSuccess, "biattention: memset failed: %s", cudaGetErrorString(e));
   MF_BY_DTYPE(dtype,
-              (attn_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)fv, qv_pitch, mq, mv, ms, (__nv_bfloat16*)feat_out, feat_out_pitch, map_out, heads, dim_head, J, V, scale)),
-              (attn_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)q, (const float*)fv, qv_pitch, mq, mv, ms, (float*)feat_out, feat_out_pitch, map_out, heads, dim_head, J, V, scale)))
+              (attn_fwd_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)fv, qv_pitch, mq, mv, ms, (__nv_bfloat16*)feat_out, feat_out_pitch, map_out, heads, dim_head, J, V, scale)),
+              (attn_fwd_kernel<float><<<grid, 128, 0, st>>>((const float*)q, (const float*)fv, qv_pitch, mq, mv, ms, (float*)feat_out, feat_out_pitch, map_out, heads, dim_head, J, V, scale)))
   return check_launch("biattention_forward");
 }
 
@@ -741,9 +752,9 @@ extern "C" int rsb_biattention_backward(const void* q, const void* fv, int qv_pi
   RSB_REQUIRE(e == cudaSuccess, "biattention_backward: memset failed: %s", cudaGetErrorString(e));
   e = cudaMemsetAsync(dmv, 0, mbytes, st);
   RSB_REQUIRE(e == cudaSuccess, "biattention_backward: memset failed: %s", cudaGetErrorString(e));
-  dim3 grid(mf_voxel_blocks(V, sms, rows), rows);
+  dim3 grid(mf_voxel_blocks(V, sms, rows, 6), rows);   // 132 registers: three 128-thread blocks per SM
   MF_BY_DTYPE(dtype,
-              (attn_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)fv, qv_pitch, mq, mv, ms, (const __nv_bfloat16*)dfeat_out, dfeat_out_pitch, dmap_out, tj, (__nv_bfloat16*)dq, (__nv_bfloat16*)dfv, dqv_pitch, dmq, dmv, heads, dim_head, J, V, scale)),
-              (attn_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)q, (const float*)fv, qv_pitch, mq, mv, ms, (const float*)dfeat_out, dfeat_out_pitch, dmap_out, tj, (float*)dq, (float*)dfv, dqv_pitch, dmq, dmv, heads, dim_head, J, V, scale)))
+              (attn_bwd_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)fv, qv_pitch, mq, mv, ms, (const __nv_bfloat16*)dfeat_out, dfeat_out_pitch, dmap_out, tj, (__nv_bfloat16*)dq, (__nv_bfloat16*)dfv, dqv_pitch, dmq, dmv, heads, dim_head, J, V, scale)),
+              (attn_bwd_kernel<float><<<grid, 128, 0, st>>>((const float*)q, (const float*)fv, qv_pitch, mq, mv, ms, (const float*)dfeat_out, dfeat_out_pitch, dmap_out, tj, (float*)dq, (float*)dfv, dqv_pitch, dmq, dmv, heads, dim_head, J, V, scale)))
   return check_launch("biattention_backward");
 }

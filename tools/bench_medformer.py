@@ -96,6 +96,9 @@ def main():
             f.write(f"# launches {len(prof)}  total {tot:.2f} ms\n")
             for k, (n, t, fl) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
                 f.write(f"{k:36s} {n:5d} launches {t:8.3f} ms {t / tot:6.3f}" + (f" {fl / t / 1e9:8.1f} TF/s" if fl else "") + "\n")
+            f.write("# the 40 longest launches\n")
+            for fam, flops, e0, e1, what in sorted(prof, key=lambda r: -r[2].elapsed_time(r[3]))[:40]:
+                f.write(f"{e0.elapsed_time(e1) * 1e3:9.1f} us  {what}\n")
     if a.schedule in ("graph", "both"):
         # the whole step (forward, loss, backward, clip + AdamW + EMA) as one CUDA graph: B200TrainStep is model-agnostic
         from rsuper_b200.optim import B200AdamW
