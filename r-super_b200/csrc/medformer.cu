@@ -101,11 +101,11 @@ __global__ void dwconv3_kernel(const T* __restrict__ a, long long ap, const floa
     const int x0 = static_cast<int>(ru - row * rpr) * kDwRun;
     const int z = static_cast<int>(row / static_cast<unsigned>(H));
     const int yy = static_cast<int>(row - static_cast<unsigned>(z) * H);
-    float acc[kDwRun][8];
+    float2 acc[kDwRun][4];           // packed fp32 pairs: the 96 FMAs per (dz, dy) issue as 48 FFMA2
 #pragma unroll
     for (int i = 0; i < kDwRun; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+      for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
     for (int dz = 0; dz < 3; ++dz) {
       const int zz = z + dz - 1;
       if (zz < 0 || zz >= D) continue;
@@ -113,34 +113,38 @@ __global__ void dwconv3_kernel(const T* __restrict__ a, long long ap, const floa
         const int y2 = yy + dy - 1;
         if (y2 < 0 || y2 >= H) continue;
         const long long rowbase = ((static_cast<long long>(n) * D + zz) * H + y2) * W;
-        float col[kDwRun + 2][8];
+        float2 col[kDwRun + 2][4];
 #pragma unroll
         for (int i = 0; i < kDwRun + 2; ++i) {
           const int x2 = x0 + i - 1;
+          float f[8];
           if (x2 >= 0 && x2 < W) {
-            Vec8<T>::load(a + (rowbase + x2) * ap + m.cg * 8, col[i]);
+            Vec8<T>::load(a + (rowbase + x2) * ap + m.cg * 8, f);
           } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) col[i][j] = 0.f;
+            for (int j = 0; j < 8; ++j) f[j] = 0.f;
           }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) col[i][j] = make_float2(f[2 * j], f[2 * j + 1]);
         }
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
-          const float* wt = sm_w + ((dz * 3 + dy) * 3 + dx) * row_w + cl0;
-          float w8[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) w8[j] = wt[j];
+          const float4* wt = reinterpret_cast<const float4*>(sm_w + ((dz * 3 + dy) * 3 + dx) * row_w + cl0);
+          const float4 wa = wt[0], wb = wt[1];
+          const float2 w2[4] = {make_float2(wa.x, wa.y), make_float2(wa.z, wa.w), make_float2(wb.x, wb.y), make_float2(wb.z, wb.w)};
 #pragma unroll
           for (int i = 0; i < kDwRun; ++i)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(col[i + dx][j], w8[j], acc[i][j]);
+            for (int j = 0; j < 4; ++j) acc[i][j] = __ffma2_rn(col[i + dx][j], w2[j], acc[i][j]);
         }
       }
     }
     const long long obase = ((static_cast<long long>(n) * D + z) * H + yy) * W;
 #pragma unroll
-    for (int i = 0; i < kDwRun; ++i)
-      if (x0 + i < W) Vec8<T>::store(y + (obase + x0 + i) * yp + m.cg * 8, acc[i]);
+    for (int i = 0; i < kDwRun; ++i) {
+      const float o[8] = {acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y, acc[i][2].x, acc[i][2].y, acc[i][3].x, acc[i][3].y};
+      if (x0 + i < W) Vec8<T>::store(y + (obase + x0 + i) * yp + m.cg * 8, o);
+    }
   }
 }
 
@@ -151,7 +155,11 @@ __global__ void dwconv3_wgrad_kernel(const T* __restrict__ a, long long ap, cons
   extern __shared__ float sm_acc[];   // [9][cgb * 8]
   const int CG = C / 8;
   const int n = blockIdx.y;
-  const int chunk = static_cast<int>(blockIdx.z) / 3, dz = static_cast<int>(blockIdx.z) % 3;
+  // blockIdx.x = 3 * (voxel range) + kd: the three blocks that read the same voxel range are scheduled together, so two of
+  // the three passes over dy / a hit L2 (with kd on blockIdx.z they ran as three separate sweeps: 854 MB of DRAM traffic for
+  // 268 MB of tensors at 256 channels x 64^3, profiles/r02_medformer_kernels_ncu_summary.txt)
+  const int chunk = static_cast<int>(blockIdx.z), dz = static_cast<int>(blockIdx.x) % 3;
+  const int bx = static_cast<int>(blockIdx.x) / 3, nbx = static_cast<int>(gridDim.x) / 3;
   const int cg0 = chunk * cgb;
   const int row = cgb * 8;
   for (int i = threadIdx.x; i < 9 * row; i += blockDim.x) sm_acc[i] = 0.f;
@@ -168,8 +176,8 @@ __global__ void dwconv3_wgrad_kernel(const T* __restrict__ a, long long ap, cons
     for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
   if (active) {
     // contiguous voxel range per block (see dwconv3_kernel): the three input rows of plane z + dz - 1 stay in L1 from row to row
-    const long long per = ((V + gridDim.x - 1) / gridDim.x + vpb - 1) / vpb * vpb;
-    const long long v_lo = static_cast<long long>(blockIdx.x) * per;
+    const long long per = ((V + nbx - 1) / nbx + vpb - 1) / vpb * vpb;
+    const long long v_lo = static_cast<long long>(bx) * per;
     const long long v_hi = v_lo + per < V ? v_lo + per : V;
     for (long long v = v_lo + threadIdx.x / cgb; v < v_hi; v += vpb) {
       const unsigned vu = static_cast<unsigned>(v);
@@ -310,16 +318,17 @@ __global__ void col_softmax_partial_kernel(const T* __restrict__ x, long long xp
   colstats_block_flush(sm, m, s, partial + (static_cast<long long>(n) * gridDim.x + blockIdx.x) * 64);
 }
 
-// ms[row * 64 + {k, 32 + k}] = merged (max, sum) over the nblk partials of a row; one warp per row
+// ms[row * 64 + {k, 32 + k}] = merged (max, sum) over the nblk partials of a row; one block of 8 warps per row: warp w merges
+// the partials w, w + 8, ..., warp 0 merges the eight results (a single warp walking 256 partials took 64 us)
 __global__ void colstats_merge_kernel(const float* __restrict__ partial, int nblk, float* __restrict__ ms) {
-  const int row = blockIdx.x, lane = threadIdx.x;
+  __shared__ float sm[8 * 64];
+  const int row = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   float m = -INFINITY, s = 0.f;
-  for (int b = 0; b < nblk; ++b) {
+  for (int b = warp; b < nblk; b += nwarps) {
     const float* p = partial + (static_cast<long long>(row) * nblk + b) * 64;
     online_merge(m, s, p[lane], p[32 + lane]);
   }
-  ms[static_cast<long long>(row) * 64 + lane] = m;
-  ms[static_cast<long long>(row) * 64 + 32 + lane] = s;
+  colstats_block_flush(sm, m, s, ms + static_cast<long long>(row) * 64);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -625,7 +634,7 @@ extern "C" int rsb_dwconv3_wgrad(const void* a, int a_pitch, const void* dy, int
   cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * 27 * C, st);
   RSB_REQUIRE(e == cudaSuccess, "dwconv3_wgrad: memset failed: %s", cudaGetErrorString(e));
   const MfGrid g = mf_grid(C, V, sms, 3, 16);
-  dim3 grid(g.gx, N, g.chunks * 3);
+  dim3 grid(g.gx * 3, N, g.chunks);
   const size_t sm = sizeof(float) * 9 * g.cgb * 8;
   MF_BY_DTYPE(dtype,
               (dwconv3_wgrad_kernel<__nv_bfloat16><<<grid, kMfBlock, sm, st>>>((const __nv_bfloat16*)a, a_pitch, (const __nv_bfloat16*)dy, dy_pitch, dw, D, H, W, C, g.cgb)),
@@ -685,7 +694,7 @@ extern "C" int rsb_softmax_pool_forward(const void* feat, int feat_pitch, const 
   MF_BY_DTYPE(dtype,
               (col_softmax_partial_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)logit, logit_pitch, K, V, workspace)),
               (col_softmax_partial_kernel<float><<<grid, 256, 0, st>>>((const float*)logit, logit_pitch, K, V, workspace)))
-  colstats_merge_kernel<<<N, 32, 0, st>>>(workspace, nblk, ms);
+  colstats_merge_kernel<<<N, 256, 0, st>>>(workspace, nblk, ms);
   cudaError_t e = cudaMemsetAsync(smap, 0, sizeof(float) * static_cast<size_t>(N) * C * K, st);
   RSB_REQUIRE(e == cudaSuccess, "softmax_pool: memset failed: %s", cudaGetErrorString(e));
   MF_BY_DTYPE(dtype,
@@ -727,7 +736,7 @@ extern "C" int rsb_biattention_forward(const void* q, const void* fv, int qv_pit
   MF_BY_DTYPE(dtype,
               (attn_colstats_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>((const __nv_bfloat16*)q, qv_pitch, mq, workspace, heads, dim_head, J, V, scale)),
               (attn_colstats_kernel<float><<<grid, 128, 0, st>>>((const float*)q, qv_pitch, mq, workspace, heads, dim_head, J, V, scale)))
-  colstats_merge_kernel<<<rows, 32, 0, st>>>(workspace, nblk, ms);
+  colstats_merge_kernel<<<rows, 256, 0, st>>>(workspace, nblk, ms);
   cudaError_t e = cudaMemsetAsync(map_out, 0, sizeof(float) * static_cast<size_t>(rows) * J * dim_head, st);
   RSB_REQUIRE(e == cudaSuccess, "biattention: memset failed: %s", cudaGetErrorString(e));
   MF_BY_DTYPE(dtype,

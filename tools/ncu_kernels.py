@@ -96,3 +96,27 @@ if want("conv"):
     ops.conv3_forward(a64, ops.conv3_pack_weights(w64), torch.empty_like(a64), out_stats=torch.zeros(N, 64, 2, device=dev))
 torch.cuda.synchronize()
 print("done")
+
+if "mf" in which:
+    # ---- MedFormer voxel-side kernels (csrc/medformer.cu) at the shapes of the yaml configuration, 1 x 128^3 ----
+    a = rnd(1, 64, 64, 64, 256)                       # PatchMerging of down1: 8 * 32 channels at 64^3
+    wdw = (torch.randn(256, 1, 3, 3, 3, generator=g) / 5).to(dev)
+    ops.dwconv3(a, wdw)
+    ops.dwconv3_wgrad(a, rnd(1, 64, 64, 64, 256))
+    h = rnd(1, 32, 32, 32, 512)                       # MBConv of down2 / up2: 4 * 128 channels at 32^3
+    wd2 = (torch.randn(512, 1, 3, 3, 3, generator=g) / 5).to(dev)
+    ops.dwconv3(h, wd2)
+    ops.dwconv3_wgrad(h, rnd(1, 32, 32, 32, 512))
+    s = torch.rand(1, 512, generator=g).to(dev)
+    ops.scale_channels(h, s)
+    ops.channel_dot(h, h)
+    qv = rnd(1, 32, 32, 32, 256)                      # attention of down2 / up2: 128 channels, 4 heads of 32
+    mq = torch.randn(1, 4, 27, 32, generator=g).to(dev)
+    mv = torch.randn(1, 4, 27, 32, generator=g).to(dev)
+    fo, mo, ms = ops.biattention_forward(qv, mq, mv, 4)
+    ops.biattention_backward(qv, mq, mv, ms, rnd(1, 32, 32, 32, 128), torch.randn(1, 4, 27, 32, generator=g).to(dev),
+                             torch.randn(1, 4, 27, generator=g).to(dev), 4)
+    feat, logit = rnd(1, 32, 32, 32, 128), rnd(1, 32, 32, 32, 32)
+    smap, ms2 = ops.softmax_pool_forward(feat, logit, 27)
+    ops.softmax_pool_backward(feat, logit, ms2, torch.randn(1, 128, 27, generator=g).to(dev), torch.randn(1, 27, generator=g).to(dev))
+    torch.cuda.synchronize()
