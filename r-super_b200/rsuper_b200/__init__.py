@@ -2,6 +2,7 @@
 
 Host-side mirror of the reference's plugin interface for this path:
   * `rsuper_b200.unet.B200UNet`            <-> rsuper_train/model/dim3/unet.py:UNet
+  * `rsuper_b200.medformer.B200MedFormer`  <-> rsuper_train/model/dim3/medformer.py:MedFormer
   * `rsuper_b200.plugin.get_model`         <-> rsuper_train/model/utils.py:get_model
   * `rsuper_b200.losses.calculate_loss`    <-> rsuper_train/training/losses_foundation.py:calculate_loss
   * `rsuper_b200.optim.B200AdamW`          <-> get_optimizer (AdamW) + clip_grad_norm_ + update_ema_variables, train_ddp.py:352-357
