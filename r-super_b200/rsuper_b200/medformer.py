@@ -446,6 +446,14 @@ class B200MedFormer(nn.Module):
         self._plan_key = None
         self._pad = {}
 
+    def __getstate__(self):
+        # copy.deepcopy (EMA copies, training/utils.py:154-161) / pickling: the pack plan holds raw pointers of THIS module's
+        # parameters and is rebuilt on the first forward of the copy
+        d = self.__dict__.copy()
+        d["_plan"], d["_plan_key"], d["_pad"] = None, None, {}
+        d.pop("_P", None)
+        return d
+
     # ---- packed tensor-core weight images: one persistent plan, refreshed by one launch per forward --------------------------
     @staticmethod
     def _is_tensor_conv(name: str, p: torch.Tensor) -> bool:
