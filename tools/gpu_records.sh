@@ -23,3 +23,9 @@ for f in ("cfg2", "cfg2_fp32", "cfg3", "cfg4", "cfg5"):
     except Exception as e:
         print(f, "unreadable:", e)
 PY
+# MedFormer (row N1): not a bench.py workload (the north-star metric is the UNet step) — its own timing script
+timeout 900 python tools/bench_medformer.py --batch 2 --side 128 --schedule graph > gpurun_out/${tag}_medformer_bench_b2.json 2> gpurun_out/${tag}_medformer_bench_b2.err
+tail -c 900 gpurun_out/${tag}_medformer_bench_b2.json
+# the reference arm exactly as the driver launches it
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${tag}_bench_reference_arm.json 2> gpurun_out/${tag}_bench_reference_arm.err
+tail -c 600 gpurun_out/${tag}_bench_reference_arm.json
