@@ -35,7 +35,17 @@ def main():
     from oracle.unet_ref import synthetic_image
     from rsuper_b200 import losses, ops
     from rsuper_b200.medformer import B200MedFormer
-    dev = torch.device("cuda:0")
+    # under torchrun (WORLD_SIZE > 1): one rank per GPU, weak scaling, the flat-gradient all-reduce of B200TrainStep inside the graph
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    pg = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+        a.no_torch, a.schedule = True, "graph"
     torch.manual_seed(0)
     c = FULL
     classes = ["organ", "pancreatic_lesion"]
@@ -43,8 +53,8 @@ def main():
                         chan_num=c["chan_num"], num_heads=c["num_heads"], fusion_depth=c["fusion_depth"], fusion_dim=c["fusion_dim"],
                         fusion_heads=c["fusion_heads"], expansion=c["expansion"], aux_loss=True, precision=a.precision).to(dev)
     S = a.side
-    x = synthetic_image(a.batch, S, S, S, seed=3, device=dev)
-    batch = synth.make_batch(["mask"] * a.batch, classes, (S, S, S), seed=5, device=dev)
+    x = synthetic_image(a.batch, S, S, S, seed=3 + rank, device=dev)
+    batch = synth.make_batch(["mask"] * a.batch, classes, (S, S, S), seed=5 + rank, device=dev)
     args = LR.default_args(report_volume_loss_basic=0.0)
     args.nan_check = False
 
@@ -110,8 +120,14 @@ def main():
         def loss_fn(out, lab):
             return losses.calculate_loss(out, lab, None, args, None, None, None, None, classes)["overall"]
         torch.cuda.reset_peak_memory_stats()
-        step = B200TrainStep(net, loss_fn, opt, [x, batch["label"]], schedule="graph", warmup=2)
+        step = B200TrainStep(net, loss_fn, opt, [x, batch["label"]], schedule="graph", warmup=2, process_group=pg)
         ms, loss = timed(lambda: step(x, batch["label"]))
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)          # a step takes as long as the slowest rank
+            ms = float(t.item())
+            vox *= world
+            res["n_gpus"] = world
         res["graph_full_step"] = {"ms_per_step": round(ms, 2), "mvox_per_s": round(vox / ms / 1e3, 2), "loss": loss,
                                   "gpu_launches": step.launches_per_step, "includes": "clip + AdamW + EMA",
                                   "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2)}
@@ -138,7 +154,14 @@ def main():
                               "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2)}
             except Exception as e:  # noqa: BLE001
                 res[label] = {"error": repr(e)[:200]}
-    print(json.dumps(res))
+    if rank == 0:
+        print(json.dumps(res), flush=True)
+    if world > 1:
+        # same teardown as bench.py: a captured NCCL collective keeps the communicator busy in destroy_process_group
+        del step
+        torch.cuda.synchronize()
+        dist.barrier()
+        os._exit(0)
 
 
 if __name__ == "__main__":
