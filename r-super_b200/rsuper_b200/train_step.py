@@ -365,8 +365,40 @@ class B200TrainStep:
             if p in self.opt.state and len(self.opt.state[p]):
                 self.opt.state[p]["step"] -= 1
 
+    # -- input prefetch: the next batch's host -> device copy runs on a copy stream beside the current step ----------------------
+    def prefetch(self, *inputs) -> None:
+        """Start the asynchronous upload of the NEXT batch (pinned host tensors, or device tensors) into staging buffers on a
+        dedicated copy stream; the following `step()` call without arguments consumes it.  What a prefetching data loader does
+        (the reference: DataLoader(pin_memory=True) + `.cuda(non_blocking=True)`, train_ddp.py:311-318): the copy engine works
+        while the SMs run the current step, instead of in front of the next one."""
+        dev = self.loss.device
+        if getattr(self, "_stage", None) is None:
+            self._stage = [None if t is None else torch.empty_like(t) for t in self.static]
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._copy_done = torch.cuda.Event()
+            self._stage_free = torch.cuda.Event()
+            self._stage_free.record(torch.cuda.current_stream(dev))
+        self._copy_stream.wait_event(self._stage_free)            # the previous batch has left the staging buffers
+        with torch.cuda.stream(self._copy_stream):
+            for dst, src in zip(self._stage, inputs):
+                if dst is not None:
+                    dst.copy_(src, non_blocking=True)
+            self._copy_done.record(self._copy_stream)
+        self._prefetched = True
+
     def __call__(self, *inputs) -> torch.Tensor:
-        """One train step.  inputs mirror example_inputs; pinned host tensors are copied asynchronously into the static inputs."""
+        """One train step.  inputs mirror example_inputs; pinned host tensors are copied asynchronously into the static inputs.
+        Called without arguments after `prefetch(...)`: the staged batch is moved into the static inputs (device to device)."""
+        if not inputs:
+            if not getattr(self, "_prefetched", False):
+                raise RuntimeError("B200TrainStep(): call prefetch(...) first, or pass the inputs")
+            cur = torch.cuda.current_stream(self.loss.device)
+            cur.wait_event(self._copy_done)
+            for dst, src in zip(self.static, self._stage):
+                if dst is not None:
+                    dst.copy_(src, non_blocking=True)
+            self._stage_free.record(cur)
+            self._prefetched = False
         for dst, src in zip(self.static, inputs):
             if dst is not None:
                 dst.copy_(src, non_blocking=True)

@@ -778,6 +778,56 @@ def test_graphed_train_step_matches_eager(cuda_dev):
     assert tot / cnt <= 0.25 * 6e-4
 
 
+def test_train_step_prefetch_feeds_the_same_batches(cuda_dev):
+    """B200TrainStep.prefetch (next batch uploaded from pinned host memory on a copy stream while the current step runs) against
+    passing the same host batches to step(...) directly: two alternating batches, identical initial state — the same losses step
+    by step (the right batch reaches the right step) and the same parameters."""
+    from oracle import losses_ref as LR
+    from oracle import synth
+    from oracle.unet_ref import synthetic_image, synthetic_state_dict
+    from rsuper_b200 import losses
+    from rsuper_b200.optim import B200AdamW
+    from rsuper_b200.train_step import B200TrainStep
+    from rsuper_b200.unet import B200UNet
+    classes = ["organ", "pancreatic_lesion"]
+    batches = []
+    for seed in (5, 6):
+        x = synthetic_image(2, 32, 32, 32, seed=seed).pin_memory()
+        lab = synth.make_batch(["mask", "mask"], classes, (32, 32, 32), seed=seed + 3, device="cpu")["label"].contiguous().pin_memory()
+        batches.append((x, lab))
+    args = LR.default_args(report_volume_loss_basic=0.0)
+    args.nan_check = False
+    loss_fn = lambda out, lb: losses.calculate_loss(out, lb, None, args, None, None, None, None, classes)["overall"]
+    order = [0, 1, 1, 0, 1]
+    runs = []
+    for prefetch in (False, True):
+        net = B200UNet(1, 16, num_classes=2, precision="bf16").to(cuda_dev)
+        net.load_state_dict(synthetic_state_dict(16, 2, device=cuda_dev))
+        params = list(net.parameters())
+        opt = B200AdamW(params, lr=6e-4, weight_decay=0.05, max_norm=1.0, capturable=True)
+        step = B200TrainStep(net, loss_fn, opt, [t.to(cuda_dev) for t in batches[0]], schedule="graph", warmup=1)
+        ls = []
+        if prefetch:
+            with pytest.raises(RuntimeError, match="prefetch"):
+                step()
+            step.prefetch(*batches[order[0]])
+            for i in range(len(order)):
+                loss = step()
+                if i + 1 < len(order):
+                    step.prefetch(*batches[order[i + 1]])          # overlaps with the step that was just enqueued
+                ls.append(loss.item())
+        else:
+            for b in order:
+                ls.append(step(*batches[b]).item())
+        runs.append((ls, [p.detach().clone() for p in params]))
+    (l0, p0), (l1, p1) = runs
+    print(f"[prefetch] direct losses {l0}, prefetched losses {l1}")
+    assert all(abs(a - b) <= 2e-3 * abs(a) for a, b in zip(l0, l1))
+    assert abs(l0[0] - l0[1]) > 1e-2 * abs(l0[0])                 # the two batches are distinguishable by their loss
+    for a, b in zip(p0, p1):
+        assert (a - b).abs().max().item() <= 2 * len(order) * 6e-4 * 1.05
+
+
 def test_split_schedule_matches_eager_on_report_batches(cuda_dev):
     """B200TrainStep(schedule='split') — UNet forward and backward + optimizer as two CUDA graphs, calculate_loss with the
     Volume / Ball report losses (host-controlled tumour loop) launched eagerly in between — against schedule='eager' from
