@@ -17,7 +17,7 @@ Workloads (BASELINE.json configs; reference UNet base 32, 5 levels, BasicBlock/I
 
 Prints ONE JSON line (rank 0).  `value` = whole-job Mvoxels/s with inputs resident in HBM (CUDA events around the K steps,
 nothing else recorded, max over ranks); `e2e` = the same through the public API with pinned HOST buffers (H2D of every
-input tensor and D2H of the loss inside the timed region); `roofline` / `kernels` = a separate profiled pass of the same K
+input tensor — prefetched on a copy stream beside the previous step, B200TrainStep.prefetch — and D2H of the loss inside the timed region); `roofline` / `kernels` = a separate profiled pass of the same K
 steps inside this script (every launch bracketed by CUDA events on its stream, one stream, so that a kernel's events time
 that kernel alone): the dominant kernel (tcgen05 implicit-GEMM conv: fprop + dgrad launches) vs its algorithmic FLOPs and
 the measured bf16 peak; `cpu_baseline` = the reference's own modules (oracle/_ref, staged by oracle/build_ref.py) timed on
