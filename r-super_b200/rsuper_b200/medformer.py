@@ -35,6 +35,57 @@ EPS_DEF = 1e-5   # PatchMerging.norm / BidirectionAttentionBlock.norm1, norm2 (t
 
 
 # ------------------------------------------------------------------------------------------------
+# weight gradients beside the backward chain (only under B200TrainStep, which owns the gradient buffers and joins the stream)
+# ------------------------------------------------------------------------------------------------
+class _Side:
+    """Second stream for the weight gradients of the voxel-side convolutions.  The data-gradient chain (tensor-core dgrads,
+    InstanceNorm-backward passes) is what the rest of backward waits for; the weight gradients (latency-bound depthwise
+    reductions, 3x3x3 wgrad GEMMs, 1x1x1 GEMMs) are needed only by the optimizer.  With `enabled`, a Function's backward
+    launches its weight gradient on this stream, adds it into the parameter's preallocated `.grad` there and returns None for
+    it; B200TrainStep turns it on around its body (its `.grad`s are views of one flat buffer, zeroed on the main stream before
+    the forward pass) and calls `join()` before the all-reduce / optimizer.  Operand tensors stay referenced until the join:
+    the caching allocator must not hand their memory to main-stream work while the side stream still reads it."""
+    enabled = False
+    stream = None
+    keep: list = []
+
+    @classmethod
+    def get(cls, device):
+        if cls.stream is None or cls.stream.device != device:
+            cls.stream = torch.cuda.Stream(device=device)
+        return cls.stream
+
+    @classmethod
+    def usable(cls, p) -> bool:
+        return cls.enabled and isinstance(p, torch.Tensor) and p.grad is not None and p.is_cuda
+
+    @classmethod
+    def run(cls, p, fn, *operands):
+        """fn() -> gradient of p, launched on the side stream and accumulated into p.grad there."""
+        side = cls.get(p.device)
+        side.wait_stream(torch.cuda.current_stream(p.device))        # operands come from work already enqueued on the main stream
+        with torch.cuda.stream(side):
+            g = fn()
+            p.grad.add_(g.reshape(p.grad.shape))
+        cls.keep.append((operands, g))
+
+    @classmethod
+    def join(cls):
+        if cls.stream is not None and cls.keep:
+            torch.cuda.current_stream(cls.stream.device).wait_stream(cls.stream)
+        cls.keep = []
+
+
+def set_side_stream(enabled: bool) -> bool:
+    prev, _Side.enabled = _Side.enabled, bool(enabled)
+    return prev
+
+
+def join_side_stream() -> None:
+    _Side.join()
+
+
+# ------------------------------------------------------------------------------------------------
 # autograd Functions over the kernels (all activations: contiguous NDHWC)
 # ------------------------------------------------------------------------------------------------
 class _NormAct(torch.autograd.Function):
@@ -94,6 +145,7 @@ class _ConvNA(torch.autograd.Function):
                           pointwise=pointwise)
         ctx.save_for_backward(x, st, img_t, *op)
         ctx.cfg = (norm, slope, eps, pointwise, cout, tuple(w.shape), res is not None)
+        ctx.param = w
         if y_st is None:
             y_st = torch.empty(0, device=x.device)
         ctx.mark_non_differentiable(y_st)
@@ -108,19 +160,25 @@ class _ConvNA(torch.autograd.Function):
         split = len(op) > 1
         cin = x.shape[4]
         dw = dx = None
-        if ctx.needs_input_grad[2] and pointwise:
-            a2, g2 = [t.reshape(-1, cin) for t in op], [t.reshape(-1, cout) for t in d_op]
-            dw = _gemm_tn_f32(g2[0], a2[0])
-            if split:
-                dw = dw + _gemm_tn_f32(g2[0], a2[1]) + _gemm_tn_f32(g2[1], a2[0])
-            dw = dw[:wshape[0]].reshape(wshape)
-        elif ctx.needs_input_grad[2]:
+        def weight_gradient():
+            if pointwise:
+                a2, g2 = [t.reshape(-1, cin) for t in op], [t.reshape(-1, cout) for t in d_op]
+                g = _gemm_tn_f32(g2[0], a2[0])
+                if split:
+                    g = g + _gemm_tn_f32(g2[0], a2[1]) + _gemm_tn_f32(g2[1], a2[0])
+                return g[:wshape[0]].reshape(wshape)
             dw27 = torch.empty((cout, cin, 3, 3, 3), dtype=torch.float32, device=x.device)
             ops.conv3_wgrad(op[0], d_op[0], dw27)
             if split:
                 ops.conv3_wgrad(op[1], d_op[0], dw27, accumulate=True)
                 ops.conv3_wgrad(op[0], d_op[1], dw27, accumulate=True)
-            dw = dw27[:wshape[0]]
+            return dw27[:wshape[0]]
+
+        if ctx.needs_input_grad[2]:
+            if _Side.usable(ctx.param):
+                _Side.run(ctx.param, weight_gradient, op, d_op)       # lands in param.grad on the side stream; autograd gets None
+            else:
+                dw = weight_gradient()
         if ctx.needs_input_grad[0]:
             lo = d_op[1] if split else None
             dx = torch.empty_like(x)
@@ -140,13 +198,19 @@ class _DwConv(torch.autograd.Function):
     @staticmethod
     def forward(ctx, a, w):
         ctx.save_for_backward(a, w)
+        ctx.param = w
         return ops.dwconv3(a, w)
 
     @staticmethod
     def backward(ctx, dy):
         a, w = ctx.saved_tensors
         dy = dy.contiguous()
-        dw = ops.dwconv3_wgrad(a, dy).view_as(w) if ctx.needs_input_grad[1] else None
+        dw = None
+        if ctx.needs_input_grad[1]:
+            if _Side.usable(ctx.param):
+                _Side.run(ctx.param, lambda: ops.dwconv3_wgrad(a, dy), a, dy)
+            else:
+                dw = ops.dwconv3_wgrad(a, dy).view_as(w)
         da = ops.dwconv3(dy, w, flip=True) if ctx.needs_input_grad[0] else None
         return da, dw
 

@@ -213,8 +213,13 @@ class B200TrainStep:
         return w if async_op else None
 
     def _body(self):
+        from . import medformer as mf_mod
         from . import unet as unet_mod
         prev = unet_mod.set_side_stream(self.side_stream)
+        # B200MedFormer's Functions may run their weight gradients on a second stream only here: the gradients land in the flat
+        # buffer's views (zeroed below, on the main stream, before the forward pass) and the stream is joined before the
+        # all-reduce / optimizer read them
+        prev_mf = mf_mod.set_side_stream(self.side_stream and self.flat_grad.is_cuda)
         try:
             if self.sink is None or not self.sink.covers_all():
                 self.flat_grad.zero_()             # p.grad are views: autograd accumulates in place
@@ -223,11 +228,14 @@ class B200TrainStep:
             out = self.net(self.static[0])
             loss = self.loss_fn(out, *self.static[1:])
             loss.backward()
+            mf_mod.join_side_stream()
             self._allreduce()
             self.opt.step()
             self.loss.copy_(loss.detach())
         finally:
             unet_mod.set_side_stream(prev)
+            mf_mod.set_side_stream(prev_mf)
+            mf_mod.join_side_stream()
 
     def _capture_stream(self):
         import os

@@ -290,3 +290,43 @@ def test_medformer_vs_reference_golden_and_oracle(cuda_dev, precision="fp32"):
 
 def test_medformer_bf16_mode(cuda_dev):
     test_medformer_vs_reference_golden_and_oracle(cuda_dev, "bf16")
+
+
+def test_medformer_train_step_graph_and_side_stream(cuda_dev):
+    """B200TrainStep is model-agnostic: the whole MedFormer step (forward, calculate_loss on [final, aux], backward, clip + AdamW +
+    EMA) as one CUDA graph, with the weight gradients of the voxel-side convolutions on a second stream (they land in the flat
+    gradient buffer there; joined before the optimizer) against the same graph with everything on one stream, from identical
+    state: same losses step by step, same parameters within optimizer rounding."""
+    from oracle import losses_ref as LR
+    from oracle import synth
+    from oracle.unet_ref import synthetic_image
+    from rsuper_b200 import losses
+    from rsuper_b200.optim import B200AdamW
+    from rsuper_b200.train_step import B200TrainStep
+    golden = medformer_golden()
+    classes = ["organ", "pancreatic_lesion"]
+    x = synthetic_image(1, S, S, S, seed=3, device=cuda_dev)
+    lab = synth.make_batch(["mask"], classes, (S, S, S), seed=5, device=cuda_dev)["label"]
+    args = LR.default_args(report_volume_loss_basic=0.0)
+    args.nan_check = False
+    loss_fn = lambda out, lb: losses.calculate_loss(out, lb, None, args, None, None, None, None, classes)["overall"]
+    runs = []
+    for side in (False, True):
+        net, _ = _make(cuda_dev, "fp32", golden)
+        params = list(net.parameters())
+        opt = B200AdamW(params, lr=1e-4, weight_decay=0.05, max_norm=1.0, ema_params=[p.detach().clone() for p in params], capturable=True)
+        step = B200TrainStep(net, loss_fn, opt, [x, lab], schedule="graph", side_stream=side, warmup=1)
+        ls = [step(x, lab).item() for _ in range(3)]
+        assert step.launches_per_step > 300
+        runs.append((ls, [p.detach().clone() for p in params]))
+    (l0, p0), (l1, p1) = runs
+    print(f"[medformer step] one stream {l0}, weight gradients on the second stream {l1}")
+    assert all(abs(a - b) <= 2e-2 * abs(a) for a, b in zip(l0, l1)) and abs(l0[0] - l1[0]) <= 2e-3 * abs(l0[0])
+    assert l0[-1] < l0[0]                                     # it trains
+    tot = cnt = 0.0
+    for a, b in zip(p0, p1):
+        d = (a - b).abs()
+        assert torch.isfinite(b).all() and d.max().item() <= 2 * 4 * 1e-4 * 1.05
+        tot += d.sum().item(); cnt += d.numel()
+    assert tot / cnt <= 0.25 * 1e-4
+
