@@ -234,7 +234,7 @@ def test_emulated_bottleneck_unet_vs_reference_and_oracle(emulated, monkeypatch)
     U.test_bottleneck_unet_vs_reference_and_oracle(CPU, "fp32")
 
 
-@pytest.mark.parametrize("block", ["BasicBlock", pytest.param("Bottleneck", marks=_slow)])
+@pytest.mark.parametrize("block", [pytest.param("BasicBlock", marks=_slow), pytest.param("Bottleneck", marks=_slow)])
 def test_emulated_transposed_conv_upsampling_variant(emulated, monkeypatch, block):
     """up_mode='transposed' (1x1x1 conv to 8 C channels + depth-to-space, space-to-depth + summed-bias backward) on the CPU."""
     import test_unet_gpu as U
