@@ -449,7 +449,8 @@ def main():
         # untimed: first use of the prefetch path (staging buffers, copy stream, pinned-memory bookkeeping are created here)
         for _ in range(2):
             step.prefetch(*host_inputs)
-            step().item()
+            step()
+            step.loss_async().get()
     barrier()
     t0 = time.perf_counter()
     lv = 0.0
@@ -460,12 +461,19 @@ def main():
     else:
         # the loop of a prefetching loader: while step i runs, the copy engine uploads batch i + 1 from pinned host memory
         # (B200TrainStep.prefetch: copy stream + staging buffers); K uploads, K steps and K loss read-backs inside the region
+        # ... and every step's loss comes back through a 4-byte pinned copy + event (B200TrainStep.loss_async), looked at after
+        # the NEXT step has been enqueued, so the GPU never waits for the host between two replays
         step.prefetch(*host_inputs)
+        pending = None
         for i in range(args.steps):
-            loss = step()
+            step()
+            h = step.loss_async()
             if i + 1 < args.steps:
                 step.prefetch(*host_inputs)
-            lv = loss.item()
+            if pending is not None:
+                lv = pending.get()
+            pending = h
+        lv = pending.get()
     torch.cuda.synchronize()
     ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
     clocks = sampler.stop() if rank == 0 else None  # sampled every 50 ms across BOTH timed regions (same work)

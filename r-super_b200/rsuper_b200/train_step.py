@@ -136,6 +136,17 @@ class _FlatGradSink:
         return ok
 
 
+class _LossRead:
+    __slots__ = ("buf", "ev")
+
+    def __init__(self, buf, ev):
+        self.buf, self.ev = buf, ev
+
+    def get(self) -> float:
+        self.ev.synchronize()
+        return B200TrainStep.check(float(self.buf))
+
+
 class B200TrainStep:
     def __init__(self, net: torch.nn.Module, loss_fn: Callable, optimizer: B200AdamW, example_inputs: Sequence[Optional[torch.Tensor]],
                  *, schedule: str = "graph", process_group=None, side_stream: Optional[bool] = None, warmup: int = 3):
@@ -393,6 +404,19 @@ class B200TrainStep:
                     dst.copy_(src, non_blocking=True)
             self._copy_done.record(self._copy_stream)
         self._prefetched = True
+
+    def loss_async(self):
+        """Asynchronous read-back of the loss of the step that was just enqueued: a 4-byte copy into pinned host memory + an
+        event.  `.get()` on the returned handle waits for THAT copy only, so the caller can enqueue step i + 1 before it
+        looks at loss i (`loss.item()` would drain the stream, and the GPU would idle while the host prepares the next step)."""
+        if getattr(self, "_rd", None) is None:
+            self._rd = [(torch.empty((), dtype=torch.float32).pin_memory(), torch.cuda.Event()) for _ in range(4)]
+            self._rd_i = -1
+        self._rd_i = (self._rd_i + 1) % len(self._rd)
+        buf, ev = self._rd[self._rd_i]
+        buf.copy_(self.loss, non_blocking=True)
+        ev.record(torch.cuda.current_stream(self.loss.device))
+        return _LossRead(buf, ev)
 
     def __call__(self, *inputs) -> torch.Tensor:
         """One train step.  inputs mirror example_inputs; pinned host tensors are copied asynchronously into the static inputs.

@@ -813,11 +813,16 @@ def test_train_step_prefetch_feeds_the_same_batches(cuda_dev):
             with pytest.raises(RuntimeError, match="prefetch"):
                 step()
             step.prefetch(*batches[order[0]])
+            pending = None
             for i in range(len(order)):
-                loss = step()
+                step()
+                h = step.loss_async()                              # 4-byte pinned copy + event: read one step late
                 if i + 1 < len(order):
                     step.prefetch(*batches[order[i + 1]])          # overlaps with the step that was just enqueued
-                ls.append(loss.item())
+                if pending is not None:
+                    ls.append(pending.get())
+                pending = h
+            ls.append(pending.get())
         else:
             for b in order:
                 ls.append(step(*batches[b]).item())
