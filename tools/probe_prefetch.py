@@ -51,6 +51,22 @@ def v_prefetch_late(n):      # prefetch issued after the loss read-back (no over
     for i in range(n):
         loss = step(); loss.item()
         if i + 1 < n: step.prefetch(x, lab)
+def v_prefetch_async(n):      # loss read one step late through a pinned 4-byte copy + event
+    step.prefetch(x, lab)
+    pending = None
+    for i in range(n):
+        step(); h = step.loss_async()
+        if i + 1 < n: step.prefetch(x, lab)
+        if pending is not None: pending.get()
+        pending = h
+    pending.get()
+def v_dev_async(n):           # device inputs, async loss
+    pending = None
+    for i in range(n):
+        step(xd, ld); h = step.loss_async()
+        if pending is not None: pending.get()
+        pending = h
+    pending.get()
 def v_h2d_only(n):
     for _ in range(n):
         xd.copy_(x, non_blocking=True); ld.copy_(lab, non_blocking=True)
@@ -62,4 +78,8 @@ run("pinned host inputs through step(...), .item()", v_direct)
 run("prefetch on copy stream, .item()", v_prefetch)
 run("prefetch on copy stream, no read-back", v_prefetch_noitem)
 run("prefetch issued after .item()", v_prefetch_late)
+run("prefetch on copy stream, loss_async one step late", v_prefetch_async)
+run("device inputs, loss_async one step late", v_dev_async)
+run("prefetch on copy stream, .item() (again)", v_prefetch)
+run("device inputs, no read-back (again)", v_dev)
 run("H2D copies alone (24 MB)", v_h2d_only)
