@@ -281,12 +281,14 @@ class _Up2(torch.autograd.Function):
     def forward(ctx, x, size):
         n, _, _, _, c = x.shape
         y = torch.empty((n,) + tuple(size) + (c,), dtype=x.dtype, device=x.device)
-        ops.upsample_forward(x, y)
+        y_st = torch.zeros((n, c, 2), dtype=torch.float32, device=x.device)      # (sum, sumsq) of y from the kernel's epilogue
+        ops.upsample_forward(x, y, y_st)
         ctx.in_shape = x.shape
-        return y
+        ctx.mark_non_differentiable(y_st)
+        return y, y_st
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _unused):
         dy = dy.contiguous()
         dx = torch.empty(ctx.in_shape, dtype=dy.dtype, device=dy.device)
         ops.upsample_backward(dy, dx)
@@ -300,10 +302,12 @@ class _ChannelMean(torch.autograd.Function):
     def forward(ctx, h):
         ctx.shape, ctx.dtype = h.shape, h.dtype
         v = h.shape[1] * h.shape[2] * h.shape[3]
-        return ops.channel_stats(h)[..., 0].contiguous() / v
+        st = ops.channel_stats(h)                       # (sum, sumsq): the caller derives the statistics of h * gate from them
+        ctx.mark_non_differentiable(st)
+        return st[..., 0].contiguous() / v, st
 
     @staticmethod
-    def backward(ctx, dm):
+    def backward(ctx, dm, _unused):
         n, d, h, w_, c = ctx.shape
         return (dm / (d * h * w_)).to(ctx.dtype).view(n, 1, 1, 1, c).expand(ctx.shape)
 
@@ -576,11 +580,13 @@ class B200MedFormer(nn.Module):
         P = self._P
         h = self._cna(x, pre + "expand_proj.conv.weight")
         h = _DwConv.apply(self._norm_act(h, EPS_CNA, 0.0), P[pre + "depthwise.conv.weight"])
-        s = _ChannelMean.apply(h)                                                      # SEBlock (conv_layers.py:159-173)
+        s, st_h = _ChannelMean.apply(h)                                                # SEBlock (conv_layers.py:159-173)
         w0, w2 = P[pre + "se.excitation.0.weight"], P[pre + "se.excitation.2.weight"]
         s = F.relu(F.linear(s, w0.flatten(1), P[pre + "se.excitation.0.bias"]))
         s = torch.sigmoid(F.linear(s, w2.flatten(1), P[pre + "se.excitation.2.bias"]))
         h = _Scale.apply(h, s)
+        g = s.detach().contiguous()
+        h.rsb_stats = torch.stack([st_h[..., 0] * g, st_h[..., 1] * g * g], dim=-1).contiguous()   # sums of h * gate: no statistics pass
         return self._cna(h, pre + "pointwise.conv.weight", act=False, res=x)
 
     def _attention_block(self, x, smap, pre, heads):
@@ -626,7 +632,10 @@ class B200MedFormer(nn.Module):
     def _up(self, x1, x2, map1, map2, i):
         pre = f"up{i}."
         c = self.cfg
-        feat = torch.cat([_Up2.apply(x1, tuple(x2.shape[1:4])), x2], dim=4)
+        up, up_st = _Up2.apply(x1, tuple(x2.shape[1:4]))
+        feat = torch.cat([up, x2], dim=4)
+        if getattr(x2, "rsb_stats", None) is not None:
+            feat.rsb_stats = torch.cat([up_st, x2.rsb_stats], dim=1).contiguous()      # both halves already carry their sums
         key = pre + "map_reduction.weight"
         smap = F.conv3d(torch.cat([map1, map2], dim=1), self._P[key]) if (key in self._P and map2 is not None) else map1
         out, smap = self._layer(feat, smap, pre + "trans_blocks.", c["trans_num"][3 + i], c["num_heads"][3 + i])
