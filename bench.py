@@ -361,9 +361,8 @@ def main():
         args.warmup = 3
     if world > 1:
         os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")   # NCCL collectives are captured into the step's CUDA graph
-    from oracle import losses_ref as LR  # only for default_args (plain namespace of hyper-parameters)
-    from oracle import synth             # synthetic batch generator (shared with the tests)
-    from rsuper_b200 import losses, ops
+    from rsuper_b200 import synthetic as synth   # synthetic batches with the reference loader's contract + the loss hyper-parameters
+    from rsuper_b200 import losses, ops          # (nothing under oracle/ is imported on this arm)
     from rsuper_b200.optim import B200AdamW
     from rsuper_b200.train_step import B200TrainStep
     from rsuper_b200.unet import B200UNet
@@ -386,12 +385,11 @@ def main():
     opt = B200AdamW(params, lr=6e-4, betas=(0.9, 0.999), weight_decay=0.05, eps=1e-5, max_norm=1.0, ema_params=ema, ema_alpha=0.99,
                     capturable=True)
     report = cfg["report"]
-    largs = LR.default_args() if report else LR.default_args(report_volume_loss_basic=0.0)
+    largs = synth.default_loss_args() if report else synth.default_loss_args(report_volume_loss_basic=0.0)
     largs.nan_check = False                 # a host sync: the loss value is NaN-checked after .item() instead (B200TrainStep.check)
     # synthetic batch (seeded per rank); host copies pinned for the e2e leg
     bt = synth.make_batch(kinds, classes, shape, seed=seed_lab, device="cpu")
-    from oracle.unet_ref import synthetic_image
-    bt["image"] = synthetic_image(B, *shape, seed=seed_img)
+    bt["image"] = synth.synthetic_image(B, *shape, seed=seed_img)
     keys = ["image", "label"] + (["unk_channels", "mask", "volumes", "diameters"] if report else [])
     host = {k: bt[k].contiguous().pin_memory() for k in keys}
     devb = {k: host[k].to(dev) for k in keys}

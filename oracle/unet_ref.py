@@ -234,15 +234,4 @@ def _fill_state_dict(shapes, gain, device):
     return sd
 
 
-def synthetic_image(n: int, d: int, h: int, w: int, seed: int = 0, device="cpu") -> torch.Tensor:
-    """Deterministic CT-like patch in [-3, 3] (N(0,1)-scale, |x| <= 100)."""
-    zz, yy, xx = torch.meshgrid(torch.arange(d, dtype=torch.float64), torch.arange(h, dtype=torch.float64),
-                                torch.arange(w, dtype=torch.float64), indexing="ij")
-    out = []
-    for i in range(n):
-        s = float(seed * 7 + i)
-        v = (torch.sin(0.37 * zz + 0.11 * s) + torch.cos(0.23 * yy * (1 + 0.01 * s)) * torch.sin(0.31 * xx + s)
-             + 0.5 * torch.sin(0.05 * (zz * yy + xx) + 0.7 * s) + 0.8 * torch.sin(12.9898 * zz + 78.233 * yy + 37.719 * xx + s))
-        out.append(v)
-    img = torch.stack(out).unsqueeze(1).to(torch.float32)
-    return img.clamp_(-3, 3).to(device)
+from oracle.synth import synthetic_image  # noqa: E402,F401  (data construction lives in rsuper_b200.synthetic)

@@ -29,10 +29,7 @@ def main():
     ap.add_argument("--schedule", default="graph", choices=["graph", "eager", "both"])
     ap.add_argument("--trace", default="")
     a = ap.parse_args()
-    from oracle import losses_ref as LR
-    from oracle import synth
-    from oracle.medformer_ref import medformer_forward
-    from oracle.unet_ref import synthetic_image
+    from rsuper_b200 import synthetic as synth
     from rsuper_b200 import losses, ops
     from rsuper_b200.medformer import B200MedFormer
     # under torchrun (WORLD_SIZE > 1): one rank per GPU, weak scaling, the flat-gradient all-reduce of B200TrainStep inside the graph
@@ -53,9 +50,9 @@ def main():
                         chan_num=c["chan_num"], num_heads=c["num_heads"], fusion_depth=c["fusion_depth"], fusion_dim=c["fusion_dim"],
                         fusion_heads=c["fusion_heads"], expansion=c["expansion"], aux_loss=True, precision=a.precision).to(dev)
     S = a.side
-    x = synthetic_image(a.batch, S, S, S, seed=3 + rank, device=dev)
+    x = synth.synthetic_image(a.batch, S, S, S, seed=3 + rank, device=dev)
     batch = synth.make_batch(["mask"] * a.batch, classes, (S, S, S), seed=5 + rank, device=dev)
-    args = LR.default_args(report_volume_loss_basic=0.0)
+    args = synth.default_loss_args(report_volume_loss_basic=0.0)
     args.nan_check = False
 
     def step_ours():
@@ -132,6 +129,9 @@ def main():
                                   "gpu_launches": step.launches_per_step, "includes": "clip + AdamW + EMA",
                                   "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2)}
     if not a.no_torch:
+        # the stock-PyTorch arm: the oracle restatement of the reference module (test infrastructure, only imported here)
+        from oracle import losses_ref as LR
+        from oracle.medformer_ref import medformer_forward
         torch.manual_seed(0)
         sd = {k: v.detach().clone().requires_grad_(True) for k, v in net.named_parameters()}
         for label, ctx in (("torch_fp32", None), ("torch_bf16_autocast", torch.autocast("cuda", dtype=torch.bfloat16))):
