@@ -335,3 +335,52 @@ def test_medformer_train_step_graph_and_side_stream(cuda_dev):
     assert all(v == v and v < 1e6 for v in l0 + l1)
     for a, b in zip(p0, p1):
         assert torch.isfinite(b).all() and (a - b).abs().max().item() <= 2 * 4 * 1e-4 * 1.05
+
+
+def test_medformer_full_configuration_vs_oracle(cuda_dev):
+    """config/abdomenatlas_ufo/medformer_3d.yaml as it trains (base 32, channels up to 320, 8 * 256 = 2048-channel patch merging,
+    heads of 32 dimensions, 12 + 6 attention blocks) at 64^3 with the module's own (seeded) initialisation: logits and
+    deep-supervision head of the fp32 mode against the oracle in fp32 on the same device, bf16 mode against the same; loss and
+    the whole gradient vector of the fp32 mode against the oracle's autograd."""
+    from oracle import losses_ref as LR
+    from oracle import synth
+    from oracle.medformer_ref import DEFAULT_CFG as c
+    from oracle.medformer_ref import medformer_forward
+    from oracle.unet_ref import synthetic_image
+    from rsuper_b200 import losses
+    from rsuper_b200.medformer import B200MedFormer
+    classes = ["organ", "pancreatic_lesion"]
+    side = 64
+    x = synthetic_image(1, side, side, side, seed=3, device=cuda_dev)
+    batch = synth.make_batch(["mask"], classes, (side, side, side), seed=5, device=cuda_dev)
+    args = LR.default_args(report_volume_loss_basic=0.0)
+    state = None
+    for precision in ("fp32", "bf16"):
+        torch.manual_seed(7)
+        net = B200MedFormer(1, 2, base_chan=c["base_chan"], map_size=c["map_size"], conv_num=c["conv_num"], trans_num=c["trans_num"],
+                            chan_num=c["chan_num"], num_heads=c["num_heads"], fusion_depth=c["fusion_depth"], fusion_dim=c["fusion_dim"],
+                            fusion_heads=c["fusion_heads"], expansion=c["expansion"], aux_loss=True, precision=precision).to(cuda_dev)
+        if state is None:
+            state = {k: v.detach().clone() for k, v in net.named_parameters()}
+        net.load_state_dict(state, strict=True)
+        out = net(x)
+        sdr = {k: v.clone().requires_grad_(True) for k, v in state.items()}
+        ref = medformer_forward(x, sdr, c)
+        for got, want, key in zip(out["segmentation"], ref["segmentation"], ("logits", "aux")):
+            e = rel(got.detach(), want.detach())
+            agree = (got.argmax(1) == want.argmax(1)).float().mean().item()
+            print(f"[medformer full {precision}] {key}: rel err vs oracle {e:.3e}, argmax agreement {agree:.5f}")
+            assert e <= (1e-3 if precision == "fp32" else 8e-2) and agree >= (0.9995 if precision == "fp32" else 0.97)
+        loss = losses.calculate_loss(out, batch["label"], None, args, None, None, None, None, classes)["overall"]
+        lr = LR.calculate_loss(ref, batch["label"].long(), None, args, None, None, None, None, classes)["overall"]
+        print(f"[medformer full {precision}] loss {loss.item():.6f} (oracle {lr.item():.6f})")
+        assert abs(loss.item() - lr.item()) <= (1e-4 if precision == "fp32" else 2e-2) * abs(lr.item())
+        if precision == "fp32":
+            loss.backward()
+            lr.backward()
+            P = dict(net.named_parameters())
+            num = sum((P[k].grad.double() - sdr[k].grad.double()).norm().item() ** 2 for k in state) ** 0.5
+            den = sum(sdr[k].grad.double().norm().item() ** 2 for k in state) ** 0.5
+            print(f"[medformer full fp32] gradient: whole-vector rel diff vs the oracle's fp32 autograd {num / den:.3e}")
+            assert all(torch.isfinite(P[k].grad).all() for k in state) and num / den <= 5e-2
+
